@@ -1,0 +1,116 @@
+"""ctypes loader for libvsm_oracle.so (TEST INFRASTRUCTURE ONLY, see vsm_oracle.h).
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libvsm_oracle.so")
+DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "vsm_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libvsm_oracle.so"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        f32p, i64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        _lib.vsm_oracle_l2sqr.restype = C.c_float
+        _lib.vsm_oracle_l2sqr.argtypes = [f32p, f32p]
+        _lib.vsm_oracle_knn.restype = None
+        _lib.vsm_oracle_knn.argtypes = [f32p, C.c_int, C.c_int64, f32p, C.c_int64, C.c_int64,
+                                        C.c_int, i64p, f32p, C.c_int]
+        _lib.vsm_oracle_match_features.restype = C.c_int
+        _lib.vsm_oracle_match_features.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_float, C.c_int,
+                                                   C.c_void_p, i32p, C.c_void_p, i32p, C.c_int]
+        _lib.vsm_oracle_segmented.restype = None
+        _lib.vsm_oracle_segmented.argtypes = [f32p, C.c_int, f32p, i64p, C.c_int, C.c_float,
+                                              i32p, C.c_void_p, C.c_int]
+        _lib.vsm_oracle_merge_top2.restype = None
+        _lib.vsm_oracle_merge_top2.argtypes = [i64p, f32p, C.c_int, C.c_int, i64p, f32p]
+        _lib.vsm_oracle_gen_rows.restype = None
+        _lib.vsm_oracle_gen_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, f32p]
+    return _lib
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def l2sqr(a, b):
+    a, pa = _f32(a)
+    b, pb = _f32(b)
+    return np.float32(lib().vsm_oracle_l2sqr(pa, pb))
+
+
+def knn(q, t, k=2, threads=0):
+    """(idx[nq,k] int64, dist[nq,k] fp32); missing neighbours: idx -1, dist FLT_MAX."""
+    q, pq = _f32(q)
+    t, pt = _f32(t)
+    nq, nt = q.shape[0], t.shape[0]
+    idx = np.empty((nq, k), np.int64)
+    dist = np.empty((nq, k), np.float32)
+    lib().vsm_oracle_knn(pq, nq, 256, pt, nt, 256, k,
+                         idx.ctypes.data_as(C.POINTER(C.c_int64)),
+                         dist.ctypes.data_as(C.POINTER(C.c_float)), threads)
+    return idx, dist
+
+
+def match_features(q, t, ratio=0.75, mutual=False, threads=0):
+    """Slam::match_features (src/Slam.cpp:1140-1172).  Returns (good, raw) DMATCH arrays."""
+    q, pq = _f32(q)
+    t, pt = _f32(t)
+    nq, nt = q.shape[0], t.shape[0]
+    good = np.zeros(max(nq, 1), DMATCH)
+    raw = np.zeros(max(nq, 1), DMATCH)
+    ng, nr = C.c_int32(0), C.c_int32(0)
+    lib().vsm_oracle_match_features(pq, nq, pt, nt, ratio, int(mutual),
+                                    good.ctypes.data, C.byref(ng), raw.ctypes.data, C.byref(nr), threads)
+    return good[:ng.value].copy(), raw[:nr.value].copy()
+
+
+def segmented(q, db, seg_off, ratio=0.75, threads=0):
+    """LoopCloser::detect matching block (src/LoopCloser.cpp:43-62).
+    Returns (counts[nseg], list of DMATCH arrays per segment)."""
+    q, pq = _f32(q)
+    db, pdb = _f32(db)
+    seg_off = np.ascontiguousarray(seg_off, np.int64)
+    nseg, nq = len(seg_off) - 1, q.shape[0]
+    counts = np.zeros(nseg, np.int32)
+    m = np.zeros((nseg, max(nq, 1)), DMATCH)
+    lib().vsm_oracle_segmented(pq, nq, pdb, seg_off.ctypes.data_as(C.POINTER(C.c_int64)), nseg, ratio,
+                               counts.ctypes.data_as(C.POINTER(C.c_int32)), m.ctypes.data, threads)
+    return counts, [m[s, :counts[s]].copy() for s in range(nseg)]
+
+
+def merge_top2(idx_in, dist_in):
+    idx_in = np.ascontiguousarray(idx_in, np.int64)
+    dist_in = np.ascontiguousarray(dist_in, np.float32)
+    ns, nq = idx_in.shape[0], idx_in.shape[1]
+    io = np.empty((nq, 2), np.int64)
+    do = np.empty((nq, 2), np.float32)
+    lib().vsm_oracle_merge_top2(idx_in.ctypes.data_as(C.POINTER(C.c_int64)),
+                                dist_in.ctypes.data_as(C.POINTER(C.c_float)), ns, nq,
+                                io.ctypes.data_as(C.POINTER(C.c_int64)),
+                                do.ctypes.data_as(C.POINTER(C.c_float)))
+    return io, do
+
+
+def gen_rows(seed, set_id, row0, n):
+    out = np.empty((n, 256), np.float32)
+    lib().vsm_oracle_gen_rows(seed, set_id, row0, n, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
