@@ -1,0 +1,189 @@
+/*
+ * vsm.h -- C ABI of the B200-native descriptor-matching engine (libvsm.so).
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of
+ * salah-dev-stu/visual-slam-pipeline: brute-force kNN (k=2) over 256-d fp32
+ * SuperPoint descriptors + Lowe ratio test (+ optional mutual-NN filter), and
+ * top-2 search against a device-resident keyframe descriptor database.
+ *
+ * The reference has no plugin/FFI layer; it calls OpenCV directly.  Each entry
+ * point below cites the reference call it replaces (paths relative to the
+ * reference root).  `include/vsm_cv.hpp` is the header-only C++ adaptor that
+ * gives these calls the reference's own signatures
+ * (cv::Mat in, std::vector<cv::DMatch> out).
+ *
+ * Conventions
+ *   - plain C types only; every function returns a vsm_status (0 = OK) and never
+ *     throws.  vsm_last_error(ctx) gives the message of the last failure.
+ *   - descriptors are row-major fp32, 256 columns, contiguous rows (row stride =
+ *     1024 B), exactly what FeatureExtractor produces
+ *     (src/FeatureExtractor.cpp:170-205).
+ *   - the caller owns all host buffers; the library copies in and never keeps a
+ *     host pointer after returning.  Output arrays are caller-allocated.
+ *   - results equal cv::BFMatcher(NORM_L2).knnMatch on the same input: identical
+ *     indices, identical fp32 distance bits (OpenCV 4.13 baseline build), ties
+ *     to the lowest train index.
+ *   - a context is single-caller (the reference matches on one thread,
+ *     src/main.cpp:1520); calls are synchronous.
+ *   - there is NO CPU fallback: without a CUDA device vsm_create fails with
+ *     VSM_ERR_NO_DEVICE.
+ */
+#ifndef VSM_H
+#define VSM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSM_DIM 256
+
+typedef enum {
+    VSM_OK = 0,
+    VSM_ERR_INVALID = 1,     /* bad argument */
+    VSM_ERR_NO_DEVICE = 2,   /* no usable CUDA device / not sm_100 */
+    VSM_ERR_CUDA = 3,        /* CUDA runtime/driver failure (message in vsm_last_error) */
+    VSM_ERR_CAPACITY = 4,    /* store / scratch capacity exceeded */
+    VSM_ERR_NOT_FOUND = 5    /* unknown keyframe handle */
+} vsm_status;
+
+/* Mirror of cv::DMatch {int queryIdx; int trainIdx; int imgIdx; float distance;}
+ * (OpenCV core/types.hpp), 16 bytes; vsm_cv.hpp static_asserts the equality. */
+typedef struct {
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx;
+    float distance;
+} vsm_dmatch;
+
+typedef enum {
+    VSM_ENGINE_AUTO = 0,     /* tensor-core path (tcgen05) with exact fp32 re-score */
+    VSM_ENGINE_TENSOR = 1,   /* same, forced */
+    VSM_ENGINE_SIMT = 2      /* exact fp32 CUDA-core brute force (debug / cross-check) */
+} vsm_engine;
+
+typedef struct {
+    int32_t device;              /* CUDA device ordinal */
+    int32_t engine;              /* vsm_engine */
+    int64_t scratch_rows;        /* initial capacity for transient descriptor rows (queries,
+                                    pair frames, ragged batches); grows on demand; 0 = 8192 */
+    int64_t store_rows;          /* initial capacity of the keyframe store in rows; it grows
+                                    on demand; 0 = allocate at the first add */
+    int32_t reserved[8];         /* [0]: tiles per slice segment (0 = default 16) */
+} vsm_opts;
+
+typedef struct vsm_ctx vsm_ctx;
+
+/* Counters of the last call (for parity reports and the bench). */
+typedef struct {
+    int64_t candidates;          /* (query,row) pairs re-scored in exact fp32 */
+    int64_t flagged_slices;      /* (query,slice) pairs that fell back to an exact slice scan */
+    int64_t kernel_launches;     /* kernels launched by the last call */
+    float   device_ms;           /* device time of the last call (CUDA events, incl. copies) */
+} vsm_stats;
+
+void        vsm_default_opts(vsm_opts* opts);
+int         vsm_create(const vsm_opts* opts, vsm_ctx** out);
+void        vsm_destroy(vsm_ctx* ctx);
+const char* vsm_last_error(const vsm_ctx* ctx);       /* ctx may be NULL: create() errors */
+const char* vsm_version(void);
+int         vsm_get_stats(const vsm_ctx* ctx, vsm_stats* out);
+
+/* Pinned host memory for callers that want DMA without a staging copy. */
+int  vsm_host_alloc(void** ptr, int64_t bytes);
+void vsm_host_free(void* ptr);
+
+/* ---- pair matching ------------------------------------------------------- */
+
+/* Replaces cv::DescriptorMatcher::knnMatch(query, train, knn, 2) at
+ * src/Slam.cpp:1149, :567, :764 and src/LoopCloser.cpp:51.
+ * idx/dist are [nq][2]; a missing neighbour (nt < 2) is idx = -1, dist = FLT_MAX
+ * (the reference drops those lists with its `m.size() >= 2` guard). */
+int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt,
+             int32_t* idx, float* dist);
+
+/* Replaces Slam::match_features(desc1, desc2, raw_out) for float descriptors
+ * (src/Slam.cpp:1140-1172; decl include/Slam.h:69-70): kNN k=2, then
+ *   raw  = every m[0] whose list has 2 entries                     (:1152-1153)
+ *   good = those with m[0].distance < ratio * m[1].distance (fp32)  (:1154)
+ * both in query order.  ratio is Config::L2_RATIO_THRESHOLD (0.75f) or
+ * FLANN_RATIO_THRESHOLD (0.7f) (include/Config.h:53-55).  mutual != 0 adds the
+ * north-star mutual-NN filter: keep m only if query is also train's nearest.
+ * good and raw must each hold nq entries; raw/n_raw may be NULL.
+ * nq == 0 or nt == 0 -> OK with zero outputs (:1143). */
+int vsm_match_pair(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt,
+                   float ratio, int32_t mutual,
+                   vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw);
+
+/* Ragged batch of independent pairs in one launch (BASELINE configs[4]).
+ * query/train: concatenated rows; q_off/t_off: n_pairs+1 row offsets.
+ * good: concatenated, pair p's survivors start at good[q_off[p]]; n_good[p] entries. */
+int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs,
+                    const float* query, const int32_t* q_off,
+                    const float* train, const int32_t* t_off,
+                    float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good);
+
+/* ---- device-resident keyframe store (Frame::descriptors_, Map::frames_) ---- */
+
+/* Mirrors Map::add_frame for a keyframe (src/Map.cpp, include/Frame.h:37,61):
+ * uploads the N x 256 descriptor matrix once; fp32 master + bf16 shadow live on
+ * the device.  Rows are appended; *handle identifies the keyframe (segment). */
+int vsm_store_add(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int32_t* handle);
+/* Same, from a device pointer (bulk loads; no host round trip). */
+int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, int64_t n, int32_t* handle);
+/* Adopt an externally owned device fp32 matrix as the whole store (no copy of the
+ * fp32 master; builds the bf16 shadow).  seg_off: nseg+1 row offsets or NULL (one segment). */
+int vsm_store_adopt_device(vsm_ctx* ctx, const float* d_desc, int64_t n_rows,
+                           const int64_t* seg_off, int32_t nseg);
+int vsm_store_clear(vsm_ctx* ctx);
+int vsm_store_info(const vsm_ctx* ctx, int64_t* n_rows, int32_t* n_keyframes);
+
+/* Slam::match_features(ref_kf->descriptors(), cur->descriptors()) with the reference
+ * keyframe already resident (src/Slam.cpp:841: query = stored keyframe, train = current). */
+int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t n_cur,
+                        float ratio, int32_t mutual,
+                        vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw);
+
+/* Global top-2 per query over every row of the store -- the stacked-matrix search of
+ * src/Slam.cpp:546-574 and :744-774 (knnMatch(frame, all_descs, 2)).
+ * idx: [nq][2] store row (+ row_offset, for sharded stores), dist: [nq][2]. */
+int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset,
+                int64_t* idx, float* dist);
+
+/* LoopCloser::detect matching block (src/LoopCloser.cpp:43-62): for every stored
+ * keyframe s: top-2 WITHIN the keyframe, ratio test, survivors counted.
+ * counts: [n_keyframes].  matches (may be NULL): [n_keyframes][nq], survivors of
+ * keyframe s first in query order, trainIdx keyframe-local, imgIdx = s. */
+int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
+                     int32_t* counts, vsm_dmatch* matches);
+
+/* ---- device-pointer variants (resident data; multi-GPU plumbing) ---------- */
+
+/* vsm_db_top2 with query and outputs already on this context's device.
+ * d_idx: int64 [nq][2], d_dist: float [nq][2].  Asynchronous on the context stream
+ * unless sync != 0. */
+int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset,
+                       int64_t* d_idx, float* d_dist, int32_t sync);
+
+/* Merge per-shard top-2 lists (e.g. after an NCCL all-gather) by (distance, index).
+ * d_idx_in/d_dist_in: [nshard][nq][2] with GLOBAL indices (-1 = empty). */
+int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_dist_in,
+                          int32_t nshard, int32_t nq, int64_t* d_idx_out, float* d_dist_out,
+                          int32_t sync);
+
+/* Raw CUDA stream of the context (cudaStream_t as void*), for event timing. */
+void* vsm_stream(vsm_ctx* ctx);
+/* Run on a caller-owned stream (e.g. the stream an NCCL collective is enqueued on). */
+int   vsm_set_stream(vsm_ctx* ctx, void* cuda_stream);
+int   vsm_sync(vsm_ctx* ctx);
+
+/* Debug / bring-up: the raw tensor-core accumulators (bf16 dot products q.t) of the
+ * first 128 queries x first 256 train rows, written to out[128*256] (host). */
+int vsm_debug_tile_scores(vsm_ctx* ctx, const float* query, int32_t nq, const float* train,
+                          int32_t nt, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSM_H */

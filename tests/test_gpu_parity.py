@@ -1,0 +1,211 @@
+"""GPU parity: the CUDA path (through the C ABI of libvsm.so) against the CPU oracle and the
+committed cv2 golden answers.  Bar: identical indices, bit-identical fp32 distances, identical
+ratio / mutual decisions -- no tolerance (the re-score reproduces OpenCV's fp32 arithmetic)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import cases, gen, oracle
+import vsm_b200
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def tc():
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def simt():
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_SIMT)
+    yield m
+    m.close()
+
+
+def bf16_round(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def test_tensor_core_tile_is_the_bf16_dot(tc):
+    """Raw tcgen05 accumulators of the first 128x256 tile = dot products of the bf16-rounded rows
+    (validates the TMA swizzle, the UMMA descriptors and the TMEM read-back)."""
+    q, t = gen.rows(1, 0, 0, 128), gen.rows(1, 1, 0, 256)
+    got = tc.debug_tile_scores(q, t)
+    want = bf16_round(q).astype(np.float64) @ bf16_round(t).astype(np.float64).T
+    assert np.abs(got - want).max() < 2e-5
+    # ragged: fewer rows than the tile on both sides
+    q, t = gen.rows(2, 0, 0, 77), gen.rows(2, 1, 0, 201)
+    got = tc.debug_tile_scores(q, t)[:77, :201]
+    want = bf16_round(q).astype(np.float64) @ bf16_round(t).astype(np.float64).T
+    assert np.abs(got - want).max() < 2e-5
+
+
+@pytest.mark.parametrize("name", list(cases.PAIR_CASES))
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+def test_knn_equals_oracle_and_golden(name, engine, request):
+    m = request.getfixturevalue(engine)
+    q, t = cases.PAIR_CASES[name]()
+    idx, dist = m.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(bits(dist), bits(od))
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(bits(dist), bits(g["dist"]))
+
+
+@pytest.mark.parametrize("name", list(cases.PAIR_CASES))
+@pytest.mark.parametrize("ratio", cases.RATIOS)
+def test_match_features_equals_golden(name, ratio, tc):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    q, t = cases.PAIR_CASES[name]()
+    for mutual, key in ((False, "good"), (True, "mutual")):
+        good, raw = tc.match_features(q, t, ratio, mutual=mutual)
+        want = g[f"{key}_{int(ratio * 100)}"]
+        assert np.array_equal(good["queryIdx"], want)
+        assert np.array_equal(good["trainIdx"], g["idx"][want, 0])
+        assert np.array_equal(bits(good["distance"]), bits(g["dist"][want, 0]))
+        assert np.all(good["imgIdx"] == 0)
+        has2 = np.nonzero(g["idx"][:, 1] >= 0)[0]
+        assert np.array_equal(raw["queryIdx"], has2)
+        assert np.array_equal(raw["trainIdx"], g["idx"][has2, 0])
+        og, orw = oracle.match_features(q, t, ratio, mutual=mutual)
+        assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+
+
+def test_empty_inputs(tc):
+    z = np.zeros((0, 256), np.float32)
+    t = gen.rows(0, 0, 0, 10)
+    for a, b in ((z, t), (t, z), (z, z)):
+        good, raw = tc.match_features(a, b)
+        assert len(good) == 0 and len(raw) == 0          # src/Slam.cpp:1143
+    idx, dist = tc.knn_match(t, z)
+    assert np.all(idx == -1) and np.all(dist == np.finfo(np.float32).max)
+
+
+def test_keyframe_store_global_and_segmented(tc):
+    g = np.load(os.path.join(GOLDEN, "db_small.npz"))
+    q, db, seg_off = cases.db_case()
+    tc.clear_store()
+    handles = [tc.add_keyframe(s, db[seg_off[s]:seg_off[s + 1]]) for s in range(len(seg_off) - 1)]
+    assert handles == list(range(len(seg_off) - 1))
+    assert tc.store_info() == (db.shape[0], len(seg_off) - 1)
+    # stacked-matrix search (src/Slam.cpp:546-574)
+    idx, dist = tc.search_map_points(q)
+    assert np.array_equal(idx, g["gidx"]) and np.array_equal(bits(dist), bits(g["gdist"]))
+    idx2, _ = tc.search_map_points(q, row_offset=1000)
+    assert np.array_equal(idx2, g["gidx"] + 1000)
+    # LoopCloser::detect block (src/LoopCloser.cpp:43-62)
+    for col, ratio in enumerate(cases.RATIOS):
+        counts, lists = tc.detect_candidates(q, ratio)
+        assert np.array_equal(counts, g["counts"][:, col])
+        oc, ol = oracle.segmented(q, db, seg_off, ratio)
+        for s in range(len(lists)):
+            assert lists[s].tobytes() == ol[s].tobytes()
+    # Slam::match_features(ref_kf, cur) with the keyframe resident (src/Slam.cpp:841)
+    for s in (0, 3, 5, 7, 15):
+        kf = db[seg_off[s]:seg_off[s + 1]]
+        for mutual in (False, True):
+            good, raw = tc.match_to_keyframe(handles[s], q, 0.75, mutual=mutual, want_raw=True)
+            og, orw = oracle.match_features(kf, q, 0.75, mutual=mutual)
+            assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+    tc.clear_store()
+    assert tc.store_info() == (0, 0)
+
+
+def test_small_segments_force_overflow_path(simt):
+    """seg_tiles=1 + a train set full of near-duplicates: more than three candidates per slice,
+    so the select kernel must fall back to exact slice scans -- and still be exact."""
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, seg_tiles=1)
+    q, t = cases.PAIR_CASES["neardup_db"]()
+    idx, dist = m.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    assert m.stats()["flagged_slices"] > 0
+    m.close()
+
+
+def test_ragged_batch(tc):
+    sizes = [(200, 2048), (777, 1301), (1, 5), (300, 0), (0, 40), (2048, 200), (513, 511), (129, 257)]
+    qs, ts = [], []
+    for i, (nq, nt) in enumerate(sizes):
+        if nq and nt:
+            a, b, _ = gen.planted(40 + i, nq, nt, 0.6, 0.08)
+        else:
+            a, b = gen.rows(40 + i, 0, 0, nq), gen.rows(40 + i, 1, 0, nt)
+        qs.append(a)
+        ts.append(b)
+    for mutual in (False, True):
+        got = tc.match_batch(qs, ts, 0.75, mutual=mutual)
+        for a, b, g in zip(qs, ts, got):
+            og, _ = oracle.match_features(a, b, 0.75, mutual=mutual)
+            assert g.tobytes() == og.tobytes()
+
+
+def test_random_sizes_property(tc):
+    """Random ragged sizes, planted pairs: TC engine == oracle, bit for bit."""
+    rng = np.random.default_rng(7)
+    for it in range(6):
+        nq, nt = int(rng.integers(1, 1500)), int(rng.integers(1, 3000))
+        q, t, _ = gen.planted(100 + it, nq, nt, 0.5, 0.09)
+        idx, dist = tc.knn_match(q, t)
+        oi, od = oracle.knn(q, t, 2)
+        assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+
+
+def test_non_unit_norms_still_exact(tc):
+    """Rows with very different norms defeat the dot-only ranking; the margin widens and
+    the result stays exact."""
+    rng = np.random.default_rng(3)
+    q = gen.rows(5, 0, 0, 200) * rng.uniform(0.5, 2.0, (200, 1)).astype(np.float32)
+    t = gen.rows(5, 1, 0, 900) * rng.uniform(0.5, 2.0, (900, 1)).astype(np.float32)
+    idx, dist = tc.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+
+
+def test_merge_kernel_matches_oracle(tc):
+    import torch
+    q, db, _ = cases.db_case()
+    nshard = 3
+    cuts = np.linspace(0, db.shape[0], nshard + 1).astype(np.int64)
+    ii, dd = [], []
+    for s in range(nshard):
+        i, d = oracle.knn(q, db[cuts[s]:cuts[s + 1]], 2)
+        ii.append(np.where(i >= 0, i + cuts[s], -1))
+        dd.append(d)
+    want_i, want_d = oracle.merge_top2(np.stack(ii), np.stack(dd))
+    di = torch.from_numpy(np.stack(ii)).cuda()
+    ddv = torch.from_numpy(np.stack(dd)).cuda()
+    oi = torch.empty((q.shape[0], 2), dtype=torch.int64, device="cuda")
+    od = torch.empty((q.shape[0], 2), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    tc.merge_top2_device(di.data_ptr(), ddv.data_ptr(), nshard, q.shape[0], oi.data_ptr(), od.data_ptr(), sync=True)
+    assert np.array_equal(oi.cpu().numpy(), want_i) and np.array_equal(bits(od.cpu().numpy()), bits(want_d))
+
+
+def test_device_resident_db_search(tc):
+    import torch
+    q, db, seg_off = cases.db_case()
+    d_db = torch.from_numpy(db).cuda()
+    d_q = torch.from_numpy(q).cuda()
+    torch.cuda.synchronize()
+    tc.adopt_device_matrix(d_db.data_ptr(), db.shape[0], seg_off)
+    oi = torch.empty((q.shape[0], 2), dtype=torch.int64, device="cuda")
+    od = torch.empty((q.shape[0], 2), dtype=torch.float32, device="cuda")
+    tc.db_top2_device(d_q.data_ptr(), q.shape[0], 5000, oi.data_ptr(), od.data_ptr(), sync=True)
+    wi, wd = oracle.knn(q, db, 2)
+    assert np.array_equal(oi.cpu().numpy(), wi + 5000) and np.array_equal(bits(od.cpu().numpy()), bits(wd))
+    counts, _ = tc.detect_candidates(q, 0.75, want_matches=False)
+    oc, _ = oracle.segmented(q, db, seg_off, 0.75)
+    assert np.array_equal(counts, oc)
+    tc.clear_store()

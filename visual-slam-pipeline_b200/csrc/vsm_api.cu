@@ -1,0 +1,821 @@
+// vsm_api.cu -- host side of libvsm.so: context, device-resident descriptor arenas,
+// launch planning and the C ABI declared in include/vsm.h.
+//
+// There is no CPU fallback anywhere in this file: every entry point either runs the
+// CUDA kernels or returns an error code.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vsm.h"
+#include "vsm_common.cuh"
+#include "vsm_kernels.cuh"
+#include "vsm_tc.cuh"
+
+using namespace vsm;
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+thread_local std::string g_create_error;
+
+struct Arena {
+    float* f32 = nullptr;            // fp32 master rows (exact re-score reads these)
+    __nv_bfloat16* b16 = nullptr;    // bf16 shadow (tensor-core operand, TMA source)
+    float* n2 = nullptr;             // squared norms
+    int64_t cap = 0;                 // rows
+    bool own_f32 = true;
+    CUtensorMap map;
+};
+
+struct Seg {
+    int64_t row0;
+    int32_t count;
+    int32_t frame_id;
+};
+
+// Host description of one kNN problem before planning.
+struct HProblem {
+    const float* q_f32;  const float* q_n2;  int64_t q_row;  int q_store;  int nq;
+    const float* t_f32;  int64_t t_row;  int t_store;  int nt;
+    int64_t out_off;
+};
+
+struct HJob {
+    int64_t fwd_off, back_off, good_off, raw_off;
+    int nq, nt, img_idx;
+    float ratio;
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct vsm_ctx {
+    int device = 0;
+    int engine = VSM_ENGINE_AUTO;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    Arena scratch, store;
+    int64_t store_rows = 0;
+    std::vector<Seg> segs;
+    uint32_t* d_store_stats = nullptr;   // {min, max} squared norm over the store
+    DevBuf<uint8_t> d_desc;
+    uint8_t* h_desc = nullptr;
+    size_t h_desc_cap = 0;
+    DevBuf<PartialRec> d_recs;
+    DevBuf<int32_t> d_out_idx;
+    DevBuf<float> d_out_dist;
+    DevBuf<uint8_t> d_result;            // DMatch lists followed by the counts
+    uint8_t* h_result = nullptr;
+    size_t h_result_cap = 0;
+    unsigned long long* d_counters = nullptr;
+    float* d_dump = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    vsm_stats stats{};
+    int launches = 0;
+    std::string err;
+    PFN_encodeTiled encode = nullptr;
+    int seg_tiles = 16;
+};
+
+namespace {
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            char b_[512];                                                                            \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = b_;                                                                           \
+            return VSM_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define TRY(call)                    \
+    do {                             \
+        int s_ = (call);             \
+        if (s_ != VSM_OK) return s_; \
+    } while (0)
+
+int fail(vsm_ctx* ctx, int code, const char* msg) {
+    ctx->err = msg;
+    return code;
+}
+
+template <class T>
+int ensure(vsm_ctx* ctx, DevBuf<T>& b, size_t n) {
+    if (n <= b.cap) return VSM_OK;
+    size_t want = std::max(n, b.cap + b.cap / 2);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CK(cudaMalloc(&b.p, want * sizeof(T)));
+    b.cap = want;
+    return VSM_OK;
+}
+
+int ensure_host(vsm_ctx* ctx, uint8_t*& p, size_t& cap, size_t n) {
+    if (n <= cap) return VSM_OK;
+    size_t want = std::max(n, cap * 2);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (p) CK(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    CK(cudaMallocHost(&p, want));
+    cap = want;
+    return VSM_OK;
+}
+
+int encode_map(vsm_ctx* ctx, Arena& a) {
+    // bf16 [cap rows][256], box = 64 columns x 128 rows, SWIZZLE_128B (rows of 128 bytes)
+    cuuint64_t gdim[2] = {(cuuint64_t)VSM_DIM, (cuuint64_t)a.cap};
+    cuuint64_t gstr[1] = {(cuuint64_t)VSM_DIM * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {64u, 128u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = ctx->encode(&a.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.b16, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[128];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+        ctx->err = b;
+        return VSM_ERR_CUDA;
+    }
+    return VSM_OK;
+}
+
+// Grow an arena to hold `rows`; keeps the first `keep` rows.
+int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
+    if (rows <= a.cap && a.b16) return VSM_OK;
+    int64_t want = std::max<int64_t>(rows, a.cap + a.cap / 2);
+    want = (want + 255) / 256 * 256;
+    CK(cudaStreamSynchronize(ctx->stream));
+    float* f32 = nullptr; __nv_bfloat16* b16 = nullptr; float* n2 = nullptr;
+    if (a.own_f32) CK(cudaMalloc(&f32, (size_t)want * VSM_DIM * sizeof(float)));
+    CK(cudaMalloc(&b16, (size_t)want * VSM_DIM * sizeof(__nv_bfloat16)));
+    CK(cudaMalloc(&n2, (size_t)want * sizeof(float)));
+    if (keep > 0) {
+        if (a.own_f32) CK(cudaMemcpy(f32, a.f32, (size_t)keep * VSM_DIM * sizeof(float), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(b16, a.b16, (size_t)keep * VSM_DIM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(n2, a.n2, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    if (a.own_f32) { if (a.f32) CK(cudaFree(a.f32)); a.f32 = f32; }
+    if (a.b16) CK(cudaFree(a.b16));
+    if (a.n2) CK(cudaFree(a.n2));
+    a.b16 = b16; a.n2 = n2; a.cap = want;
+    return encode_map(ctx, a);
+}
+
+void arena_free(Arena& a) {
+    if (a.own_f32 && a.f32) cudaFree(a.f32);
+    if (a.b16) cudaFree(a.b16);
+    if (a.n2) cudaFree(a.n2);
+    a = Arena();
+}
+
+int launch_convert(vsm_ctx* ctx, const float* src, __nv_bfloat16* dst, float* n2, int64_t rows, uint32_t* stats) {
+    if (rows <= 0) return VSM_OK;
+    int64_t blocks = std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->num_sms * 16);
+    convert_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, dst, n2, rows, stats);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return VSM_OK;
+}
+
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+int begin_call(vsm_ctx* ctx) {
+    ctx->err.clear();
+    ctx->launches = 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    return VSM_OK;
+}
+
+int end_call(vsm_ctx* ctx, bool sync) {
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (sync) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        unsigned long long c[2];
+        CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+        ctx->stats.candidates = (int64_t)c[0];
+        ctx->stats.flagged_slices = (int64_t)c[1];
+        ctx->stats.device_ms = ms;
+    }
+    ctx->stats.kernel_launches = ctx->launches;
+    return VSM_OK;
+}
+
+// Plans, uploads and launches: tensor-core pass -> select/re-score -> filter.
+// The scratch stats slot lives at the head of the descriptor block; `conv_*` describes
+// the scratch rows that still have to be converted (after the block is uploaded, because
+// the upload re-arms the slot).
+int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::vector<HJob>& jobs,
+                 int64_t total_out, int64_t total_matches, const float* conv_src, int64_t conv_row0,
+                 int64_t conv_rows, int dump_first = 0) {
+    const bool exact = ctx->engine == VSM_ENGINE_SIMT;
+    const int P = (int)probs.size();
+    std::vector<Problem> dp(P);
+    std::vector<int32_t> qb(P + 1, 0);
+    std::vector<TcUnit> units;
+    std::vector<SliceInfo> slices;
+    int64_t nrecs = 0;
+
+    int64_t total_qtiles = 0;
+    for (auto& p : probs) if (p.nq > 0 && p.nt > 0) total_qtiles += (p.nq + TILE_M - 1) / TILE_M;
+    const int64_t budget = std::max<int64_t>(1, total_qtiles ? ctx->num_sms / total_qtiles : 1);
+
+    // device addresses inside the descriptor block are fixed up after the layout is known
+    for (int i = 0; i < P; i++) {
+        const HProblem& hp = probs[i];
+        Problem& d = dp[i];
+        memset(&d, 0, sizeof d);
+        d.q_f32 = hp.q_f32; d.t_f32 = hp.t_f32; d.q_n2 = hp.q_n2;
+        d.out_off = hp.out_off; d.nq = hp.nq; d.nt = hp.nt;
+        d.slice_off = (int32_t)slices.size();
+        d.partial_off = nrecs;
+        d.exact = (exact || hp.nt == 0) ? 1 : 0;
+        qb[i + 1] = qb[i] + (hp.nq + SELECT_WARPS - 1) / SELECT_WARPS;
+        if (hp.nq <= 0 || hp.nt <= 0) { d.nslices = 0; continue; }
+        if (d.exact) {
+            SliceInfo si = {0, hp.nt, -1, 0};
+            slices.push_back(si);
+            d.nslices = 1;
+            continue;
+        }
+        const int ntiles = (hp.nt + TILE_N - 1) / TILE_N;
+        int nranges = (int)std::min<int64_t>(ntiles, budget);
+        const int tpr = (ntiles + nranges - 1) / nranges;
+        nranges = (ntiles + tpr - 1) / tpr;
+        const int seg = std::min(tpr, ctx->seg_tiles);
+        const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
+        std::vector<int> range_slice0(nranges);
+        for (int r = 0; r < nranges; r++) {
+            range_slice0[r] = (int)slices.size() - d.slice_off;
+            const int tile0 = r * tpr, tile1 = std::min(ntiles, tile0 + tpr);
+            for (int t0 = tile0; t0 < tile1; t0 += seg) {
+                const int32_t i0 = t0 * TILE_N;
+                const int32_t cnt = std::min<int64_t>((int64_t)std::min(seg, tile1 - t0) * TILE_N, hp.nt - i0);
+                for (int h = 0; h < 2; h++) { SliceInfo si = {i0, cnt, h, 0}; slices.push_back(si); }
+            }
+        }
+        d.nslices = (int)slices.size() - d.slice_off;
+        for (int r = 0; r < nranges; r++) {
+            const int tile0 = r * tpr, tile1 = std::min(ntiles, tile0 + tpr);
+            for (int qt = 0; qt < nqt; qt++) {
+                TcUnit u;
+                memset(&u, 0, sizeof u);
+                u.q_n2 = hp.q_n2 + (int64_t)qt * TILE_M;
+                u.t_stats = nullptr;                                    // fixed up below
+                u.rec_base = nrecs + (int64_t)qt * TILE_M * d.nslices + range_slice0[r];
+                u.rec_stride = d.nslices;
+                u.q_row = (int32_t)(hp.q_row + (int64_t)qt * TILE_M);
+                u.t_row = (int32_t)(hp.t_row + (int64_t)tile0 * TILE_N);
+                u.t_index0 = tile0 * TILE_N;
+                u.t_count = (int32_t)std::min<int64_t>((int64_t)(tile1 - tile0) * TILE_N, hp.nt - u.t_index0);
+                u.q_valid = std::min(TILE_M, hp.nq - qt * TILE_M);
+                u.seg_tiles = seg;
+                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0);
+                u.dump = (dump_first && units.empty()) ? 1 : 0;
+                u.pad = i;                                              // problem index, for the fix-up
+                units.push_back(u);
+            }
+        }
+        nrecs += (int64_t)hp.nq * d.nslices;
+    }
+
+    // descriptor block: [scratch stats 16 B][Problem][q_block0][TcUnit][SliceInfo][FilterJob]
+    const size_t off_prob = 16;
+    const size_t off_qb = align16(off_prob + sizeof(Problem) * P);
+    const size_t off_unit = align16(off_qb + sizeof(int32_t) * (P + 1));
+    const size_t off_slice = align16(off_unit + sizeof(TcUnit) * units.size());
+    const size_t off_job = align16(off_slice + sizeof(SliceInfo) * slices.size());
+    const size_t total = align16(off_job + sizeof(FilterJob) * jobs.size());
+    TRY(ensure(ctx, ctx->d_desc, total));
+    TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
+    TRY(ensure(ctx, ctx->d_recs, (size_t)std::max<int64_t>(nrecs, 1)));
+    TRY(ensure(ctx, ctx->d_out_idx, (size_t)std::max<int64_t>(total_out * 2, 2)));
+    TRY(ensure(ctx, ctx->d_out_dist, (size_t)std::max<int64_t>(total_out * 2, 2)));
+    const size_t result_bytes = (size_t)total_matches * sizeof(DMatch) + jobs.size() * 2 * sizeof(int32_t);
+    TRY(ensure(ctx, ctx->d_result, std::max<size_t>(result_bytes, 16)));
+
+    uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_desc.p);
+    for (int i = 0; i < P; i++) dp[i].t_stats = probs[i].t_store ? ctx->d_store_stats : d_scratch_stats;
+    for (auto& u : units) { u.t_stats = dp[u.pad].t_stats; u.pad = 0; }
+
+    uint8_t* h = ctx->h_desc;
+    uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};                         // {min=+inf, max=0}
+    memcpy(h, arm, 16);
+    memcpy(h + off_prob, dp.data(), sizeof(Problem) * P);
+    memcpy(h + off_qb, qb.data(), sizeof(int32_t) * (P + 1));
+    if (!units.empty()) memcpy(h + off_unit, units.data(), sizeof(TcUnit) * units.size());
+    if (!slices.empty()) memcpy(h + off_slice, slices.data(), sizeof(SliceInfo) * slices.size());
+    std::vector<FilterJob> fj(jobs.size());
+    for (size_t j = 0; j < jobs.size(); j++) {
+        memset(&fj[j], 0, sizeof(FilterJob));
+        fj[j].fwd_off = jobs[j].fwd_off; fj[j].back_off = jobs[j].back_off;
+        fj[j].good_off = jobs[j].good_off; fj[j].raw_off = jobs[j].raw_off;
+        fj[j].nq = jobs[j].nq; fj[j].nt = jobs[j].nt; fj[j].img_idx = jobs[j].img_idx; fj[j].ratio = jobs[j].ratio;
+    }
+    if (!fj.empty()) memcpy(h + off_job, fj.data(), sizeof(FilterJob) * fj.size());
+    CK(cudaMemcpyAsync(ctx->d_desc.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+
+    if (conv_rows > 0)
+        TRY(launch_convert(ctx, conv_src, ctx->scratch.b16 + conv_row0 * VSM_DIM, ctx->scratch.n2 + conv_row0,
+                           conv_rows, d_scratch_stats));
+
+    uint8_t* dd = ctx->d_desc.p;
+    if (!units.empty()) {
+        const CUtensorMap& ms = ctx->scratch.map;
+        const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
+        tc::tc_top3_kernel<<<(unsigned)units.size(), tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
+            ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (qb[P] > 0) {
+        select_kernel<<<(unsigned)qb[P], SELECT_WARPS * 32, 0, ctx->stream>>>(
+            reinterpret_cast<const Problem*>(dd + off_prob), P, reinterpret_cast<const int32_t*>(dd + off_qb),
+            ctx->d_recs.p, reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_idx.p, ctx->d_out_dist.p,
+            ctx->d_counters);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (!jobs.empty()) {
+        DMatch* dm = reinterpret_cast<DMatch*>(ctx->d_result.p);
+        int32_t* dc = reinterpret_cast<int32_t*>(ctx->d_result.p + (size_t)total_matches * sizeof(DMatch));
+        filter_kernel<<<(unsigned)jobs.size(), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const FilterJob*>(dd + off_job), ctx->d_out_idx.p, ctx->d_out_dist.p, dm, dc);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return VSM_OK;
+}
+
+// Host rows -> scratch fp32 rows [row0, row0+n).
+int upload_scratch(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n) {
+    if (n <= 0) return VSM_OK;
+    CK(cudaMemcpyAsync(ctx->scratch.f32 + row0 * VSM_DIM, src, (size_t)n * VSM_DIM * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    return VSM_OK;
+}
+
+int fetch_result(vsm_ctx* ctx, size_t bytes) {
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(bytes, 16)));
+    if (bytes) CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return VSM_OK;
+}
+
+HProblem scratch_vs_scratch(vsm_ctx* ctx, int64_t q_row, int nq, int64_t t_row, int nt, int64_t out_off) {
+    HProblem p;
+    p.q_f32 = ctx->scratch.f32 + q_row * VSM_DIM; p.q_n2 = ctx->scratch.n2 + q_row; p.q_row = q_row;
+    p.q_store = 0; p.nq = nq;
+    p.t_f32 = ctx->scratch.f32 + t_row * VSM_DIM; p.t_row = t_row; p.t_store = 0; p.nt = nt;
+    p.out_off = out_off;
+    return p;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------
+extern "C" {
+
+void vsm_default_opts(vsm_opts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->engine = VSM_ENGINE_AUTO;
+}
+
+const char* vsm_version(void) { return "vsm-b200 0.1 (sm_100a, tcgen05)"; }
+
+const char* vsm_last_error(const vsm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
+    if (!out) return VSM_ERR_INVALID;
+    *out = nullptr;
+    vsm_opts o;
+    if (opts) o = *opts; else vsm_default_opts(&o);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || o.device < 0 || o.device >= ndev) {
+        cudaGetLastError();
+        g_create_error = "no usable CUDA device (this library has no CPU fallback)";
+        return VSM_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, o.device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only";
+        return VSM_ERR_NO_DEVICE;
+    }
+    vsm_ctx* ctx = new vsm_ctx();
+    ctx->device = o.device;
+    ctx->engine = o.engine;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (o.reserved[0] > 0) ctx->seg_tiles = o.reserved[0];
+    auto bail = [&](int code) {
+        g_create_error = ctx->err;
+        vsm_destroy(ctx);
+        return code;
+    };
+    auto init = [&]() -> int {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ctx->ev0));
+        CK(cudaEventCreate(&ctx->ev1));
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, VSM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        ctx->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+        CK(cudaMalloc(&ctx->d_store_stats, 16));
+        uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};
+        CK(cudaMemcpy(ctx->d_store_stats, arm, 16, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
+        CK(cudaFuncSetAttribute(tc::tc_top3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        TRY(arena_reserve(ctx, ctx->scratch, o.scratch_rows > 0 ? o.scratch_rows : 8192, 0));
+        if (o.store_rows > 0) TRY(arena_reserve(ctx, ctx->store, o.store_rows, 0));
+        return VSM_OK;
+    };
+    int s = init();
+    if (s != VSM_OK) return bail(s);
+    *out = ctx;
+    return VSM_OK;
+}
+
+void vsm_destroy(vsm_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    arena_free(ctx->scratch);
+    arena_free(ctx->store);
+    if (ctx->d_store_stats) cudaFree(ctx->d_store_stats);
+    if (ctx->d_desc.p) cudaFree(ctx->d_desc.p);
+    if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
+    if (ctx->d_recs.p) cudaFree(ctx->d_recs.p);
+    if (ctx->d_out_idx.p) cudaFree(ctx->d_out_idx.p);
+    if (ctx->d_out_dist.p) cudaFree(ctx->d_out_dist.p);
+    if (ctx->d_result.p) cudaFree(ctx->d_result.p);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_dump) cudaFree(ctx->d_dump);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int vsm_get_stats(const vsm_ctx* ctx, vsm_stats* out) {
+    if (!ctx || !out) return VSM_ERR_INVALID;
+    *out = ctx->stats;
+    return VSM_OK;
+}
+
+int vsm_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return VSM_ERR_INVALID;
+    return cudaMallocHost(ptr, (size_t)bytes) == cudaSuccess ? VSM_OK : VSM_ERR_CUDA;
+}
+void vsm_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+void* vsm_stream(vsm_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int vsm_set_stream(vsm_ctx* ctx, void* stream) {
+    if (!ctx) return VSM_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) CK(cudaStreamDestroy(ctx->stream));
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
+    return VSM_OK;
+}
+
+int vsm_sync(vsm_ctx* ctx) {
+    if (!ctx) return VSM_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VSM_OK;
+}
+
+// ---- pair matching ---------------------------------------------------------------------
+int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt, int32_t* idx,
+             float* dist) {
+    if (!ctx || nq < 0 || nt < 0 || (nq > 0 && (!query || !idx || !dist)) || (nt > 0 && !train))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_knn2: bad argument") : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + nt, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    TRY(upload_scratch(ctx, train, nq, nt));
+    std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
+    TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + nt));
+    CK(cudaMemcpyAsync(idx, ctx->d_out_idx.p, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist, ctx->d_out_dist.p, (size_t)nq * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int nt, float ratio, int mutual,
+                        vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw,
+                        const float* conv_src, int64_t conv_row0, int64_t conv_rows) {
+    const bool want_raw = raw && n_raw;
+    HJob j;
+    j.fwd_off = 0; j.back_off = mutual ? nq : -1; j.good_off = 0; j.raw_off = want_raw ? nq : -1;
+    j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
+    const int64_t total_matches = (int64_t)nq * (want_raw ? 2 : 1);
+    TRY(run_problems(ctx, probs, {j}, (int64_t)nq + (mutual ? nt : 0), total_matches, conv_src, conv_row0, conv_rows));
+    const size_t bytes = (size_t)total_matches * sizeof(DMatch) + 2 * sizeof(int32_t);
+    TRY(fetch_result(ctx, bytes));
+    TRY(end_call(ctx, true));
+    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result + (size_t)total_matches * sizeof(DMatch));
+    *n_good = c[0];
+    memcpy(good, ctx->h_result, (size_t)c[0] * sizeof(DMatch));
+    if (want_raw) {
+        *n_raw = c[1];
+        memcpy(raw, ctx->h_result + (size_t)nq * sizeof(DMatch), (size_t)c[1] * sizeof(DMatch));
+    }
+    return VSM_OK;
+}
+
+int vsm_match_pair(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt, float ratio,
+                   int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
+    if (!ctx || nq < 0 || nt < 0 || !n_good || (nq > 0 && (!query || !good)) || (nt > 0 && !train))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_pair: bad argument") : VSM_ERR_INVALID;
+    *n_good = 0;
+    if (n_raw) *n_raw = 0;
+    if (nq == 0 || nt == 0) return VSM_OK;                              // src/Slam.cpp:1143
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + nt, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    TRY(upload_scratch(ctx, train, nq, nt));
+    std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
+    if (mutual) probs.push_back(scratch_vs_scratch(ctx, nq, nt, 0, nq, nq));
+    return match_common(ctx, probs, nq, nt, ratio, mutual, good, n_good, raw, n_raw, ctx->scratch.f32, 0,
+                        (int64_t)nq + nt);
+}
+
+int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int32_t* q_off, const float* train,
+                    const int32_t* t_off, float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good) {
+    if (!ctx || n_pairs < 0 || (n_pairs > 0 && (!q_off || !t_off || !n_good)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_batch: bad argument") : VSM_ERR_INVALID;
+    if (n_pairs == 0) return VSM_OK;
+    const int64_t NQ = q_off[n_pairs], NT = t_off[n_pairs];
+    for (int p = 0; p < n_pairs; p++) {
+        if (q_off[p + 1] < q_off[p] || t_off[p + 1] < t_off[p])
+            return fail(ctx, VSM_ERR_INVALID, "vsm_match_batch: offsets must be non-decreasing");
+        n_good[p] = 0;
+    }
+    if (NQ == 0) return VSM_OK;
+    if (!query || !good || (NT > 0 && !train)) return fail(ctx, VSM_ERR_INVALID, "vsm_match_batch: null buffer");
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, NQ + NT, 0));
+    TRY(upload_scratch(ctx, query, 0, NQ));
+    TRY(upload_scratch(ctx, train, NQ, NT));
+    std::vector<HProblem> probs;
+    std::vector<HJob> jobs;
+    for (int p = 0; p < n_pairs; p++) {
+        const int nq = q_off[p + 1] - q_off[p], nt = t_off[p + 1] - t_off[p];
+        probs.push_back(scratch_vs_scratch(ctx, q_off[p], nq, NQ + t_off[p], nt, q_off[p]));
+        if (mutual) probs.push_back(scratch_vs_scratch(ctx, NQ + t_off[p], nt, q_off[p], nq, NQ + t_off[p]));
+        HJob j;
+        j.fwd_off = q_off[p]; j.back_off = mutual ? NQ + t_off[p] : -1; j.good_off = q_off[p]; j.raw_off = -1;
+        j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
+        jobs.push_back(j);
+    }
+    TRY(run_problems(ctx, probs, jobs, NQ + (mutual ? NT : 0), NQ, ctx->scratch.f32, 0, NQ + NT));
+    const size_t bytes = (size_t)NQ * sizeof(DMatch) + (size_t)n_pairs * 2 * sizeof(int32_t);
+    TRY(fetch_result(ctx, bytes));
+    TRY(end_call(ctx, true));
+    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result + (size_t)NQ * sizeof(DMatch));
+    for (int p = 0; p < n_pairs; p++) {
+        n_good[p] = c[2 * p];
+        memcpy(good + q_off[p], ctx->h_result + (size_t)q_off[p] * sizeof(DMatch), (size_t)c[2 * p] * sizeof(DMatch));
+    }
+    return VSM_OK;
+}
+
+// ---- keyframe store ------------------------------------------------------------------
+static int store_append(vsm_ctx* ctx, int32_t frame_id, const float* src, int64_t n, cudaMemcpyKind kind,
+                        int32_t* handle) {
+    if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it first");
+    TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + std::max<int64_t>(n, 1), ctx->store_rows));
+    const int64_t row0 = ctx->store_rows;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, src, (size_t)n * VSM_DIM * sizeof(float), kind, ctx->stream));
+        TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
+                           ctx->store.n2 + row0, n, ctx->d_store_stats));
+        if (kind == cudaMemcpyHostToDevice) CK(cudaStreamSynchronize(ctx->stream));   // caller may reuse src
+    }
+    Seg s = {row0, (int32_t)n, frame_id};
+    ctx->segs.push_back(s);
+    ctx->store_rows += n;
+    if (handle) *handle = (int32_t)ctx->segs.size() - 1;
+    return VSM_OK;
+}
+
+int vsm_store_add(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int32_t* handle) {
+    if (!ctx || n < 0 || (n > 0 && !desc)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_add: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    return store_append(ctx, frame_id, desc, n, cudaMemcpyHostToDevice, handle);
+}
+
+int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, int64_t n, int32_t* handle) {
+    if (!ctx || n < 0 || n > INT32_MAX || (n > 0 && !d_desc))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_add_device: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    return store_append(ctx, frame_id, d_desc, n, cudaMemcpyDeviceToDevice, handle);
+}
+
+int vsm_store_clear(vsm_ctx* ctx) {
+    if (!ctx) return VSM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->store.own_f32) arena_free(ctx->store);
+    ctx->store_rows = 0;
+    ctx->segs.clear();
+    uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};
+    CK(cudaMemcpy(ctx->d_store_stats, arm, 16, cudaMemcpyHostToDevice));
+    return VSM_OK;
+}
+
+int vsm_store_adopt_device(vsm_ctx* ctx, const float* d_desc, int64_t n_rows, const int64_t* seg_off, int32_t nseg) {
+    if (!ctx || !d_desc || n_rows <= 0 || n_rows > INT32_MAX || (seg_off && nseg <= 0))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_adopt_device: bad argument") : VSM_ERR_INVALID;
+    TRY(vsm_store_clear(ctx));
+    arena_free(ctx->store);
+    ctx->store.own_f32 = false;
+    ctx->store.f32 = const_cast<float*>(d_desc);
+    TRY(arena_reserve(ctx, ctx->store, n_rows, 0));
+    ctx->launches = 0;
+    TRY(launch_convert(ctx, d_desc, ctx->store.b16, ctx->store.n2, n_rows, ctx->d_store_stats));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->store_rows = n_rows;
+    if (seg_off) {
+        for (int s = 0; s < nseg; s++) {
+            if (seg_off[s + 1] < seg_off[s] || seg_off[s + 1] > n_rows)
+                return fail(ctx, VSM_ERR_INVALID, "vsm_store_adopt_device: bad segment offsets");
+            Seg g = {seg_off[s], (int32_t)(seg_off[s + 1] - seg_off[s]), s};
+            ctx->segs.push_back(g);
+        }
+    } else {
+        Seg g = {0, (int32_t)n_rows, 0};
+        ctx->segs.push_back(g);
+    }
+    return VSM_OK;
+}
+
+int vsm_store_info(const vsm_ctx* ctx, int64_t* n_rows, int32_t* n_keyframes) {
+    if (!ctx) return VSM_ERR_INVALID;
+    if (n_rows) *n_rows = ctx->store_rows;
+    if (n_keyframes) *n_keyframes = (int32_t)ctx->segs.size();
+    return VSM_OK;
+}
+
+int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t n_cur, float ratio, int32_t mutual,
+                        vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
+    if (!ctx || n_cur < 0 || !n_good || (n_cur > 0 && !cur))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_to_stored: bad argument") : VSM_ERR_INVALID;
+    if (handle < 0 || handle >= (int)ctx->segs.size()) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown keyframe handle");
+    const Seg sg = ctx->segs[handle];
+    *n_good = 0;
+    if (n_raw) *n_raw = 0;
+    if (sg.count == 0 || n_cur == 0) return VSM_OK;
+    if (!good) return fail(ctx, VSM_ERR_INVALID, "vsm_match_to_stored: null output");
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, n_cur, 0));
+    TRY(upload_scratch(ctx, cur, 0, n_cur));
+    HProblem f;
+    f.q_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + sg.row0; f.q_row = sg.row0;
+    f.q_store = 1; f.nq = sg.count;
+    f.t_f32 = ctx->scratch.f32; f.t_row = 0; f.t_store = 0; f.nt = n_cur; f.out_off = 0;
+    std::vector<HProblem> probs{f};
+    if (mutual) {
+        HProblem b;
+        b.q_f32 = ctx->scratch.f32; b.q_n2 = ctx->scratch.n2; b.q_row = 0; b.q_store = 0; b.nq = n_cur;
+        b.t_f32 = f.q_f32; b.t_row = sg.row0; b.t_store = 1; b.nt = sg.count; b.out_off = sg.count;
+        probs.push_back(b);
+    }
+    return match_common(ctx, probs, sg.count, n_cur, ratio, mutual, good, n_good, raw, n_raw, ctx->scratch.f32, 0, n_cur);
+}
+
+// ---- database search -------------------------------------------------------------------
+static int db_problem(vsm_ctx* ctx, const float* q_f32, int nq, HProblem& p) {
+    p.q_f32 = q_f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
+    p.t_f32 = ctx->store.f32; p.t_row = 0; p.t_store = 1; p.nt = (int)ctx->store_rows; p.out_off = 0;
+    return VSM_OK;
+}
+
+int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset, int64_t* idx, float* dist) {
+    if (!ctx || nq < 0 || (nq > 0 && (!query || !idx || !dist)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2: bad argument") : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    HProblem p;
+    db_problem(ctx, ctx->scratch.f32, nq, p);
+    TRY(run_problems(ctx, {p}, {}, nq, 0, ctx->scratch.f32, 0, nq));
+    const size_t nb = (size_t)nq * 2 * sizeof(int32_t);
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, nb));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_out_idx.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(dist, ctx->d_out_dist.p, (size_t)nq * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(end_call(ctx, true));
+    const int32_t* li = reinterpret_cast<const int32_t*>(ctx->h_result);
+    for (int i = 0; i < nq * 2; i++) idx[i] = li[i] < 0 ? -1 : (int64_t)li[i] + row_offset;
+    return VSM_OK;
+}
+
+int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset, int64_t* d_idx,
+                       float* d_dist, int32_t sync) {
+    if (!ctx || nq < 0 || (nq > 0 && (!d_query || !d_idx || !d_dist)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_device: bad argument") : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    HProblem p;
+    db_problem(ctx, d_query, nq, p);
+    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq));
+    widen_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_idx.p, ctx->d_out_dist.p, nq * 2,
+                                                                 row_offset, d_idx, d_dist);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return end_call(ctx, sync != 0);
+}
+
+int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, int32_t* counts, vsm_dmatch* matches) {
+    if (!ctx || nq < 0 || (nq > 0 && !query) || !counts)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_segmented: bad argument") : VSM_ERR_INVALID;
+    const int nseg = (int)ctx->segs.size();
+    for (int s = 0; s < nseg; s++) counts[s] = 0;
+    if (nq == 0 || nseg == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    std::vector<HProblem> probs;
+    std::vector<HJob> jobs;
+    for (int s = 0; s < nseg; s++) {
+        const Seg& sg = ctx->segs[s];
+        HProblem p;
+        p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
+        p.t_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; p.t_row = sg.row0; p.t_store = 1; p.nt = sg.count;
+        p.out_off = (int64_t)s * nq;
+        probs.push_back(p);
+        HJob j;
+        j.fwd_off = p.out_off; j.back_off = -1; j.good_off = (int64_t)s * nq; j.raw_off = -1;
+        j.nq = nq; j.nt = sg.count; j.img_idx = s; j.ratio = ratio;
+        jobs.push_back(j);
+    }
+    const int64_t total_matches = (int64_t)nseg * nq;
+    TRY(run_problems(ctx, probs, jobs, total_matches, total_matches, ctx->scratch.f32, 0, nq));
+    const size_t mbytes = (size_t)total_matches * sizeof(DMatch);
+    const size_t cbytes = (size_t)nseg * 2 * sizeof(int32_t);
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, cbytes));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p + mbytes, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (matches) CK(cudaMemcpyAsync(matches, ctx->d_result.p, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(end_call(ctx, true));
+    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result);
+    for (int s = 0; s < nseg; s++) counts[s] = c[2 * s];
+    return VSM_OK;
+}
+
+int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_dist_in, int32_t nshard, int32_t nq,
+                          int64_t* d_idx_out, float* d_dist_out, int32_t sync) {
+    if (!ctx || nshard <= 0 || nq < 0 || (nq > 0 && (!d_idx_in || !d_dist_in || !d_idx_out || !d_dist_out)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_merge_top2_device: bad argument") : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(d_idx_in, d_dist_in, nshard, nq, d_idx_out, d_dist_out);
+    CK(cudaGetLastError());
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return VSM_OK;
+}
+
+int vsm_debug_tile_scores(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt, float* out) {
+    if (!ctx || !query || !train || !out || nq <= 0 || nt <= 0)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_debug_tile_scores: bad argument") : VSM_ERR_INVALID;
+    if (ctx->engine == VSM_ENGINE_SIMT) return fail(ctx, VSM_ERR_INVALID, "no tensor-core pass in the SIMT engine");
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + nt, 0));
+    CK(cudaMemsetAsync(ctx->d_dump, 0, TILE_M * TILE_N * sizeof(float), ctx->stream));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    TRY(upload_scratch(ctx, train, nq, nt));
+    std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
+    TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + nt, 1));
+    CK(cudaMemcpyAsync(out, ctx->d_dump, TILE_M * TILE_N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return end_call(ctx, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// vsm_common.cuh -- shared device types and the canonical exact distance.
+//
+// Exactness contract: every distance this library REPORTS is computed by
+// canon_l2sqr_halfwarp() below, which reproduces, operation for operation, the
+// fp32 arithmetic of OpenCV's normL2Sqr_ baseline path (4 accumulators x 4 lanes,
+// separate mul and add, ((d0+d1)+d2)+d3, then (x0+x2)+(x1+x3)) followed by a
+// correctly rounded sqrt -- what cv::BFMatcher(NORM_L2) computes behind
+// src/Slam.cpp:1149 / src/LoopCloser.cpp:51 of the reference.  The tensor-core
+// pass only NOMINATES candidates; it never decides an index or a distance.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <float.h>
+
+#define VSM_DIM 256
+#define VSM_TOPK 3                 // approximate entries kept per (query, slice)
+
+namespace vsm {
+
+// Geometry of the tensor-core kernel (vsm_tc.cuh).
+constexpr int TILE_M = 128;        // queries per CTA (TMEM lanes)
+constexpr int TILE_N = 256;        // train rows per MMA tile (TMEM columns of one stage)
+constexpr int HALF_N = 128;        // columns one epilogue warp-group owns in every tile
+
+// Approximate per-(query, slice) record written by the tensor-core kernel: the three
+// largest bf16 dot products q.t of the slice, descending.  -inf / -1 = empty.
+struct PartialRec {
+    float   s[VSM_TOPK];
+    int32_t i[VSM_TOPK];           // logical train index inside the train set
+};
+
+// One CTA of the tensor-core kernel: one 128-query tile x a contiguous train range.
+struct TcUnit {
+    const float*    q_n2;          // squared norms of the tile's query rows
+    const uint32_t* t_stats;       // {min, max} squared norm of the train set (float bits)
+    int64_t rec_base;              // record index of (tile row 0, the unit's first slice)
+    int32_t rec_stride;            // records per query (= slices of the problem)
+    int32_t q_row;                 // first query row (tensor-map row coordinate)
+    int32_t t_row;                 // first train row of the range (tensor-map row coordinate)
+    int32_t t_count;               // valid train rows in the range (>= 1)
+    int32_t t_index0;              // logical train index of the range's first row
+    int32_t q_valid;               // valid query rows in the tile (1..128)
+    int32_t seg_tiles;             // tiles per slice segment (records flushed every seg_tiles tiles)
+    int32_t maps;                  // bit0: query rows in store map, bit1: train rows in store map
+    int32_t dump;                  // debug: write raw accumulators of tile 0
+    int32_t pad;
+};
+
+// A slice = the train rows one epilogue thread scanned for one record:
+//   half >= 0: columns [half*128, half*128+128) of every 256-row tile of
+//              [t_index0, t_index0 + t_count)
+//   half <  0: the contiguous range itself (exact SIMT engine).
+struct SliceInfo {
+    int32_t t_index0;
+    int32_t t_count;
+    int32_t half;
+    int32_t pad;
+};
+
+// One kNN problem (query set vs train set), consumed by the select/re-score kernel.
+struct Problem {
+    const float*    q_f32;         // first query row (fp32 master)
+    const float*    t_f32;         // first train row (fp32 master)
+    const float*    q_n2;          // squared norms of the query rows
+    const uint32_t* t_stats;       // {min, max} squared norm of the train set (float bits)
+    int64_t partial_off;           // first PartialRec of the problem
+    int64_t out_off;               // outputs at out_*[(out_off + q) * 2 ...]
+    int32_t nq, nt;
+    int32_t nslices;
+    int32_t slice_off;             // first SliceInfo of this problem
+    int32_t exact;                 // 1: no tensor-core records, scan every slice exactly
+    int32_t pad;
+};
+
+// One pair for the filter kernel (match_features semantics).
+struct FilterJob {
+    int64_t fwd_off;               // top-2 of query->train at out_*[(fwd_off + q) * 2]
+    int64_t back_off;              // top-2 of train->query (mutual only), else -1
+    int64_t good_off;              // output slot offsets (in dmatch units)
+    int64_t raw_off;               // -1: no raw output
+    int32_t nq, nt;
+    int32_t img_idx;
+    int32_t pad;
+    float   ratio;
+    int32_t pad2;
+};
+
+struct DMatch {
+    int32_t queryIdx, trainIdx, imgIdx;
+    float distance;
+};
+
+__device__ __forceinline__ bool better(float d, int32_t i, float bd, int32_t bi) {
+    // (distance, index) lexicographic == one sequential pass with strict-< insertion
+    return d < bd || (d == bd && (uint32_t)i < (uint32_t)bi);
+}
+
+__device__ __forceinline__ void insert2(float d, int32_t i, float& d0, int32_t& i0, float& d1, int32_t& i1) {
+    if (better(d, i, d1, i1)) {
+        if (better(d, i, d0, i0)) { d1 = d0; i1 = i0; d0 = d; i0 = i; }
+        else { d1 = d; i1 = i; }
+    }
+}
+
+// Half-warp exact squared distance.  lane16 owns elements k = 16*i + lane16,
+// i.e. OpenCV's accumulator a = lane16/4, SIMD lane l = lane16%4.
+// qreg[i] = q[16*i + lane16].  Result valid in lane16 == 0 of each half-warp.
+__device__ __forceinline__ float canon_l2sqr_halfwarp(const float (&qreg)[16],
+                                                      const float* __restrict__ t, int lane16) {
+    float tv[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) tv[i] = __ldg(t + 16 * i + lane16);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float d = __fsub_rn(qreg[i], tv[i]);
+        acc = __fadd_rn(__fmul_rn(d, d), acc);          // no FMA: mul, then add
+    }
+    const unsigned full = 0xffffffffu;
+    float v1 = __shfl_down_sync(full, acc, 4, 16);
+    float v2 = __shfl_down_sync(full, acc, 8, 16);
+    float v3 = __shfl_down_sync(full, acc, 12, 16);
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(acc, v1), v2), v3);   // ((d0+d1)+d2)+d3, lanes 0..3
+    float h = __fadd_rn(s, __shfl_down_sync(full, s, 2, 16));     // (x0+x2), (x1+x3)
+    return __fadd_rn(h, __shfl_down_sync(full, h, 1, 16));        // lane 0
+}
+
+__device__ __forceinline__ void load_qreg(float (&qreg)[16], const float* __restrict__ q, int lane16) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) qreg[i] = __ldg(q + 16 * i + lane16);
+}
+
+// Half-width of the interval that is guaranteed to contain the exact dot product q.t
+// (and, through it, the ordering by the canonical fp32 distance) around the value the
+// tensor-core pass computed from bf16-rounded operands, in dot-product units:
+//   |bf16(q).bf16(t) - q.t| <= ((1+2^-9)^2 - 1) |q||t|  <  (2^-8 + 2^-17) |q||t|
+//   fp32 accumulation inside the MMA and the rounding of the canonical distance are
+//   covered by the 2^-10 |q||t| and 2^-14 (|q|^2+|t|^2) terms;
+//   ranking by the dot product alone (instead of |t|^2 - 2 q.t) is off by at most
+//   (max|t|^2 - min|t|^2) / 4 around the mid norm.
+// Used by BOTH the tensor-core epilogue and the select kernel (same bits).
+__device__ __forceinline__ float dot_margin(float qn2, float tmin2, float tmax2) {
+    float qn = sqrtf(qn2), tn = sqrtf(tmax2);
+    return 0.0049f * qn * tn + 0.25f * (tmax2 - tmin2) + 6.2e-5f * (qn2 + tmax2);
+}
+
+}  // namespace vsm

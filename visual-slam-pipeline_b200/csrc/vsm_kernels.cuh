@@ -1,0 +1,251 @@
+// vsm_kernels.cuh -- the CUDA-core kernels around the tensor-core pass:
+//   convert_kernel  fp32 rows -> bf16 shadow + squared norms (+ min/max norm of the set)
+//   select_kernel   per query: threshold the approximate records, re-score the survivors
+//                   with the canonical fp32 distance, keep the exact top-2
+//   filter_kernel   Slam::match_features' loop (src/Slam.cpp:1151-1158) + mutual-NN,
+//                   order-preserving compaction into DMatch lists
+//   merge_kernel    per-shard top-2 lists -> global top-2 by (distance, index)
+#pragma once
+
+#include "vsm_common.cuh"
+
+namespace vsm {
+
+// One warp per row: 8 floats per lane.
+__global__ void __launch_bounds__(256)
+convert_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, float* __restrict__ n2,
+               int64_t nrows, uint32_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float lo = INFINITY, hi = 0.f;
+    for (int64_t row = warp0; row < nrows; row += nwarps) {
+        const float4* p = reinterpret_cast<const float4*>(src + row * VSM_DIM) + lane * 2;
+        float4 a = __ldg(p), b = __ldg(p + 1);
+        float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __nv_bfloat162 o0 = __floats2bfloat162_rn(a.x, a.y), o1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 o2 = __floats2bfloat162_rn(b.x, b.y), o3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 packed;
+        packed.x = *reinterpret_cast<uint32_t*>(&o0);
+        packed.y = *reinterpret_cast<uint32_t*>(&o1);
+        packed.z = *reinterpret_cast<uint32_t*>(&o2);
+        packed.w = *reinterpret_cast<uint32_t*>(&o3);
+        reinterpret_cast<uint4*>(dst + row * VSM_DIM)[lane] = packed;
+        if (lane == 0) n2[row] = s;
+        lo = fminf(lo, s);
+        hi = fmaxf(hi, s);
+    }
+    if (lane == 0 && lo <= hi) {
+        // non-negative floats order like their bit patterns
+        atomicMin(stats, __float_as_uint(lo));
+        atomicMax(stats + 1, __float_as_uint(hi));
+    }
+}
+
+// ---- select / exact re-score ---------------------------------------------------
+constexpr int SELECT_WARPS = 4;
+
+struct Best2 {
+    float d0, d1;
+    int32_t i0, i1;
+};
+
+__device__ __forceinline__ int32_t slice_row(const SliceInfo& si, int r) {
+    // r-th row of the slice as an offset into the slice's range, or -1 past the end
+    int off = si.half < 0 ? r : (r / HALF_N) * TILE_N + si.half * HALF_N + (r % HALF_N);
+    return off < si.t_count ? off : -1;
+}
+__device__ __forceinline__ int slice_span(const SliceInfo& si) {
+    return si.half < 0 ? si.t_count : ((si.t_count + TILE_N - 1) / TILE_N) * HALF_N;
+}
+
+// Both half-warps score one train row each (j0 for lanes 0-15, j1 for 16-31; <0 = idle).
+__device__ __forceinline__ void score_pair(const float (&qreg)[16], const float* __restrict__ t_f32,
+                                           int32_t j, int l16, Best2& b) {
+    const bool act = j >= 0;
+    float d2 = canon_l2sqr_halfwarp(qreg, t_f32 + (size_t)(act ? j : 0) * VSM_DIM, l16);
+    if (act && l16 == 0) insert2(__fsqrt_rn(d2), j, b.d0, b.i0, b.d1, b.i1);
+}
+
+__global__ void __launch_bounds__(SELECT_WARPS * 32)
+select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t* __restrict__ q_block0,
+              const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
+              int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
+              unsigned long long* __restrict__ counters) {
+    // blockIdx -> problem (q_block0 is the exclusive prefix of blocks per problem)
+    int lo = 0, hi = nproblems - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(q_block0 + mid) <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const Problem P = problems[lo];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = ((int)blockIdx.x - __ldg(q_block0 + lo)) * SELECT_WARPS + warp;
+    if (q >= P.nq) return;
+    const int h = lane >> 4, l16 = lane & 15;
+    const unsigned full = 0xffffffffu;
+
+    float qreg[16];
+    load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
+    Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
+    unsigned long long n_cand = 0, n_flag = 0;
+    const SliceInfo* sl = slices + P.slice_off;
+
+    if (P.exact) {
+        for (int s = 0; s < P.nslices; s++) {
+            const SliceInfo si = sl[s];
+            const int span = slice_span(si);
+            for (int r = h; r < span + h; r += 2) {
+                int off = r < span ? slice_row(si, r) : -1;
+                score_pair(qreg, P.t_f32, off >= 0 ? si.t_index0 + off : -1, l16, best);
+            }
+        }
+    } else {
+        const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
+        // pass 1: the second largest approximate dot over every record of the query
+        float a0 = -INFINITY, a1 = -INFINITY;
+        for (int s = lane; s < P.nslices; s += 32) {
+#pragma unroll
+            for (int e = 0; e < VSM_TOPK; e++) {
+                float v = rq[s].s[e];
+                if (v > a0) { a1 = a0; a0 = v; } else if (v > a1) a1 = v;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float b0 = __shfl_xor_sync(full, a0, o), b1 = __shfl_xor_sync(full, a1, o);
+            if (b0 > a0) { a1 = fmaxf(a0, b1); a0 = b0; } else a1 = fmaxf(a1, b0);
+        }
+        const float tmin2 = __uint_as_float(__ldg(P.t_stats)), tmax2 = __uint_as_float(__ldg(P.t_stats + 1));
+        const float thr = a1 - 2.f * dot_margin(__ldg(P.q_n2 + q), tmin2, tmax2);   // -inf if < 2 entries
+
+        // pass 2: survivors -> exact distance; overflowing slices -> exact scan
+        for (int s0 = 0; s0 < P.nslices; s0 += 32) {
+            const int s = s0 + lane;
+            PartialRec rec;
+#pragma unroll
+            for (int e = 0; e < VSM_TOPK; e++) { rec.s[e] = -INFINITY; rec.i[e] = -1; }
+            if (s < P.nslices) rec = rq[s];
+            const bool flagged = rec.i[2] >= 0 && rec.s[2] > thr;
+#pragma unroll
+            for (int e = 0; e < VSM_TOPK; e++) {
+                unsigned m = __ballot_sync(full, !flagged && rec.i[e] >= 0 && rec.s[e] > thr);
+                n_cand += __popc(m);
+                while (m) {
+                    int l0 = __ffs(m) - 1; m &= m - 1;
+                    int l1 = -1;
+                    if (m) { l1 = __ffs(m) - 1; m &= m - 1; }
+                    int src = h == 0 ? l0 : l1;
+                    int32_t j = __shfl_sync(full, rec.i[e], src < 0 ? 0 : src);
+                    score_pair(qreg, P.t_f32, src < 0 ? -1 : j, l16, best);
+                }
+            }
+            unsigned fm = __ballot_sync(full, flagged);
+            n_flag += __popc(fm);
+            while (fm) {
+                int l0 = __ffs(fm) - 1; fm &= fm - 1;
+                const SliceInfo si = sl[s0 + l0];
+                const int span = slice_span(si);
+                for (int r = h; r < span + h; r += 2) {
+                    int off = r < span ? slice_row(si, r) : -1;
+                    score_pair(qreg, P.t_f32, off >= 0 ? si.t_index0 + off : -1, l16, best);
+                }
+            }
+        }
+    }
+    // merge the two half-warps (lane 16 -> lane 0)
+    float od0 = __shfl_sync(full, best.d0, 16), od1 = __shfl_sync(full, best.d1, 16);
+    int32_t oi0 = __shfl_sync(full, best.i0, 16), oi1 = __shfl_sync(full, best.i1, 16);
+    if (lane == 0) {
+        if (oi0 >= 0) insert2(od0, oi0, best.d0, best.i0, best.d1, best.i1);
+        if (oi1 >= 0) insert2(od1, oi1, best.d0, best.i0, best.d1, best.i1);
+        const int64_t o = (P.out_off + q) * 2;
+        out_idx[o] = best.i0; out_idx[o + 1] = best.i1;
+        out_dist[o] = best.d0; out_dist[o + 1] = best.d1;
+        if (n_cand) atomicAdd(counters, n_cand);
+        if (n_flag) atomicAdd(counters + 1, n_flag);
+    }
+}
+
+// ---- match_features filter loop --------------------------------------------------
+// One block per pair.  good = lists with two entries whose best passes the fp32 ratio
+// test (and, if asked, the mutual-NN test); raw = every list with two entries.
+// Query order is preserved (block-wide scan per 256 queries).
+__global__ void __launch_bounds__(256)
+filter_kernel(const FilterJob* __restrict__ jobs, const int32_t* __restrict__ out_idx,
+              const float* __restrict__ out_dist, DMatch* __restrict__ matches, int32_t* __restrict__ counts) {
+    const FilterJob J = jobs[blockIdx.x];
+    __shared__ int wsum[2][8];
+    __shared__ int base[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { base[0] = 0; base[1] = 0; }
+    __syncthreads();
+    for (int q0 = 0; q0 < J.nq; q0 += 256) {
+        const int q = q0 + threadIdx.x;
+        bool is_raw = false, is_good = false;
+        DMatch m = {q, -1, J.img_idx, 0.f};
+        if (q < J.nq) {
+            const int64_t o = (J.fwd_off + q) * 2;
+            const int32_t i0 = out_idx[o], i1 = out_idx[o + 1];
+            const float d0 = out_dist[o], d1 = out_dist[o + 1];
+            m.trainIdx = i0; m.distance = d0;
+            is_raw = i1 >= 0;                                    // m.size() >= 2   (Slam.cpp:1152)
+            is_good = is_raw && d0 < __fmul_rn(J.ratio, d1);     // fp32 product   (Slam.cpp:1154)
+            if (is_good && J.back_off >= 0) is_good = out_idx[(J.back_off + i0) * 2] == q;
+        }
+        const unsigned br = __ballot_sync(0xffffffffu, is_raw), bg = __ballot_sync(0xffffffffu, is_good);
+        if (lane == 0) { wsum[0][warp] = __popc(bg); wsum[1][warp] = __popc(br); }
+        __syncthreads();
+        int pg = base[0], pr = base[1];
+        for (int w = 0; w < warp; w++) { pg += wsum[0][w]; pr += wsum[1][w]; }
+        const unsigned below = (1u << lane) - 1u;
+        if (is_good) matches[J.good_off + pg + __popc(bg & below)] = m;
+        if (is_raw && J.raw_off >= 0) matches[J.raw_off + pr + __popc(br & below)] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tg = 0, tr = 0;
+            for (int w = 0; w < 8; w++) { tg += wsum[0][w]; tr += wsum[1][w]; }
+            base[0] += tg; base[1] += tr;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { counts[2 * blockIdx.x] = base[0]; counts[2 * blockIdx.x + 1] = base[1]; }
+}
+
+// ---- shard merge ---------------------------------------------------------------------
+// idx_in/dist_in: [nshard][nq][2] global indices (-1 = empty) -> [nq][2].
+__global__ void merge_kernel(const int64_t* __restrict__ idx_in, const float* __restrict__ dist_in, int nshard,
+                             int nq, int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int64_t i0 = -1, i1 = -1;
+    float d0 = FLT_MAX, d1 = FLT_MAX;
+    for (int s = 0; s < nshard; s++) {
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const int64_t j = idx_in[((int64_t)s * nq + q) * 2 + p];
+            const float d = dist_in[((int64_t)s * nq + q) * 2 + p];
+            if (j < 0) continue;
+            const bool b1 = i1 < 0 || d < d1 || (d == d1 && j < i1);
+            if (!b1) continue;
+            const bool b0 = i0 < 0 || d < d0 || (d == d0 && j < i0);
+            if (b0) { d1 = d0; i1 = i0; d0 = d; i0 = j; } else { d1 = d; i1 = j; }
+        }
+    }
+    idx_out[2 * q] = i0; idx_out[2 * q + 1] = i1;
+    dist_out[2 * q] = d0; dist_out[2 * q + 1] = d1;
+}
+
+// int32 local top-2 -> int64 global (row offset added), for the device-pointer DB search.
+__global__ void widen_kernel(const int32_t* __restrict__ idx_in, const float* __restrict__ dist_in, int n,
+                             int64_t row_offset, int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t j = idx_in[i];
+    idx_out[i] = j < 0 ? -1 : (int64_t)j + row_offset;
+    dist_out[i] = dist_in[i];
+}
+
+}  // namespace vsm

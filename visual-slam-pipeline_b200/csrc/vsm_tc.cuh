@@ -1,0 +1,382 @@
+// vsm_tc.cuh -- the tensor-core pass: bf16 q.t tiles on tcgen05 with a fused
+// per-query top-3 epilogue (sm_100a only).
+//
+// One CTA = one TcUnit = 128 query rows x a contiguous range of train rows.
+//   warp 0      TMA producer: the 128x256 bf16 query tile once (4 boxes of 64 columns,
+//               SWIZZLE_128B), then the train rows as a ring of 4 stages, each stage one
+//               64-column K-chunk of a 256-row tile (2 boxes of 128 rows, 32 KB).
+//   warp 1      MMA issuer (one thread): per 256-row tile 16 x tcgen05.mma
+//               cta_group::1 kind::f16 M=128 N=256 K=16, fp32 accumulators in TMEM,
+//               two accumulator stages (2 x 256 columns = all 512 TMEM columns).
+//   warp 2      TMEM allocator.
+//   warps 4-11  epilogue: two warp-groups; group h owns columns [128h, 128h+128) of
+//               every tile.  Thread = one query row (TMEM lane).  tcgen05.ld 32 columns
+//               at a time; per 8 values one max-tree and one compare against the
+//               thread's threshold; the rare survivors go into a register top-3.
+//
+// What the epilogue keeps (see dot_margin in vsm_common.cuh for the bound): for each
+// slice (seg_tiles tiles of one column half) the three largest approximate dots among
+// the values v with v > g2 - 2*margin, g2 = the second largest value this thread has
+// seen so far in the whole unit.  g2 never exceeds the final global second-best, so a
+// value the select kernel needs (v > a2 - 2*margin) is never filtered here; it can only
+// be displaced by three larger values of the same slice, which the select kernel
+// detects (third entry above its threshold) and answers with an exact scan of the slice.
+#pragma once
+
+#include <cuda.h>
+#include "vsm_common.cuh"
+
+namespace vsm {
+namespace tc {
+
+constexpr int KCHUNK = 64;                       // bf16 per 128-byte swizzle row
+constexpr int NCHUNK = VSM_DIM / KCHUNK;         // 4 K-chunks
+constexpr int STAGES = 4;                        // train-chunk ring depth
+constexpr uint32_t Q_SUB_BYTES = TILE_M * 128;   // 16 KB: 128 rows x 64 bf16
+constexpr uint32_t T_STAGE_BYTES = TILE_N * 128; // 32 KB: 256 rows x 64 bf16
+constexpr uint32_t SMEM_Q = 0;
+constexpr uint32_t SMEM_T = NCHUNK * Q_SUB_BYTES;                 // 65536
+constexpr uint32_t SMEM_BAR = SMEM_T + STAGES * T_STAGE_BYTES;    // 196608
+constexpr uint32_t SMEM_BYTES = SMEM_BAR + 256 + 1024;            // + alignment slack
+constexpr int THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; it++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((it & 1023u) == 1023u) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) __trap();     // ~2 s at 2 GHz
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 in, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all MMAs issued so far by this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (asynchronous).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    __syncwarp();                                       // .sync.aligned: the warp must be converged
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// Wait for this thread's outstanding tcgen05.ld; the registers pass through the
+// statement so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    __syncwarp();
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :
+        : "memory");
+}
+
+// Shared-memory matrix descriptor: K-major operand, SWIZZLE_128B, rows of 64 bf16
+// (128 B), 8-row groups 1024 B apart (what the TMA boxes above produce).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);      // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused with swizzle)
+    d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, N=256, M=128.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
+                           ((uint32_t)(TILE_M >> 4) << 24);
+
+// ---- epilogue state -------------------------------------------------------------
+struct Top3 {
+    float b0, b1, b2;          // slice top-3, descending
+    int32_t i0, i1, i2;        // unit-relative column offsets
+    float g1, g2;              // two largest values seen in the whole unit
+    float margin2;             // 2 * dot_margin
+    float thr;                 // max(b2, g2 - margin2): values <= thr are dropped
+};
+
+__device__ __forceinline__ void top3_reset_slice(Top3& s) {
+    s.b0 = s.b1 = s.b2 = -INFINITY;
+    s.i0 = s.i1 = s.i2 = -1;
+    s.thr = s.g2 - s.margin2;      // -inf while fewer than two values were seen
+}
+
+__device__ __forceinline__ void top3_insert(Top3& s, float v, int32_t col) {
+    if (v > s.b1) {
+        s.b2 = s.b1; s.i2 = s.i1;
+        if (v > s.b0) { s.b1 = s.b0; s.i1 = s.i0; s.b0 = v; s.i0 = col; }
+        else { s.b1 = v; s.i1 = col; }
+    } else { s.b2 = v; s.i2 = col; }
+    if (v > s.g2) {
+        if (v > s.g1) { s.g2 = s.g1; s.g1 = v; }
+        else s.g2 = v;
+    }
+    s.thr = fmaxf(s.b2, s.g2 - s.margin2);
+}
+
+// 32 accumulator values of one thread = columns [col0, col0+32) of the unit's range.
+template <bool MASKED>
+__device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], int32_t col0, int32_t t_count) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            v[e] = __uint_as_float(r[8 * g + e]);
+            if (MASKED && col0 + 8 * g + e >= t_count) v[e] = -INFINITY;
+        }
+        float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        if (m > s.thr) {
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                if (v[e] > s.thr) top3_insert(s, v[e], col0 + 8 * g + e);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_constant__ CUtensorMap map_store,
+               const TcUnit* __restrict__ units, PartialRec* __restrict__ recs, float* __restrict__ dump) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + SMEM_BAR;
+    // barriers (8 B each): 0 q_full, 1..4 full[], 5..8 empty[], 9..10 tmem_full[], 11..12 tmem_empty[]
+    const uint32_t BAR_QFULL = bar_base;
+    const uint32_t BAR_FULL = bar_base + 8;
+    const uint32_t BAR_EMPTY = bar_base + 8 + 8 * STAGES;
+    const uint32_t BAR_TFULL = bar_base + 8 + 16 * STAGES;
+    const uint32_t BAR_TEMPTY = BAR_TFULL + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_BAR + 192);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const TcUnit u = units[blockIdx.x];
+    const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
+    const CUtensorMap* mq = (u.maps & 1) ? &map_store : &map_scratch;
+    const CUtensorMap* mt = (u.maps & 2) ? &map_store : &map_scratch;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(mq);
+        prefetch_tensormap(mt);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(BAR_QFULL, 1);
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(BAR_FULL + 8 * i, 1);
+            mbar_init(BAR_EMPTY + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(BAR_TFULL + 8 * i, 1);
+            mbar_init(BAR_TEMPTY + 8 * i, 8);          // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_base + SMEM_BAR + 192, TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(BAR_QFULL, NCHUNK * Q_SUB_BYTES);
+            for (int c = 0; c < NCHUNK; c++)
+                tma_load_2d(smem_base + SMEM_Q + c * Q_SUB_BYTES, mq, c * KCHUNK, u.q_row, BAR_QFULL);
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int n = 0; n < ntiles; n++) {
+                const int row = u.t_row + n * TILE_N;
+                for (int c = 0; c < NCHUNK; c++) {
+                    mbar_wait(BAR_EMPTY + 8 * slot, ph ^ 1);
+                    mbar_expect_tx(BAR_FULL + 8 * slot, T_STAGE_BYTES);
+                    const uint32_t dst = smem_base + SMEM_T + slot * T_STAGE_BYTES;
+                    tma_load_2d(dst, mt, c * KCHUNK, row, BAR_FULL + 8 * slot);
+                    tma_load_2d(dst + T_STAGE_BYTES / 2, mt, c * KCHUNK, row + TILE_N / 2, BAR_FULL + 8 * slot);
+                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(BAR_QFULL, 0);
+            tcgen05_fence_after();
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int n = 0; n < ntiles; n++) {
+                const int st = n & 1;
+                mbar_wait(BAR_TEMPTY + 8 * st, ((n >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + st * TILE_N;
+                for (int c = 0; c < NCHUNK; c++) {
+                    mbar_wait(BAR_FULL + 8 * slot, ph);
+                    tcgen05_fence_after();
+                    const uint64_t a0 = umma_smem_desc(smem_base + SMEM_Q + c * Q_SUB_BYTES);
+                    const uint64_t b0 = umma_smem_desc(smem_base + SMEM_T + slot * T_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KCHUNK / 16; k++)            // 32 bytes = 2 address units per K=16
+                        umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, IDESC, (c | k) != 0);
+                    umma_commit(BAR_EMPTY + 8 * slot);               // frees the smem stage
+                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                }
+                umma_commit(BAR_TFULL + 8 * st);                     // accumulator stage complete
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue =====
+        const int half = (warp - EPI_WARP0) >> 2;
+        const int quarter = warp & 3;                              // TMEM lanes this warp may read
+        const int row = quarter * 32 + lane;
+        const bool row_valid = row < u.q_valid;
+        Top3 s;
+        s.g1 = s.g2 = -INFINITY;
+        {
+            const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
+            const float tmin2 = __uint_as_float(__ldg(u.t_stats));
+            const float tmax2 = __uint_as_float(__ldg(u.t_stats + 1));
+            s.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
+        }
+        top3_reset_slice(s);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
+        int seg = 0, seg_left = u.seg_tiles;
+        for (int n = 0; n < ntiles; n++) {
+            const int st = n & 1;
+            mbar_wait(BAR_TFULL + 8 * st, (n >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t taddr = lane_addr + st * TILE_N;
+            const int32_t col_tile = n * TILE_N + half * HALF_N;
+            const bool full_tile = (n + 1) * TILE_N <= u.t_count;
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+            tmem_ld_wait(ra);
+            tmem_ld32(taddr + 32, rb);
+            if (u.dump && n == 0) {
+                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + e] = __uint_as_float(ra[e]);
+            }
+            if (full_tile) scan32<false>(s, ra, col_tile, u.t_count); else scan32<true>(s, ra, col_tile, u.t_count);
+            tmem_ld_wait(rb);
+            tmem_ld32(taddr + 64, ra);
+            if (u.dump && n == 0) {
+                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 32 + e] = __uint_as_float(rb[e]);
+            }
+            if (full_tile) scan32<false>(s, rb, col_tile + 32, u.t_count); else scan32<true>(s, rb, col_tile + 32, u.t_count);
+            tmem_ld_wait(ra);
+            tmem_ld32(taddr + 96, rb);
+            if (u.dump && n == 0) {
+                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 64 + e] = __uint_as_float(ra[e]);
+            }
+            if (full_tile) scan32<false>(s, ra, col_tile + 64, u.t_count); else scan32<true>(s, ra, col_tile + 64, u.t_count);
+            tmem_ld_wait(rb);
+            // all TMEM reads of this stage are complete: hand it back to the MMA warp
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+            if (u.dump && n == 0) {
+                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 96 + e] = __uint_as_float(rb[e]);
+            }
+            if (full_tile) scan32<false>(s, rb, col_tile + 96, u.t_count); else scan32<true>(s, rb, col_tile + 96, u.t_count);
+
+            if (--seg_left == 0 || n == ntiles - 1) {
+                if (row_valid) {
+                    PartialRec rec;
+                    rec.s[0] = s.b0; rec.s[1] = s.b1; rec.s[2] = s.b2;
+                    rec.i[0] = s.i0 >= 0 ? u.t_index0 + s.i0 : -1;
+                    rec.i[1] = s.i1 >= 0 ? u.t_index0 + s.i1 : -1;
+                    rec.i[2] = s.i2 >= 0 ? u.t_index0 + s.i2 : -1;
+                    recs[u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half] = rec;
+                }
+                seg++;
+                seg_left = u.seg_tiles;
+                top3_reset_slice(s);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+}  // namespace vsm

@@ -1,0 +1,274 @@
+"""ctypes binding of libvsm.so and a thin Python mirror of the reference's matcher interface.
+
+Names follow the reference (salah-dev-stu/visual-slam-pipeline):
+  Matcher.match_features(desc1, desc2, ratio)   <- Slam::match_features      src/Slam.cpp:1140-1172
+  Matcher.knn_match(query, train)               <- DescriptorMatcher::knnMatch src/Slam.cpp:1149
+  Matcher.add_keyframe / match_to_keyframe      <- Frame::descriptors_ kept on the device (include/Frame.h:61)
+  Matcher.search_map_points(frame_desc)         <- stacked-matrix search       src/Slam.cpp:546-574, 744-774
+  Matcher.detect_candidates(frame_desc)         <- LoopCloser::detect block    src/LoopCloser.cpp:43-62
+
+This module never computes a match on the CPU: if libvsm.so is missing or there is no
+B200, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT = 0, 1, 2
+DIM = 256
+
+
+class VsmError(RuntimeError):
+    pass
+
+
+class _Opts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("engine", C.c_int32), ("scratch_rows", C.c_int64),
+                ("store_rows", C.c_int64), ("reserved", C.c_int32 * 8)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("candidates", C.c_int64), ("flagged_slices", C.c_int64), ("kernel_launches", C.c_int64),
+                ("device_ms", C.c_float)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libvsm.so")
+
+
+_lib = None
+SYMBOLS = {
+    "vsm_default_opts": (None, [C.POINTER(_Opts)]),
+    "vsm_create": (C.c_int, [C.POINTER(_Opts), C.POINTER(C.c_void_p)]),
+    "vsm_destroy": (None, [C.c_void_p]),
+    "vsm_last_error": (C.c_char_p, [C.c_void_p]),
+    "vsm_version": (C.c_char_p, []),
+    "vsm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(_Stats)]),
+    "vsm_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "vsm_host_free": (None, [C.c_void_p]),
+    "vsm_knn2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsm_match_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
+                                 C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]),
+    "vsm_match_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsm_store_add": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "vsm_store_add_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
+    "vsm_store_adopt_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "vsm_store_clear": (C.c_int, [C.c_void_p]),
+    "vsm_store_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "vsm_match_to_stored": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
+                                      C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]),
+    "vsm_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsm_merge_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_int32]),
+    "vsm_stream": (C.c_void_p, [C.c_void_p]),
+    "vsm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vsm_sync": (C.c_int, [C.c_void_p]),
+    "vsm_debug_tile_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+}
+
+
+def load_library():
+    """dlopen libvsm.so and type every exported entry point (no CUDA call is made)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise VsmError(f"{path} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _rows(a, name):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] != DIM:
+        raise ValueError(f"{name}: expected an N x {DIM} float32 matrix, got {a.shape}")
+    return a
+
+
+class Matcher:
+    """One matching context on one GPU (single caller, synchronous calls)."""
+
+    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0):
+        self._lib = load_library()
+        o = _Opts()
+        self._lib.vsm_default_opts(C.byref(o))
+        o.device, o.engine, o.scratch_rows, o.store_rows = device, engine, scratch_rows, store_rows
+        o.reserved[0] = seg_tiles
+        h = C.c_void_p()
+        st = self._lib.vsm_create(C.byref(o), C.byref(h))
+        if st != 0:
+            raise VsmError(f"vsm_create failed ({st}): {self._lib.vsm_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vsm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st != 0:
+            raise VsmError(f"libvsm error {st}: {self._lib.vsm_last_error(self._h).decode()}")
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def lib(self):
+        return self._lib
+
+    def stats(self):
+        s = _Stats()
+        self._ck(self._lib.vsm_get_stats(self._h, C.byref(s)))
+        return {"candidates": s.candidates, "flagged_slices": s.flagged_slices,
+                "kernel_launches": s.kernel_launches, "device_ms": s.device_ms}
+
+    # -- cv::DescriptorMatcher::knnMatch(query, train, knn, 2) ---------------------------
+    def knn_match(self, query, train):
+        """(idx[nq,2] int32, dist[nq,2] fp32); a missing neighbour is idx -1 / dist FLT_MAX."""
+        q, t = _rows(query, "query"), _rows(train, "train")
+        idx = np.empty((q.shape[0], 2), np.int32)
+        dist = np.empty((q.shape[0], 2), np.float32)
+        self._ck(self._lib.vsm_knn2(self._h, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
+                                    idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
+    # -- Slam::match_features(desc1, desc2, raw_out) ----------------------------------------
+    def match_features(self, desc1, desc2, ratio=0.75, mutual=False, want_raw=True):
+        """Returns (good, raw) DMATCH arrays in query order; raw is None if not asked for."""
+        q, t = _rows(desc1, "desc1"), _rows(desc2, "desc2")
+        nq = q.shape[0]
+        good = np.zeros(max(nq, 1), DMATCH)
+        raw = np.zeros(max(nq, 1), DMATCH) if want_raw else None
+        ng, nr = C.c_int32(0), C.c_int32(0)
+        self._ck(self._lib.vsm_match_pair(self._h, q.ctypes.data, nq, t.ctypes.data, t.shape[0], ratio, int(mutual),
+                                          good.ctypes.data, C.byref(ng),
+                                          raw.ctypes.data if want_raw else None, C.byref(nr) if want_raw else None))
+        return good[:ng.value], (raw[:nr.value] if want_raw else None)
+
+    def match_batch(self, queries, trains, ratio=0.75, mutual=False):
+        """Ragged batch: lists of N_i x 256 matrices -> list of DMATCH arrays (one launch sequence)."""
+        n = len(queries)
+        assert n == len(trains)
+        q_off = np.zeros(n + 1, np.int32)
+        t_off = np.zeros(n + 1, np.int32)
+        q_off[1:] = np.cumsum([len(a) for a in queries])
+        t_off[1:] = np.cumsum([len(a) for a in trains])
+        qa = _rows(np.concatenate(queries) if n else np.zeros((0, DIM), np.float32), "queries")
+        ta = _rows(np.concatenate(trains) if n else np.zeros((0, DIM), np.float32), "trains")
+        return self.match_batch_packed(qa, q_off, ta, t_off, ratio, mutual)
+
+    def match_batch_packed(self, qa, q_off, ta, t_off, ratio=0.75, mutual=False, out=None):
+        n = len(q_off) - 1
+        good = out if out is not None else np.zeros(max(int(q_off[-1]), 1), DMATCH)
+        n_good = np.zeros(max(n, 1), np.int32)
+        self._ck(self._lib.vsm_match_batch(self._h, n, qa.ctypes.data, q_off.ctypes.data, ta.ctypes.data,
+                                           t_off.ctypes.data, ratio, int(mutual), good.ctypes.data,
+                                           n_good.ctypes.data))
+        return [good[q_off[p]:q_off[p] + n_good[p]] for p in range(n)]
+
+    # -- device-resident keyframe store -----------------------------------------------------
+    def add_keyframe(self, frame_id, desc):
+        d = _rows(desc, "desc")
+        h = C.c_int32(-1)
+        self._ck(self._lib.vsm_store_add(self._h, frame_id, d.ctypes.data, d.shape[0], C.byref(h)))
+        return h.value
+
+    def add_keyframe_device(self, frame_id, dev_ptr, n):
+        h = C.c_int32(-1)
+        self._ck(self._lib.vsm_store_add_device(self._h, frame_id, C.c_void_p(dev_ptr), n, C.byref(h)))
+        return h.value
+
+    def adopt_device_matrix(self, dev_ptr, n_rows, seg_off=None):
+        if seg_off is not None:
+            seg_off = np.ascontiguousarray(seg_off, np.int64)
+            self._ck(self._lib.vsm_store_adopt_device(self._h, C.c_void_p(dev_ptr), n_rows, seg_off.ctypes.data,
+                                                      len(seg_off) - 1))
+        else:
+            self._ck(self._lib.vsm_store_adopt_device(self._h, C.c_void_p(dev_ptr), n_rows, None, 0))
+
+    def clear_store(self):
+        self._ck(self._lib.vsm_store_clear(self._h))
+
+    def store_info(self):
+        r, k = C.c_int64(0), C.c_int32(0)
+        self._ck(self._lib.vsm_store_info(self._h, C.byref(r), C.byref(k)))
+        return r.value, k.value
+
+    def match_to_keyframe(self, handle, cur_desc, ratio=0.75, mutual=False, want_raw=False):
+        """Slam::match_features(ref_kf->descriptors(), cur->descriptors()) with the keyframe resident."""
+        t = _rows(cur_desc, "cur_desc")
+        cap = max(self.store_info()[0], 1)
+        good = np.zeros(cap, DMATCH)
+        raw = np.zeros(cap, DMATCH) if want_raw else None
+        ng, nr = C.c_int32(0), C.c_int32(0)
+        self._ck(self._lib.vsm_match_to_stored(self._h, handle, t.ctypes.data, t.shape[0], ratio, int(mutual),
+                                               good.ctypes.data, C.byref(ng),
+                                               raw.ctypes.data if want_raw else None,
+                                               C.byref(nr) if want_raw else None))
+        return good[:ng.value].copy(), (raw[:nr.value].copy() if want_raw else None)
+
+    def search_map_points(self, frame_desc, row_offset=0):
+        """Global top-2 of every query row over the whole store (src/Slam.cpp:546-574)."""
+        q = _rows(frame_desc, "frame_desc")
+        idx = np.empty((q.shape[0], 2), np.int64)
+        dist = np.empty((q.shape[0], 2), np.float32)
+        self._ck(self._lib.vsm_db_top2(self._h, q.ctypes.data, q.shape[0], row_offset, idx.ctypes.data,
+                                       dist.ctypes.data))
+        return idx, dist
+
+    def detect_candidates(self, frame_desc, ratio=0.75, want_matches=True):
+        """LoopCloser::detect matching block: per stored keyframe, top-2 inside the keyframe +
+        ratio test.  Returns (counts[nkf], [DMATCH array per keyframe] or None)."""
+        q = _rows(frame_desc, "frame_desc")
+        nkf = self.store_info()[1]
+        counts = np.zeros(max(nkf, 1), np.int32)
+        m = np.zeros((max(nkf, 1), max(q.shape[0], 1)), DMATCH) if want_matches else None
+        self._ck(self._lib.vsm_db_segmented(self._h, q.ctypes.data, q.shape[0], ratio, counts.ctypes.data,
+                                            m.ctypes.data if want_matches else None))
+        counts = counts[:nkf]
+        return counts, ([m[s, :counts[s]] for s in range(nkf)] if want_matches else None)
+
+    # -- device-pointer plumbing (resident queries, sharded search) -------------------------
+    def db_top2_device(self, d_query_ptr, nq, row_offset, d_idx_ptr, d_dist_ptr, sync=False):
+        self._ck(self._lib.vsm_db_top2_device(self._h, C.c_void_p(d_query_ptr), nq, row_offset,
+                                              C.c_void_p(d_idx_ptr), C.c_void_p(d_dist_ptr), int(sync)))
+
+    def merge_top2_device(self, d_idx_in, d_dist_in, nshard, nq, d_idx_out, d_dist_out, sync=False):
+        self._ck(self._lib.vsm_merge_top2_device(self._h, C.c_void_p(d_idx_in), C.c_void_p(d_dist_in), nshard, nq,
+                                                 C.c_void_p(d_idx_out), C.c_void_p(d_dist_out), int(sync)))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self._lib.vsm_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def stream(self):
+        return self._lib.vsm_stream(self._h)
+
+    def sync(self):
+        self._ck(self._lib.vsm_sync(self._h))
+
+    def debug_tile_scores(self, query, train):
+        q, t = _rows(query, "query"), _rows(train, "train")
+        out = np.zeros((128, 256), np.float32)
+        self._ck(self._lib.vsm_debug_tile_scores(self._h, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
+                                                 out.ctypes.data))
+        return out
