@@ -81,6 +81,8 @@ typedef struct {
     int64_t flagged_slices;      /* (query,slice) pairs that fell back to an exact slice scan */
     int64_t kernel_launches;     /* kernels launched by the last call */
     float   device_ms;           /* device time of the last call (CUDA events, incl. copies) */
+    float   tc_ms;               /* device time of the tensor-core kernel of the last call */
+    float   select_ms;           /* device time of the select / exact re-score kernel */
 } vsm_stats;
 
 void        vsm_default_opts(vsm_opts* opts);
@@ -88,7 +90,7 @@ int         vsm_create(const vsm_opts* opts, vsm_ctx** out);
 void        vsm_destroy(vsm_ctx* ctx);
 const char* vsm_last_error(const vsm_ctx* ctx);       /* ctx may be NULL: create() errors */
 const char* vsm_version(void);
-int         vsm_get_stats(const vsm_ctx* ctx, vsm_stats* out);
+int         vsm_get_stats(vsm_ctx* ctx, vsm_stats* out);
 
 /* Pinned host memory for callers that want DMA without a staging copy. */
 int  vsm_host_alloc(void** ptr, int64_t bytes);

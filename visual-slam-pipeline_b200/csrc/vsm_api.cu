@@ -85,6 +85,8 @@ struct vsm_ctx {
     unsigned long long* d_counters = nullptr;
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_tc0 = nullptr, ev_tc1 = nullptr, ev_sel1 = nullptr;
+    bool timed_tc = false, timed_sel = false, pending_stats = false;
     vsm_stats stats{};
     int launches = 0;
     std::string err;
@@ -200,25 +202,38 @@ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 int begin_call(vsm_ctx* ctx) {
     ctx->err.clear();
     ctx->launches = 0;
+    ctx->timed_tc = ctx->timed_sel = false;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     return VSM_OK;
 }
 
+// Reads the event timings and counters of the last call (the stream must be idle).
+int collect_stats(vsm_ctx* ctx) {
+    if (!ctx->pending_stats) return VSM_OK;
+    ctx->pending_stats = false;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.device_ms = ms;
+    ctx->stats.tc_ms = ctx->stats.select_ms = 0.f;
+    if (ctx->timed_tc) CK(cudaEventElapsedTime(&ctx->stats.tc_ms, ctx->ev_tc0, ctx->ev_tc1));
+    if (ctx->timed_sel) CK(cudaEventElapsedTime(&ctx->stats.select_ms, ctx->timed_tc ? ctx->ev_tc1 : ctx->ev_tc0, ctx->ev_sel1));
+    unsigned long long c[2];
+    CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    ctx->stats.candidates = (int64_t)c[0];
+    ctx->stats.flagged_slices = (int64_t)c[1];
+    return VSM_OK;
+}
+
 int end_call(vsm_ctx* ctx, bool sync) {
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->stats.kernel_launches = ctx->launches;
+    ctx->pending_stats = true;
     if (sync) {
         CK(cudaStreamSynchronize(ctx->stream));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        unsigned long long c[2];
-        CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
-        ctx->stats.candidates = (int64_t)c[0];
-        ctx->stats.flagged_slices = (int64_t)c[1];
-        ctx->stats.device_ms = ms;
+        return collect_stats(ctx);
     }
-    ctx->stats.kernel_launches = ctx->launches;
     return VSM_OK;
 }
 
@@ -341,6 +356,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                            conv_rows, d_scratch_stats));
 
     uint8_t* dd = ctx->d_desc.p;
+    CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
     if (!units.empty()) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
@@ -348,6 +364,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
         ctx->launches++;
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
+        ctx->timed_tc = true;
     }
     if (qb[P] > 0) {
         select_kernel<<<(unsigned)qb[P], SELECT_WARPS * 32, 0, ctx->stream>>>(
@@ -356,6 +374,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ctx->d_counters);
         ctx->launches++;
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
+        ctx->timed_sel = true;
     }
     if (!jobs.empty()) {
         DMatch* dm = reinterpret_cast<DMatch*>(ctx->d_result.p);
@@ -437,6 +457,9 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
+        CK(cudaEventCreate(&ctx->ev_tc0));
+        CK(cudaEventCreate(&ctx->ev_tc1));
+        CK(cudaEventCreate(&ctx->ev_sel1));
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -476,12 +499,19 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_tc0) cudaEventDestroy(ctx->ev_tc0);
+    if (ctx->ev_tc1) cudaEventDestroy(ctx->ev_tc1);
+    if (ctx->ev_sel1) cudaEventDestroy(ctx->ev_sel1);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
-int vsm_get_stats(const vsm_ctx* ctx, vsm_stats* out) {
+int vsm_get_stats(vsm_ctx* ctx, vsm_stats* out) {
     if (!ctx || !out) return VSM_ERR_INVALID;
+    if (ctx->pending_stats) {                  // an asynchronous call: wait for it, then read its events
+        CK(cudaStreamSynchronize(ctx->stream));
+        TRY(collect_stats(ctx));
+    }
     *out = ctx->stats;
     return VSM_OK;
 }
