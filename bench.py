@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- the loop-closure descriptor search (BASELINE.json configs[3]) on N B200s.
+
+Step = one query batch (2000 x 256-d fp32 SuperPoint-shaped descriptors) answered with its exact
+global top-2 over a 20M-descriptor keyframe database partitioned across the N GPUs of the box:
+per rank the tcgen05 bf16 pass + exact fp32 re-score (libvsm.so), then an NCCL all-gather of the
+[nq][2] lists and a merge kernel.  Total work is fixed as N grows ("strong" scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        one rank per GPU under torchrun for N > 1
+  python bench.py --impl reference ...                        the reference's CPU matcher
+                                                              (cv2.BFMatcher, the OpenCV code the
+                                                              reference calls) on a bounded sample
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident; `e2e` is the same
+search through host buffers (H2D of the queries and D2H of the result inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DB query TFLOP/s (exact top-2 loop-closure search, 2*nq*nt*256 FLOP per query batch)"
+NQ = 2000
+TOTAL_ROWS = 20_000_000          # 10K keyframes x 2000 descriptors
+KF_ROWS = 2000
+N_PLANTED = 400                  # 20 % of the queries are noisy re-observations of DB rows
+SIGMA = 0.05
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ---- synthetic data ---------------------------------------------------------------------------
+def make_queries(torch, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(1234)
+    q = torch.randn((NQ, 256), generator=g, device=device, dtype=torch.float32)
+    q = q / q.norm(dim=1, keepdim=True)
+    noise = torch.randn((N_PLANTED, 256), generator=g, device=device, dtype=torch.float32) * SIGMA
+    return q, noise
+
+
+def make_shard(torch, device, rank, world, q, noise, total_rows):
+    rows = total_rows // world
+    off = rank * rows
+    if rank == world - 1:
+        rows = total_rows - off
+    db = torch.empty((rows, 256), dtype=torch.float32, device=device)
+    g = torch.Generator(device=device)
+    chunk = 1 << 20
+    for c0 in range(0, rows, chunk):
+        g.manual_seed(10_000 + (off + c0) // chunk)
+        n = min(chunk, rows - c0)
+        x = torch.randn((n, 256), generator=g, device=device, dtype=torch.float32)
+        db[c0:c0 + n] = x / x.norm(dim=1, keepdim=True)
+    # plant: DB row r_i re-observes query i (noise renormalised), wherever r_i lives
+    stride = total_rows // N_PLANTED
+    planted = [i * stride + 17 for i in range(N_PLANTED)]
+    for i, r in enumerate(planted):
+        if off <= r < off + rows:
+            v = q[i] + noise[i]
+            db[r - off] = v / v.norm()
+    return db, off, planted
+
+
+# ---- reference arm ----------------------------------------------------------------------------
+def cpu_matcher():
+    """The reference's CPU path for float descriptors as BASELINE.json names it:
+    cv::BFMatcher(NORM_L2).knnMatch(q, t, 2).  cv2 wraps the same OpenCV C++ code the reference
+    links (src/Slam.cpp:1149); if cv2 is absent the CPU oracle port is timed instead."""
+    try:
+        import cv2
+        cores = cv2.getNumThreads()
+        bf = cv2.BFMatcher(cv2.NORM_L2)
+        return (lambda q, t: bf.knnMatch(q, t, k=2)), cores, "reference", f"cv2 {cv2.__version__} BFMatcher.knnMatch k=2"
+    except Exception:
+        from oracle import oracle
+        cores = os.cpu_count() or 1
+        return (lambda q, t: oracle.knn(q, t, 2, threads=cores)), cores, "port", "oracle/vsm_oracle.c knn k=2"
+
+
+def cpu_data(n_rows, seed=7):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((NQ, 256), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t = rng.standard_normal((n_rows, 256), dtype=np.float32)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    return q, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fn, cores, kind, what = cpu_matcher()
+    n_rows = args.ref_rows
+    q, t = cpu_data(n_rows)
+    for _ in range(args.warmup):
+        fn(q, t)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(q, t)
+    dt = (time.perf_counter() - t0) / args.steps
+    flops = 2.0 * NQ * n_rows * 256
+    val = flops / dt / 1e12
+    sample = f"{what}; each step = {NQ} queries x {n_rows}-row sample of the {TOTAL_ROWS}-row DB (brute force is linear in rows)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, args.rows),
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus, total_rows):
+    return {"workload": f"loop-closure search: {NQ} query descriptors x {total_rows}-descriptor keyframe DB "
+                        f"({total_rows // KF_ROWS} keyframes x {KF_ROWS}), exact global top-2 per query "
+                        "(BASELINE configs[3])",
+            "nq": NQ, "db_rows": total_rows, "dim": 256, "sharding": f"db rows / {n_gpus} GPUs, allgather+merge",
+            "l2": "inputs larger than L2 (bf16 shard >= 1.28 GB vs 126 MB L2); no flush needed"}
+
+
+# ---- extra: the pair-matching configs (rank 0, N = 1) ------------------------------------------------
+def extra_pair_numbers(torch, vsm_b200, device):
+    import numpy as np
+    out = {}
+    m = vsm_b200.Matcher(device=device, engine=vsm_b200.ENGINE_TENSOR)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+
+    def unit(n):
+        x = torch.randn((n, 256), generator=g, device="cuda")
+        return x / x.norm(dim=1, keepdim=True)
+
+    def planted_from(prev, overlap=0.6, sigma=0.06):
+        n = prev.shape[0]
+        nxt = unit(n)
+        k = int(overlap * n)
+        src = torch.randperm(n, generator=g, device="cuda")[:k]
+        dst = torch.randperm(n, generator=g, device="cuda")[:k]
+        v = prev[src] + sigma * torch.randn((k, 256), generator=g, device="cuda")
+        nxt[dst] = v / v.norm(dim=1, keepdim=True)
+        return nxt
+
+    # configs[1]: 2544 consecutive 1000x1000 frame pairs, mutual-NN + ratio 0.75, host buffers in and out
+    npairs = 2544
+    frames = torch.empty((npairs + 1, 1000, 256), dtype=torch.float32).pin_memory()
+    cur = unit(1000)
+    frames[0].copy_(cur)
+    for f in range(1, npairs + 1):
+        cur = planted_from(cur)
+        frames[f].copy_(cur)
+    torch.cuda.synchronize()
+    fr = frames.numpy()
+    lat, nmatch = [], 0
+    for f in range(20):
+        m.match_features(fr[f], fr[f + 1], 0.75, mutual=True, want_raw=False)
+    t_all = time.perf_counter()
+    for f in range(npairs):
+        t0 = time.perf_counter()
+        good, _ = m.match_features(fr[f], fr[f + 1], 0.75, mutual=True, want_raw=False)
+        lat.append(time.perf_counter() - t0)
+        nmatch += len(good)
+    t_all = time.perf_counter() - t_all
+    lat.sort()
+    out["tracking_1000x1000_mutual_ratio"] = {
+        "pairs": npairs, "p50_us": lat[len(lat) // 2] * 1e6, "p99_us": lat[int(len(lat) * 0.99)] * 1e6,
+        "matches_per_s": nmatch / t_all, "pair_distances_per_s": npairs * 1e6 / t_all,
+        "timing": "host wall clock per call incl. H2D of both frames and D2H of the DMatch list",
+        "device_ms_last": m.stats()["device_ms"], "launches_per_pair": m.stats()["kernel_launches"]}
+    # configs[0]: 2000 x 2000, k=2 + ratio 0.8
+    a = unit(2000)
+    b = planted_from(a, 0.6, 0.08)
+    ha, hb = a.cpu().numpy(), b.cpu().numpy()
+    for _ in range(5):
+        m.match_features(ha, hb, 0.8, want_raw=False)
+    ts = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        good, _ = m.match_features(ha, hb, 0.8, want_raw=False)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    out["pair_2000x2000_ratio08"] = {"p50_us": ts[len(ts) // 2] * 1e6, "matches": int(len(good)),
+                                     "device_ms": m.stats()["device_ms"], "tc_ms": m.stats()["tc_ms"]}
+    # configs[4]: 64 ragged pairs, sizes U{200..2048}, mutual + ratio
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(200, 2049, size=(64, 2))
+    qs, tsets = [], []
+    for nq, nt in sizes:
+        base = unit(int(max(nq, nt)))
+        nxt = planted_from(base, 0.6, 0.08)
+        qs.append(base[:nq].cpu().numpy())
+        tsets.append(nxt[:nt].cpu().numpy())
+    q_off = np.zeros(65, np.int32); t_off = np.zeros(65, np.int32)
+    q_off[1:] = np.cumsum(sizes[:, 0]); t_off[1:] = np.cumsum(sizes[:, 1])
+    qa, ta = np.concatenate(qs), np.concatenate(tsets)
+    for _ in range(3):
+        m.match_batch_packed(qa, q_off, ta, t_off, 0.75, True)
+    tb = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        res = m.match_batch_packed(qa, q_off, ta, t_off, 0.75, True)
+        tb.append(time.perf_counter() - t0)
+    tb.sort()
+    flops = float(sum(2.0 * a_ * b_ * 256 for a_, b_ in sizes))
+    st = m.stats()
+    out["ragged_batch_64"] = {"p50_ms": tb[len(tb) // 2] * 1e3, "useful_gflop": flops / 1e9,
+                              "matches": int(sum(len(r) for r in res)), "device_ms": st["device_ms"],
+                              "tc_ms": st["tc_ms"], "tc_useful_tflops": flops / (st["tc_ms"] * 1e-3) / 1e12 if st["tc_ms"] else None}
+    m.close()
+    return out
+
+
+# ---- main arm -----------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import vsm_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = torch.device("cuda", local)
+    total_rows = args.rows
+
+    sh = vsm_b200.load_sharded()
+    db = sh.ShardedDB(local, rank, world)
+    q, noise = make_queries(torch, device)
+    shard, off, planted = make_shard(torch, device, rank, world, q, noise, total_rows)
+    seg = None   # one segment per shard for the global search
+    db.adopt(shard, off, seg)
+    hq = q.cpu().pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also sizes every buffer and the NCCL communicator)
+    for _ in range(max(args.warmup, 3)):
+        db.search_device(q)
+        db.search_host(hq)
+    db.stream.synchronize()
+    launches_per_step = db.launches_per_search()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # -- device-resident timing ------------------------------------------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tc_ms = []
+    t_wall0 = time.time()
+    with torch.cuda.stream(db.stream):
+        e0.record()
+    for _ in range(args.steps):
+        oi, od = db.search_device(q)
+        tc_ms.append(db.matcher.stats()["tc_ms"])     # waits for this step, reads the kernel's events
+    with torch.cuda.stream(db.stream):
+        e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    # -- end to end through host buffers -------------------------------------------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(db.stream):
+        f0.record()
+    for _ in range(args.steps):
+        hi, hd = db.search_host(hq)
+        db.stream.synchronize()                        # the caller reads the result every step
+    with torch.cuda.stream(db.stream):
+        f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+    if sampler:
+        sampler.stop()
+
+    flops = 2.0 * NQ * total_rows * 256
+    per_step = ms / args.steps
+    per_step_e2e = ms_e2e / args.steps
+    if rank == 0:
+        import numpy as np
+        peak_tf, peak_hbm, peak_src = peaks()
+        # sanity: every planted query must find its DB row as the nearest neighbour
+        got = hi.numpy()[:N_PLANTED, 0]
+        recovered = int((got == np.array(planted)).sum())
+        st = db.matcher.stats()
+        tc_avg = sum(tc_ms) / len(tc_ms)
+        shard_flops = 2.0 * NQ * shard.shape[0] * 256
+        achieved = shard_flops / (tc_avg * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": flops / (per_step * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world, total_rows),
+            "clocks": clocks,
+            "e2e": {"value": flops / (per_step_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": per_step_e2e,
+                    "h2d_bytes_per_step": NQ * 1024, "d2h_bytes_per_step": NQ * 2 * 12,
+                    "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "tc_top3_kernel", "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": args.traffic,
+                         "peak_source": peak_src, "kernel_ms": tc_avg,
+                         "algorithmic": "2*nq*shard_rows*256 FLOP per launch",
+                         "hbm_gbs": (shard.shape[0] * 512 + NQ * 512) / (tc_avg * 1e-3) / 1e9, "hbm_peak": peak_hbm},
+            "check": {"planted_recovered": f"{recovered}/{N_PLANTED}", "candidates_rescored": st["candidates"],
+                      "flagged_slices": st["flagged_slices"], "select_ms": st["select_ms"]},
+            "matches_per_s": NQ / (per_step * 1e-3),
+        }
+        if world == 1 and not args.no_cpu:
+            fn, cores, kind, what = cpu_matcher()
+            n = args.cpu_rows
+            cq, ct = cpu_data(n)
+            fn(cq[:200], ct[:2000])
+            t0 = time.perf_counter()
+            reps = 0
+            while True:
+                fn(cq, ct)
+                reps += 1
+                if time.perf_counter() - t0 > 10.0 or reps >= 20:
+                    break
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": 2.0 * NQ * n * 256 / dt / 1e12, "unit": "TFLOP/s", "cores": cores,
+                                    "kind": kind, "sample": f"{what}; {NQ} queries x {n}-row sample of the DB, {reps} repetitions"}
+        if world == 1 and not args.no_extra:
+            # free the big shard first: the pair configs need little memory
+            line["extra"] = extra_pair_numbers(torch, vsm_b200, local)
+        print(json.dumps(line))
+    db.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vsm", choices=["vsm", "reference"])
+    ap.add_argument("--rows", type=int, default=TOTAL_ROWS, help="database rows in total (default: configs[3], 20M)")
+    ap.add_argument("--ref-rows", type=int, default=100_000, help="reference arm: DB sample rows per step")
+    ap.add_argument("--cpu-rows", type=int, default=100_000, help="cpu_baseline: DB sample rows")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,7 +70,7 @@ typedef struct {
                                     pair frames, ragged batches); grows on demand; 0 = 8192 */
     int64_t store_rows;          /* initial capacity of the keyframe store in rows; it grows
                                     on demand; 0 = allocate at the first add */
-    int32_t reserved[8];         /* [0]: tiles per slice segment (0 = default 16) */
+    int32_t reserved[8];         /* [0]: tiles per slice segment (0 = automatic) */
 } vsm_opts;
 
 typedef struct vsm_ctx vsm_ctx;
@@ -182,6 +182,10 @@ int   vsm_sync(vsm_ctx* ctx);
 
 /* Debug / bring-up: the raw tensor-core accumulators (bf16 dot products q.t) of the
  * first 128 queries x first 256 train rows, written to out[128*256] (host). */
+/* Debug: raw copy of the 128 KB debug buffer (tile scores, or -- with VSM_DEBUG_TIMELINE set --
+ * clock64 stamps of unit 0: [0..4095] accumulator ready, [4096..] loads issued, [8192..] MMA
+ * issued, [12288..] epilogue done, per tile). */
+int vsm_debug_fetch_dump(vsm_ctx* ctx, void* out, int64_t bytes);
 int vsm_debug_tile_scores(vsm_ctx* ctx, const float* query, int32_t nq, const float* train,
                           int32_t nt, float* out);
 

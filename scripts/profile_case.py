@@ -1,0 +1,72 @@
+"""Small driver for ncu / sweeps: runs one named case a few times and prints the library's own
+event timings.  Usage: python scripts/profile_case.py <case> [reps]
+  pair1000   1000x1000 match_features, mutual + ratio (BASELINE configs[1])
+  pair2000   2000x2000 knn + ratio 0.8 (configs[0])
+  db:<rows>:<nq>   global top-2 of nq queries over a <rows>-row resident DB (configs[2]/[3])
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import vsm_b200
+
+
+def unit(n, g):
+    x = torch.randn((n, 256), generator=g, device="cuda")
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def main():
+    case = sys.argv[1]
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR)
+    if case.startswith("pair"):
+        n = int(case[4:])
+        a = unit(n, g)
+        b = unit(n, g)
+        k = int(0.6 * n)
+        v = a[:k] + 0.06 * torch.randn((k, 256), generator=g, device="cuda")
+        b[:k] = v / v.norm(dim=1, keepdim=True)
+        ha = a.cpu().pin_memory().numpy()
+        hb = b.cpu().pin_memory().numpy()
+        for r in range(reps + 3):
+            t0 = time.perf_counter()
+            good, _ = m.match_features(ha, hb, 0.75, mutual=True, want_raw=False)
+            dt = time.perf_counter() - t0
+            print(case, "wall_us", round(dt * 1e6, 1), "matches", len(good), m.stats())
+    else:
+        _, rows, nq = case.split(":")
+        rows, nq = int(rows), int(nq)
+        db = torch.empty((rows, 256), device="cuda")
+        for c0 in range(0, rows, 1 << 20):
+            n = min(1 << 20, rows - c0)
+            db[c0:c0 + n] = unit(n, g)
+        q = unit(nq, g)
+        torch.cuda.synchronize()
+        m.adopt_device_matrix(db.data_ptr(), rows)
+        oi = torch.empty((nq, 2), dtype=torch.int64, device="cuda")
+        od = torch.empty((nq, 2), dtype=torch.float32, device="cuda")
+        for r in range(reps + 3):
+            m.db_top2_device(q.data_ptr(), nq, 0, oi.data_ptr(), od.data_ptr(), sync=True)
+            st = m.stats()
+            tf = 2.0 * nq * rows * 256 / (st["tc_ms"] * 1e-3) / 1e12
+            print(case, "tc_TFLOPs", round(tf, 1), st)
+        if os.environ.get("VSM_DEBUG_TIMELINE"):
+            tl = m.debug_timeline()
+            nt = int((tl[0] > 0).sum())
+            t0 = tl[1][0]
+            print("tiles", nt)
+            for n in list(range(0, min(nt, 24))) + list(range(24, nt, max(1, nt // 40))):
+                print(n, "load_issued", tl[1][n] - t0, "mma_issue", tl[2][n] - t0, "acc_ready", tl[0][n] - t0,
+                      "epi_done", tl[3][n] - t0)
+    m.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -7,3 +7,9 @@ The directory name carries a hyphen, so import it through the repo-root shim:
 """
 from .matcher import (DMATCH, Matcher, VsmError, lib_path, load_library,  # noqa: F401
                       ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT)
+
+
+def load_sharded():
+    """The multi-GPU database search (imports torch lazily)."""
+    from . import sharded as _s
+    return _s

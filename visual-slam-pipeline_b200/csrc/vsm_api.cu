@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -82,7 +83,11 @@ struct vsm_ctx {
     DevBuf<uint8_t> d_result;            // DMatch lists followed by the counts
     uint8_t* h_result = nullptr;
     size_t h_result_cap = 0;
-    unsigned long long* d_counters = nullptr;
+    // zeroed per call: [0] candidates, [1] flagged slices (u64), [2] rescan work count, then
+    // per output query the shared second-best hints and the rescan locks (u32 each)
+    DevBuf<uint8_t> d_aux;
+    unsigned long long* d_counters = nullptr;    // = d_aux.p
+    DevBuf<WorkItem> d_work;
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_tc0 = nullptr, ev_tc1 = nullptr, ev_sel1 = nullptr;
@@ -91,7 +96,7 @@ struct vsm_ctx {
     int launches = 0;
     std::string err;
     PFN_encodeTiled encode = nullptr;
-    int seg_tiles = 16;
+    int seg_tiles = 0;                   // 0 = automatic
 };
 
 namespace {
@@ -199,13 +204,14 @@ int launch_convert(vsm_ctx* ctx, const float* src, __nv_bfloat16* dst, float* n2
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+constexpr uint32_t WORK_CAP = 1u << 18;          // rescan work items (4 MB); beyond it select scans inline
+
 int begin_call(vsm_ctx* ctx) {
     ctx->err.clear();
     ctx->launches = 0;
     ctx->timed_tc = ctx->timed_sel = false;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     return VSM_OK;
 }
 
@@ -219,8 +225,8 @@ int collect_stats(vsm_ctx* ctx) {
     ctx->stats.tc_ms = ctx->stats.select_ms = 0.f;
     if (ctx->timed_tc) CK(cudaEventElapsedTime(&ctx->stats.tc_ms, ctx->ev_tc0, ctx->ev_tc1));
     if (ctx->timed_sel) CK(cudaEventElapsedTime(&ctx->stats.select_ms, ctx->timed_tc ? ctx->ev_tc1 : ctx->ev_tc0, ctx->ev_sel1));
-    unsigned long long c[2];
-    CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    unsigned long long c[2] = {0, 0};
+    if (ctx->d_counters) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.candidates = (int64_t)c[0];
     ctx->stats.flagged_slices = (int64_t)c[1];
     return VSM_OK;
@@ -249,6 +255,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     std::vector<Problem> dp(P);
     std::vector<int32_t> qb(P + 1, 0);
     std::vector<TcUnit> units;
+    std::vector<int> unit_prob;
     std::vector<SliceInfo> slices;
     int64_t nrecs = 0;
 
@@ -278,7 +285,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         int nranges = (int)std::min<int64_t>(ntiles, budget);
         const int tpr = (ntiles + nranges - 1) / nranges;
         nranges = (ntiles + tpr - 1) / tpr;
-        const int seg = std::min(tpr, ctx->seg_tiles);
+        // slice length: short slices keep an overflow re-scan cheap, long ones keep the record
+        // stream small next to the database stream
+        const int seg_pref = ctx->seg_tiles > 0 ? ctx->seg_tiles : (ntiles <= 4096 ? 16 : 64);
+        const int seg = std::min(tpr, seg_pref);
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
         std::vector<int> range_slice0(nranges);
         for (int r = 0; r < nranges; r++) {
@@ -307,9 +317,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 u.q_valid = std::min(TILE_M, hp.nq - qt * TILE_M);
                 u.seg_tiles = seg;
                 u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0);
-                u.dump = (dump_first && units.empty()) ? 1 : 0;
-                u.pad = i;                                              // problem index, for the fix-up
+                u.dump = (dump_first && units.empty()) ? dump_first : 0;
+                u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 : 0;
                 units.push_back(u);
+                unit_prob.push_back(i);
             }
         }
         nrecs += (int64_t)hp.nq * d.nslices;
@@ -330,9 +341,21 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     const size_t result_bytes = (size_t)total_matches * sizeof(DMatch) + jobs.size() * 2 * sizeof(int32_t);
     TRY(ensure(ctx, ctx->d_result, std::max<size_t>(result_bytes, 16)));
 
+    const size_t aux_bytes = 32 + (size_t)std::max<int64_t>(total_out, 1) * 2 * sizeof(uint32_t);
+    TRY(ensure(ctx, ctx->d_aux, aux_bytes));
+    TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
+    ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
+    uint32_t* d_hints = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32);
+    uint32_t* d_locks = d_hints + std::max<int64_t>(total_out, 1);
+    CK(cudaMemsetAsync(ctx->d_aux.p, 0, aux_bytes, ctx->stream));
+
     uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_desc.p);
     for (int i = 0; i < P; i++) dp[i].t_stats = probs[i].t_store ? ctx->d_store_stats : d_scratch_stats;
-    for (auto& u : units) { u.t_stats = dp[u.pad].t_stats; u.pad = 0; }
+    for (size_t k = 0; k < units.size(); k++) {
+        const int i = unit_prob[k];
+        units[k].t_stats = dp[i].t_stats;
+        units[k].hint = d_hints + probs[i].out_off + (units[k].q_row - probs[i].q_row);
+    }
 
     uint8_t* h = ctx->h_desc;
     uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};                         // {min=+inf, max=0}
@@ -360,8 +383,12 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     if (!units.empty()) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
-        tc::tc_top3_kernel<<<(unsigned)units.size(), tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-            ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
+        if (dump_first)
+            tc::tc_top3_kernel<true><<<(unsigned)units.size(), tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
+                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
+        else
+            tc::tc_top3_kernel<false><<<(unsigned)units.size(), tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
+                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
         ctx->launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
@@ -371,9 +398,17 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         select_kernel<<<(unsigned)qb[P], SELECT_WARPS * 32, 0, ctx->stream>>>(
             reinterpret_cast<const Problem*>(dd + off_prob), P, reinterpret_cast<const int32_t*>(dd + off_qb),
             ctx->d_recs.p, reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_idx.p, ctx->d_out_dist.p,
-            ctx->d_counters);
+            ctx->d_counters, ctx->d_work.p, WORK_CAP);
         ctx->launches++;
         CK(cudaGetLastError());
+        if (!units.empty()) {
+            // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
+            rescan_kernel<<<(unsigned)ctx->num_sms * 2, 128, 0, ctx->stream>>>(
+                reinterpret_cast<const Problem*>(dd + off_prob), reinterpret_cast<const SliceInfo*>(dd + off_slice),
+                ctx->d_work.p, ctx->d_counters, WORK_CAP, ctx->d_out_idx.p, ctx->d_out_dist.p, d_locks);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
         ctx->timed_sel = true;
     }
@@ -468,9 +503,9 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaMalloc(&ctx->d_store_stats, 16));
         uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};
         CK(cudaMemcpy(ctx->d_store_stats, arm, 16, cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
-        CK(cudaFuncSetAttribute(tc::tc_top3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::tc_top3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::tc_top3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
         TRY(arena_reserve(ctx, ctx->scratch, o.scratch_rows > 0 ? o.scratch_rows : 8192, 0));
         if (o.store_rows > 0) TRY(arena_reserve(ctx, ctx->store, o.store_rows, 0));
         return VSM_OK;
@@ -495,7 +530,8 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_out_dist.p) cudaFree(ctx->d_out_dist.p);
     if (ctx->d_result.p) cudaFree(ctx->d_result.p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
-    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_aux.p) cudaFree(ctx->d_aux.p);
+    if (ctx->d_work.p) cudaFree(ctx->d_work.p);
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -777,7 +813,8 @@ int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t r
     TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
     HProblem p;
     db_problem(ctx, d_query, nq, p);
-    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq));
+    static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? 2 : 0;
+    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
     widen_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_idx.p, ctx->d_out_dist.p, nq * 2,
                                                                  row_offset, d_idx, d_dist);
     ctx->launches++;
@@ -830,6 +867,13 @@ int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_
     merge_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(d_idx_in, d_dist_in, nshard, nq, d_idx_out, d_dist_out);
     CK(cudaGetLastError());
     if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return VSM_OK;
+}
+
+int vsm_debug_fetch_dump(vsm_ctx* ctx, void* out, int64_t bytes) {
+    if (!ctx || !out || bytes <= 0 || bytes > (int64_t)(TILE_M * TILE_N * sizeof(float))) return VSM_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->d_dump, (size_t)bytes, cudaMemcpyDeviceToHost));
     return VSM_OK;
 }
 

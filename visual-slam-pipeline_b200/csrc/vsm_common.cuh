@@ -44,8 +44,9 @@ struct TcUnit {
     int32_t q_valid;               // valid query rows in the tile (1..128)
     int32_t seg_tiles;             // tiles per slice segment (records flushed every seg_tiles tiles)
     int32_t maps;                  // bit0: query rows in store map, bit1: train rows in store map
-    int32_t dump;                  // debug: write raw accumulators of tile 0
-    int32_t pad;
+    int32_t dump;                  // debug: 1 = raw accumulators of tile 0, 2 = clock64 timeline
+    int32_t prefetch;              // this CTA issues the L2 prefetches for its train range
+    uint32_t* hint;                // per query row: shared lower bound on the global second-best dot
 };
 
 // A slice = the train rows one epilogue thread scanned for one record:
@@ -137,13 +138,14 @@ __device__ __forceinline__ void load_qreg(float (&qreg)[16], const float* __rest
 // tensor-core pass computed from bf16-rounded operands, in dot-product units:
 //   |bf16(q).bf16(t) - q.t| <= ((1+2^-9)^2 - 1) |q||t|  <  (2^-8 + 2^-17) |q||t|
 //   fp32 accumulation inside the MMA and the rounding of the canonical distance are
-//   covered by the 2^-10 |q||t| and 2^-14 (|q|^2+|t|^2) terms;
+//   covered by a 2^-10 |q||t| and the 2^-14 (|q|^2+|t|^2) term; the epilogue's index
+//   packing (low 13 mantissa bits) moves a value by < 2^-10 |q||t| more;
 //   ranking by the dot product alone (instead of |t|^2 - 2 q.t) is off by at most
 //   (max|t|^2 - min|t|^2) / 4 around the mid norm.
 // Used by BOTH the tensor-core epilogue and the select kernel (same bits).
 __device__ __forceinline__ float dot_margin(float qn2, float tmin2, float tmax2) {
     float qn = sqrtf(qn2), tn = sqrtf(tmax2);
-    return 0.0049f * qn * tn + 0.25f * (tmax2 - tmin2) + 6.2e-5f * (qn2 + tmax2);
+    return 0.0059f * qn * tn + 0.25f * (tmax2 - tmin2) + 6.2e-5f * (qn2 + tmax2);
 }
 
 }  // namespace vsm

@@ -69,11 +69,18 @@ __device__ __forceinline__ void score_pair(const float (&qreg)[16], const float*
     if (act && l16 == 0) insert2(__fsqrt_rn(d2), j, b.d0, b.i0, b.d1, b.i1);
 }
 
+// An overflowing slice is re-scanned exactly by rescan_kernel, RESCAN_ROWS slice rows per
+// work item, so that one unlucky query does not serialise thousands of rows in one warp.
+constexpr int RESCAN_ROWS = 256;
+struct WorkItem {
+    int32_t problem, q, slice, r0;
+};
+
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
 select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t* __restrict__ q_block0,
               const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
               int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
-              unsigned long long* __restrict__ counters) {
+              unsigned long long* __restrict__ counters, WorkItem* __restrict__ work, uint32_t work_cap) {
     // blockIdx -> problem (q_block0 is the exclusive prefix of blocks per problem)
     int lo = 0, hi = nproblems - 1;
     while (lo < hi) {
@@ -142,8 +149,24 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
                     score_pair(qreg, P.t_f32, src < 0 ? -1 : j, l16, best);
                 }
             }
-            unsigned fm = __ballot_sync(full, flagged);
-            n_flag += __popc(fm);
+            n_flag += __popc(__ballot_sync(full, flagged));
+            // hand the overflowing slices to rescan_kernel; scan inline only if its list is full
+            bool inline_scan = false;
+            if (flagged) {
+                const int span = slice_span(sl[s]);
+                const uint32_t nitem = (uint32_t)((span + RESCAN_ROWS - 1) / RESCAN_ROWS);
+                uint32_t* wcount = reinterpret_cast<uint32_t*>(counters + 2);
+                const uint32_t base = atomicAdd(wcount, nitem);
+                if (base + nitem <= work_cap) {
+                    for (uint32_t k = 0; k < nitem; k++) {
+                        WorkItem w = {lo, q, s, (int32_t)(k * RESCAN_ROWS)};
+                        work[base + k] = w;
+                    }
+                } else {
+                    inline_scan = true;
+                }
+            }
+            unsigned fm = __ballot_sync(full, inline_scan);
             while (fm) {
                 int l0 = __ffs(fm) - 1; fm &= fm - 1;
                 const SliceInfo si = sl[s0 + l0];
@@ -166,6 +189,56 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
         out_dist[o] = best.d0; out_dist[o + 1] = best.d1;
         if (n_cand) atomicAdd(counters, n_cand);
         if (n_flag) atomicAdd(counters + 1, n_flag);
+    }
+}
+
+// One block per work item: exact top-2 over RESCAN_ROWS rows of one slice for one query,
+// merged into the query's result under a per-query lock.
+__global__ void __launch_bounds__(128)
+rescan_kernel(const Problem* __restrict__ problems, const SliceInfo* __restrict__ slices,
+              const WorkItem* __restrict__ work, const unsigned long long* __restrict__ counters, uint32_t work_cap,
+              int32_t* out_idx, float* out_dist, uint32_t* __restrict__ locks) {
+    const uint32_t nwork = min(*reinterpret_cast<const uint32_t*>(counters + 2), work_cap);
+    __shared__ Best2 part[8];
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    for (uint32_t it = blockIdx.x; it < nwork; it += gridDim.x) {
+        const WorkItem w = work[it];
+        const Problem P = problems[w.problem];
+        const SliceInfo si = slices[P.slice_off + w.slice];
+        const int span = slice_span(si);
+        const int r1 = min(span, w.r0 + RESCAN_ROWS);
+        float qreg[16];
+        load_qreg(qreg, P.q_f32 + (size_t)w.q * VSM_DIM, l16);
+        Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
+        // 8 half-warps stride the rows; every lane of a warp runs the same trip count
+        for (int k = 0; k < RESCAN_ROWS / 8; k++) {
+            const int r = w.r0 + k * 8 + hw;
+            int off = r < r1 ? slice_row(si, r) : -1;
+            score_pair(qreg, P.t_f32, off >= 0 ? si.t_index0 + off : -1, l16, best);
+        }
+        if (l16 == 0) part[hw] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < 8; k++) {
+                if (part[k].i0 >= 0) insert2(part[k].d0, part[k].i0, best.d0, best.i0, best.d1, best.i1);
+                if (part[k].i1 >= 0) insert2(part[k].d1, part[k].i1, best.d0, best.i0, best.d1, best.i1);
+            }
+            const int64_t key = P.out_off + w.q;
+            while (atomicCAS(locks + key, 0u, 1u) != 0u) __nanosleep(100);
+            __threadfence();
+            volatile int32_t* oi = out_idx + key * 2;
+            volatile float* od = out_dist + key * 2;
+            Best2 cur = {od[0], od[1], oi[0], oi[1]};
+            // the slice's earlier survivors may already be in the result: skip equal indices
+            if (best.i0 >= 0 && best.i0 != cur.i0 && best.i0 != cur.i1)
+                insert2(best.d0, best.i0, cur.d0, cur.i0, cur.d1, cur.i1);
+            if (best.i1 >= 0 && best.i1 != cur.i0 && best.i1 != cur.i1)
+                insert2(best.d1, best.i1, cur.d0, cur.i0, cur.d1, cur.i1);
+            oi[0] = cur.i0; oi[1] = cur.i1; od[0] = cur.d0; od[1] = cur.d1;
+            __threadfence();
+            atomicExch(locks + key, 0u);
+        }
+        __syncthreads();
     }
 }
 

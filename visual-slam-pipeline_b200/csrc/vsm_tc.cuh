@@ -41,6 +41,7 @@ constexpr uint32_t SMEM_BYTES = SMEM_BAR + 256 + 1024;            // + alignment
 constexpr int THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int L2_AHEAD = 4;                      // tiles of L2 prefetch distance
 
 // ---- PTX wrappers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -87,6 +88,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -163,53 +169,67 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE
                            ((uint32_t)(TILE_M >> 4) << 24);
 
 // ---- epilogue state -------------------------------------------------------------
+// Slice top-3 as PACKED floats: the low 13 mantissa bits of an accumulator value are
+// replaced by its column number inside the slice (a slice is at most 64 tiles x 128
+// columns = 2^13), so the whole (value, index) top-3 update is five FMNMX and no branch.
+// The packing moves a value by < 2^-10 relative; dot_margin() accounts for it.
+constexpr uint32_t PACK_MASK = 0xFFFFE000u;
+constexpr float MASKED_VALUE = -3.0e38f;       // a column past the end of the train range
+
 struct Top3 {
-    float b0, b1, b2;          // slice top-3, descending
-    int32_t i0, i1, i2;        // unit-relative column offsets
-    float g1, g2;              // two largest values seen in the whole unit
+    float b0, b1, b2;          // slice top-3 (packed), descending; -inf = empty
+    float G;                   // lower bound on the query's global second-best dot
     float margin2;             // 2 * dot_margin
-    float thr;                 // max(b2, g2 - margin2): values <= thr are dropped
+    float thr;                 // max(b2, max(G, b1) - margin2): values <= thr are dropped
+    float published;           // last bound pushed to the shared hint
 };
 
+__device__ __forceinline__ void top3_update_thr(Top3& s) {
+    s.thr = fmaxf(s.b2, fmaxf(s.G, s.b1) - s.margin2);
+}
 __device__ __forceinline__ void top3_reset_slice(Top3& s) {
+    s.G = fmaxf(s.G, s.b1);                     // second best of a subset <= global second best
     s.b0 = s.b1 = s.b2 = -INFINITY;
-    s.i0 = s.i1 = s.i2 = -1;
-    s.thr = s.g2 - s.margin2;      // -inf while fewer than two values were seen
+    top3_update_thr(s);
+}
+__device__ __forceinline__ void top3_push(Top3& s, float x) {
+    float t0 = fmaxf(s.b0, x), x1 = fminf(s.b0, x);
+    float t1 = fmaxf(s.b1, x1), x2 = fminf(s.b1, x1);
+    s.b0 = t0; s.b1 = t1; s.b2 = fmaxf(s.b2, x2);
+}
+// monotone float <-> uint32 (for atomicMax on the shared bound); 0 = "nothing yet"
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__device__ __forceinline__ void top3_insert(Top3& s, float v, int32_t col) {
-    if (v > s.b1) {
-        s.b2 = s.b1; s.i2 = s.i1;
-        if (v > s.b0) { s.b1 = s.b0; s.i1 = s.i0; s.b0 = v; s.i0 = col; }
-        else { s.b1 = v; s.i1 = col; }
-    } else { s.b2 = v; s.i2 = col; }
-    if (v > s.g2) {
-        if (v > s.g1) { s.g2 = s.g1; s.g1 = v; }
-        else s.g2 = v;
-    }
-    s.thr = fmaxf(s.b2, s.g2 - s.margin2);
-}
-
-// 32 accumulator values of one thread = columns [col0, col0+32) of the unit's range.
+// 32 accumulator values of one thread: slice columns [scol0, scol0+32), unit columns
+// [ucol0, ucol0+32).
 template <bool MASKED>
-__device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], int32_t col0, int32_t t_count) {
+__device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], uint32_t scol0, int32_t ucol0,
+                                       int32_t t_count) {
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             v[e] = __uint_as_float(r[8 * g + e]);
-            if (MASKED && col0 + 8 * g + e >= t_count) v[e] = -INFINITY;
+            if (MASKED && ucol0 + 8 * g + e >= t_count) v[e] = MASKED_VALUE;
         }
         float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
         if (m > s.thr) {
 #pragma unroll
             for (int e = 0; e < 8; e++)
-                if (v[e] > s.thr) top3_insert(s, v[e], col0 + 8 * g + e);
+                top3_push(s, __uint_as_float((__float_as_uint(v[e]) & PACK_MASK) | (scol0 + 8 * g + e)));
+            top3_update_thr(s);
         }
     }
 }
 
+template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_constant__ CUtensorMap map_store,
                const TcUnit* __restrict__ units, PartialRec* __restrict__ recs, float* __restrict__ dump) {
@@ -265,8 +285,18 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
             uint32_t ph = 0;
             for (int n = 0; n < ntiles; n++) {
                 const int row = u.t_row + n * TILE_N;
+                if (u.prefetch && n + L2_AHEAD < ntiles) {
+                    // pull a tile several iterations ahead into L2: the 4-stage smem ring only
+                    // covers an L2 hit, not a DRAM miss
+                    const int prow = row + L2_AHEAD * TILE_N;
+                    for (int c = 0; c < NCHUNK; c++) {
+                        tma_prefetch_l2_2d(mt, c * KCHUNK, prow);
+                        tma_prefetch_l2_2d(mt, c * KCHUNK, prow + TILE_N / 2);
+                    }
+                }
                 for (int c = 0; c < NCHUNK; c++) {
                     mbar_wait(BAR_EMPTY + 8 * slot, ph ^ 1);
+                    if (DEBUG && u.dump == 2 && c == 0 && n < 4096) reinterpret_cast<long long*>(dump)[4096 + n] = clock64();
                     mbar_expect_tx(BAR_FULL + 8 * slot, T_STAGE_BYTES);
                     const uint32_t dst = smem_base + SMEM_T + slot * T_STAGE_BYTES;
                     tma_load_2d(dst, mt, c * KCHUNK, row, BAR_FULL + 8 * slot);
@@ -286,6 +316,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                 const int st = n & 1;
                 mbar_wait(BAR_TEMPTY + 8 * st, ((n >> 1) & 1) ^ 1);
                 tcgen05_fence_after();
+                if (DEBUG && u.dump == 2 && n < 4096) reinterpret_cast<long long*>(dump)[8192 + n] = clock64();
                 const uint32_t d_tmem = tmem_base + st * TILE_N;
                 for (int c = 0; c < NCHUNK; c++) {
                     mbar_wait(BAR_FULL + 8 * slot, ph);
@@ -308,64 +339,82 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         const int row = quarter * 32 + lane;
         const bool row_valid = row < u.q_valid;
         Top3 s;
-        s.g1 = s.g2 = -INFINITY;
+        s.b0 = s.b1 = s.b2 = -INFINITY;
+        s.G = s.published = -INFINITY;
         {
             const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
             const float tmin2 = __uint_as_float(__ldg(u.t_stats));
             const float tmax2 = __uint_as_float(__ldg(u.t_stats + 1));
             s.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
         }
-        top3_reset_slice(s);
+        top3_update_thr(s);
+        volatile uint32_t* hint = u.hint + (row_valid ? row : 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
-        int seg = 0, seg_left = u.seg_tiles;
+        int seg = 0, seg_tile = 0;
         for (int n = 0; n < ntiles; n++) {
             const int st = n & 1;
+            // bound published by the other CTAs / warps working on the same query (a second-best
+            // of any subset of the train set is a lower bound on the global second-best)
+            const uint32_t h = *hint;
             mbar_wait(BAR_TFULL + 8 * st, (n >> 1) & 1);
             tcgen05_fence_after();
+            if (DEBUG && u.dump == 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)
+                reinterpret_cast<long long*>(dump)[n] = clock64();
+            if (h != 0u) { s.G = fmaxf(s.G, dec_ordered(h)); top3_update_thr(s); }
             const uint32_t taddr = lane_addr + st * TILE_N;
-            const int32_t col_tile = n * TILE_N + half * HALF_N;
+            const int32_t ucol = n * TILE_N + half * HALF_N;           // unit-relative column of this thread's chunk 0
+            const uint32_t scol = (uint32_t)seg_tile * HALF_N;         // slice-relative
             const bool full_tile = (n + 1) * TILE_N <= u.t_count;
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr, ra);
             tmem_ld_wait(ra);
             tmem_ld32(taddr + 32, rb);
-            if (u.dump && n == 0) {
+            if (DEBUG && u.dump == 1 && n == 0)
                 for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + e] = __uint_as_float(ra[e]);
-            }
-            if (full_tile) scan32<false>(s, ra, col_tile, u.t_count); else scan32<true>(s, ra, col_tile, u.t_count);
+            if (full_tile) scan32<false>(s, ra, scol, ucol, u.t_count); else scan32<true>(s, ra, scol, ucol, u.t_count);
             tmem_ld_wait(rb);
             tmem_ld32(taddr + 64, ra);
-            if (u.dump && n == 0) {
+            if (DEBUG && u.dump == 1 && n == 0)
                 for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 32 + e] = __uint_as_float(rb[e]);
-            }
-            if (full_tile) scan32<false>(s, rb, col_tile + 32, u.t_count); else scan32<true>(s, rb, col_tile + 32, u.t_count);
+            if (full_tile) scan32<false>(s, rb, scol + 32, ucol + 32, u.t_count); else scan32<true>(s, rb, scol + 32, ucol + 32, u.t_count);
             tmem_ld_wait(ra);
             tmem_ld32(taddr + 96, rb);
-            if (u.dump && n == 0) {
+            if (DEBUG && u.dump == 1 && n == 0)
                 for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 64 + e] = __uint_as_float(ra[e]);
-            }
-            if (full_tile) scan32<false>(s, ra, col_tile + 64, u.t_count); else scan32<true>(s, ra, col_tile + 64, u.t_count);
+            if (full_tile) scan32<false>(s, ra, scol + 64, ucol + 64, u.t_count); else scan32<true>(s, ra, scol + 64, ucol + 64, u.t_count);
             tmem_ld_wait(rb);
             // all TMEM reads of this stage are complete: hand it back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
-            if (u.dump && n == 0) {
+            if (DEBUG && u.dump == 1 && n == 0)
                 for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 96 + e] = __uint_as_float(rb[e]);
-            }
-            if (full_tile) scan32<false>(s, rb, col_tile + 96, u.t_count); else scan32<true>(s, rb, col_tile + 96, u.t_count);
+            if (full_tile) scan32<false>(s, rb, scol + 96, ucol + 96, u.t_count); else scan32<true>(s, rb, scol + 96, ucol + 96, u.t_count);
+            if (DEBUG && u.dump == 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)
+                reinterpret_cast<long long*>(dump)[12288 + n] = clock64();
 
-            if (--seg_left == 0 || n == ntiles - 1) {
+            const float L = fmaxf(s.G, s.b1);
+            if (row_valid && L > s.published) {
+                atomicMax(const_cast<uint32_t*>(hint), enc_ordered(L));
+                s.published = L;
+            }
+            if (++seg_tile == u.seg_tiles || n == ntiles - 1) {
                 if (row_valid) {
+                    // slice column -> logical train index
+                    const int32_t base = u.t_index0 + seg * u.seg_tiles * TILE_N + half * HALF_N;
                     PartialRec rec;
-                    rec.s[0] = s.b0; rec.s[1] = s.b1; rec.s[2] = s.b2;
-                    rec.i[0] = s.i0 >= 0 ? u.t_index0 + s.i0 : -1;
-                    rec.i[1] = s.i1 >= 0 ? u.t_index0 + s.i1 : -1;
-                    rec.i[2] = s.i2 >= 0 ? u.t_index0 + s.i2 : -1;
+                    const float b[3] = {s.b0, s.b1, s.b2};
+#pragma unroll
+                    for (int e = 0; e < 3; e++) {
+                        const uint32_t c = __float_as_uint(b[e]) & ~PACK_MASK;
+                        const bool ok = b[e] > -1.0e38f;               // not empty, not a masked column
+                        rec.s[e] = ok ? b[e] : -INFINITY;
+                        rec.i[e] = ok ? base + (int32_t)(c / HALF_N) * TILE_N + (int32_t)(c % HALF_N) : -1;
+                    }
                     recs[u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half] = rec;
                 }
                 seg++;
-                seg_left = u.seg_tiles;
+                seg_tile = 0;
                 top3_reset_slice(s);
             }
         }

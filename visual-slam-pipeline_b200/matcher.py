@@ -69,6 +69,7 @@ SYMBOLS = {
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
     "vsm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsm_sync": (C.c_int, [C.c_void_p]),
+    "vsm_debug_fetch_dump": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vsm_debug_tile_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
@@ -266,6 +267,11 @@ class Matcher:
 
     def sync(self):
         self._ck(self._lib.vsm_sync(self._h))
+
+    def debug_timeline(self):
+        out = np.zeros(16384, np.int64)
+        self._ck(self._lib.vsm_debug_fetch_dump(self._h, out.ctypes.data, out.nbytes))
+        return out.reshape(4, 4096)
 
     def debug_tile_scores(self, query, train):
         q, t = _rows(query, "query"), _rows(train, "train")
