@@ -287,7 +287,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         nranges = (ntiles + tpr - 1) / tpr;
         // slice length: short slices keep an overflow re-scan cheap, long ones keep the record
         // stream small next to the database stream
-        const int seg_pref = ctx->seg_tiles > 0 ? ctx->seg_tiles : (ntiles <= 4096 ? 16 : 64);
+        const int seg_pref = ctx->seg_tiles > 0 ? ctx->seg_tiles
+                                                : (ntiles > 4096 ? 64 : std::max(1, std::min(16, ntiles / 16)));
         const int seg = std::min(tpr, seg_pref);
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
         std::vector<int> range_slice0(nranges);

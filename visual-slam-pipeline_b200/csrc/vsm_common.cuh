@@ -15,7 +15,7 @@
 #include <float.h>
 
 #define VSM_DIM 256
-#define VSM_TOPK 3                 // approximate entries kept per (query, slice)
+#define VSM_TOPK 4                 // approximate entries kept per (query, slice)
 
 namespace vsm {
 
@@ -24,12 +24,16 @@ constexpr int TILE_M = 128;        // queries per CTA (TMEM lanes)
 constexpr int TILE_N = 256;        // train rows per MMA tile (TMEM columns of one stage)
 constexpr int HALF_N = 128;        // columns one epilogue warp-group owns in every tile
 
-// Approximate per-(query, slice) record written by the tensor-core kernel: the three
-// largest bf16 dot products q.t of the slice, descending.  -inf / -1 = empty.
-struct PartialRec {
-    float   s[VSM_TOPK];
-    int32_t i[VSM_TOPK];           // logical train index inside the train set
+// Approximate per-(query, slice) record written by the tensor-core kernel: the four
+// largest bf16 dot products q.t of the slice, descending, PACKED: the low 13 mantissa bits
+// hold the column number inside the slice (column c = row (c/128)*256 + half*128 + c%128
+// of the slice's range).  -inf = empty.
+struct __align__(16) PartialRec {
+    float s[VSM_TOPK];
 };
+constexpr uint32_t PACK_MASK = 0xFFFFE000u;
+constexpr float MASKED_VALUE = -3.0e38f;       // a column past the end of the train range
+constexpr float VALID_FLOOR = -1.0e38f;        // record entries above this are real columns
 
 // One CTA of the tensor-core kernel: one 128-query tile x a contiguous train range.
 struct TcUnit {

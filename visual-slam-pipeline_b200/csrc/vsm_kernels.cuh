@@ -114,9 +114,11 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
         // pass 1: the second largest approximate dot over every record of the query
         float a0 = -INFINITY, a1 = -INFINITY;
         for (int s = lane; s < P.nslices; s += 32) {
+            const float4 rv = *reinterpret_cast<const float4*>(rq + s);
+            const float rs[VSM_TOPK] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-            for (int e = 0; e < VSM_TOPK; e++) {
-                float v = rq[s].s[e];
+            for (int e = 0; e < 2; e++) {                // entries are sorted: only the first two matter
+                float v = rs[e];
                 if (v > a0) { a1 = a0; a0 = v; } else if (v > a1) a1 = v;
             }
         }
@@ -131,21 +133,27 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
         // pass 2: survivors -> exact distance; overflowing slices -> exact scan
         for (int s0 = 0; s0 < P.nslices; s0 += 32) {
             const int s = s0 + lane;
-            PartialRec rec;
-#pragma unroll
-            for (int e = 0; e < VSM_TOPK; e++) { rec.s[e] = -INFINITY; rec.i[e] = -1; }
-            if (s < P.nslices) rec = rq[s];
-            const bool flagged = rec.i[2] >= 0 && rec.s[2] > thr;
+            float4 rv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            SliceInfo my = {0, 0, 0, 0};
+            if (s < P.nslices) {
+                rv = *reinterpret_cast<const float4*>(rq + s);
+                my = sl[s];
+            }
+            const float rs[VSM_TOPK] = {rv.x, rv.y, rv.z, rv.w};
+            const bool flagged = rs[VSM_TOPK - 1] > VALID_FLOOR && rs[VSM_TOPK - 1] > thr;
 #pragma unroll
             for (int e = 0; e < VSM_TOPK; e++) {
-                unsigned m = __ballot_sync(full, !flagged && rec.i[e] >= 0 && rec.s[e] > thr);
+                // packed entry -> logical train index
+                const uint32_t c = __float_as_uint(rs[e]) & ~PACK_MASK;
+                const int32_t cand = my.t_index0 + (int32_t)(c / HALF_N) * TILE_N + my.half * HALF_N + (int32_t)(c % HALF_N);
+                unsigned m = __ballot_sync(full, !flagged && rs[e] > VALID_FLOOR && rs[e] > thr);
                 n_cand += __popc(m);
                 while (m) {
                     int l0 = __ffs(m) - 1; m &= m - 1;
                     int l1 = -1;
                     if (m) { l1 = __ffs(m) - 1; m &= m - 1; }
                     int src = h == 0 ? l0 : l1;
-                    int32_t j = __shfl_sync(full, rec.i[e], src < 0 ? 0 : src);
+                    int32_t j = __shfl_sync(full, cand, src < 0 ? 0 : src);
                     score_pair(qreg, P.t_f32, src < 0 ? -1 : j, l16, best);
                 }
             }
@@ -153,7 +161,7 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
             // hand the overflowing slices to rescan_kernel; scan inline only if its list is full
             bool inline_scan = false;
             if (flagged) {
-                const int span = slice_span(sl[s]);
+                const int span = slice_span(my);
                 const uint32_t nitem = (uint32_t)((span + RESCAN_ROWS - 1) / RESCAN_ROWS);
                 uint32_t* wcount = reinterpret_cast<uint32_t*>(counters + 2);
                 const uint32_t base = atomicAdd(wcount, nitem);

@@ -169,33 +169,31 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE
                            ((uint32_t)(TILE_M >> 4) << 24);
 
 // ---- epilogue state -------------------------------------------------------------
-// Slice top-3 as PACKED floats: the low 13 mantissa bits of an accumulator value are
+// Slice top-4 as PACKED floats: the low 13 mantissa bits of an accumulator value are
 // replaced by its column number inside the slice (a slice is at most 64 tiles x 128
-// columns = 2^13), so the whole (value, index) top-3 update is five FMNMX and no branch.
+// columns = 2^13), so the whole (value, index) top-4 update is seven FMNMX and no branch.
 // The packing moves a value by < 2^-10 relative; dot_margin() accounts for it.
-constexpr uint32_t PACK_MASK = 0xFFFFE000u;
-constexpr float MASKED_VALUE = -3.0e38f;       // a column past the end of the train range
-
 struct Top3 {
-    float b0, b1, b2;          // slice top-3 (packed), descending; -inf = empty
+    float b0, b1, b2, b3;      // slice top-4 (packed), descending; -inf = empty
     float G;                   // lower bound on the query's global second-best dot
     float margin2;             // 2 * dot_margin
-    float thr;                 // max(b2, max(G, b1) - margin2): values <= thr are dropped
+    float thr;                 // max(b3, max(G, b1) - margin2): values <= thr are dropped
     float published;           // last bound pushed to the shared hint
 };
 
 __device__ __forceinline__ void top3_update_thr(Top3& s) {
-    s.thr = fmaxf(s.b2, fmaxf(s.G, s.b1) - s.margin2);
+    s.thr = fmaxf(s.b3, fmaxf(s.G, s.b1) - s.margin2);
 }
 __device__ __forceinline__ void top3_reset_slice(Top3& s) {
     s.G = fmaxf(s.G, s.b1);                     // second best of a subset <= global second best
-    s.b0 = s.b1 = s.b2 = -INFINITY;
+    s.b0 = s.b1 = s.b2 = s.b3 = -INFINITY;
     top3_update_thr(s);
 }
 __device__ __forceinline__ void top3_push(Top3& s, float x) {
     float t0 = fmaxf(s.b0, x), x1 = fminf(s.b0, x);
     float t1 = fmaxf(s.b1, x1), x2 = fminf(s.b1, x1);
-    s.b0 = t0; s.b1 = t1; s.b2 = fmaxf(s.b2, x2);
+    float t2 = fmaxf(s.b2, x2), x3 = fminf(s.b2, x2);
+    s.b0 = t0; s.b1 = t1; s.b2 = t2; s.b3 = fmaxf(s.b3, x3);
 }
 // monotone float <-> uint32 (for atomicMax on the shared bound); 0 = "nothing yet"
 __device__ __forceinline__ uint32_t enc_ordered(float f) {
@@ -339,7 +337,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         const int row = quarter * 32 + lane;
         const bool row_valid = row < u.q_valid;
         Top3 s;
-        s.b0 = s.b1 = s.b2 = -INFINITY;
+        s.b0 = s.b1 = s.b2 = s.b3 = -INFINITY;
         s.G = s.published = -INFINITY;
         {
             const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
@@ -400,18 +398,8 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
             }
             if (++seg_tile == u.seg_tiles || n == ntiles - 1) {
                 if (row_valid) {
-                    // slice column -> logical train index
-                    const int32_t base = u.t_index0 + seg * u.seg_tiles * TILE_N + half * HALF_N;
-                    PartialRec rec;
-                    const float b[3] = {s.b0, s.b1, s.b2};
-#pragma unroll
-                    for (int e = 0; e < 3; e++) {
-                        const uint32_t c = __float_as_uint(b[e]) & ~PACK_MASK;
-                        const bool ok = b[e] > -1.0e38f;               // not empty, not a masked column
-                        rec.s[e] = ok ? b[e] : -INFINITY;
-                        rec.i[e] = ok ? base + (int32_t)(c / HALF_N) * TILE_N + (int32_t)(c % HALF_N) : -1;
-                    }
-                    recs[u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half] = rec;
+                    const float4 rec = make_float4(s.b0, s.b1, s.b2, s.b3);
+                    *reinterpret_cast<float4*>(recs + u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half) = rec;
                 }
                 seg++;
                 seg_tile = 0;
