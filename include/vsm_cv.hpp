@@ -1,0 +1,193 @@
+/*
+ * vsm_cv.hpp -- header-only C++ adaptor over the C ABI of libvsm.so (include/vsm.h) that
+ * gives the B200 matcher the reference's own call-site signatures:
+ *
+ *   Slam::match_features(desc1, desc2, raw_out)          src/Slam.cpp:1140-1172, include/Slam.h:69-70
+ *   cv::DescriptorMatcher::knnMatch(query, train, knn, 2) src/Slam.cpp:1149, :567, :764; src/LoopCloser.cpp:51
+ *   LoopCloser::detect's per-keyframe block               src/LoopCloser.cpp:43-62
+ *
+ * cv::Mat (N x 256, CV_32F) in, std::vector<cv::DMatch> out.  With OpenCV's headers on the
+ * include path the adaptor uses cv::Mat / cv::DMatch directly; without them (this build
+ * image has none) it falls back to two minimal stand-ins with the same member names, so
+ * the same call-site code compiles either way.
+ *
+ * Errors surface as std::runtime_error, like the cv::Exception the reference never catches.
+ */
+#ifndef VSM_CV_HPP
+#define VSM_CV_HPP
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vsm.h"
+
+#if defined(__has_include)
+#if __has_include(<opencv2/core.hpp>) && !defined(VSM_CV_NO_OPENCV)
+#include <opencv2/core.hpp>
+#define VSM_CV_HAVE_OPENCV 1
+#endif
+#endif
+
+namespace vsm_cv {
+
+#ifdef VSM_CV_HAVE_OPENCV
+using Mat = cv::Mat;
+using DMatch = cv::DMatch;
+inline bool is_f32_256(const Mat& m) { return m.type() == CV_32F && m.cols == VSM_DIM; }
+#else
+/* cv::DMatch (opencv2/core/types.hpp): same members, same order, 16 bytes. */
+struct DMatch {
+    int queryIdx = -1, trainIdx = -1, imgIdx = -1;
+    float distance = 3.402823466e+38f;
+    DMatch() {}
+    DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+    DMatch(int q, int t, int i, float d) : queryIdx(q), trainIdx(t), imgIdx(i), distance(d) {}
+    bool operator<(const DMatch& m) const { return distance < m.distance; }
+};
+/* The slice of cv::Mat the matcher call sites use: a borrowed row-major fp32 matrix. */
+struct Mat {
+    int rows = 0, cols = 0;
+    const float* data = nullptr;
+    size_t step = 0;                                   /* bytes per row */
+    Mat() {}
+    Mat(int r, int c, const float* p, size_t step_bytes = 0)
+        : rows(r), cols(c), data(p), step(step_bytes ? step_bytes : (size_t)c * sizeof(float)) {}
+    bool empty() const { return rows == 0 || cols == 0 || !data; }
+    bool isContinuous() const { return step == (size_t)cols * sizeof(float); }
+    template <class T> const T* ptr(int r = 0) const {
+        return reinterpret_cast<const T*>(reinterpret_cast<const char*>(data) + (size_t)r * step);
+    }
+};
+inline bool is_f32_256(const Mat& m) { return m.cols == VSM_DIM; }
+#endif
+
+static_assert(sizeof(DMatch) == sizeof(vsm_dmatch), "cv::DMatch must be the 16-byte struct vsm_dmatch mirrors");
+
+class DescriptorMatcher {
+public:
+    explicit DescriptorMatcher(int device = 0, int engine = VSM_ENGINE_AUTO) {
+        vsm_opts o;
+        vsm_default_opts(&o);
+        o.device = device;
+        o.engine = engine;
+        if (vsm_create(&o, &ctx_) != VSM_OK) throw std::runtime_error(std::string("vsm_create: ") + vsm_last_error(nullptr));
+    }
+    ~DescriptorMatcher() { vsm_destroy(ctx_); }
+    DescriptorMatcher(const DescriptorMatcher&) = delete;
+    DescriptorMatcher& operator=(const DescriptorMatcher&) = delete;
+
+    /* Slam::match_features for float descriptors (src/Slam.cpp:1140-1172): kNN k=2, raw = every
+     * m[0] of a two-entry list, result = those passing m[0].distance < ratio * m[1].distance.
+     * The reference's ratio is Config::L2_RATIO_THRESHOLD = 0.75f (include/Config.h:53). */
+    std::vector<DMatch> match_features(const Mat& desc1, const Mat& desc2, std::vector<DMatch>* raw_out = nullptr,
+                                       float ratio = 0.75f, bool mutual = false) {
+        std::vector<DMatch> good;
+        if (raw_out) raw_out->clear();
+        if (desc1.empty() || desc2.empty()) return good;                  /* src/Slam.cpp:1143 */
+        std::vector<float> b1, b2;
+        const float* q = rows_of(desc1, b1);
+        const float* t = rows_of(desc2, b2);
+        good.resize(desc1.rows);
+        if (raw_out) raw_out->resize(desc1.rows);
+        int32_t ng = 0, nr = 0;
+        check(vsm_match_pair(ctx_, q, desc1.rows, t, desc2.rows, ratio, mutual ? 1 : 0,
+                             reinterpret_cast<vsm_dmatch*>(good.data()), &ng,
+                             raw_out ? reinterpret_cast<vsm_dmatch*>(raw_out->data()) : nullptr, raw_out ? &nr : nullptr));
+        good.resize(ng);
+        if (raw_out) raw_out->resize(nr);
+        return good;
+    }
+
+    /* cv::DescriptorMatcher::knnMatch(query, train, knn, 2): lists may hold fewer than two
+     * entries when train has fewer than two rows (the reference guards with m.size() >= 2). */
+    void knnMatch(const Mat& query, const Mat& train, std::vector<std::vector<DMatch>>& knn, int k = 2) {
+        if (k != 2) throw std::runtime_error("vsm_cv::knnMatch: only k = 2 (the reference's call sites)");
+        knn.assign(query.rows, std::vector<DMatch>());
+        if (query.empty()) return;
+        std::vector<float> b1, b2;
+        const float* q = rows_of(query, b1);
+        const float* t = train.empty() ? nullptr : rows_of(train, b2);
+        std::vector<int32_t> idx((size_t)query.rows * 2);
+        std::vector<float> dist((size_t)query.rows * 2);
+        check(vsm_knn2(ctx_, q, query.rows, t, train.empty() ? 0 : train.rows, idx.data(), dist.data()));
+        for (int i = 0; i < query.rows; i++)
+            for (int p = 0; p < 2; p++)
+                if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, idx[2 * i + p], 0, dist[2 * i + p]));
+    }
+
+    /* Keyframe descriptors kept on the device (Frame::descriptors_, include/Frame.h:61). */
+    int add_keyframe(int frame_id, const Mat& desc) {
+        std::vector<float> b;
+        int32_t h = -1;
+        check(vsm_store_add(ctx_, frame_id, desc.empty() ? nullptr : rows_of(desc, b), desc.empty() ? 0 : desc.rows, &h));
+        return h;
+    }
+    void clear_keyframes() { check(vsm_store_clear(ctx_)); }
+
+    /* match_features(ref_kf->descriptors(), cur->descriptors(), raw) with ref_kf resident (src/Slam.cpp:841). */
+    std::vector<DMatch> match_features(int keyframe_handle, int keyframe_rows, const Mat& cur,
+                                       std::vector<DMatch>* raw_out = nullptr, float ratio = 0.75f, bool mutual = false) {
+        std::vector<DMatch> good(keyframe_rows > 0 ? keyframe_rows : 1);
+        if (raw_out) raw_out->assign(good.size(), DMatch());
+        std::vector<float> b;
+        int32_t ng = 0, nr = 0;
+        check(vsm_match_to_stored(ctx_, keyframe_handle, cur.empty() ? nullptr : rows_of(cur, b), cur.empty() ? 0 : cur.rows,
+                                  ratio, mutual ? 1 : 0, reinterpret_cast<vsm_dmatch*>(good.data()), &ng,
+                                  raw_out ? reinterpret_cast<vsm_dmatch*>(raw_out->data()) : nullptr, raw_out ? &nr : nullptr));
+        good.resize(ng);
+        if (raw_out) raw_out->resize(nr);
+        return good;
+    }
+
+    /* LoopCloser::detect, lines 43-62: per stored keyframe the ratio-test survivors of a kNN
+     * inside that keyframe.  good_matches[s] is what the reference builds at :54-60; the caller
+     * keeps its own eligibility rules (:44-48) and the >= 30 gate (:62). */
+    void detect_candidates(const Mat& cur, float ratio, std::vector<std::vector<DMatch>>& good_matches) {
+        int64_t rows = 0;
+        int32_t nkf = 0;
+        check(vsm_store_info(ctx_, &rows, &nkf));
+        good_matches.assign(nkf, std::vector<DMatch>());
+        if (cur.empty() || nkf == 0) return;
+        std::vector<float> b;
+        std::vector<int32_t> counts(nkf);
+        std::vector<DMatch> flat((size_t)nkf * cur.rows);
+        check(vsm_db_segmented(ctx_, rows_of(cur, b), cur.rows, ratio, counts.data(), reinterpret_cast<vsm_dmatch*>(flat.data())));
+        for (int s = 0; s < nkf; s++)
+            good_matches[s].assign(flat.begin() + (size_t)s * cur.rows, flat.begin() + (size_t)s * cur.rows + counts[s]);
+    }
+
+    /* knnMatch(frame_desc, all_descs, knn, 2) over every stored row (src/Slam.cpp:567, :764). */
+    void search_store(const Mat& frame_desc, std::vector<std::vector<DMatch>>& knn) {
+        knn.assign(frame_desc.rows, std::vector<DMatch>());
+        if (frame_desc.empty()) return;
+        std::vector<float> b;
+        std::vector<int64_t> idx((size_t)frame_desc.rows * 2);
+        std::vector<float> dist((size_t)frame_desc.rows * 2);
+        check(vsm_db_top2(ctx_, rows_of(frame_desc, b), frame_desc.rows, 0, idx.data(), dist.data()));
+        for (int i = 0; i < frame_desc.rows; i++)
+            for (int p = 0; p < 2; p++)
+                if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, (int)idx[2 * i + p], 0, dist[2 * i + p]));
+    }
+
+    vsm_ctx* handle() { return ctx_; }
+
+private:
+    vsm_ctx* ctx_ = nullptr;
+
+    void check(int st) {
+        if (st != VSM_OK) throw std::runtime_error(std::string("libvsm: ") + vsm_last_error(ctx_));
+    }
+    /* contiguous N x 256 fp32 rows of m (copied only if m is a strided view) */
+    static const float* rows_of(const Mat& m, std::vector<float>& tmp) {
+        if (!is_f32_256(m)) throw std::runtime_error("vsm_cv: descriptors must be N x 256 CV_32F");
+        if (m.isContinuous()) return m.template ptr<float>(0);
+        tmp.resize((size_t)m.rows * VSM_DIM);
+        for (int r = 0; r < m.rows; r++) std::memcpy(&tmp[(size_t)r * VSM_DIM], m.template ptr<float>(r), VSM_DIM * sizeof(float));
+        return tmp.data();
+    }
+};
+
+}  // namespace vsm_cv
+#endif /* VSM_CV_HPP */
