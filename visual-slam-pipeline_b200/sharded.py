@@ -14,6 +14,40 @@ import torch
 from .matcher import Matcher, ENGINE_TENSOR
 
 
+def partition_keyframes(seg_off, world):
+    """Split keyframes (row offsets seg_off[0..nkf]) into `world` contiguous blocks of WHOLE
+    keyframes with near-equal row counts.  Returns [(kf_begin, kf_end, row_begin, row_end)] per rank.
+    A keyframe is never split, so the per-keyframe (LoopCloser) epilogue stays rank-local."""
+    seg_off = [int(x) for x in seg_off]
+    nkf, total = len(seg_off) - 1, seg_off[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r // world
+        k = cuts[-1]
+        while k < nkf and seg_off[k] < target:          # first keyframe starting at/after the target
+            k += 1
+        if k > cuts[-1] and k <= nkf and (seg_off[k] - target) > (target - seg_off[k - 1]):
+            k -= 1                                       # the previous boundary is closer
+        cuts.append(max(k, cuts[-1]))
+    cuts.append(nkf)
+    return [(cuts[r], cuts[r + 1], seg_off[cuts[r]], seg_off[cuts[r + 1]]) for r in range(world)]
+
+
+def gather_and_merge(l_idx, l_dist, world, group, merge, g_idx=None, g_dist=None):
+    """The exchange step of the sharded search: all-gather every rank's [nq,2] (global index,
+    distance) lists and merge them by (distance, index).  `merge(g_idx, g_dist)` -> (idx, dist).
+    Works on CUDA tensors (NCCL) and on CPU tensors (gloo; used by the CPU tests)."""
+    if world == 1:
+        return l_idx, l_dist
+    if g_idx is None:
+        g_idx = torch.empty((world,) + tuple(l_idx.shape), dtype=l_idx.dtype, device=l_idx.device)
+        g_dist = torch.empty((world,) + tuple(l_dist.shape), dtype=l_dist.dtype, device=l_dist.device)
+    # concatenated-along-dim-0 form (accepted by both NCCL and gloo): [world*nq, 2] views
+    torch.distributed.all_gather_into_tensor(g_idx.view(-1, *l_idx.shape[1:]), l_idx, group=group)
+    torch.distributed.all_gather_into_tensor(g_dist.view(-1, *l_dist.shape[1:]), l_dist, group=group)
+    return merge(g_idx, g_dist)
+
+
 class ShardedDB:
     def __init__(self, device, rank=0, world=1, group=None, engine=ENGINE_TENSOR):
         self.rank, self.world, self.group = rank, world, group
@@ -62,10 +96,11 @@ class ShardedDB:
             self.matcher.db_top2_device(d_q.data_ptr(), nq, self.row_offset, self.l_idx.data_ptr(),
                                         self.l_dist.data_ptr(), sync=False)
             if self.world > 1:
-                torch.distributed.all_gather_into_tensor(self.g_idx, self.l_idx, group=self.group)
-                torch.distributed.all_gather_into_tensor(self.g_dist, self.l_dist, group=self.group)
-                self.matcher.merge_top2_device(self.g_idx.data_ptr(), self.g_dist.data_ptr(), self.world, nq,
-                                               self.o_idx.data_ptr(), self.o_dist.data_ptr(), sync=False)
+                def merge(g_idx, g_dist):
+                    self.matcher.merge_top2_device(g_idx.data_ptr(), g_dist.data_ptr(), self.world, nq,
+                                                   self.o_idx.data_ptr(), self.o_dist.data_ptr(), sync=False)
+                    return self.o_idx, self.o_dist
+                gather_and_merge(self.l_idx, self.l_dist, self.world, self.group, merge, self.g_idx, self.g_dist)
         return self.o_idx, self.o_dist
 
     def search_host(self, h_q):
