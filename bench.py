@@ -172,6 +172,15 @@ def run_reference(args):
     }))
 
 
+def committed_traffic(shard_rows):
+    """dram bytes per tc_top3_kernel launch from the committed `ncu --set full` capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)["tc_top3_kernel"].get(str(int(shard_rows)))
+    except Exception:
+        return None
+
+
 def workload_config(n_gpus, total_rows):
     return {"workload": f"loop-closure search: {NQ} query descriptors x {total_rows}-descriptor keyframe DB "
                         f"({total_rows // KF_ROWS} keyframes x {KF_ROWS}), exact global top-2 per query "
@@ -378,7 +387,8 @@ def run_gpu(args):
                     "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": "tc_top3_kernel", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": args.traffic,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": args.traffic if args.traffic is not None else committed_traffic(shard.shape[0]),
                          "peak_source": peak_src, "kernel_ms": tc_avg,
                          "algorithmic": "2*nq*shard_rows*256 FLOP per launch",
                          "hbm_gbs": (shard.shape[0] * 512 + NQ * 512) / (tc_avg * 1e-3) / 1e9, "hbm_peak": peak_hbm},
@@ -422,7 +432,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=100_000, help="cpu_baseline: DB sample rows")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per launch (default: the committed ncu capture in profiles/, if one matches)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
