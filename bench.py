@@ -221,22 +221,47 @@ def extra_pair_numbers(torch, vsm_b200, device):
         frames[f].copy_(cur)
     torch.cuda.synchronize()
     fr = frames.numpy()
-    lat, nmatch = [], 0
+
+    def run_sequence(step):
+        lat, nmatch = [], 0
+        t_all = time.perf_counter()
+        for f in range(npairs):
+            t0 = time.perf_counter()
+            nmatch += step(f)
+            lat.append(time.perf_counter() - t0)
+        t_all = time.perf_counter() - t_all
+        lat.sort()
+        return {"pairs": npairs, "p50_us": lat[len(lat) // 2] * 1e6, "p99_us": lat[int(len(lat) * 0.99)] * 1e6,
+                "matches_per_s": nmatch / t_all, "pairs_per_s": npairs / t_all,
+                "pair_distances_per_s": npairs * 1e6 / t_all}
+
+    # (a) Slam::match_features as the reference calls it: both frames come from the host every call
     for f in range(20):
         m.match_features(fr[f], fr[f + 1], 0.75, mutual=True, want_raw=False)
-    t_all = time.perf_counter()
-    for f in range(npairs):
-        t0 = time.perf_counter()
-        good, _ = m.match_features(fr[f], fr[f + 1], 0.75, mutual=True, want_raw=False)
-        lat.append(time.perf_counter() - t0)
-        nmatch += len(good)
-    t_all = time.perf_counter() - t_all
-    lat.sort()
-    out["tracking_1000x1000_mutual_ratio"] = {
-        "pairs": npairs, "p50_us": lat[len(lat) // 2] * 1e6, "p99_us": lat[int(len(lat) * 0.99)] * 1e6,
-        "matches_per_s": nmatch / t_all, "pair_distances_per_s": npairs * 1e6 / t_all,
-        "timing": "host wall clock per call incl. H2D of both frames and D2H of the DMatch list",
-        "device_ms_last": m.stats()["device_ms"], "launches_per_pair": m.stats()["kernel_launches"]}
+    r = run_sequence(lambda f: len(m.match_features(fr[f], fr[f + 1], 0.75, mutual=True, want_raw=False)[0]))
+    r.update({"timing": "host wall clock per call incl. H2D of BOTH frames (pinned) and D2H of the DMatch list",
+              "device_ms_last": m.stats()["device_ms"], "launches_per_pair": m.stats()["kernel_launches"]})
+    out["tracking_1000x1000_mutual_ratio_both_frames_from_host"] = r
+    # (b) the tracking step with the reference frame resident (vsm_track): one frame uploaded per pair
+    mt = vsm_b200.Matcher(device=device, engine=vsm_b200.ENGINE_TENSOR, store_rows=(npairs + 64) * 1000)
+    state = {"h": mt.track(-1, 0, fr[0], ref_rows=1000)[2]}
+
+    def step(f):
+        good, _, h = mt.track(state["h"], f + 1, fr[f + 1], 0.75, mutual=True, ref_rows=1000)
+        state["h"] = h
+        return len(good)
+
+    for f in range(20):
+        step(f)
+    mt.clear_store()
+    state["h"] = mt.track(-1, 0, fr[0], ref_rows=1000)[2]
+    r = run_sequence(step)
+    st = mt.stats()
+    r.update({"timing": "host wall clock per call incl. H2D of the current frame (pinned) and D2H of the DMatch list",
+              "device_ms_last": st["device_ms"], "tc_ms_last": st["tc_ms"], "select_ms_last": st["select_ms"],
+              "launches_per_pair": st["kernel_launches"]})
+    out["tracking_1000x1000_mutual_ratio"] = r
+    mt.close()
     # configs[0]: 2000 x 2000, k=2 + ratio 0.8
     a = unit(2000)
     b = planted_from(a, 0.6, 0.08)

@@ -147,6 +147,16 @@ int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t 
                         float ratio, int32_t mutual,
                         vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw);
 
+/* The tracking step of Slam::process_frame (src/Slam.cpp:838-842: ref = last keyframe or last
+ * frame; matches = match_features(ref->descriptors(), frame->descriptors(), &raw)) for a
+ * sequence: uploads the current frame ONCE, straight into the store as a new keyframe
+ * (*cur_handle), and matches the resident reference `ref_handle` against it (query = reference,
+ * train = current).  ref_handle < 0: only store the frame (first frame of a sequence).
+ * good / raw must hold as many entries as the reference keyframe has rows. */
+int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* cur, int32_t n_cur,
+              float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw,
+              int32_t* cur_handle);
+
 /* Global top-2 per query over every row of the store -- the stacked-matrix search of
  * src/Slam.cpp:546-574 and :744-774 (knnMatch(frame, all_descs, 2)).
  * idx: [nq][2] store row (+ row_offset, for sharded stores), dist: [nq][2]. */

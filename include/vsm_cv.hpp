@@ -141,6 +141,23 @@ public:
         return good;
     }
 
+    /* The tracking match of Slam::process_frame (src/Slam.cpp:838-842) for a sequence: the current
+     * frame goes to the device once and becomes keyframe *cur_handle; ref_handle < 0 = first frame. */
+    std::vector<DMatch> track(int ref_handle, int ref_rows, int frame_id, const Mat& cur, int* cur_handle,
+                              std::vector<DMatch>* raw_out = nullptr, float ratio = 0.75f, bool mutual = false) {
+        std::vector<DMatch> good(ref_rows > 0 ? ref_rows : 1);
+        if (raw_out) raw_out->assign(good.size(), DMatch());
+        std::vector<float> b;
+        int32_t ng = 0, nr = 0, h = -1;
+        check(vsm_track(ctx_, ref_handle, frame_id, cur.empty() ? nullptr : rows_of(cur, b), cur.empty() ? 0 : cur.rows,
+                        ratio, mutual ? 1 : 0, reinterpret_cast<vsm_dmatch*>(good.data()), &ng,
+                        raw_out ? reinterpret_cast<vsm_dmatch*>(raw_out->data()) : nullptr, raw_out ? &nr : nullptr, &h));
+        if (cur_handle) *cur_handle = h;
+        good.resize(ng);
+        if (raw_out) raw_out->resize(nr);
+        return good;
+    }
+
     /* LoopCloser::detect, lines 43-62: per stored keyframe the ratio-test survivors of a kNN
      * inside that keyframe.  good_matches[s] is what the reference builds at :54-60; the caller
      * keeps its own eligibility rules (:44-48) and the >= 30 gate (:62). */

@@ -209,3 +209,20 @@ def test_device_resident_db_search(tc):
     oc, _ = oracle.segmented(q, db, seg_off, 0.75)
     assert np.array_equal(counts, oc)
     tc.clear_store()
+
+
+def test_track_sequence(tc):
+    """vsm_track: each frame is uploaded once and matched against the resident previous frame
+    (src/Slam.cpp:838-842); results equal match_features on the same two frames."""
+    frames = gen.video(3, 5, 400)
+    tc.clear_store()
+    _, _, h = tc.track(-1, 0, frames[0])
+    for f in range(1, 5):
+        for_mutual = (f % 2 == 0)
+        good, raw, h2 = tc.track(h, f, frames[f], 0.75, mutual=for_mutual, want_raw=True)
+        og, orw = oracle.match_features(frames[f - 1], frames[f], 0.75, mutual=for_mutual)
+        assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+        assert len(good) > 100
+        h = h2
+    assert tc.store_info() == (2000, 5)
+    tc.clear_store()

@@ -77,6 +77,10 @@ struct vsm_ctx {
     DevBuf<uint8_t> d_desc;
     uint8_t* h_desc = nullptr;
     size_t h_desc_cap = 0;
+    std::vector<uint8_t> desc_build, desc_last;      // descriptor block cache (skip identical uploads)
+    const uint8_t* desc_dev = nullptr;
+    cudaEvent_t ev_desc = nullptr;
+    bool desc_copy_pending = false;
     DevBuf<PartialRec> d_recs;
     DevBuf<int32_t> d_out_idx;
     DevBuf<float> d_out_dist;
@@ -327,8 +331,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         nrecs += (int64_t)hp.nq * d.nslices;
     }
 
-    // descriptor block: [scratch stats 16 B][Problem][q_block0][TcUnit][SliceInfo][FilterJob]
-    const size_t off_prob = 16;
+    // descriptor block: [Problem][q_block0][TcUnit][SliceInfo][FilterJob]
+    const size_t off_prob = 0;
     const size_t off_qb = align16(off_prob + sizeof(Problem) * P);
     const size_t off_unit = align16(off_qb + sizeof(int32_t) * (P + 1));
     const size_t off_slice = align16(off_unit + sizeof(TcUnit) * units.size());
@@ -342,15 +346,15 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     const size_t result_bytes = (size_t)total_matches * sizeof(DMatch) + jobs.size() * 2 * sizeof(int32_t);
     TRY(ensure(ctx, ctx->d_result, std::max<size_t>(result_bytes, 16)));
 
-    const size_t aux_bytes = 32 + (size_t)std::max<int64_t>(total_out, 1) * 2 * sizeof(uint32_t);
+    const size_t aux_bytes = 48 + (size_t)std::max<int64_t>(total_out, 1) * 2 * sizeof(uint32_t);
     TRY(ensure(ctx, ctx->d_aux, aux_bytes));
     TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
     ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
-    uint32_t* d_hints = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32);
+    uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32);
+    uint32_t* d_hints = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 48);
     uint32_t* d_locks = d_hints + std::max<int64_t>(total_out, 1);
     CK(cudaMemsetAsync(ctx->d_aux.p, 0, aux_bytes, ctx->stream));
 
-    uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_desc.p);
     for (int i = 0; i < P; i++) dp[i].t_stats = probs[i].t_store ? ctx->d_store_stats : d_scratch_stats;
     for (size_t k = 0; k < units.size(); k++) {
         const int i = unit_prob[k];
@@ -358,22 +362,32 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         units[k].hint = d_hints + probs[i].out_off + (units[k].q_row - probs[i].q_row);
     }
 
-    uint8_t* h = ctx->h_desc;
-    uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};                         // {min=+inf, max=0}
-    memcpy(h, arm, 16);
+    // build the block; upload it only if it differs from what the device already holds
+    // (tracking calls repeat the same shapes frame after frame)
+    std::vector<uint8_t>& blk = ctx->desc_build;
+    blk.assign(total, 0);
+    uint8_t* h = blk.data();
     memcpy(h + off_prob, dp.data(), sizeof(Problem) * P);
     memcpy(h + off_qb, qb.data(), sizeof(int32_t) * (P + 1));
     if (!units.empty()) memcpy(h + off_unit, units.data(), sizeof(TcUnit) * units.size());
     if (!slices.empty()) memcpy(h + off_slice, slices.data(), sizeof(SliceInfo) * slices.size());
-    std::vector<FilterJob> fj(jobs.size());
     for (size_t j = 0; j < jobs.size(); j++) {
-        memset(&fj[j], 0, sizeof(FilterJob));
-        fj[j].fwd_off = jobs[j].fwd_off; fj[j].back_off = jobs[j].back_off;
-        fj[j].good_off = jobs[j].good_off; fj[j].raw_off = jobs[j].raw_off;
-        fj[j].nq = jobs[j].nq; fj[j].nt = jobs[j].nt; fj[j].img_idx = jobs[j].img_idx; fj[j].ratio = jobs[j].ratio;
+        FilterJob fj;
+        memset(&fj, 0, sizeof fj);
+        fj.fwd_off = jobs[j].fwd_off; fj.back_off = jobs[j].back_off;
+        fj.good_off = jobs[j].good_off; fj.raw_off = jobs[j].raw_off;
+        fj.nq = jobs[j].nq; fj.nt = jobs[j].nt; fj.img_idx = jobs[j].img_idx; fj.ratio = jobs[j].ratio;
+        memcpy(h + off_job + j * sizeof(FilterJob), &fj, sizeof fj);
     }
-    if (!fj.empty()) memcpy(h + off_job, fj.data(), sizeof(FilterJob) * fj.size());
-    CK(cudaMemcpyAsync(ctx->d_desc.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->desc_dev != ctx->d_desc.p || ctx->desc_last != blk) {
+        if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));   // h_desc may still be in flight
+        memcpy(ctx->h_desc, h, total);
+        CK(cudaMemcpyAsync(ctx->d_desc.p, ctx->h_desc, total, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_desc, ctx->stream));
+        ctx->desc_copy_pending = true;
+        ctx->desc_last = blk;
+        ctx->desc_dev = ctx->d_desc.p;
+    }
 
     if (conv_rows > 0)
         TRY(launch_convert(ctx, conv_src, ctx->scratch.b16 + conv_row0 * VSM_DIM, ctx->scratch.n2 + conv_row0,
@@ -496,14 +510,14 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaEventCreate(&ctx->ev_tc0));
         CK(cudaEventCreate(&ctx->ev_tc1));
         CK(cudaEventCreate(&ctx->ev_sel1));
+        CK(cudaEventCreateWithFlags(&ctx->ev_desc, cudaEventDisableTiming));
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, VSM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
         ctx->encode = reinterpret_cast<PFN_encodeTiled>(fn);
         CK(cudaMalloc(&ctx->d_store_stats, 16));
-        uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};
-        CK(cudaMemcpy(ctx->d_store_stats, arm, 16, cudaMemcpyHostToDevice));
+        CK(cudaMemset(ctx->d_store_stats, 0, 16));
         CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
         CK(cudaFuncSetAttribute(tc::tc_top3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
         CK(cudaFuncSetAttribute(tc::tc_top3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
@@ -539,6 +553,7 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->ev_tc0) cudaEventDestroy(ctx->ev_tc0);
     if (ctx->ev_tc1) cudaEventDestroy(ctx->ev_tc1);
     if (ctx->ev_sel1) cudaEventDestroy(ctx->ev_sel1);
+    if (ctx->ev_desc) cudaEventDestroy(ctx->ev_desc);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -713,8 +728,7 @@ int vsm_store_clear(vsm_ctx* ctx) {
     if (!ctx->store.own_f32) arena_free(ctx->store);
     ctx->store_rows = 0;
     ctx->segs.clear();
-    uint32_t arm[4] = {0x7f800000u, 0u, 0u, 0u};
-    CK(cudaMemcpy(ctx->d_store_stats, arm, 16, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_store_stats, 0, 16));
     return VSM_OK;
 }
 
@@ -776,6 +790,47 @@ int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t 
         probs.push_back(b);
     }
     return match_common(ctx, probs, sg.count, n_cur, ratio, mutual, good, n_good, raw, n_raw, ctx->scratch.f32, 0, n_cur);
+}
+
+int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* cur, int32_t n_cur, float ratio,
+              int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw, int32_t* cur_handle) {
+    if (!ctx || n_cur < 0 || !n_good || (n_cur > 0 && !cur) || !cur_handle)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_track: bad argument") : VSM_ERR_INVALID;
+    if (ref_handle >= (int)ctx->segs.size()) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown keyframe handle");
+    if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it first");
+    *n_good = 0;
+    if (n_raw) *n_raw = 0;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + std::max<int64_t>(n_cur, 1), ctx->store_rows));
+    const int64_t row0 = ctx->store_rows;
+    if (n_cur > 0) {
+        CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, cur, (size_t)n_cur * VSM_DIM * sizeof(float),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
+                           ctx->store.n2 + row0, n_cur, ctx->d_store_stats));
+    }
+    Seg ns = {row0, n_cur, frame_id};
+    ctx->segs.push_back(ns);
+    ctx->store_rows += n_cur;
+    *cur_handle = (int32_t)ctx->segs.size() - 1;
+    const Seg ref = ref_handle >= 0 ? ctx->segs[ref_handle] : Seg{0, 0, 0};
+    if (ref_handle < 0 || ref.count == 0 || n_cur == 0) {
+        CK(cudaStreamSynchronize(ctx->stream));                          // the caller may reuse `cur`
+        return end_call(ctx, true);
+    }
+    if (!good) return fail(ctx, VSM_ERR_INVALID, "vsm_track: null output");
+    HProblem f;
+    f.q_f32 = ctx->store.f32 + ref.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + ref.row0; f.q_row = ref.row0;
+    f.q_store = 1; f.nq = ref.count;
+    f.t_f32 = ctx->store.f32 + row0 * VSM_DIM; f.t_row = row0; f.t_store = 1; f.nt = n_cur; f.out_off = 0;
+    std::vector<HProblem> probs{f};
+    if (mutual) {
+        HProblem b;
+        b.q_f32 = f.t_f32; b.q_n2 = ctx->store.n2 + row0; b.q_row = row0; b.q_store = 1; b.nq = n_cur;
+        b.t_f32 = f.q_f32; b.t_row = ref.row0; b.t_store = 1; b.nt = ref.count; b.out_off = ref.count;
+        probs.push_back(b);
+    }
+    return match_common(ctx, probs, ref.count, n_cur, ratio, mutual, good, n_good, raw, n_raw, nullptr, 0, 0);
 }
 
 // ---- database search -------------------------------------------------------------------

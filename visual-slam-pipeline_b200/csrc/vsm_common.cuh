@@ -38,7 +38,7 @@ constexpr float VALID_FLOOR = -1.0e38f;        // record entries above this are 
 // One CTA of the tensor-core kernel: one 128-query tile x a contiguous train range.
 struct TcUnit {
     const float*    q_n2;          // squared norms of the tile's query rows
-    const uint32_t* t_stats;       // {min, max} squared norm of the train set (float bits)
+    const uint32_t* t_stats;       // norm statistics of the train set (see stats_read)
     int64_t rec_base;              // record index of (tile row 0, the unit's first slice)
     int32_t rec_stride;            // records per query (= slices of the problem)
     int32_t q_row;                 // first query row (tensor-map row coordinate)
@@ -64,12 +64,21 @@ struct SliceInfo {
     int32_t pad;
 };
 
+// {min, max} squared norm of a row set, kept so that an all-zero slot means "no rows yet":
+// slot[0] = max over rows of ~bits(n2) (i.e. the inverted minimum), slot[1] = max of bits(n2)
+// (non-negative floats order like their bit patterns).
+__device__ __forceinline__ void stats_read(const uint32_t* slot, float& tmin2, float& tmax2) {
+    tmin2 = __uint_as_float(~__ldg(slot));
+    tmax2 = __uint_as_float(__ldg(slot + 1));
+    if (!(tmin2 <= tmax2)) { tmin2 = 0.f; tmax2 = 0.f; }      // empty set
+}
+
 // One kNN problem (query set vs train set), consumed by the select/re-score kernel.
 struct Problem {
     const float*    q_f32;         // first query row (fp32 master)
     const float*    t_f32;         // first train row (fp32 master)
     const float*    q_n2;          // squared norms of the query rows
-    const uint32_t* t_stats;       // {min, max} squared norm of the train set (float bits)
+    const uint32_t* t_stats;       // norm statistics of the train set (see stats_read)
     int64_t partial_off;           // first PartialRec of the problem
     int64_t out_off;               // outputs at out_*[(out_off + q) * 2 ...]
     int32_t nq, nt;

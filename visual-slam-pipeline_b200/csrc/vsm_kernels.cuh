@@ -38,8 +38,7 @@ convert_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, f
         hi = fmaxf(hi, s);
     }
     if (lane == 0 && lo <= hi) {
-        // non-negative floats order like their bit patterns
-        atomicMin(stats, __float_as_uint(lo));
+        atomicMax(stats, ~__float_as_uint(lo));            // see stats_read
         atomicMax(stats + 1, __float_as_uint(hi));
     }
 }
@@ -97,7 +96,7 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
     float qreg[16];
     load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
     Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
-    unsigned long long n_cand = 0, n_flag = 0;
+    unsigned long long n_cand = 0, n_flag = 0;      // n_cand is per lane (summed at the end)
     const SliceInfo* sl = slices + P.slice_off;
 
     if (P.exact) {
@@ -127,7 +126,8 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
             float b0 = __shfl_xor_sync(full, a0, o), b1 = __shfl_xor_sync(full, a1, o);
             if (b0 > a0) { a1 = fmaxf(a0, b1); a0 = b0; } else a1 = fmaxf(a1, b0);
         }
-        const float tmin2 = __uint_as_float(__ldg(P.t_stats)), tmax2 = __uint_as_float(__ldg(P.t_stats + 1));
+        float tmin2, tmax2;
+        stats_read(P.t_stats, tmin2, tmax2);
         const float thr = a1 - 2.f * dot_margin(__ldg(P.q_n2 + q), tmin2, tmax2);   // -inf if < 2 entries
 
         // pass 2: survivors -> exact distance; overflowing slices -> exact scan
@@ -141,21 +141,29 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
             }
             const float rs[VSM_TOPK] = {rv.x, rv.y, rv.z, rv.w};
             const bool flagged = rs[VSM_TOPK - 1] > VALID_FLOOR && rs[VSM_TOPK - 1] > thr;
+            // this lane's surviving entries (a bit per entry) and their logical train indices
+            int32_t cand[VSM_TOPK];
+            unsigned mine = 0;
 #pragma unroll
             for (int e = 0; e < VSM_TOPK; e++) {
-                // packed entry -> logical train index
                 const uint32_t c = __float_as_uint(rs[e]) & ~PACK_MASK;
-                const int32_t cand = my.t_index0 + (int32_t)(c / HALF_N) * TILE_N + my.half * HALF_N + (int32_t)(c % HALF_N);
-                unsigned m = __ballot_sync(full, !flagged && rs[e] > VALID_FLOOR && rs[e] > thr);
-                n_cand += __popc(m);
-                while (m) {
-                    int l0 = __ffs(m) - 1; m &= m - 1;
-                    int l1 = -1;
-                    if (m) { l1 = __ffs(m) - 1; m &= m - 1; }
-                    int src = h == 0 ? l0 : l1;
-                    int32_t j = __shfl_sync(full, cand, src < 0 ? 0 : src);
-                    score_pair(qreg, P.t_f32, src < 0 ? -1 : j, l16, best);
-                }
+                cand[e] = my.t_index0 + (int32_t)(c / HALF_N) * TILE_N + my.half * HALF_N + (int32_t)(c % HALF_N);
+                if (!flagged && rs[e] > VALID_FLOOR && rs[e] > thr) mine |= 1u << e;
+            }
+            n_cand += __popc(mine);
+            // two survivors per round (one per half-warp), taken from the two lowest lanes that have any
+            unsigned any = __ballot_sync(full, mine != 0);
+            while (any) {
+                const int l0 = __ffs(any) - 1;
+                const unsigned rest = any & (any - 1);
+                const int l1 = rest ? __ffs(rest) - 1 : -1;
+                const int e0 = __ffs(mine) - 1;                              // this lane's next entry
+                const int32_t pop = e0 == 0 ? cand[0] : e0 == 1 ? cand[1] : e0 == 2 ? cand[2] : cand[3];
+                const int src = h == 0 ? l0 : l1;
+                const int32_t j = __shfl_sync(full, pop, src < 0 ? 0 : src);
+                score_pair(qreg, P.t_f32, src < 0 ? -1 : j, l16, best);
+                if (lane == l0 || lane == l1) mine &= mine - 1;
+                any = __ballot_sync(full, mine != 0);
             }
             n_flag += __popc(__ballot_sync(full, flagged));
             // hand the overflowing slices to rescan_kernel; scan inline only if its list is full
@@ -186,6 +194,9 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
             }
         }
     }
+    unsigned long long n_cand_warp = n_cand;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_cand_warp += __shfl_xor_sync(full, n_cand_warp, o);
     // merge the two half-warps (lane 16 -> lane 0)
     float od0 = __shfl_sync(full, best.d0, 16), od1 = __shfl_sync(full, best.d1, 16);
     int32_t oi0 = __shfl_sync(full, best.i0, 16), oi1 = __shfl_sync(full, best.i1, 16);
@@ -195,7 +206,7 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
         const int64_t o = (P.out_off + q) * 2;
         out_idx[o] = best.i0; out_idx[o + 1] = best.i1;
         out_dist[o] = best.d0; out_dist[o + 1] = best.d1;
-        if (n_cand) atomicAdd(counters, n_cand);
+        if (n_cand_warp) atomicAdd(counters, n_cand_warp);
         if (n_flag) atomicAdd(counters + 1, n_flag);
     }
 }

@@ -341,8 +341,8 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         s.G = s.published = -INFINITY;
         {
             const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
-            const float tmin2 = __uint_as_float(__ldg(u.t_stats));
-            const float tmax2 = __uint_as_float(__ldg(u.t_stats + 1));
+            float tmin2, tmax2;
+            stats_read(u.t_stats, tmin2, tmax2);
             s.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
         }
         top3_update_thr(s);

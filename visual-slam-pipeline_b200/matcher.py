@@ -61,6 +61,8 @@ SYMBOLS = {
     "vsm_store_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "vsm_match_to_stored": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]),
+    "vsm_track": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
+                            C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vsm_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
@@ -228,6 +230,20 @@ class Matcher:
                                                raw.ctypes.data if want_raw else None,
                                                C.byref(nr) if want_raw else None))
         return good[:ng.value].copy(), (raw[:nr.value].copy() if want_raw else None)
+
+    def track(self, ref_handle, frame_id, cur_desc, ratio=0.75, mutual=False, want_raw=False, ref_rows=None):
+        """Slam::process_frame's tracking match (src/Slam.cpp:838-842) for a sequence: the current
+        frame is uploaded once, into the store; returns (good, raw, handle of the current frame)."""
+        t = _rows(cur_desc, "cur_desc")
+        cap = max(ref_rows if ref_rows is not None else self.store_info()[0], 1)
+        if not hasattr(self, "_trk") or len(self._trk[0]) < cap:
+            self._trk = (np.zeros(cap, DMATCH), np.zeros(cap, DMATCH))
+        good, raw = self._trk
+        ng, nr, h = C.c_int32(0), C.c_int32(0), C.c_int32(-1)
+        self._ck(self._lib.vsm_track(self._h, ref_handle, frame_id, t.ctypes.data, t.shape[0], ratio, int(mutual),
+                                     good.ctypes.data, C.byref(ng), raw.ctypes.data if want_raw else None,
+                                     C.byref(nr) if want_raw else None, C.byref(h)))
+        return good[:ng.value].copy(), (raw[:nr.value].copy() if want_raw else None), h.value
 
     def search_map_points(self, frame_desc, row_offset=0):
         """Global top-2 of every query row over the whole store (src/Slam.cpp:546-574)."""
