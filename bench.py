@@ -189,6 +189,39 @@ def workload_config(n_gpus, total_rows):
             "l2": "inputs larger than L2 (bf16 shard >= 1.28 GB vs 126 MB L2); no flush needed"}
 
 
+def parity_report(vsm_b200, device, q, t, cpu_result):
+    """Indices / fp32 distance bits / ratio decisions of the CUDA path vs the CPU matcher's answer
+    on the cpu_baseline sample (north star: identical except exact ties or |d0 - r*d1| <= 1e-5 r d1)."""
+    import numpy as np
+    nq = q.shape[0]
+    ci = -np.ones((nq, 2), np.int64)
+    cd = np.full((nq, 2), np.finfo(np.float32).max, np.float32)
+    if isinstance(cpu_result, tuple):                      # oracle port: (idx, dist)
+        ci, cd = cpu_result[0].astype(np.int64), cpu_result[1]
+    else:                                                  # cv2: list of DMatch lists
+        for i, ms in enumerate(cpu_result):
+            for p_, m_ in enumerate(ms):
+                ci[i, p_], cd[i, p_] = m_.trainIdx, m_.distance
+    with vsm_b200.Matcher(device=device, engine=vsm_b200.ENGINE_TENSOR) as m:
+        gi, gd = m.knn_match(q, t)
+        st = m.stats()
+    same_idx = (gi == ci).all(axis=1)
+    same_bits = (gd.view(np.uint32) == cd.view(np.uint32)).all(axis=1)
+    rep = {"sample": f"{nq} x {t.shape[0]}", "identical_indices": int(same_idx.sum()),
+           "identical_distance_bits": int(same_bits.sum()), "queries": nq,
+           "candidates_rescored": st["candidates"], "rescanned_slices": st["flagged_slices"]}
+    for r in (0.70, 0.75, 0.80):
+        rr = np.float32(r)
+        dec_g = gd[:, 0] < rr * gd[:, 1]
+        dec_c = cd[:, 0] < rr * cd[:, 1]
+        rep[f"ratio_{int(r * 100)}_decisions_identical"] = int((dec_g == dec_c).sum())
+    bad = ~(same_idx & same_bits)
+    ties = bad & (cd[:, 0] == cd[:, 1])
+    rep["exempt_exact_ties"] = int(ties.sum())
+    rep["unexplained_mismatches"] = int((bad & ~ties).sum())
+    return rep
+
+
 # ---- extra: the pair-matching configs (rank 0, N = 1) ------------------------------------------------
 def extra_pair_numbers(torch, vsm_b200, device):
     import numpy as np
@@ -255,7 +288,12 @@ def extra_pair_numbers(torch, vsm_b200, device):
         step(f)
     mt.clear_store()
     state["h"] = mt.track(-1, 0, fr[0], ref_rows=1000)[2]
+    mt.set_profiling(False)          # the per-kernel events cost a few microseconds per call
     r = run_sequence(step)
+    mt.set_profiling(True)
+    mt.clear_store()
+    state["h"] = mt.track(-1, 0, fr[0], ref_rows=1000)[2]
+    step(0)
     st = mt.stats()
     r.update({"timing": "host wall clock per call incl. H2D of the current frame (pinned) and D2H of the DMatch list",
               "device_ms_last": st["device_ms"], "tc_ms_last": st["tc_ms"], "select_ms_last": st["select_ms"],
@@ -397,6 +435,9 @@ def run_gpu(args):
         # sanity: every planted query must find its DB row as the nearest neighbour
         got = hi.numpy()[:N_PLANTED, 0]
         recovered = int((got == np.array(planted)).sum())
+        # the same seeded database gives the same answer for every N: compare this across runs
+        chk = (int((hi.numpy().astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
+               ^ int(hd.numpy().view(np.uint32).astype(np.uint64).sum()))
         st = db.matcher.stats()
         tc_avg = sum(tc_ms) / len(tc_ms)
         shard_flops = 2.0 * NQ * shard.shape[0] * 256
@@ -417,7 +458,7 @@ def run_gpu(args):
                          "peak_source": peak_src, "kernel_ms": tc_avg,
                          "algorithmic": "2*nq*shard_rows*256 FLOP per launch",
                          "hbm_gbs": (shard.shape[0] * 512 + NQ * 512) / (tc_avg * 1e-3) / 1e9, "hbm_peak": peak_hbm},
-            "check": {"planted_recovered": f"{recovered}/{N_PLANTED}", "candidates_rescored": st["candidates"],
+            "check": {"planted_recovered": f"{recovered}/{N_PLANTED}", "result_checksum": f"{chk:016x}", "candidates_rescored": st["candidates"],
                       "flagged_slices": st["flagged_slices"], "select_ms": st["select_ms"]},
             "matches_per_s": NQ / (per_step * 1e-3),
         }
@@ -434,6 +475,8 @@ def run_gpu(args):
                 if time.perf_counter() - t0 > 10.0 or reps >= 20:
                     break
             dt = (time.perf_counter() - t0) / reps
+            # parity on the same sample: the CUDA path against what the CPU matcher just returned
+            line["parity"] = parity_report(vsm_b200, local, cq, ct, fn(cq, ct))
             line["cpu_baseline"] = {"value": 2.0 * NQ * n * 256 / dt / 1e12, "unit": "TFLOP/s", "cores": cores,
                                     "kind": kind, "sample": f"{what}; {NQ} queries x {n}-row sample of the DB, {reps} repetitions"}
         if world == 1 and not args.no_extra:

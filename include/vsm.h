@@ -189,6 +189,8 @@ void* vsm_stream(vsm_ctx* ctx);
 /* Run on a caller-owned stream (e.g. the stream an NCCL collective is enqueued on). */
 int   vsm_set_stream(vsm_ctx* ctx, void* cuda_stream);
 int   vsm_sync(vsm_ctx* ctx);
+/* Per-kernel CUDA events (tc_ms / select_ms in vsm_stats); on by default, a few microseconds per call. */
+int   vsm_set_profiling(vsm_ctx* ctx, int32_t on);
 
 /* Debug / bring-up: the raw tensor-core accumulators (bf16 dot products q.t) of the
  * first 128 queries x first 256 train rows, written to out[128*256] (host). */

@@ -82,13 +82,12 @@ struct vsm_ctx {
     cudaEvent_t ev_desc = nullptr;
     bool desc_copy_pending = false;
     DevBuf<PartialRec> d_recs;
-    DevBuf<int32_t> d_out_idx;
-    DevBuf<float> d_out_dist;
+    unsigned long long* d_out_key = nullptr;     // [query][2] result keys, inside d_aux (zeroed per call)
     DevBuf<uint8_t> d_result;            // DMatch lists followed by the counts
     uint8_t* h_result = nullptr;
     size_t h_result_cap = 0;
     // zeroed per call: [0] candidates, [1] flagged slices (u64), [2] rescan work count, then
-    // per output query the shared second-best hints and the rescan locks (u32 each)
+    // per output query the shared second-best hint (u32) and the two result keys (u64)
     DevBuf<uint8_t> d_aux;
     unsigned long long* d_counters = nullptr;    // = d_aux.p
     DevBuf<WorkItem> d_work;
@@ -101,6 +100,7 @@ struct vsm_ctx {
     std::string err;
     PFN_encodeTiled encode = nullptr;
     int seg_tiles = 0;                   // 0 = automatic
+    bool profiling = true;               // per-kernel events (tc_ms / select_ms)
 };
 
 namespace {
@@ -341,18 +341,18 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     TRY(ensure(ctx, ctx->d_desc, total));
     TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
     TRY(ensure(ctx, ctx->d_recs, (size_t)std::max<int64_t>(nrecs, 1)));
-    TRY(ensure(ctx, ctx->d_out_idx, (size_t)std::max<int64_t>(total_out * 2, 2)));
-    TRY(ensure(ctx, ctx->d_out_dist, (size_t)std::max<int64_t>(total_out * 2, 2)));
     const size_t result_bytes = (size_t)total_matches * sizeof(DMatch) + jobs.size() * 2 * sizeof(int32_t);
     TRY(ensure(ctx, ctx->d_result, std::max<size_t>(result_bytes, 16)));
 
-    const size_t aux_bytes = 48 + (size_t)std::max<int64_t>(total_out, 1) * 2 * sizeof(uint32_t);
+    const size_t nout = (size_t)std::max<int64_t>(total_out, 1);
+    const size_t off_keys = align16(48 + nout * sizeof(uint32_t));
+    const size_t aux_bytes = off_keys + nout * 2 * sizeof(unsigned long long);
     TRY(ensure(ctx, ctx->d_aux, aux_bytes));
     TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
     ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
     uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32);
     uint32_t* d_hints = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 48);
-    uint32_t* d_locks = d_hints + std::max<int64_t>(total_out, 1);
+    ctx->d_out_key = reinterpret_cast<unsigned long long*>(ctx->d_aux.p + off_keys);
     CK(cudaMemsetAsync(ctx->d_aux.p, 0, aux_bytes, ctx->stream));
 
     for (int i = 0; i < P; i++) dp[i].t_stats = probs[i].t_store ? ctx->d_store_stats : d_scratch_stats;
@@ -394,7 +394,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                            conv_rows, d_scratch_stats));
 
     uint8_t* dd = ctx->d_desc.p;
-    CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
+    if (ctx->profiling) CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
     if (!units.empty()) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
@@ -406,32 +406,34 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
         ctx->launches++;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
-        ctx->timed_tc = true;
+        if (ctx->profiling) {
+            CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
+            ctx->timed_tc = true;
+        }
     }
     if (qb[P] > 0) {
         select_kernel<<<(unsigned)qb[P], SELECT_WARPS * 32, 0, ctx->stream>>>(
             reinterpret_cast<const Problem*>(dd + off_prob), P, reinterpret_cast<const int32_t*>(dd + off_qb),
-            ctx->d_recs.p, reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_idx.p, ctx->d_out_dist.p,
+            ctx->d_recs.p, reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key,
             ctx->d_counters, ctx->d_work.p, WORK_CAP);
         ctx->launches++;
         CK(cudaGetLastError());
         if (!units.empty()) {
             // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
-            rescan_kernel<<<(unsigned)ctx->num_sms * 2, 128, 0, ctx->stream>>>(
-                reinterpret_cast<const Problem*>(dd + off_prob), reinterpret_cast<const SliceInfo*>(dd + off_slice),
-                ctx->d_work.p, ctx->d_counters, WORK_CAP, ctx->d_out_idx.p, ctx->d_out_dist.p, d_locks);
+            rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, WORK_CAP);
             ctx->launches++;
             CK(cudaGetLastError());
         }
-        CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
-        ctx->timed_sel = true;
+        if (ctx->profiling) {
+            CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
+            ctx->timed_sel = true;
+        }
     }
     if (!jobs.empty()) {
         DMatch* dm = reinterpret_cast<DMatch*>(ctx->d_result.p);
         int32_t* dc = reinterpret_cast<int32_t*>(ctx->d_result.p + (size_t)total_matches * sizeof(DMatch));
-        filter_kernel<<<(unsigned)jobs.size(), 256, 0, ctx->stream>>>(
-            reinterpret_cast<const FilterJob*>(dd + off_job), ctx->d_out_idx.p, ctx->d_out_dist.p, dm, dc);
+        filter_kernel<<<(unsigned)jobs.size(), FILTER_THREADS, 0, ctx->stream>>>(
+            reinterpret_cast<const FilterJob*>(dd + off_job), ctx->d_out_key, dm, dc);
         ctx->launches++;
         CK(cudaGetLastError());
     }
@@ -450,6 +452,23 @@ int fetch_result(vsm_ctx* ctx, size_t bytes) {
     TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(bytes, 16)));
     if (bytes) CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return VSM_OK;
+}
+
+// [query][2] result keys of the first nq queries -> pinned host buffer
+int fetch_keys(vsm_ctx* ctx, int64_t nq) {
+    const size_t nb = (size_t)nq * 2 * sizeof(unsigned long long);
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(nb, 16)));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_out_key, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    return VSM_OK;
+}
+
+// host twin of key_decode (vsm_kernels.cuh)
+void decode_key(unsigned long long k, int64_t& idx, float& dist) {
+    if (k == 0ull) { idx = -1; dist = FLT_MAX; return; }
+    k = ~k;
+    idx = (int64_t)(uint32_t)k;
+    uint32_t b = (uint32_t)(k >> 32);
+    memcpy(&dist, &b, 4);
 }
 
 HProblem scratch_vs_scratch(vsm_ctx* ctx, int64_t q_row, int nq, int64_t t_row, int nt, int64_t out_off) {
@@ -541,8 +560,6 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_desc.p) cudaFree(ctx->d_desc.p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     if (ctx->d_recs.p) cudaFree(ctx->d_recs.p);
-    if (ctx->d_out_idx.p) cudaFree(ctx->d_out_idx.p);
-    if (ctx->d_out_dist.p) cudaFree(ctx->d_out_dist.p);
     if (ctx->d_result.p) cudaFree(ctx->d_result.p);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->d_aux.p) cudaFree(ctx->d_aux.p);
@@ -585,6 +602,12 @@ int vsm_set_stream(vsm_ctx* ctx, void* stream) {
     return VSM_OK;
 }
 
+int vsm_set_profiling(vsm_ctx* ctx, int32_t on) {
+    if (!ctx) return VSM_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return VSM_OK;
+}
+
 int vsm_sync(vsm_ctx* ctx) {
     if (!ctx) return VSM_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -603,9 +626,15 @@ int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, i
     TRY(upload_scratch(ctx, train, nq, nt));
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
     TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + nt));
-    CK(cudaMemcpyAsync(idx, ctx->d_out_idx.p, (size_t)nq * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(dist, ctx->d_out_dist.p, (size_t)nq * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    return end_call(ctx, true);
+    TRY(fetch_keys(ctx, nq));
+    TRY(end_call(ctx, true));
+    const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
+    for (int i = 0; i < nq * 2; i++) {
+        int64_t j;
+        decode_key(k[i], j, dist[i]);
+        idx[i] = (int32_t)j;
+    }
+    return VSM_OK;
 }
 
 static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int nt, float ratio, int mutual,
@@ -850,13 +879,13 @@ int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset
     HProblem p;
     db_problem(ctx, ctx->scratch.f32, nq, p);
     TRY(run_problems(ctx, {p}, {}, nq, 0, ctx->scratch.f32, 0, nq));
-    const size_t nb = (size_t)nq * 2 * sizeof(int32_t);
-    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, nb));
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_out_idx.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(dist, ctx->d_out_dist.p, (size_t)nq * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(fetch_keys(ctx, nq));
     TRY(end_call(ctx, true));
-    const int32_t* li = reinterpret_cast<const int32_t*>(ctx->h_result);
-    for (int i = 0; i < nq * 2; i++) idx[i] = li[i] < 0 ? -1 : (int64_t)li[i] + row_offset;
+    const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
+    for (int i = 0; i < nq * 2; i++) {
+        decode_key(k[i], idx[i], dist[i]);
+        if (idx[i] >= 0) idx[i] += row_offset;
+    }
     return VSM_OK;
 }
 
@@ -871,8 +900,7 @@ int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t r
     db_problem(ctx, d_query, nq, p);
     static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? 2 : 0;
     TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
-    widen_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_idx.p, ctx->d_out_dist.p, nq * 2,
-                                                                 row_offset, d_idx, d_dist);
+    widen_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_key, nq * 2, row_offset, d_idx, d_dist);
     ctx->launches++;
     CK(cudaGetLastError());
     return end_call(ctx, sync != 0);

@@ -121,11 +121,7 @@ __device__ __forceinline__ void insert2(float d, int32_t i, float& d0, int32_t& 
 // Half-warp exact squared distance.  lane16 owns elements k = 16*i + lane16,
 // i.e. OpenCV's accumulator a = lane16/4, SIMD lane l = lane16%4.
 // qreg[i] = q[16*i + lane16].  Result valid in lane16 == 0 of each half-warp.
-__device__ __forceinline__ float canon_l2sqr_halfwarp(const float (&qreg)[16],
-                                                      const float* __restrict__ t, int lane16) {
-    float tv[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) tv[i] = __ldg(t + 16 * i + lane16);
+__device__ __forceinline__ float canon_l2sqr_halfwarp_regs(const float (&qreg)[16], const float (&tv)[16]) {
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -139,6 +135,14 @@ __device__ __forceinline__ float canon_l2sqr_halfwarp(const float (&qreg)[16],
     float s = __fadd_rn(__fadd_rn(__fadd_rn(acc, v1), v2), v3);   // ((d0+d1)+d2)+d3, lanes 0..3
     float h = __fadd_rn(s, __shfl_down_sync(full, s, 2, 16));     // (x0+x2), (x1+x3)
     return __fadd_rn(h, __shfl_down_sync(full, h, 1, 16));        // lane 0
+}
+
+__device__ __forceinline__ float canon_l2sqr_halfwarp(const float (&qreg)[16],
+                                                      const float* __restrict__ t, int lane16) {
+    float tv[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) tv[i] = __ldg(t + 16 * i + lane16);
+    return canon_l2sqr_halfwarp_regs(qreg, tv);
 }
 
 __device__ __forceinline__ void load_qreg(float (&qreg)[16], const float* __restrict__ q, int lane16) {

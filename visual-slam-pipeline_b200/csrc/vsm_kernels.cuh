@@ -51,6 +51,24 @@ struct Best2 {
     int32_t i0, i1;
 };
 
+// Result slots are 64-bit keys ~((distance bits << 32) | index): for non-negative distances
+// the integer order of the un-inverted key is the (distance, index) order, so "keep the two
+// best" is a two-step atomicMax cascade on zero-initialised memory (0 = empty) -- no lock.
+__device__ __forceinline__ unsigned long long result_key(float d, int32_t i) {
+    return ~(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)i);
+}
+__device__ __forceinline__ void key_decode(unsigned long long k, int32_t& i, float& d) {
+    if (k == 0ull) { i = -1; d = FLT_MAX; return; }
+    k = ~k;
+    i = (int32_t)(uint32_t)k;
+    d = __uint_as_float((uint32_t)(k >> 32));
+}
+__device__ __forceinline__ void key_push(unsigned long long* slot2, unsigned long long k) {
+    const unsigned long long old = atomicMax(slot2, k);
+    const unsigned long long loser = old < k ? old : k;
+    if (loser != 0ull) atomicMax(slot2 + 1, loser);
+}
+
 __device__ __forceinline__ int32_t slice_row(const SliceInfo& si, int r) {
     // r-th row of the slice as an offset into the slice's range, or -1 past the end
     int off = si.half < 0 ? r : (r / HALF_N) * TILE_N + si.half * HALF_N + (r % HALF_N);
@@ -70,15 +88,19 @@ __device__ __forceinline__ void score_pair(const float (&qreg)[16], const float*
 
 // An overflowing slice is re-scanned exactly by rescan_kernel, RESCAN_ROWS slice rows per
 // work item, so that one unlucky query does not serialise thousands of rows in one warp.
-constexpr int RESCAN_ROWS = 256;
-struct WorkItem {
-    int32_t problem, q, slice, r0;
+constexpr int RESCAN_ROWS = 128;
+struct WorkItem {                      // self-contained: no descriptor look-ups in rescan_kernel
+    const float* q;                    // the query row
+    const float* t;                    // first row of the train set
+    unsigned long long* key;           // the query's two result slots
+    SliceInfo si;
+    int32_t r0, pad;
 };
 
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
 select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t* __restrict__ q_block0,
               const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
-              int32_t* __restrict__ out_idx, float* __restrict__ out_dist,
+              unsigned long long* __restrict__ out_key,
               unsigned long long* __restrict__ counters, WorkItem* __restrict__ work, uint32_t work_cap) {
     // blockIdx -> problem (q_block0 is the exclusive prefix of blocks per problem)
     int lo = 0, hi = nproblems - 1;
@@ -175,7 +197,8 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
                 const uint32_t base = atomicAdd(wcount, nitem);
                 if (base + nitem <= work_cap) {
                     for (uint32_t k = 0; k < nitem; k++) {
-                        WorkItem w = {lo, q, s, (int32_t)(k * RESCAN_ROWS)};
+                        WorkItem w = {P.q_f32 + (size_t)q * VSM_DIM, P.t_f32, out_key + (P.out_off + q) * 2, my,
+                                      (int32_t)(k * RESCAN_ROWS), 0};
                         work[base + k] = w;
                     }
                 } else {
@@ -203,59 +226,55 @@ select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t
     if (lane == 0) {
         if (oi0 >= 0) insert2(od0, oi0, best.d0, best.i0, best.d1, best.i1);
         if (oi1 >= 0) insert2(od1, oi1, best.d0, best.i0, best.d1, best.i1);
-        const int64_t o = (P.out_off + q) * 2;
-        out_idx[o] = best.i0; out_idx[o + 1] = best.i1;
-        out_dist[o] = best.d0; out_dist[o + 1] = best.d1;
+        // plain stores: this warp is the only writer of the slots until rescan_kernel runs
+        unsigned long long* o = out_key + (P.out_off + q) * 2;
+        o[0] = best.i0 >= 0 ? result_key(best.d0, best.i0) : 0ull;
+        o[1] = best.i1 >= 0 ? result_key(best.d1, best.i1) : 0ull;
         if (n_cand_warp) atomicAdd(counters, n_cand_warp);
         if (n_flag) atomicAdd(counters + 1, n_flag);
     }
 }
 
 // One block per work item: exact top-2 over RESCAN_ROWS rows of one slice for one query,
-// merged into the query's result under a per-query lock.
-__global__ void __launch_bounds__(128)
-rescan_kernel(const Problem* __restrict__ problems, const SliceInfo* __restrict__ slices,
-              const WorkItem* __restrict__ work, const unsigned long long* __restrict__ counters, uint32_t work_cap,
-              int32_t* out_idx, float* out_dist, uint32_t* __restrict__ locks) {
+// pushed into the query's result slots with the atomicMax cascade.  16 half-warps, each
+// scoring two rows per step (both rows' loads are in flight together).
+__global__ void __launch_bounds__(256)
+rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __restrict__ counters, uint32_t work_cap) {
     const uint32_t nwork = min(*reinterpret_cast<const uint32_t*>(counters + 2), work_cap);
-    __shared__ Best2 part[8];
+    __shared__ Best2 part[16];
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     for (uint32_t it = blockIdx.x; it < nwork; it += gridDim.x) {
         const WorkItem w = work[it];
-        const Problem P = problems[w.problem];
-        const SliceInfo si = slices[P.slice_off + w.slice];
+        const SliceInfo si = w.si;
         const int span = slice_span(si);
         const int r1 = min(span, w.r0 + RESCAN_ROWS);
         float qreg[16];
-        load_qreg(qreg, P.q_f32 + (size_t)w.q * VSM_DIM, l16);
+        load_qreg(qreg, w.q, l16);
         Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
-        // 8 half-warps stride the rows; every lane of a warp runs the same trip count
-        for (int k = 0; k < RESCAN_ROWS / 8; k++) {
-            const int r = w.r0 + k * 8 + hw;
-            int off = r < r1 ? slice_row(si, r) : -1;
-            score_pair(qreg, P.t_f32, off >= 0 ? si.t_index0 + off : -1, l16, best);
+        for (int k = 0; k < RESCAN_ROWS / 32; k++) {
+            const int ra = w.r0 + k * 32 + hw, rb = ra + 16;
+            const int offa = ra < r1 ? slice_row(si, ra) : -1, offb = rb < r1 ? slice_row(si, rb) : -1;
+            const int32_t ja = offa >= 0 ? si.t_index0 + offa : -1, jb = offb >= 0 ? si.t_index0 + offb : -1;
+            float ta[16], tb[16];                      // issue both rows' loads before either reduction
+            const float* pa = w.t + (size_t)(ja >= 0 ? ja : 0) * VSM_DIM;
+            const float* pb = w.t + (size_t)(jb >= 0 ? jb : 0) * VSM_DIM;
+#pragma unroll
+            for (int i = 0; i < 16; i++) { ta[i] = __ldg(pa + 16 * i + l16); tb[i] = __ldg(pb + 16 * i + l16); }
+            const float da = canon_l2sqr_halfwarp_regs(qreg, ta), db = canon_l2sqr_halfwarp_regs(qreg, tb);
+            if (l16 == 0) {
+                if (ja >= 0) insert2(__fsqrt_rn(da), ja, best.d0, best.i0, best.d1, best.i1);
+                if (jb >= 0) insert2(__fsqrt_rn(db), jb, best.d0, best.i0, best.d1, best.i1);
+            }
         }
         if (l16 == 0) part[hw] = best;
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int k = 1; k < 8; k++) {
+            for (int k = 1; k < 16; k++) {
                 if (part[k].i0 >= 0) insert2(part[k].d0, part[k].i0, best.d0, best.i0, best.d1, best.i1);
                 if (part[k].i1 >= 0) insert2(part[k].d1, part[k].i1, best.d0, best.i0, best.d1, best.i1);
             }
-            const int64_t key = P.out_off + w.q;
-            while (atomicCAS(locks + key, 0u, 1u) != 0u) __nanosleep(100);
-            __threadfence();
-            volatile int32_t* oi = out_idx + key * 2;
-            volatile float* od = out_dist + key * 2;
-            Best2 cur = {od[0], od[1], oi[0], oi[1]};
-            // the slice's earlier survivors may already be in the result: skip equal indices
-            if (best.i0 >= 0 && best.i0 != cur.i0 && best.i0 != cur.i1)
-                insert2(best.d0, best.i0, cur.d0, cur.i0, cur.d1, cur.i1);
-            if (best.i1 >= 0 && best.i1 != cur.i0 && best.i1 != cur.i1)
-                insert2(best.d1, best.i1, cur.d0, cur.i0, cur.d1, cur.i1);
-            oi[0] = cur.i0; oi[1] = cur.i1; od[0] = cur.d0; od[1] = cur.d1;
-            __threadfence();
-            atomicExch(locks + key, 0u);
+            if (best.i0 >= 0) key_push(w.key, result_key(best.d0, best.i0));
+            if (best.i1 >= 0) key_push(w.key, result_key(best.d1, best.i1));
         }
         __syncthreads();
     }
@@ -264,28 +283,35 @@ rescan_kernel(const Problem* __restrict__ problems, const SliceInfo* __restrict_
 // ---- match_features filter loop --------------------------------------------------
 // One block per pair.  good = lists with two entries whose best passes the fp32 ratio
 // test (and, if asked, the mutual-NN test); raw = every list with two entries.
-// Query order is preserved (block-wide scan per 256 queries).
-__global__ void __launch_bounds__(256)
-filter_kernel(const FilterJob* __restrict__ jobs, const int32_t* __restrict__ out_idx,
-              const float* __restrict__ out_dist, DMatch* __restrict__ matches, int32_t* __restrict__ counts) {
+// Query order is preserved (block-wide scan per 1024 queries).
+constexpr int FILTER_THREADS = 1024;
+__global__ void __launch_bounds__(FILTER_THREADS)
+filter_kernel(const FilterJob* __restrict__ jobs, const unsigned long long* __restrict__ out_key,
+              DMatch* __restrict__ matches, int32_t* __restrict__ counts) {
     const FilterJob J = jobs[blockIdx.x];
-    __shared__ int wsum[2][8];
+    __shared__ int wsum[2][FILTER_THREADS / 32];
     __shared__ int base[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { base[0] = 0; base[1] = 0; }
     __syncthreads();
-    for (int q0 = 0; q0 < J.nq; q0 += 256) {
+    for (int q0 = 0; q0 < J.nq; q0 += FILTER_THREADS) {
         const int q = q0 + threadIdx.x;
         bool is_raw = false, is_good = false;
         DMatch m = {q, -1, J.img_idx, 0.f};
         if (q < J.nq) {
             const int64_t o = (J.fwd_off + q) * 2;
-            const int32_t i0 = out_idx[o], i1 = out_idx[o + 1];
-            const float d0 = out_dist[o], d1 = out_dist[o + 1];
+            int32_t i0, i1;
+            float d0, d1;
+            key_decode(out_key[o], i0, d0);
+            key_decode(out_key[o + 1], i1, d1);
             m.trainIdx = i0; m.distance = d0;
             is_raw = i1 >= 0;                                    // m.size() >= 2   (Slam.cpp:1152)
             is_good = is_raw && d0 < __fmul_rn(J.ratio, d1);     // fp32 product   (Slam.cpp:1154)
-            if (is_good && J.back_off >= 0) is_good = out_idx[(J.back_off + i0) * 2] == q;
+            if (is_good && J.back_off >= 0) {
+                int32_t bi; float bd;
+                key_decode(out_key[(J.back_off + i0) * 2], bi, bd);
+                is_good = bi == q;
+            }
         }
         const unsigned br = __ballot_sync(0xffffffffu, is_raw), bg = __ballot_sync(0xffffffffu, is_good);
         if (lane == 0) { wsum[0][warp] = __popc(bg); wsum[1][warp] = __popc(br); }
@@ -298,7 +324,7 @@ filter_kernel(const FilterJob* __restrict__ jobs, const int32_t* __restrict__ ou
         __syncthreads();
         if (threadIdx.x == 0) {
             int tg = 0, tr = 0;
-            for (int w = 0; w < 8; w++) { tg += wsum[0][w]; tr += wsum[1][w]; }
+            for (int w = 0; w < FILTER_THREADS / 32; w++) { tg += wsum[0][w]; tr += wsum[1][w]; }
             base[0] += tg; base[1] += tr;
         }
         __syncthreads();
@@ -330,14 +356,15 @@ __global__ void merge_kernel(const int64_t* __restrict__ idx_in, const float* __
     dist_out[2 * q] = d0; dist_out[2 * q + 1] = d1;
 }
 
-// int32 local top-2 -> int64 global (row offset added), for the device-pointer DB search.
-__global__ void widen_kernel(const int32_t* __restrict__ idx_in, const float* __restrict__ dist_in, int n,
-                             int64_t row_offset, int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+// result keys -> int64 global index (row offset added) + distance, for the device-pointer DB search.
+__global__ void widen_kernel(const unsigned long long* __restrict__ out_key, int n, int64_t row_offset,
+                             int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t j = idx_in[i];
+    int32_t j; float d;
+    key_decode(out_key[i], j, d);
     idx_out[i] = j < 0 ? -1 : (int64_t)j + row_offset;
-    dist_out[i] = dist_in[i];
+    dist_out[i] = d;
 }
 
 }  // namespace vsm

@@ -71,6 +71,7 @@ SYMBOLS = {
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
     "vsm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsm_sync": (C.c_int, [C.c_void_p]),
+    "vsm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "vsm_debug_fetch_dump": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vsm_debug_tile_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
 }
@@ -277,6 +278,9 @@ class Matcher:
 
     def set_stream(self, cuda_stream):
         self._ck(self._lib.vsm_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_profiling(self, on):
+        self._ck(self._lib.vsm_set_profiling(self._h, int(on)))
 
     def stream(self):
         return self._lib.vsm_stream(self._h)
