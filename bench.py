@@ -105,11 +105,15 @@ def make_shard(torch, device, rank, world, q, noise, total_rows):
     db = torch.empty((rows, 256), dtype=torch.float32, device=device)
     g = torch.Generator(device=device)
     chunk = 1 << 20
-    for c0 in range(0, rows, chunk):
-        g.manual_seed(10_000 + (off + c0) // chunk)
-        n = min(chunk, rows - c0)
-        x = torch.randn((n, 256), generator=g, device=device, dtype=torch.float32)
-        db[c0:c0 + n] = x / x.norm(dim=1, keepdim=True)
+    # rows are generated on a GLOBAL chunk grid (seed = chunk number), so the database -- and hence
+    # the answer and its checksum -- is the same for every number of shards
+    for gc in range(off // chunk, (off + rows + chunk - 1) // chunk):
+        g.manual_seed(10_000 + gc)
+        x = torch.randn((chunk, 256), generator=g, device=device, dtype=torch.float32)
+        x = x / x.norm(dim=1, keepdim=True)
+        lo, hi = max(off, gc * chunk), min(off + rows, (gc + 1) * chunk)
+        db[lo - off:hi - off] = x[lo - gc * chunk:hi - gc * chunk]
+    del x
     # plant: DB row r_i re-observes query i (noise renormalised), wherever r_i lives
     stride = total_rows // N_PLANTED
     planted = [i * stride + 17 for i in range(N_PLANTED)]
@@ -196,7 +200,7 @@ def parity_report(vsm_b200, device, q, t, cpu_result):
     nq = q.shape[0]
     ci = -np.ones((nq, 2), np.int64)
     cd = np.full((nq, 2), np.finfo(np.float32).max, np.float32)
-    if isinstance(cpu_result, tuple):                      # oracle port: (idx, dist)
+    if len(cpu_result) == 2 and isinstance(cpu_result[0], np.ndarray):      # oracle port: (idx, dist)
         ci, cd = cpu_result[0].astype(np.int64), cpu_result[1]
     else:                                                  # cv2: list of DMatch lists
         for i, ms in enumerate(cpu_result):
