@@ -63,8 +63,9 @@ def main():
             t0 = tl[1][0]
             print("tiles", nt)
             for n in list(range(0, min(nt, 24))) + list(range(24, nt, max(1, nt // 40))):
-                print(n, "load_issued", tl[1][n] - t0, "mma_issue", tl[2][n] - t0, "acc_ready", tl[0][n] - t0,
-                      "epi_done", tl[3][n] - t0)
+                e = int(tl[3][n])
+                print(n, "load_issued", tl[1][n] - t0, "mma_issue", (int(tl[2][n]) & 0xFFFFFFFFFF) - (int(t0) & 0xFFFFFFFFFF), "mma_wait_full", int(tl[2][n]) >> 40, "acc_ready", tl[0][n] - t0,
+                      "epi_done", (e & 0xFFFFFFFFFF) - (int(t0) & 0xFFFFFFFFFF), "slow_groups", (e >> 40) & 0xFF, "hint_seen", (e >> 48) & 1)
     m.close()
 
 

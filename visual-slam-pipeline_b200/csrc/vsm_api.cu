@@ -208,6 +208,7 @@ int launch_convert(vsm_ctx* ctx, const float* src, __nv_bfloat16* dst, float* n2
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+constexpr int UNIT_TILES = 128;                  // longest train range of one work unit, in 256-row tiles
 constexpr uint32_t WORK_CAP = 1u << 18;          // rescan work items (4 MB); beyond it select scans inline
 
 int begin_call(vsm_ctx* ctx) {
@@ -286,8 +287,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             continue;
         }
         const int ntiles = (hp.nt + TILE_N - 1) / TILE_N;
+        // ranges: enough to fill the chip once, and never longer than UNIT_TILES so that the dynamic
+        // scheduler can balance the tail and neighbouring CTAs stay on neighbouring rows
         int nranges = (int)std::min<int64_t>(ntiles, budget);
-        const int tpr = (ntiles + nranges - 1) / nranges;
+        const int tpr = std::min((ntiles + nranges - 1) / nranges, UNIT_TILES);
         nranges = (ntiles + tpr - 1) / tpr;
         // slice length: short slices keep an overflow re-scan cheap, long ones keep the record
         // stream small next to the database stream
@@ -323,7 +326,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 u.seg_tiles = seg;
                 u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0);
                 u.dump = (dump_first && units.empty()) ? dump_first : 0;
-                u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 : 0;
+                // 1 + the number of tiles past this unit's end that may be prefetched as well
+                u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 + std::min(tc::L2_AHEAD, ntiles - tile1) : 0;
                 units.push_back(u);
                 unit_prob.push_back(i);
             }
@@ -398,12 +402,16 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     if (!units.empty()) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
+        const unsigned grid = (unsigned)std::min<size_t>(units.size(), (size_t)ctx->num_sms);
+        uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
         if (dump_first)
-            tc::tc_top3_kernel<true><<<(unsigned)units.size(), tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
+            tc::tc_top3_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
+                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)units.size(), d_unit_counter,
+                ctx->d_recs.p, ctx->d_dump);
         else
-            tc::tc_top3_kernel<false><<<(unsigned)units.size(), tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), ctx->d_recs.p, ctx->d_dump);
+            tc::tc_top3_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
+                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)units.size(), d_unit_counter,
+                ctx->d_recs.p, ctx->d_dump);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->profiling) {
@@ -898,7 +906,7 @@ int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t r
     TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
     HProblem p;
     db_problem(ctx, d_query, nq, p);
-    static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? 2 : 0;
+    static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? std::max(2, atoi(getenv("VSM_DEBUG_TIMELINE"))) : 0;
     TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
     widen_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_key, nq * 2, row_offset, d_idx, d_dist);
     ctx->launches++;

@@ -1,7 +1,8 @@
 // vsm_tc.cuh -- the tensor-core pass: bf16 q.t tiles on tcgen05 with a fused
 // per-query top-3 epilogue (sm_100a only).
 //
-// One CTA = one TcUnit = 128 query rows x a contiguous range of train rows.
+// A TcUnit = 128 query rows x a contiguous range of train rows; persistent CTAs (one per SM)
+// take units from an atomic counter.
 //   warp 0      TMA producer: the 128x256 bf16 query tile once (4 boxes of 64 columns,
 //               SWIZZLE_128B), then the train rows as a ring of 4 stages, each stage one
 //               64-column K-chunk of a 256-row tile (2 boxes of 128 rows, 32 KB).
@@ -37,7 +38,7 @@ constexpr uint32_t T_STAGE_BYTES = TILE_N * 128; // 32 KB: 256 rows x 64 bf16
 constexpr uint32_t SMEM_Q = 0;
 constexpr uint32_t SMEM_T = NCHUNK * Q_SUB_BYTES;                 // 65536
 constexpr uint32_t SMEM_BAR = SMEM_T + STAGES * T_STAGE_BYTES;    // 196608
-constexpr uint32_t SMEM_BYTES = SMEM_BAR + 256 + 1024;            // + alignment slack
+constexpr uint32_t SMEM_BYTES = SMEM_BAR + 512 + 1024;            // barriers + unit ring + alignment slack
 constexpr int THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr uint32_t TMEM_COLS = 512;
@@ -204,59 +205,93 @@ __device__ __forceinline__ float dec_ordered(uint32_t u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// 32 accumulator values of one thread: slice columns [scol0, scol0+32), unit columns
-// [ucol0, ucol0+32).
-template <bool MASKED>
-__device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], uint32_t scol0, int32_t ucol0,
-                                       int32_t t_count) {
+// The rare path lives OUT OF LINE (one copy for the whole kernel) and takes / returns the state
+// by value, i.e. in registers: inlined, sixteen copies of it made the epilogue loop tens of KB
+// of SASS and instruction fetch -- not the tensor pipe -- set the pace (ncu: icc hit rate 68 %,
+// stall_no_instruction 5.8 per issue).
+struct Top3Core {
+    float b0, b1, b2, b3;
+};
+__device__ __noinline__ Top3Core top3_push8(Top3Core c, float v0, float v1, float v2, float v3, float v4, float v5,
+                                            float v6, float v7, uint32_t scol) {
+    const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const float x = __uint_as_float((__float_as_uint(v[e]) & PACK_MASK) | (scol + e));
+        float t0 = fmaxf(c.b0, x), x1 = fminf(c.b0, x);
+        float t1 = fmaxf(c.b1, x1), x2 = fminf(c.b1, x1);
+        float t2 = fmaxf(c.b2, x2), x3 = fminf(c.b2, x2);
+        c.b0 = t0; c.b1 = t1; c.b2 = t2; c.b3 = fmaxf(c.b3, x3);
+    }
+    return c;
+}
+
+// 32 accumulator values of one thread = slice columns [scol0, scol0+32).
+// Fast path: four max-trees, ONE compare and ONE branch per 32 values.  The rare path re-checks
+// the four groups and pushes only those that beat the threshold (packed top-4 insert).
+__device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], uint32_t scol0, int* slow = nullptr) {
+    float m[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        float v[8];
+        const float* v = reinterpret_cast<const float*>(&r[8 * g]);
+        m[g] = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+    }
+    if (slow && __any_sync(0xffffffffu, fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > s.thr)) (*slow)++;   // debug only
+    if (fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > s.thr) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            v[e] = __uint_as_float(r[8 * g + e]);
-            if (MASKED && ucol0 + 8 * g + e >= t_count) v[e] = MASKED_VALUE;
-        }
-        float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
-        if (m > s.thr) {
-#pragma unroll
-            for (int e = 0; e < 8; e++)
-                top3_push(s, __uint_as_float((__float_as_uint(v[e]) & PACK_MASK) | (scol0 + 8 * g + e)));
-            top3_update_thr(s);
+        for (int g = 0; g < 4; g++) {
+            if (m[g] > s.thr) {
+                const float* v = reinterpret_cast<const float*>(&r[8 * g]);
+                Top3Core c = {s.b0, s.b1, s.b2, s.b3};
+                c = top3_push8(c, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], scol0 + 8 * g);
+                s.b0 = c.b0; s.b1 = c.b1; s.b2 = c.b2; s.b3 = c.b3;
+                top3_update_thr(s);
+            }
         }
     }
+}
+
+// A partial last tile: columns at or past the end of the train range become MASKED_VALUE.
+__device__ __forceinline__ void mask32(uint32_t (&r)[32], int32_t ucol0, int32_t t_count) {
+#pragma unroll
+    for (int e = 0; e < 32; e++)
+        if (ucol0 + e >= t_count) r[e] = __float_as_uint(MASKED_VALUE);
 }
 
 template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_constant__ CUtensorMap map_store,
-               const TcUnit* __restrict__ units, PartialRec* __restrict__ recs, float* __restrict__ dump) {
+               const TcUnit* __restrict__ units, int nunits, uint32_t* __restrict__ work_counter,
+               PartialRec* __restrict__ recs, float* __restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar_base = smem_base + SMEM_BAR;
-    // barriers (8 B each): 0 q_full, 1..4 full[], 5..8 empty[], 9..10 tmem_full[], 11..12 tmem_empty[]
-    const uint32_t BAR_QFULL = bar_base;
-    const uint32_t BAR_FULL = bar_base + 8;
-    const uint32_t BAR_EMPTY = bar_base + 8 + 8 * STAGES;
-    const uint32_t BAR_TFULL = bar_base + 8 + 16 * STAGES;
-    const uint32_t BAR_TEMPTY = BAR_TFULL + 16;
+    // mbarriers, 8 bytes each
+    const uint32_t BAR_QFULL = bar_base;                    // [4] query K-chunk landed
+    const uint32_t BAR_QEMPTY = bar_base + 32;              // [4] query K-chunk no longer read by any MMA
+    const uint32_t BAR_FULL = bar_base + 64;                // [STAGES] train chunk landed
+    const uint32_t BAR_EMPTY = bar_base + 96;               // [STAGES] train chunk consumed
+    const uint32_t BAR_TFULL = bar_base + 128;              // [2] accumulator stage complete
+    const uint32_t BAR_TEMPTY = bar_base + 144;             // [2] accumulator stage drained
+    const uint32_t BAR_UFULL = bar_base + 160;              // [2] unit descriptor published
+    const uint32_t BAR_UEMPTY = bar_base + 176;             // [2] unit descriptor released by MMA + epilogue
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_BAR + 192);
+    TcUnit* unit_ring = reinterpret_cast<TcUnit*>(smem_gen + SMEM_BAR + 256);     // [2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const TcUnit u = units[blockIdx.x];
-    const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
-    const CUtensorMap* mq = (u.maps & 1) ? &map_store : &map_scratch;
-    const CUtensorMap* mt = (u.maps & 2) ? &map_store : &map_scratch;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tensormap(mq);
-        prefetch_tensormap(mt);
+        prefetch_tensormap(&map_scratch);
+        prefetch_tensormap(&map_store);
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(BAR_QFULL, 1);
+        for (int i = 0; i < NCHUNK; i++) {
+            mbar_init(BAR_QFULL + 8 * i, 1);
+            mbar_init(BAR_QEMPTY + 8 * i, 1);
+        }
         for (int i = 0; i < STAGES; i++) {
             mbar_init(BAR_FULL + 8 * i, 1);
             mbar_init(BAR_EMPTY + 8 * i, 1);
@@ -264,6 +299,8 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         for (int i = 0; i < 2; i++) {
             mbar_init(BAR_TFULL + 8 * i, 1);
             mbar_init(BAR_TEMPTY + 8 * i, 8);          // one arrive per epilogue warp
+            mbar_init(BAR_UFULL + 8 * i, 1);
+            mbar_init(BAR_UEMPTY + 8 * i, 9);          // MMA thread + 8 epilogue warps
         }
         fence_barrier_init();
     }
@@ -273,61 +310,92 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Persistent CTA: units are handed out by an atomic counter in launch order (range-major,
+    // query-tile-minor), so the CTAs running together always work on neighbouring train rows:
+    // the database streams from DRAM once and every SM stays busy until the list is empty.
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== scheduler + TMA producer =====
         if (lane == 0) {
-            mbar_expect_tx(BAR_QFULL, NCHUNK * Q_SUB_BYTES);
-            for (int c = 0; c < NCHUNK; c++)
-                tma_load_2d(smem_base + SMEM_Q + c * Q_SUB_BYTES, mq, c * KCHUNK, u.q_row, BAR_QFULL);
             int slot = 0;
             uint32_t ph = 0;
-            for (int n = 0; n < ntiles; n++) {
-                const int row = u.t_row + n * TILE_N;
-                if (u.prefetch && n + L2_AHEAD < ntiles) {
-                    // pull a tile several iterations ahead into L2: the 4-stage smem ring only
-                    // covers an L2 hit, not a DRAM miss
-                    const int prow = row + L2_AHEAD * TILE_N;
-                    for (int c = 0; c < NCHUNK; c++) {
-                        tma_prefetch_l2_2d(mt, c * KCHUNK, prow);
-                        tma_prefetch_l2_2d(mt, c * KCHUNK, prow + TILE_N / 2);
+            for (uint32_t ui = 0;; ui++) {
+                const int us = ui & 1;
+                const int idx = (int)atomicAdd(work_counter, 1u);
+                mbar_wait(BAR_UEMPTY + 8 * us, ((ui >> 1) & 1) ^ 1);
+                TcUnit u;
+                if (idx < nunits) u = units[idx]; else u.t_count = 0;        // t_count 0 = no more work
+                unit_ring[us] = u;
+                mbar_arrive(BAR_UFULL + 8 * us);                             // release: publishes the slot
+                if (idx >= nunits) break;
+                const CUtensorMap* mq = (u.maps & 1) ? &map_store : &map_scratch;
+                const CUtensorMap* mt = (u.maps & 2) ? &map_store : &map_scratch;
+                const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
+                for (int n = 0; n < ntiles; n++) {
+                    const int row = u.t_row + n * TILE_N;
+                    if (u.prefetch && n + L2_AHEAD < ntiles + u.prefetch - 1) {
+                        // pull a tile several iterations ahead into L2 (also past the end of this unit,
+                        // for whoever takes the next one): the smem ring covers an L2 hit, not a DRAM miss
+                        const int prow = row + L2_AHEAD * TILE_N;
+                        for (int c = 0; c < NCHUNK; c++) {
+                            tma_prefetch_l2_2d(mt, c * KCHUNK, prow);
+                            tma_prefetch_l2_2d(mt, c * KCHUNK, prow + TILE_N / 2);
+                        }
                     }
-                }
-                for (int c = 0; c < NCHUNK; c++) {
-                    mbar_wait(BAR_EMPTY + 8 * slot, ph ^ 1);
-                    if (DEBUG && u.dump == 2 && c == 0 && n < 4096) reinterpret_cast<long long*>(dump)[4096 + n] = clock64();
-                    mbar_expect_tx(BAR_FULL + 8 * slot, T_STAGE_BYTES);
-                    const uint32_t dst = smem_base + SMEM_T + slot * T_STAGE_BYTES;
-                    tma_load_2d(dst, mt, c * KCHUNK, row, BAR_FULL + 8 * slot);
-                    tma_load_2d(dst + T_STAGE_BYTES / 2, mt, c * KCHUNK, row + TILE_N / 2, BAR_FULL + 8 * slot);
-                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                    for (int c = 0; c < NCHUNK; c++) {
+                        if (n == 0) {
+                            // this unit's query K-chunk c, as soon as the previous unit's MMAs left it
+                            mbar_wait(BAR_QEMPTY + 8 * c, (ui & 1) ^ 1);
+                            mbar_expect_tx(BAR_QFULL + 8 * c, Q_SUB_BYTES);
+                            tma_load_2d(smem_base + SMEM_Q + c * Q_SUB_BYTES, mq, c * KCHUNK, u.q_row, BAR_QFULL + 8 * c);
+                        }
+                        mbar_wait(BAR_EMPTY + 8 * slot, ph ^ 1);
+                        if (DEBUG && u.dump >= 2 && c == 0 && n < 4096) reinterpret_cast<long long*>(dump)[4096 + n] = clock64();
+                        mbar_expect_tx(BAR_FULL + 8 * slot, T_STAGE_BYTES);
+                        const uint32_t dst = smem_base + SMEM_T + slot * T_STAGE_BYTES;
+                        tma_load_2d(dst, mt, c * KCHUNK, row, BAR_FULL + 8 * slot);
+                        tma_load_2d(dst + T_STAGE_BYTES / 2, mt, c * KCHUNK, row + TILE_N / 2, BAR_FULL + 8 * slot);
+                        if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            mbar_wait(BAR_QFULL, 0);
-            tcgen05_fence_after();
             int slot = 0;
-            uint32_t ph = 0;
-            for (int n = 0; n < ntiles; n++) {
-                const int st = n & 1;
-                mbar_wait(BAR_TEMPTY + 8 * st, ((n >> 1) & 1) ^ 1);
-                tcgen05_fence_after();
-                if (DEBUG && u.dump == 2 && n < 4096) reinterpret_cast<long long*>(dump)[8192 + n] = clock64();
-                const uint32_t d_tmem = tmem_base + st * TILE_N;
-                for (int c = 0; c < NCHUNK; c++) {
-                    mbar_wait(BAR_FULL + 8 * slot, ph);
+            uint32_t ph = 0, tile_it = 0;
+            for (uint32_t ui = 0;; ui++) {
+                const int us = ui & 1;
+                mbar_wait(BAR_UFULL + 8 * us, (ui >> 1) & 1);
+                const int t_count = unit_ring[us].t_count;
+                const int dbg = DEBUG ? unit_ring[us].dump : 0;
+                mbar_arrive(BAR_UEMPTY + 8 * us);
+                if (t_count == 0) break;
+                const int ntiles = (t_count + TILE_N - 1) / TILE_N;
+                for (int n = 0; n < ntiles; n++, tile_it++) {
+                    const int st = tile_it & 1;
+                    mbar_wait(BAR_TEMPTY + 8 * st, ((tile_it >> 1) & 1) ^ 1);
                     tcgen05_fence_after();
-                    const uint64_t a0 = umma_smem_desc(smem_base + SMEM_Q + c * Q_SUB_BYTES);
-                    const uint64_t b0 = umma_smem_desc(smem_base + SMEM_T + slot * T_STAGE_BYTES);
+                    const long long t_issue = DEBUG ? clock64() : 0;
+                    long long t_wait = 0;
+                    const uint32_t d_tmem = tmem_base + st * TILE_N;
+                    for (int c = 0; c < NCHUNK; c++) {
+                        if (n == 0) mbar_wait(BAR_QFULL + 8 * c, ui & 1);
+                        mbar_wait(BAR_FULL + 8 * slot, ph);
+                        tcgen05_fence_after();
+                        const uint64_t a0 = umma_smem_desc(smem_base + SMEM_Q + c * Q_SUB_BYTES);
+                        const uint64_t b0 = umma_smem_desc(smem_base + SMEM_T + slot * T_STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < KCHUNK / 16; k++)            // 32 bytes = 2 address units per K=16
-                        umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, IDESC, (c | k) != 0);
-                    umma_commit(BAR_EMPTY + 8 * slot);               // frees the smem stage
-                    if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                        for (int k = 0; k < KCHUNK / 16; k++)            // 32 bytes = 2 address units per K=16
+                            umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, IDESC, (c | k) != 0);
+                        umma_commit(BAR_EMPTY + 8 * slot);               // frees the smem stage
+                        if (n == ntiles - 1) umma_commit(BAR_QEMPTY + 8 * c);   // last reader of this query chunk
+                        if (++slot == STAGES) { slot = 0; ph ^= 1; }
+                    }
+                    umma_commit(BAR_TFULL + 8 * st);                     // accumulator stage complete
+                    if (DEBUG && dbg >= 2 && n < 4096)     // clock at issue | cycles spent waiting for train chunks
+                        reinterpret_cast<long long*>(dump)[8192 + n] = (t_issue & 0xFFFFFFFFFFll) | (t_wait << 40);
                 }
-                umma_commit(BAR_TFULL + 8 * st);                     // accumulator stage complete
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -335,75 +403,91 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         const int half = (warp - EPI_WARP0) >> 2;
         const int quarter = warp & 3;                              // TMEM lanes this warp may read
         const int row = quarter * 32 + lane;
-        const bool row_valid = row < u.q_valid;
-        Top3 s;
-        s.b0 = s.b1 = s.b2 = s.b3 = -INFINITY;
-        s.G = s.published = -INFINITY;
-        {
-            const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
-            float tmin2, tmax2;
-            stats_read(u.t_stats, tmin2, tmax2);
-            s.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
-        }
-        top3_update_thr(s);
-        volatile uint32_t* hint = u.hint + (row_valid ? row : 0);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HALF_N;
-        int seg = 0, seg_tile = 0;
-        for (int n = 0; n < ntiles; n++) {
-            const int st = n & 1;
-            // bound published by the other CTAs / warps working on the same query (a second-best
-            // of any subset of the train set is a lower bound on the global second-best)
-            const uint32_t h = *hint;
-            mbar_wait(BAR_TFULL + 8 * st, (n >> 1) & 1);
-            tcgen05_fence_after();
-            if (DEBUG && u.dump == 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)
-                reinterpret_cast<long long*>(dump)[n] = clock64();
-            if (h != 0u) { s.G = fmaxf(s.G, dec_ordered(h)); top3_update_thr(s); }
-            const uint32_t taddr = lane_addr + st * TILE_N;
-            const int32_t ucol = n * TILE_N + half * HALF_N;           // unit-relative column of this thread's chunk 0
-            const uint32_t scol = (uint32_t)seg_tile * HALF_N;         // slice-relative
-            const bool full_tile = (n + 1) * TILE_N <= u.t_count;
-            uint32_t ra[32], rb[32];
-            tmem_ld32(taddr, ra);
-            tmem_ld_wait(ra);
-            tmem_ld32(taddr + 32, rb);
-            if (DEBUG && u.dump == 1 && n == 0)
-                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + e] = __uint_as_float(ra[e]);
-            if (full_tile) scan32<false>(s, ra, scol, ucol, u.t_count); else scan32<true>(s, ra, scol, ucol, u.t_count);
-            tmem_ld_wait(rb);
-            tmem_ld32(taddr + 64, ra);
-            if (DEBUG && u.dump == 1 && n == 0)
-                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 32 + e] = __uint_as_float(rb[e]);
-            if (full_tile) scan32<false>(s, rb, scol + 32, ucol + 32, u.t_count); else scan32<true>(s, rb, scol + 32, ucol + 32, u.t_count);
-            tmem_ld_wait(ra);
-            tmem_ld32(taddr + 96, rb);
-            if (DEBUG && u.dump == 1 && n == 0)
-                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 64 + e] = __uint_as_float(ra[e]);
-            if (full_tile) scan32<false>(s, ra, scol + 64, ucol + 64, u.t_count); else scan32<true>(s, ra, scol + 64, ucol + 64, u.t_count);
-            tmem_ld_wait(rb);
-            // all TMEM reads of this stage are complete: hand it back to the MMA warp
-            tcgen05_fence_before();
+        uint32_t tile_it = 0;
+        for (uint32_t ui = 0;; ui++) {
+            const int us = ui & 1;
+            mbar_wait(BAR_UFULL + 8 * us, (ui >> 1) & 1);
+            const TcUnit u = unit_ring[us];
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
-            if (DEBUG && u.dump == 1 && n == 0)
-                for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 96 + e] = __uint_as_float(rb[e]);
-            if (full_tile) scan32<false>(s, rb, scol + 96, ucol + 96, u.t_count); else scan32<true>(s, rb, scol + 96, ucol + 96, u.t_count);
-            if (DEBUG && u.dump == 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)
-                reinterpret_cast<long long*>(dump)[12288 + n] = clock64();
-
-            const float L = fmaxf(s.G, s.b1);
-            if (row_valid && L > s.published) {
-                atomicMax(const_cast<uint32_t*>(hint), enc_ordered(L));
-                s.published = L;
+            if (lane == 0) mbar_arrive(BAR_UEMPTY + 8 * us);
+            if (u.t_count == 0) break;
+            const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
+            const bool row_valid = row < u.q_valid;
+            Top3 s;
+            s.b0 = s.b1 = s.b2 = s.b3 = -INFINITY;
+            s.G = s.published = -INFINITY;
+            {
+                const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
+                float tmin2, tmax2;
+                stats_read(u.t_stats, tmin2, tmax2);
+                s.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
             }
-            if (++seg_tile == u.seg_tiles || n == ntiles - 1) {
-                if (row_valid) {
-                    const float4 rec = make_float4(s.b0, s.b1, s.b2, s.b3);
-                    *reinterpret_cast<float4*>(recs + u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half) = rec;
+            top3_update_thr(s);
+            volatile uint32_t* hint = u.hint + (row_valid ? row : 0);
+            int seg = 0, seg_tile = 0;
+            for (int n = 0; n < ntiles; n++, tile_it++) {
+                const int st = tile_it & 1;
+                // bound published by the other CTAs / warps working on the same query (a second-best
+                // of any subset of the train set is a lower bound on the global second-best)
+                const uint32_t h = *hint;
+                mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
+                tcgen05_fence_after();
+                if (DEBUG && u.dump >= 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)
+                    reinterpret_cast<long long*>(dump)[n] = clock64();
+                if (h != 0u) { s.G = fmaxf(s.G, dec_ordered(h)); top3_update_thr(s); }
+                const uint32_t taddr = lane_addr + st * TILE_N;
+                const int32_t ucol = n * TILE_N + half * HALF_N;           // unit-relative column of chunk 0
+                const uint32_t scol = (uint32_t)seg_tile * HALF_N;         // slice-relative
+                const bool full_tile = (n + 1) * TILE_N <= u.t_count;
+                uint32_t ra[32], rb[32];
+                int slow = 0;
+                tmem_ld32(taddr, ra);
+                tmem_ld_wait(ra);
+                tmem_ld32(taddr + 32, rb);
+                if (DEBUG && u.dump == 1 && n == 0)
+                    for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + e] = __uint_as_float(ra[e]);
+                if (!full_tile) mask32(ra, ucol, u.t_count);
+                if (!(DEBUG && u.dump == 3)) scan32(s, ra, scol, DEBUG ? &slow : nullptr);
+                tmem_ld_wait(rb);
+                tmem_ld32(taddr + 64, ra);
+                if (DEBUG && u.dump == 1 && n == 0)
+                    for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 32 + e] = __uint_as_float(rb[e]);
+                if (!full_tile) mask32(rb, ucol + 32, u.t_count);
+                if (!(DEBUG && u.dump == 3)) scan32(s, rb, scol + 32, DEBUG ? &slow : nullptr);
+                tmem_ld_wait(ra);
+                tmem_ld32(taddr + 96, rb);
+                if (DEBUG && u.dump == 1 && n == 0)
+                    for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 64 + e] = __uint_as_float(ra[e]);
+                if (!full_tile) mask32(ra, ucol + 64, u.t_count);
+                if (!(DEBUG && u.dump == 3)) scan32(s, ra, scol + 64, DEBUG ? &slow : nullptr);
+                tmem_ld_wait(rb);
+                // all TMEM reads of this stage are complete: hand it back to the MMA warp
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+                if (DEBUG && u.dump == 1 && n == 0)
+                    for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 96 + e] = __uint_as_float(rb[e]);
+                if (!full_tile) mask32(rb, ucol + 96, u.t_count);
+                if (!(DEBUG && u.dump == 3)) scan32(s, rb, scol + 96, DEBUG ? &slow : nullptr);
+                if (DEBUG && u.dump >= 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)   // clock | slow groups | hint seen
+                    reinterpret_cast<long long*>(dump)[12288 + n] =
+                        (clock64() & 0xFFFFFFFFFFll) | ((long long)slow << 40) | ((long long)(h != 0u) << 48);
+
+                const float L = fmaxf(s.G, s.b1);
+                if (row_valid && L > s.published) {
+                    atomicMax(const_cast<uint32_t*>(hint), enc_ordered(L));
+                    s.published = L;
                 }
-                seg++;
-                seg_tile = 0;
-                top3_reset_slice(s);
+                if (++seg_tile == u.seg_tiles || n == ntiles - 1) {
+                    if (row_valid) {
+                        const float4 rec = make_float4(s.b0, s.b1, s.b2, s.b3);
+                        *reinterpret_cast<float4*>(recs + u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half) = rec;
+                    }
+                    seg++;
+                    seg_tile = 0;
+                    top3_reset_slice(s);
+                }
             }
         }
     }
