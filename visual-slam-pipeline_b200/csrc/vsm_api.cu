@@ -208,7 +208,7 @@ int launch_convert(vsm_ctx* ctx, const float* src, __nv_bfloat16* dst, float* n2
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-constexpr int UNIT_TILES = 128;                  // longest train range of one work unit, in 256-row tiles
+constexpr int UNIT_TILES = 64;                   // longest train range of one work unit, in 256-row tiles
 constexpr uint32_t WORK_CAP = 1u << 18;          // rescan work items (4 MB); beyond it select scans inline
 
 int begin_call(vsm_ctx* ctx) {
@@ -266,7 +266,6 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
 
     int64_t total_qtiles = 0;
     for (auto& p : probs) if (p.nq > 0 && p.nt > 0) total_qtiles += (p.nq + TILE_M - 1) / TILE_M;
-    const int64_t budget = std::max<int64_t>(1, total_qtiles ? ctx->num_sms / total_qtiles : 1);
 
     // device addresses inside the descriptor block are fixed up after the layout is known
     for (int i = 0; i < P; i++) {
@@ -287,10 +286,14 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             continue;
         }
         const int ntiles = (hp.nt + TILE_N - 1) / TILE_N;
-        // ranges: enough to fill the chip once, and never longer than UNIT_TILES so that the dynamic
-        // scheduler can balance the tail and neighbouring CTAs stay on neighbouring rows
-        int nranges = (int)std::min<int64_t>(ntiles, budget);
-        const int tpr = std::min((ntiles + nranges - 1) / nranges, UNIT_TILES);
+        // ranges: units of at most UNIT_TILES tiles whose count is (close to) a whole number of
+        // waves over the SMs, so that the dynamic scheduler ends every CTA at about the same time
+        int nranges = 1;
+        for (int64_t k = 1; k <= 8192; k++) {
+            nranges = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)ctx->num_sms * k / std::max<int64_t>(total_qtiles, 1)));
+            if ((ntiles + nranges - 1) / nranges <= UNIT_TILES || nranges == ntiles) break;
+        }
+        const int tpr = (ntiles + nranges - 1) / nranges;
         nranges = (ntiles + tpr - 1) / tpr;
         // slice length: short slices keep an overflow re-scan cheap, long ones keep the record
         // stream small next to the database stream
