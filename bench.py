@@ -389,21 +389,25 @@ def run_gpu(args):
     launches_per_step = db.launches_per_search()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    # -- device-resident timing ------------------------------------------------------------------
+    # -- device-resident timing (no host synchronisation inside the timed region) ------------------
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tc_ms = []
     t_wall0 = time.time()
     with torch.cuda.stream(db.stream):
         e0.record()
     for _ in range(args.steps):
         oi, od = db.search_device(q)
-        tc_ms.append(db.matcher.stats()["tc_ms"])     # waits for this step, reads the kernel's events
     with torch.cuda.stream(db.stream):
         e1.record()
     barrier()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
+    # -- the dominant kernel alone: same steps again, reading the library's CUDA events around
+    #    tc_top3_kernel after every step (this synchronises, so it is kept out of `value`)
+    tc_ms = []
+    for _ in range(args.steps):
+        db.search_device(q)
+        tc_ms.append(db.matcher.stats()["tc_ms"])
     # -- end to end through host buffers -------------------------------------------------------------
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -170,6 +170,16 @@ int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset
 int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
                      int32_t* counts, vsm_dmatch* matches);
 
+/* LoopCloser::detect's candidate loop WITH its eligibility rules (src/LoopCloser.cpp:43-62):
+ * stored keyframes are visited in store order; a keyframe is skipped when
+ * cur_frame_id - frame_id < min_gap (:44, Config::LC_MIN_FRAME_GAP = 200) or it is empty (:45);
+ * of the remaining ones only every `every`-th is matched (:47-48: checked++; checked % 5 != 0 -> skip).
+ * status: [n_keyframes], -1 = skipped by those rules, otherwise the number of ratio-test
+ * survivors (the caller applies its >= Config::MIN_MATCHES gate, :62).  matches as in
+ * vsm_db_segmented.  Only the eligible keyframes are matched on the device. */
+int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every,
+                    const float* query, int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches);
+
 /* ---- device-pointer variants (resident data; multi-GPU plumbing) ---------- */
 
 /* vsm_db_top2 with query and outputs already on this context's device.
@@ -177,6 +187,14 @@ int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
  * unless sync != 0. */
 int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset,
                        int64_t* d_idx, float* d_dist, int32_t sync);
+
+/* Same search, result as two 64-bit keys per query: ~((distance bits << 32) | GLOBAL index), 0 = empty
+ * (global index = store row + row_offset, must fit 32 bits).  One buffer to all-gather instead of two. */
+int vsm_db_top2_keys_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset,
+                            uint64_t* d_keys, int32_t sync);
+/* Merge gathered keys [nshard][nq][2] -> idx [nq][2] (int64, -1 = none) + dist [nq][2]. */
+int vsm_merge_keys_device(vsm_ctx* ctx, const uint64_t* d_keys_in, int32_t nshard, int32_t nq,
+                          int64_t* d_idx_out, float* d_dist_out, int32_t sync);
 
 /* Merge per-shard top-2 lists (e.g. after an NCCL all-gather) by (distance, index).
  * d_idx_in/d_dist_in: [nshard][nq][2] with GLOBAL indices (-1 = empty). */

@@ -114,3 +114,26 @@ def gen_rows(seed, set_id, row0, n):
     out = np.empty((n, 256), np.float32)
     lib().vsm_oracle_gen_rows(seed, set_id, row0, n, out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+def loop_detect(q, db, seg_off, frame_ids, cur_frame_id, ratio=0.75, min_gap=200, every=5, threads=0):
+    """LoopCloser::detect's candidate loop (src/LoopCloser.cpp:43-62): eligibility (:44-48) then the
+    per-keyframe kNN + ratio test.  Returns status[nkf] (-1 = skipped, else survivors) and the lists."""
+    nkf = len(seg_off) - 1
+    status = -np.ones(nkf, np.int32)
+    lists = [None] * nkf
+    checked = 0
+    for s in range(nkf):
+        if cur_frame_id - frame_ids[s] < min_gap:
+            continue
+        if seg_off[s + 1] == seg_off[s]:
+            continue
+        checked += 1
+        if checked % every != 0:
+            continue
+        good, _ = match_features(q, db[seg_off[s]:seg_off[s + 1]], ratio, threads=threads)
+        good = good.copy()
+        good["imgIdx"] = s
+        status[s] = len(good)
+        lists[s] = good
+    return status, lists

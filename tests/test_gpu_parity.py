@@ -226,3 +226,23 @@ def test_track_sequence(tc):
         h = h2
     assert tc.store_info() == (2000, 5)
     tc.clear_store()
+
+
+def test_loop_detect_eligibility_and_matches(tc):
+    """vsm_loop_detect = LoopCloser::detect's loop incl. the gap >= 200 / every-5th rules."""
+    q, db, seg_off = cases.db_case()
+    nkf = len(seg_off) - 1
+    frame_ids = [30 * s for s in range(nkf)]                 # keyframe s was frame 30*s
+    tc.clear_store()
+    for s in range(nkf):
+        tc.add_keyframe(frame_ids[s], db[seg_off[s]:seg_off[s + 1]])
+    for cur_id, gap, every in ((900, 200, 5), (900, 200, 1), (650, 100, 3), (100, 200, 5)):
+        status, lists = tc.loop_detect(cur_id, q, 0.75, min_gap=gap, every=every)
+        ost, ol = oracle.loop_detect(q, db, seg_off, frame_ids, cur_id, 0.75, gap, every)
+        assert np.array_equal(status, ost)
+        for s in range(nkf):
+            if ost[s] >= 0:
+                assert lists[s].tobytes() == ol[s].tobytes()
+            else:
+                assert lists[s] is None
+    tc.clear_store()

@@ -917,40 +917,113 @@ int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t r
     return end_call(ctx, sync != 0);
 }
 
+// Per-keyframe top-2 + ratio test for the keyframes with eligible[s] != 0 (all if NULL).
+static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, const std::vector<char>* eligible,
+                          int32_t* counts, vsm_dmatch* matches) {
+    const int nseg = (int)ctx->segs.size();
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    std::vector<HProblem> probs;
+    std::vector<HJob> jobs;
+    std::vector<int> job_seg;
+    for (int s = 0; s < nseg; s++) {
+        if (eligible && !(*eligible)[s]) continue;
+        const Seg& sg = ctx->segs[s];
+        const int64_t slot = (int64_t)jobs.size();
+        HProblem p;
+        p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
+        p.t_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; p.t_row = sg.row0; p.t_store = 1; p.nt = sg.count;
+        p.out_off = slot * nq;
+        probs.push_back(p);
+        HJob j;
+        j.fwd_off = p.out_off; j.back_off = -1; j.good_off = slot * nq; j.raw_off = -1;
+        j.nq = nq; j.nt = sg.count; j.img_idx = s; j.ratio = ratio;
+        jobs.push_back(j);
+        job_seg.push_back(s);
+    }
+    if (jobs.empty()) return end_call(ctx, true);
+    const int64_t total_matches = (int64_t)jobs.size() * nq;
+    TRY(run_problems(ctx, probs, jobs, total_matches, total_matches, ctx->scratch.f32, 0, nq));
+    const size_t mbytes = (size_t)total_matches * sizeof(DMatch);
+    const size_t cbytes = jobs.size() * 2 * sizeof(int32_t);
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, cbytes));
+    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p + mbytes, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (matches) {
+        if (!eligible) {
+            CK(cudaMemcpyAsync(matches, ctx->d_result.p, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            for (size_t k = 0; k < jobs.size(); k++)       // slot k -> keyframe job_seg[k]
+                CK(cudaMemcpyAsync(matches + (size_t)job_seg[k] * nq, ctx->d_result.p + k * (size_t)nq * sizeof(DMatch),
+                                   (size_t)nq * sizeof(DMatch), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    TRY(end_call(ctx, true));
+    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result);
+    for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = c[2 * k];
+    return VSM_OK;
+}
+
+int vsm_db_top2_keys_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset, uint64_t* d_keys,
+                            int32_t sync) {
+    if (!ctx || nq < 0 || (nq > 0 && (!d_query || !d_keys)) || row_offset < 0 ||
+        row_offset + ctx->store_rows > 0xFFFFFFFFll)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_keys_device: bad argument") : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    HProblem p;
+    db_problem(ctx, d_query, nq, p);
+    static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? std::max(2, atoi(getenv("VSM_DEBUG_TIMELINE"))) : 0;
+    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
+    globalize_keys_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(
+        ctx->d_out_key, nq * 2, (uint32_t)row_offset, reinterpret_cast<unsigned long long*>(d_keys));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return end_call(ctx, sync != 0);
+}
+
+int vsm_merge_keys_device(vsm_ctx* ctx, const uint64_t* d_keys_in, int32_t nshard, int32_t nq, int64_t* d_idx_out,
+                          float* d_dist_out, int32_t sync) {
+    if (!ctx || nshard <= 0 || nq < 0 || (nq > 0 && (!d_keys_in || !d_idx_out || !d_dist_out)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_merge_keys_device: bad argument") : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    merge_keys_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(
+        reinterpret_cast<const unsigned long long*>(d_keys_in), nshard, nq, d_idx_out, d_dist_out);
+    CK(cudaGetLastError());
+    if (sync) CK(cudaStreamSynchronize(ctx->stream));
+    return VSM_OK;
+}
+
 int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, int32_t* counts, vsm_dmatch* matches) {
     if (!ctx || nq < 0 || (nq > 0 && !query) || !counts)
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_segmented: bad argument") : VSM_ERR_INVALID;
     const int nseg = (int)ctx->segs.size();
     for (int s = 0; s < nseg; s++) counts[s] = 0;
     if (nq == 0 || nseg == 0) return VSM_OK;
-    TRY(begin_call(ctx));
-    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
-    TRY(upload_scratch(ctx, query, 0, nq));
-    std::vector<HProblem> probs;
-    std::vector<HJob> jobs;
-    for (int s = 0; s < nseg; s++) {
-        const Seg& sg = ctx->segs[s];
-        HProblem p;
-        p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
-        p.t_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; p.t_row = sg.row0; p.t_store = 1; p.nt = sg.count;
-        p.out_off = (int64_t)s * nq;
-        probs.push_back(p);
-        HJob j;
-        j.fwd_off = p.out_off; j.back_off = -1; j.good_off = (int64_t)s * nq; j.raw_off = -1;
-        j.nq = nq; j.nt = sg.count; j.img_idx = s; j.ratio = ratio;
-        jobs.push_back(j);
+    return segmented_impl(ctx, query, nq, ratio, nullptr, counts, matches);
+}
+
+int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
+                    int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches) {
+    if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect: bad argument") : VSM_ERR_INVALID;
+    const int nseg = (int)ctx->segs.size();
+    std::vector<char> eligible(nseg, 0);
+    int checked = 0, any = 0;
+    for (int s = 0; s < nseg; s++) {                                  // src/LoopCloser.cpp:43-48
+        status[s] = -1;
+        if (cur_frame_id - ctx->segs[s].frame_id < min_gap) continue;
+        if (ctx->segs[s].count == 0) continue;
+        checked++;
+        if (checked % every != 0) continue;
+        eligible[s] = 1;
+        status[s] = 0;
+        any = 1;
     }
-    const int64_t total_matches = (int64_t)nseg * nq;
-    TRY(run_problems(ctx, probs, jobs, total_matches, total_matches, ctx->scratch.f32, 0, nq));
-    const size_t mbytes = (size_t)total_matches * sizeof(DMatch);
-    const size_t cbytes = (size_t)nseg * 2 * sizeof(int32_t);
-    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, cbytes));
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p + mbytes, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (matches) CK(cudaMemcpyAsync(matches, ctx->d_result.p, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(end_call(ctx, true));
-    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result);
-    for (int s = 0; s < nseg; s++) counts[s] = c[2 * s];
-    return VSM_OK;
+    if (nq == 0 || !any) return VSM_OK;                               // :22 (empty current frame)
+    return segmented_impl(ctx, query, nq, ratio, &eligible, status, matches);
 }
 
 int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_dist_in, int32_t nshard, int32_t nq,

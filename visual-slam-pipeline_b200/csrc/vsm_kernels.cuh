@@ -367,4 +367,36 @@ __global__ void widen_kernel(const unsigned long long* __restrict__ out_key, int
     dist_out[i] = d;
 }
 
+// local result keys -> keys carrying the GLOBAL index (for a single all-gather across shards)
+__global__ void globalize_keys_kernel(const unsigned long long* __restrict__ out_key, int n, uint32_t row_offset,
+                                      unsigned long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = out_key[i];
+    keys[i] = k == 0ull ? 0ull : ~((~k) + row_offset);        // index lives in the low 32 bits of ~k
+}
+
+// gathered keys [nshard][nq][2] -> global top-2: the largest two keys per query
+__global__ void merge_keys_kernel(const unsigned long long* __restrict__ keys, int nshard, int nq,
+                                  int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    for (int s = 0; s < nshard; s++) {
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const unsigned long long k = keys[((int64_t)s * nq + q) * 2 + p];
+            if (k > k0) { k1 = k0; k0 = k; } else if (k > k1) k1 = k;
+        }
+    }
+    const unsigned long long kk[2] = {k0, k1};
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (kk[p] == 0ull) { idx_out[2 * q + p] = -1; dist_out[2 * q + p] = FLT_MAX; continue; }
+        const unsigned long long u = ~kk[p];
+        idx_out[2 * q + p] = (int64_t)(uint32_t)u;
+        dist_out[2 * q + p] = __uint_as_float((uint32_t)(u >> 32));
+    }
+}
+
 }  // namespace vsm

@@ -65,7 +65,11 @@ SYMBOLS = {
                             C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vsm_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "vsm_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
+                                  C.c_void_p, C.c_void_p]),
     "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsm_db_top2_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]),
+    "vsm_merge_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_merge_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32]),
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
@@ -267,10 +271,30 @@ class Matcher:
         counts = counts[:nkf]
         return counts, ([m[s, :counts[s]] for s in range(nkf)] if want_matches else None)
 
+    def loop_detect(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, want_matches=True):
+        """LoopCloser::detect's candidate loop with its eligibility rules (src/LoopCloser.cpp:43-62).
+        Returns (status[nkf]: -1 skipped / survivor count, [DMATCH array or None per keyframe])."""
+        q = _rows(frame_desc, "frame_desc")
+        nkf = self.store_info()[1]
+        status = np.zeros(max(nkf, 1), np.int32)
+        m = np.zeros((max(nkf, 1), max(q.shape[0], 1)), DMATCH) if want_matches else None
+        self._ck(self._lib.vsm_loop_detect(self._h, cur_frame_id, min_gap, every, q.ctypes.data, q.shape[0], ratio,
+                                           status.ctypes.data, m.ctypes.data if want_matches else None))
+        status = status[:nkf]
+        return status, ([m[s, :status[s]] if status[s] >= 0 else None for s in range(nkf)] if want_matches else None)
+
     # -- device-pointer plumbing (resident queries, sharded search) -------------------------
     def db_top2_device(self, d_query_ptr, nq, row_offset, d_idx_ptr, d_dist_ptr, sync=False):
         self._ck(self._lib.vsm_db_top2_device(self._h, C.c_void_p(d_query_ptr), nq, row_offset,
                                               C.c_void_p(d_idx_ptr), C.c_void_p(d_dist_ptr), int(sync)))
+
+    def db_top2_keys_device(self, d_query_ptr, nq, row_offset, d_keys_ptr, sync=False):
+        self._ck(self._lib.vsm_db_top2_keys_device(self._h, C.c_void_p(d_query_ptr), nq, row_offset,
+                                                   C.c_void_p(d_keys_ptr), int(sync)))
+
+    def merge_keys_device(self, d_keys_in, nshard, nq, d_idx_out, d_dist_out, sync=False):
+        self._ck(self._lib.vsm_merge_keys_device(self._h, C.c_void_p(d_keys_in), nshard, nq, C.c_void_p(d_idx_out),
+                                                 C.c_void_p(d_dist_out), int(sync)))
 
     def merge_top2_device(self, d_idx_in, d_dist_in, nshard, nq, d_idx_out, d_dist_out, sync=False):
         self._ck(self._lib.vsm_merge_top2_device(self._h, C.c_void_p(d_idx_in), C.c_void_p(d_dist_in), nshard, nq,

@@ -76,8 +76,8 @@ class ShardedDB:
             self.l_idx = torch.empty((nq, 2), dtype=torch.int64, device=dev)
             self.l_dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
             if self.world > 1:
-                self.g_idx = torch.empty((self.world, nq, 2), dtype=torch.int64, device=dev)
-                self.g_dist = torch.empty((self.world, nq, 2), dtype=torch.float32, device=dev)
+                self.l_keys = torch.empty((nq, 2), dtype=torch.int64, device=dev)         # u64 bit patterns
+                self.g_keys = torch.empty((self.world * nq, 2), dtype=torch.int64, device=dev)
                 self.o_idx = torch.empty((nq, 2), dtype=torch.int64, device=dev)
                 self.o_dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
             else:
@@ -93,14 +93,15 @@ class ShardedDB:
         nq = d_q.shape[0]
         self._buffers(nq)
         with torch.cuda.stream(self.stream):
-            self.matcher.db_top2_device(d_q.data_ptr(), nq, self.row_offset, self.l_idx.data_ptr(),
-                                        self.l_dist.data_ptr(), sync=False)
-            if self.world > 1:
-                def merge(g_idx, g_dist):
-                    self.matcher.merge_top2_device(g_idx.data_ptr(), g_dist.data_ptr(), self.world, nq,
-                                                   self.o_idx.data_ptr(), self.o_dist.data_ptr(), sync=False)
-                    return self.o_idx, self.o_dist
-                gather_and_merge(self.l_idx, self.l_dist, self.world, self.group, merge, self.g_idx, self.g_dist)
+            if self.world == 1:
+                self.matcher.db_top2_device(d_q.data_ptr(), nq, self.row_offset, self.l_idx.data_ptr(),
+                                            self.l_dist.data_ptr(), sync=False)
+            else:
+                # one 16 B x nq buffer per rank: keys ~((distance bits << 32) | global index)
+                self.matcher.db_top2_keys_device(d_q.data_ptr(), nq, self.row_offset, self.l_keys.data_ptr(), sync=False)
+                torch.distributed.all_gather_into_tensor(self.g_keys, self.l_keys, group=self.group)
+                self.matcher.merge_keys_device(self.g_keys.data_ptr(), self.world, nq, self.o_idx.data_ptr(),
+                                               self.o_dist.data_ptr(), sync=False)
         return self.o_idx, self.o_dist
 
     def search_host(self, h_q):
