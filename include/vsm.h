@@ -138,6 +138,14 @@ int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, in
  * fp32 master; builds the bf16 shadow).  seg_off: nseg+1 row offsets or NULL (one segment). */
 int vsm_store_adopt_device(vsm_ctx* ctx, const float* d_desc, int64_t n_rows,
                            const int64_t* seg_off, int32_t nseg);
+/* Bulk-load the reference's feature cache (FeatureExtractor::save_cache / load_cache,
+ * src/FeatureExtractor.cpp:269-381: magic 0x53504346 "SPCF", version 1, per entry frame_idx,
+ * keypoints (7 x 4 B each), rows, cols, type, raw descriptor bytes): every entry holding an
+ * N x 256 CV_32F matrix becomes one keyframe (frame_id = frame_idx), in file order.
+ * n_loaded / n_skipped (entries of another type, e.g. the ORB fallback's CV_8U) may be NULL;
+ * first_handle receives the handle of the first keyframe added (-1 if none). */
+int vsm_store_load_spcf(vsm_ctx* ctx, const char* path, int32_t* n_loaded, int32_t* n_skipped,
+                        int32_t* first_handle);
 int vsm_store_clear(vsm_ctx* ctx);
 int vsm_store_info(const vsm_ctx* ctx, int64_t* n_rows, int32_t* n_keyframes);
 
@@ -169,6 +177,15 @@ int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset
  * keyframe s first in query order, trainIdx keyframe-local, imgIdx = s. */
 int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
                      int32_t* counts, vsm_dmatch* matches);
+
+/* The same search restricted to the store rows with mask[row] != 0 -- the map-point searches of
+ * src/Slam.cpp:546-574 (only valid map points, :553) and :744-774 (only points observed near the
+ * loop keyframe, :748-756), which the reference implements by re-stacking the selected
+ * descriptors on every call.  n_mask must equal the store's row count.  idx holds ORIGINAL store
+ * rows (the reference's mp_ids_vec[trainIdx], :768); order and ties are those of the compacted
+ * matrix the reference builds (ascending row).  -1 / FLT_MAX when fewer than k rows are selected. */
+int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8_t* mask, int64_t n_mask,
+                       int64_t* idx, float* dist);
 
 /* LoopCloser::detect's candidate loop WITH its eligibility rules (src/LoopCloser.cpp:43-62):
  * stored keyframes are visited in store order; a keyframe is skipped when

@@ -246,3 +246,59 @@ def test_loop_detect_eligibility_and_matches(tc):
             else:
                 assert lists[s] is None
     tc.clear_store()
+
+
+def test_spcf_feature_cache_bulk_load(tc, tmp_path):
+    """The reference's on-disk descriptor format (SPCF, src/FeatureExtractor.cpp:269-381) loads
+    straight into the device store; float entries become keyframes, ORB (CV_8U) entries are skipped."""
+    from oracle import spcf
+    rng = np.random.default_rng(1)
+    frames = gen.video(9, 4, 300)
+    entries = {}
+    for i, d in enumerate(frames):
+        kps = np.zeros((len(d), 7), np.float32)
+        kps[:, 0:2] = rng.uniform(0, 640, (len(d), 2))
+        entries[3 * i] = (kps, d)                                   # FRAME_STEP = 3 (include/Config.h:123)
+    entries[100] = (None, rng.integers(0, 255, (50, 32)).astype(np.uint8))    # an ORB-fallback entry
+    entries[101] = (None, np.zeros((0, 0), np.float32))                      # no features
+    path = str(tmp_path / "features.bin")
+    spcf.write(path, entries)
+    back = spcf.read(path)
+    assert np.array_equal(back[3][1], frames[1])
+    tc.clear_store()
+    loaded, skipped, h0 = tc.load_feature_cache(path)
+    assert (loaded, skipped, h0) == (4, 2, 0)
+    assert tc.store_info() == (1200, 4)
+    for f in range(1, 4):
+        good, raw = tc.match_to_keyframe(h0 + f - 1, frames[f], 0.75, want_raw=True)
+        og, orw = oracle.match_features(frames[f - 1], frames[f], 0.75)
+        assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+    # loop_detect uses the frame ids from the file
+    status, _ = tc.loop_detect(500, frames[3], min_gap=200, every=1, want_matches=False)
+    assert np.all(status >= 0)
+    tc.clear_store()
+    with pytest.raises(vsm_b200.VsmError):
+        tc.load_feature_cache(str(tmp_path / "missing.bin"))
+
+
+def test_masked_map_point_search(tc):
+    """vsm_db_top2_masked = knnMatch(frame, stack(valid map-point descriptors), 2) with indices
+    mapped back through mp_ids_vec (src/Slam.cpp:744-774)."""
+    q, db, _ = cases.db_case()
+    rng = np.random.default_rng(11)
+    tc.clear_store()
+    tc.add_keyframe(0, db)                                  # the map-point descriptors, one row per point
+    for frac in (0.7, 0.1, 0.0003, 0.0):
+        mask = (rng.random(db.shape[0]) < frac).astype(np.uint8)
+        if frac == 0.0003:
+            mask[:] = 0
+            mask[[5, 9000 % db.shape[0]]] = 1
+        ids = np.nonzero(mask)[0]                           # mp_ids_vec
+        idx, dist = tc.search_map_points_masked(q, mask)
+        oi, od = oracle.knn(q, db[ids], 2)
+        want = np.where(oi >= 0, ids[np.maximum(oi, 0)] if len(ids) else -1, -1)
+        assert np.array_equal(idx, want)
+        assert np.array_equal(bits(dist), bits(od))
+    with pytest.raises(vsm_b200.VsmError):
+        tc.search_map_points_masked(q, np.ones(3, np.uint8))
+    tc.clear_store()

@@ -91,6 +91,7 @@ struct vsm_ctx {
     DevBuf<uint8_t> d_aux;
     unsigned long long* d_counters = nullptr;    // = d_aux.p
     DevBuf<WorkItem> d_work;
+    DevBuf<int32_t> d_sel;                       // selected store rows of a masked search
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_tc0 = nullptr, ev_tc1 = nullptr, ev_sel1 = nullptr;
@@ -575,6 +576,7 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->d_aux.p) cudaFree(ctx->d_aux.p);
     if (ctx->d_work.p) cudaFree(ctx->d_work.p);
+    if (ctx->d_sel.p) cudaFree(ctx->d_sel.p);
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -759,6 +761,64 @@ int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, in
     ctx->err.clear();
     CK(cudaSetDevice(ctx->device));
     return store_append(ctx, frame_id, d_desc, n, cudaMemcpyDeviceToDevice, handle);
+}
+
+int vsm_store_load_spcf(vsm_ctx* ctx, const char* path, int32_t* n_loaded, int32_t* n_skipped, int32_t* first_handle) {
+    if (!ctx || !path) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_load_spcf: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (n_loaded) *n_loaded = 0;
+    if (n_skipped) *n_skipped = 0;
+    if (first_handle) *first_handle = -1;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_store_load_spcf: cannot open file");
+    std::vector<uint8_t> buf;
+    {
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize(sz > 0 ? (size_t)sz : 0);
+        size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+        fclose(f);
+        if (got != buf.size()) return fail(ctx, VSM_ERR_INVALID, "vsm_store_load_spcf: short read");
+    }
+    size_t pos = 0;
+    auto rd32 = [&](uint32_t& v) -> bool {
+        if (pos + 4 > buf.size()) return false;
+        memcpy(&v, buf.data() + pos, 4);
+        pos += 4;
+        return true;
+    };
+    uint32_t magic = 0, version = 0, n_entries = 0;
+    if (!rd32(magic) || !rd32(version) || !rd32(n_entries) || magic != 0x53504346u || version != 1u)
+        return fail(ctx, VSM_ERR_INVALID, "vsm_store_load_spcf: not an SPCF version-1 file");      // FeatureExtractor.cpp:281
+    CK(cudaSetDevice(ctx->device));
+    int loaded = 0, skipped = 0;
+    for (uint32_t e = 0; e < n_entries; e++) {
+        uint32_t frame_idx, num_kp, rows, cols, type;
+        if (!rd32(frame_idx) || !rd32(num_kp)) return fail(ctx, VSM_ERR_INVALID, "vsm_store_load_spcf: truncated entry");
+        pos += (size_t)num_kp * 28;                                     // x, y, size, angle, response, octave, class_id
+        if (!rd32(rows) || !rd32(cols) || !rd32(type)) return fail(ctx, VSM_ERR_INVALID, "vsm_store_load_spcf: truncated entry");
+        const int depth = type & 7;                                     // CV_MAT_DEPTH: 0 = 8U ... 5 = 32F, 6 = 64F
+        const int channels = ((type >> 3) & 511) + 1;
+        static const int depth_bytes[8] = {1, 1, 2, 2, 4, 4, 8, 2};
+        size_t nbytes = 0;
+        if ((int32_t)rows > 0 && (int32_t)cols > 0) nbytes = (size_t)rows * cols * depth_bytes[depth] * channels;
+        if (pos + nbytes > buf.size()) return fail(ctx, VSM_ERR_INVALID, "vsm_store_load_spcf: truncated descriptors");
+        if (type == 5 && cols == VSM_DIM && (int32_t)rows > 0) {        // CV_32FC1, N x 256
+            // file offsets are only 4-byte aligned by construction, which is all the copy needs
+            int32_t h = -1;
+            TRY(store_append(ctx, (int32_t)frame_idx, reinterpret_cast<const float*>(buf.data() + pos), rows,
+                             cudaMemcpyHostToDevice, &h));
+            if (loaded == 0 && first_handle) *first_handle = h;
+            loaded++;
+        } else {
+            skipped++;
+        }
+        pos += nbytes;
+    }
+    if (n_loaded) *n_loaded = loaded;
+    if (n_skipped) *n_skipped = skipped;
+    return VSM_OK;
 }
 
 int vsm_store_clear(vsm_ctx* ctx) {
@@ -961,6 +1021,39 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
     TRY(end_call(ctx, true));
     const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result);
     for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = c[2 * k];
+    return VSM_OK;
+}
+
+int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8_t* mask, int64_t n_mask, int64_t* idx,
+                       float* dist) {
+    if (!ctx || nq < 0 || (nq > 0 && (!query || !idx || !dist)) || n_mask != ctx->store_rows || (n_mask > 0 && !mask))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_masked: bad argument (mask length must equal the store rows)")
+                   : VSM_ERR_INVALID;
+    if (nq == 0) return VSM_OK;
+    std::vector<int32_t> sel;                                            // the reference's mp_ids_vec (src/Slam.cpp:757)
+    for (int64_t r = 0; r < n_mask; r++) if (mask[r]) sel.push_back((int32_t)r);
+    const int64_t ns = (int64_t)sel.size();
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + ns, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    if (ns > 0) {
+        TRY(ensure(ctx, ctx->d_sel, (size_t)ns));
+        CK(cudaMemcpyAsync(ctx->d_sel.p, sel.data(), (size_t)ns * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t blocks = std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->num_sms * 16);
+        gather_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->store.f32, ctx->d_sel.p, ns,
+                                                                      ctx->scratch.f32 + (int64_t)nq * VSM_DIM);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, (int)ns, 0)};
+    TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + ns));
+    TRY(fetch_keys(ctx, nq));
+    TRY(end_call(ctx, true));                                            // also keeps `sel` alive past the H2D
+    const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
+    for (int i = 0; i < nq * 2; i++) {
+        decode_key(k[i], idx[i], dist[i]);
+        if (idx[i] >= 0) idx[i] = sel[(size_t)idx[i]];
+    }
     return VSM_OK;
 }
 

@@ -367,6 +367,20 @@ __global__ void widen_kernel(const unsigned long long* __restrict__ out_key, int
     dist_out[i] = d;
 }
 
+// dst row k <- src row sel[k] (fp32, 1 KB rows): one warp per row, two float4 per lane
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ sel, int64_t n, float* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp0; k < n; k += nwarps) {
+        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)__ldg(sel + k) * VSM_DIM) + lane * 2;
+        float4* o = reinterpret_cast<float4*>(dst + k * VSM_DIM) + lane * 2;
+        const float4 a = __ldg(p), b = __ldg(p + 1);
+        o[0] = a; o[1] = b;
+    }
+}
+
 // local result keys -> keys carrying the GLOBAL index (for a single all-gather across shards)
 __global__ void globalize_keys_kernel(const unsigned long long* __restrict__ out_key, int n, uint32_t row_offset,
                                       unsigned long long* __restrict__ keys) {

@@ -57,6 +57,8 @@ SYMBOLS = {
     "vsm_store_add": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "vsm_store_add_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "vsm_store_adopt_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "vsm_store_load_spcf": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32)]),
     "vsm_store_clear": (C.c_int, [C.c_void_p]),
     "vsm_store_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "vsm_match_to_stored": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
@@ -64,6 +66,7 @@ SYMBOLS = {
     "vsm_track": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                             C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vsm_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vsm_db_top2_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "vsm_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                                   C.c_void_p, C.c_void_p]),
@@ -215,6 +218,13 @@ class Matcher:
         else:
             self._ck(self._lib.vsm_store_adopt_device(self._h, C.c_void_p(dev_ptr), n_rows, None, 0))
 
+    def load_feature_cache(self, path):
+        """Bulk-load the reference's SPCF feature cache (src/FeatureExtractor.cpp:269-381) into the store.
+        Returns (entries loaded as keyframes, entries skipped, handle of the first keyframe)."""
+        a, b, h = C.c_int32(0), C.c_int32(0), C.c_int32(-1)
+        self._ck(self._lib.vsm_store_load_spcf(self._h, os.fsencode(path), C.byref(a), C.byref(b), C.byref(h)))
+        return a.value, b.value, h.value
+
     def clear_store(self):
         self._ck(self._lib.vsm_store_clear(self._h))
 
@@ -257,6 +267,17 @@ class Matcher:
         dist = np.empty((q.shape[0], 2), np.float32)
         self._ck(self._lib.vsm_db_top2(self._h, q.ctypes.data, q.shape[0], row_offset, idx.ctypes.data,
                                        dist.ctypes.data))
+        return idx, dist
+
+    def search_map_points_masked(self, frame_desc, mask):
+        """Global top-2 over the store rows with mask != 0 (valid / nearby map points only,
+        src/Slam.cpp:553, :748-756).  idx = original store rows."""
+        q = _rows(frame_desc, "frame_desc")
+        mask = np.ascontiguousarray(mask, np.uint8)
+        idx = np.empty((q.shape[0], 2), np.int64)
+        dist = np.empty((q.shape[0], 2), np.float32)
+        self._ck(self._lib.vsm_db_top2_masked(self._h, q.ctypes.data, q.shape[0], mask.ctypes.data, mask.shape[0],
+                                              idx.ctypes.data, dist.ctypes.data))
         return idx, dist
 
     def detect_candidates(self, frame_desc, ratio=0.75, want_matches=True):
