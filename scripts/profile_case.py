@@ -2,6 +2,7 @@
 event timings.  Usage: python scripts/profile_case.py <case> [reps]
   pair1000   1000x1000 match_features, mutual + ratio (BASELINE configs[1])
   pair2000   2000x2000 knn + ratio 0.8 (configs[0])
+  seg:<nkf>:<rows>:<nq>  LoopCloser block: per-keyframe top-2 + ratio over nkf stored keyframes
   db:<rows>:<nq>   global top-2 of nq queries over a <rows>-row resident DB (configs[2]/[3])
 """
 import os
@@ -40,6 +41,22 @@ def main():
             good, _ = m.match_features(ha, hb, 0.75, mutual=True, want_raw=False)
             dt = time.perf_counter() - t0
             print(case, "wall_us", round(dt * 1e6, 1), "matches", len(good), m.stats())
+    elif case.startswith("seg"):
+        _, nkf, rows, nq = case.split(":")
+        nkf, rows, nq = int(nkf), int(rows), int(nq)
+        db = unit(nkf * rows, g)
+        q = unit(nq, g)
+        torch.cuda.synchronize()
+        seg = np.arange(nkf + 1, dtype=np.int64) * rows
+        m.adopt_device_matrix(db.data_ptr(), nkf * rows, seg)
+        hq = q.cpu().pin_memory().numpy()
+        for r in range(reps + 3):
+            t0 = time.perf_counter()
+            counts, _ = m.detect_candidates(hq, 0.75, want_matches=False)
+            dt = time.perf_counter() - t0
+            st = m.stats()
+            tf = 2.0 * nq * nkf * rows * 256 / (st["tc_ms"] * 1e-3) / 1e12
+            print(case, "wall_ms", round(dt * 1e3, 3), "tc_TFLOPs", round(tf, 1), "max_count", int(counts.max()), st)
     else:
         _, rows, nq = case.split(":")
         rows, nq = int(rows), int(nq)

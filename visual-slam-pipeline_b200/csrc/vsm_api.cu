@@ -424,12 +424,16 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         }
     }
     if (qb[P] > 0) {
-        select_kernel<<<(unsigned)qb[P], SELECT_WARPS * 32, 0, ctx->stream>>>(
-            reinterpret_cast<const Problem*>(dd + off_prob), P, reinterpret_cast<const int32_t*>(dd + off_qb),
-            ctx->d_recs.p, reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key,
-            ctx->d_counters, ctx->d_work.p, WORK_CAP);
-        ctx->launches++;
-        CK(cudaGetLastError());
+        int max_blocks = 0;
+        for (int i = 0; i < P; i++) max_blocks = std::max(max_blocks, (probs[i].nq + SELECT_WARPS - 1) / SELECT_WARPS);
+        for (int p0 = 0; p0 < P; p0 += 65535) {                           // gridDim.y limit
+            const int np = std::min(65535, P - p0);
+            select_kernel<<<dim3((unsigned)max_blocks, (unsigned)np), SELECT_WARPS * 32, 0, ctx->stream>>>(
+                reinterpret_cast<const Problem*>(dd + off_prob), p0, ctx->d_recs.p,
+                reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters, ctx->d_work.p, WORK_CAP);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
         if (!units.empty()) {
             // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
             rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, WORK_CAP);

@@ -98,19 +98,14 @@ struct WorkItem {                      // self-contained: no descriptor look-ups
 };
 
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
-select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t* __restrict__ q_block0,
+select_kernel(const Problem* __restrict__ problems, int problem0,
               const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
               unsigned long long* __restrict__ out_key,
               unsigned long long* __restrict__ counters, WorkItem* __restrict__ work, uint32_t work_cap) {
-    // blockIdx -> problem (q_block0 is the exclusive prefix of blocks per problem)
-    int lo = 0, hi = nproblems - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (__ldg(q_block0 + mid) <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    const Problem P = problems[lo];
+    // grid: x = block of SELECT_WARPS queries, y = problem (ragged problems: surplus blocks exit)
+    const Problem P = problems[problem0 + blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = ((int)blockIdx.x - __ldg(q_block0 + lo)) * SELECT_WARPS + warp;
+    const int q = (int)blockIdx.x * SELECT_WARPS + warp;
     if (q >= P.nq) return;
     const int h = lane >> 4, l16 = lane & 15;
     const unsigned full = 0xffffffffu;
