@@ -70,7 +70,8 @@ typedef struct {
                                     pair frames, ragged batches); grows on demand; 0 = 8192 */
     int64_t store_rows;          /* initial capacity of the keyframe store in rows; it grows
                                     on demand; 0 = allocate at the first add */
-    int32_t reserved[8];         /* [0]: tiles per slice segment (0 = automatic) */
+    int32_t reserved[8];         /* [0]: tiles per slice segment (0 = automatic);
+                                    [1]: rescan work-list capacity (0 = default; tests shrink it) */
 } vsm_opts;
 
 typedef struct vsm_ctx vsm_ctx;

@@ -302,3 +302,68 @@ def test_masked_map_point_search(tc):
     with pytest.raises(vsm_b200.VsmError):
         tc.search_map_points_masked(q, np.ones(3, np.uint8))
     tc.clear_store()
+
+
+def test_work_list_overflow_scans_inline():
+    """A rescan work list that is too small: select falls back to scanning the slice itself."""
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, seg_tiles=1, work_cap=3)
+    q, t = cases.PAIR_CASES["neardup_db"]()
+    idx, dist = m.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    assert m.stats()["flagged_slices"] > 3
+    m.close()
+
+
+def test_multi_unit_train_set(tc):
+    """A train set longer than one work unit (64 tiles) and one slice: several units and slices
+    per query tile, shared hints across them."""
+    q, t, _ = gen.planted(77, 300, 40000, 0.6, 0.08)
+    idx, dist = tc.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+
+
+def test_many_queries(tc):
+    q, t, _ = gen.planted(78, 5000, 3000, 0.5, 0.08)
+    idx, dist = tc.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    good, raw = tc.match_features(q, t, 0.8, mutual=True)
+    og, orw = oracle.match_features(q, t, 0.8, mutual=True)
+    assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+
+
+def test_alternating_shapes_and_growth():
+    """Buffers grow, the descriptor-block cache is hit and missed, the store grows while in use."""
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, scratch_rows=256)
+    m.set_profiling(False)
+    rng = np.random.default_rng(5)
+    db_rows = []
+    for it in range(12):
+        nq, nt = int(rng.integers(1, 900)), int(rng.integers(2, 1200))
+        q, t, _ = gen.planted(200 + it, nq, nt, 0.5, 0.09)
+        for rep in range(2):                                   # second call: identical descriptor block
+            good, raw = m.match_features(q, t, 0.75, mutual=bool(it & 1))
+            og, orw = oracle.match_features(q, t, 0.75, mutual=bool(it & 1))
+            assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+        m.add_keyframe(it, t)
+        db_rows.append(t)
+        db = np.concatenate(db_rows)
+        gi, gd = m.search_map_points(q)
+        oi, od = oracle.knn(q, db, 2)
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    m.close()
+
+
+def test_batch_of_many_small_pairs(tc):
+    rng = np.random.default_rng(8)
+    qs, ts = [], []
+    for i in range(150):
+        nq, nt = int(rng.integers(0, 60)), int(rng.integers(0, 90))
+        qs.append(gen.rows(300 + i, 0, 0, nq))
+        ts.append(gen.rows(300 + i, 1, 0, nt))
+    got = tc.match_batch(qs, ts, 0.9, mutual=True)
+    for a, b, g in zip(qs, ts, got):
+        og, _ = oracle.match_features(a, b, 0.9, mutual=True)
+        assert g.tobytes() == og.tobytes()

@@ -102,6 +102,7 @@ struct vsm_ctx {
     PFN_encodeTiled encode = nullptr;
     int seg_tiles = 0;                   // 0 = automatic
     bool profiling = true;               // per-kernel events (tc_ms / select_ms)
+    uint32_t work_cap = 0;               // rescan work-list capacity (0 = WORK_CAP)
 };
 
 namespace {
@@ -430,13 +431,13 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             const int np = std::min(65535, P - p0);
             select_kernel<<<dim3((unsigned)max_blocks, (unsigned)np), SELECT_WARPS * 32, 0, ctx->stream>>>(
                 reinterpret_cast<const Problem*>(dd + off_prob), p0, ctx->d_recs.p,
-                reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters, ctx->d_work.p, WORK_CAP);
+                reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters, ctx->d_work.p, ctx->work_cap);
             ctx->launches++;
             CK(cudaGetLastError());
         }
         if (!units.empty()) {
             // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
-            rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, WORK_CAP);
+            rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, ctx->work_cap);
             ctx->launches++;
             CK(cudaGetLastError());
         }
@@ -532,6 +533,7 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
     ctx->engine = o.engine;
     ctx->num_sms = prop.multiProcessorCount;
     if (o.reserved[0] > 0) ctx->seg_tiles = o.reserved[0];
+    ctx->work_cap = o.reserved[1] > 0 ? std::min<uint32_t>((uint32_t)o.reserved[1], WORK_CAP) : WORK_CAP;
     auto bail = [&](int code) {
         g_create_error = ctx->err;
         vsm_destroy(ctx);

@@ -197,7 +197,13 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
                         work[base + k] = w;
                     }
                 } else {
+                    // list full: scan inline, and void the slots this reservation still owns so
+                    // that rescan_kernel never reads a stale item
                     inline_scan = true;
+                    for (uint32_t k = base; k < work_cap && k < base + nitem; k++) {
+                        WorkItem w = {nullptr, nullptr, nullptr, my, 0, 0};
+                        work[k] = w;
+                    }
                 }
             }
             unsigned fm = __ballot_sync(full, inline_scan);
@@ -240,6 +246,7 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     for (uint32_t it = blockIdx.x; it < nwork; it += gridDim.x) {
         const WorkItem w = work[it];
+        if (w.key == nullptr) continue;                 // voided slot (block-uniform)
         const SliceInfo si = w.si;
         const int span = slice_span(si);
         const int r1 = min(span, w.r0 + RESCAN_ROWS);

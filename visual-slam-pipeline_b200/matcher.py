@@ -110,12 +110,13 @@ def _rows(a, name):
 class Matcher:
     """One matching context on one GPU (single caller, synchronous calls)."""
 
-    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0):
+    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0):
         self._lib = load_library()
         o = _Opts()
         self._lib.vsm_default_opts(C.byref(o))
         o.device, o.engine, o.scratch_rows, o.store_rows = device, engine, scratch_rows, store_rows
         o.reserved[0] = seg_tiles
+        o.reserved[1] = work_cap
         h = C.c_void_p()
         st = self._lib.vsm_create(C.byref(o), C.byref(h))
         if st != 0:
