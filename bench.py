@@ -189,7 +189,7 @@ def workload_config(n_gpus, total_rows):
     return {"workload": f"loop-closure search: {NQ} query descriptors x {total_rows}-descriptor keyframe DB "
                         f"({total_rows // KF_ROWS} keyframes x {KF_ROWS}), exact global top-2 per query "
                         "(BASELINE configs[3])",
-            "nq": NQ, "db_rows": total_rows, "dim": 256, "sharding": f"db rows / {n_gpus} GPUs, allgather+merge",
+            "nq": NQ, "db_rows": total_rows, "dim": 256, "sharding": f"db rows / {n_gpus} GPUs, per-rank exact top-2 then key exchange + merge",
             "l2": "inputs larger than L2 (bf16 shard >= 1.28 GB vs 126 MB L2); no flush needed"}
 
 
@@ -368,7 +368,7 @@ def run_gpu(args):
     total_rows = args.rows
 
     sh = vsm_b200.load_sharded()
-    db = sh.ShardedDB(local, rank, world)
+    db = sh.ShardedDB(local, rank, world, exchange=args.exchange)
     q, noise = make_queries(torch, device)
     shard, off, planted = make_shard(torch, device, rank, world, q, noise, total_rows)
     seg = None   # one segment per shard for the global search
@@ -459,7 +459,7 @@ def run_gpu(args):
             "e2e": {"value": flops / (per_step_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": per_step_e2e,
                     "h2d_bytes_per_step": NQ * 1024, "d2h_bytes_per_step": NQ * 2 * 12,
                     "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)"},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange,
             "roofline": {"bound": "tensor", "kernel": "tc_top3_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": args.traffic if args.traffic is not None else committed_traffic(shard.shape[0]),
@@ -506,6 +506,8 @@ def main():
     ap.add_argument("--rows", type=int, default=TOTAL_ROWS, help="database rows in total (default: configs[3], 20M)")
     ap.add_argument("--ref-rows", type=int, default=100_000, help="reference arm: DB sample rows per step")
     ap.add_argument("--cpu-rows", type=int, default=100_000, help="cpu_baseline: DB sample rows")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: fused peer-memory exchange (default) or NCCL all-gather + merge")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,

@@ -214,6 +214,21 @@ int vsm_db_top2_keys_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int6
 int vsm_merge_keys_device(vsm_ctx* ctx, const uint64_t* d_keys_in, int32_t nshard, int32_t nq,
                           int64_t* d_idx_out, float* d_dist_out, int32_t sync);
 
+/* ---- fused exchange over peer memory (one process per GPU, NVLink / NVSwitch) -------------------
+ * Instead of an NCCL all-gather between the search and the merge, every rank STORES its result keys
+ * straight into all peers' gather buffers (P2P over NVLink), raises a per-peer flag, waits for the
+ * peers' flags and merges -- one kernel after the local search, no collective launch.
+ *   vsm_xchg_create   allocates this rank's buffer (2 parities x world x nq_cap keys + flags) and
+ *                     returns its 64-byte CUDA IPC handle; exchange the handles between the ranks
+ *                     (any transport) and pass all of them, in rank order, to vsm_xchg_connect.
+ *                     All ranks must have connected before the first search (barrier).
+ *   vsm_db_top2_xchg_device   = vsm_db_top2_keys_device + publish + wait + merge.  Collective: every
+ *                     rank of the group must call it the same number of times with the same nq. */
+int vsm_xchg_create(vsm_ctx* ctx, int32_t rank, int32_t world, int32_t nq_cap, uint8_t handle_out[64]);
+int vsm_xchg_connect(vsm_ctx* ctx, const uint8_t* handles /* [world][64] */);
+int vsm_db_top2_xchg_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset,
+                            int64_t* d_idx_out, float* d_dist_out, int32_t sync);
+
 /* Merge per-shard top-2 lists (e.g. after an NCCL all-gather) by (distance, index).
  * d_idx_in/d_dist_in: [nshard][nq][2] with GLOBAL indices (-1 = empty). */
 int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_dist_in,

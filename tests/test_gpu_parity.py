@@ -367,3 +367,30 @@ def test_batch_of_many_small_pairs(tc):
     for a, b, g in zip(qs, ts, got):
         og, _ = oracle.match_features(a, b, 0.9, mutual=True)
         assert g.tobytes() == og.tobytes()
+
+
+def test_fused_exchange_single_rank(tc):
+    """The peer-memory exchange kernel with world = 1 (publish to self, flag, merge) must equal
+    the plain device search; the multi-rank path is exercised by bench.py --gpus N (checksum)."""
+    import torch
+    q, db, _ = cases.db_case()
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR)
+    d_db = torch.from_numpy(db).cuda()
+    d_q = torch.from_numpy(q).cuda()
+    torch.cuda.synchronize()
+    m.adopt_device_matrix(d_db.data_ptr(), db.shape[0])
+    h = m.xchg_create(0, 1, 512)
+    assert len(h) == 64
+    m.xchg_connect([h])
+    oi = torch.empty((q.shape[0], 2), dtype=torch.int64, device="cuda")
+    od = torch.empty((q.shape[0], 2), dtype=torch.float32, device="cuda")
+    wi, wd = oracle.knn(q, db, 2)
+    for step in range(3):                                   # both parities
+        oi.zero_(); od.zero_()
+        torch.cuda.synchronize()
+        m.db_top2_xchg_device(d_q.data_ptr(), q.shape[0], 1000, oi.data_ptr(), od.data_ptr(), sync=True)
+        assert np.array_equal(oi.cpu().numpy(), wi + 1000) and np.array_equal(bits(od.cpu().numpy()), bits(wd))
+    with pytest.raises(vsm_b200.VsmError):
+        big = torch.zeros((600, 256), device="cuda")
+        m.db_top2_xchg_device(big.data_ptr(), 600, 0, oi.data_ptr(), od.data_ptr(), sync=True)   # above nq_cap
+    m.close()

@@ -100,6 +100,13 @@ struct vsm_ctx {
     int launches = 0;
     std::string err;
     PFN_encodeTiled encode = nullptr;
+    // fused exchange over peer memory
+    uint8_t* xchg_buf = nullptr;
+    void* xchg_peer_ptr[XCHG_MAX_WORLD] = {};
+    XchgPeers xchg_peers{};
+    int xchg_rank = 0, xchg_world = 0, xchg_nq_cap = 0;
+    uint32_t xchg_step = 0;
+    bool xchg_connected = false;
     int seg_tiles = 0;                   // 0 = automatic
     bool profiling = true;               // per-kernel events (tc_ms / select_ms)
     uint32_t work_cap = 0;               // rescan work-list capacity (0 = WORK_CAP)
@@ -574,6 +581,9 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     arena_free(ctx->scratch);
     arena_free(ctx->store);
+    for (int r = 0; r < ctx->xchg_world; r++)
+        if (r != ctx->xchg_rank && ctx->xchg_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->xchg_peer_ptr[r]);
+    if (ctx->xchg_buf) cudaFree(ctx->xchg_buf);
     if (ctx->d_store_stats) cudaFree(ctx->d_store_stats);
     if (ctx->d_desc.p) cudaFree(ctx->d_desc.p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
@@ -1077,6 +1087,60 @@ int vsm_db_top2_keys_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int6
     TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
     globalize_keys_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->d_out_key, nq * 2, (uint32_t)row_offset, reinterpret_cast<unsigned long long*>(d_keys));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return end_call(ctx, sync != 0);
+}
+
+int vsm_xchg_create(vsm_ctx* ctx, int32_t rank, int32_t world, int32_t nq_cap, uint8_t handle_out[64]) {
+    if (!ctx || !handle_out || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world || nq_cap <= 0)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_xchg_create: bad argument") : VSM_ERR_INVALID;
+    if (ctx->xchg_buf) return fail(ctx, VSM_ERR_INVALID, "vsm_xchg_create: already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = XCHG_FLAG_BYTES + (size_t)2 * world * nq_cap * 2 * sizeof(unsigned long long);
+    CK(cudaMalloc(&ctx->xchg_buf, bytes));
+    CK(cudaMemset(ctx->xchg_buf, 0, bytes));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->xchg_buf));
+    memcpy(handle_out, &h, 64);
+    ctx->xchg_rank = rank; ctx->xchg_world = world; ctx->xchg_nq_cap = nq_cap; ctx->xchg_step = 0;
+    return VSM_OK;
+}
+
+int vsm_xchg_connect(vsm_ctx* ctx, const uint8_t* handles) {
+    if (!ctx || !handles || !ctx->xchg_buf) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_xchg_connect: create first") : VSM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->xchg_world; r++) {
+        if (r == ctx->xchg_rank) { ctx->xchg_peer_ptr[r] = ctx->xchg_buf; }
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * 64, 64);
+            CK(cudaIpcOpenMemHandle(&ctx->xchg_peer_ptr[r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        ctx->xchg_peers.base[r] = (unsigned long long)(uintptr_t)ctx->xchg_peer_ptr[r];
+    }
+    ctx->xchg_connected = true;
+    return VSM_OK;
+}
+
+int vsm_db_top2_xchg_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset, int64_t* d_idx_out,
+                            float* d_dist_out, int32_t sync) {
+    if (!ctx || nq <= 0 || !d_query || !d_idx_out || !d_dist_out || row_offset < 0 ||
+        row_offset + ctx->store_rows > 0xFFFFFFFFll)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_xchg_device: bad argument") : VSM_ERR_INVALID;
+    if (!ctx->xchg_connected || nq > ctx->xchg_nq_cap)
+        return fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_xchg_device: exchange not connected or nq above its capacity");
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    HProblem p;
+    db_problem(ctx, d_query, nq, p);
+    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq));
+    ctx->xchg_step++;
+    xchg_publish_merge_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_out_key, nq, (uint32_t)row_offset, ctx->xchg_peers,
+                                                          ctx->xchg_rank, ctx->xchg_world, ctx->xchg_nq_cap, ctx->xchg_step,
+                                                          d_idx_out, d_dist_out);
     ctx->launches++;
     CK(cudaGetLastError());
     return end_call(ctx, sync != 0);

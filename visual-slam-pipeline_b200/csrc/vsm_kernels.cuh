@@ -415,4 +415,75 @@ __global__ void merge_keys_kernel(const unsigned long long* __restrict__ keys, i
     }
 }
 
+// ---- fused exchange over peer memory -----------------------------------------------------------
+// Per rank one buffer: flags[2][XCHG_MAX_WORLD] (u32) then keys[2][world][nq_cap][2] (u64).
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr size_t XCHG_FLAG_BYTES = 2 * XCHG_MAX_WORLD * sizeof(uint32_t);      // 128
+struct XchgPeers {
+    unsigned long long base[XCHG_MAX_WORLD];       // device addresses of every rank's buffer (own = local)
+};
+__device__ __forceinline__ uint32_t* xchg_flags(unsigned long long base, int parity) {
+    return reinterpret_cast<uint32_t*>(base) + parity * XCHG_MAX_WORLD;
+}
+__device__ __forceinline__ unsigned long long* xchg_keys(unsigned long long base, int parity, int world, int nq_cap,
+                                                         int src_rank) {
+    return reinterpret_cast<unsigned long long*>(base + XCHG_FLAG_BYTES) +
+           ((size_t)parity * world + src_rank) * (size_t)nq_cap * 2;
+}
+
+// One block.  (1) publish: this rank's keys (with global indices) are stored into EVERY rank's buffer
+// -- peer stores travel over NVLink; (2) one flag per peer says "rank `rank`'s keys of step `step`
+// are complete"; (3) wait for every peer's flag in the OWN buffer; (4) merge the world x 2 keys per
+// query.  Two parities: a rank may publish step k+1 while a slower peer still merges step k.
+__global__ void __launch_bounds__(1024)
+xchg_publish_merge_kernel(const unsigned long long* __restrict__ out_key, int nq, uint32_t row_offset, XchgPeers peers,
+                          int rank, int world, int nq_cap, uint32_t step, int64_t* __restrict__ idx_out,
+                          float* __restrict__ dist_out) {
+    const int parity = step & 1;
+    const int n = nq * 2;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = out_key[i];
+        const unsigned long long g = k == 0ull ? 0ull : ~((~k) + row_offset);
+        for (int p = 0; p < world; p++) {
+            const int dst = (rank + p) % world;                         // spread the peers over time
+            xchg_keys(peers.base[dst], parity, world, nq_cap, rank)[i] = g;
+        }
+    }
+    __threadfence_system();                                             // my stores are visible system-wide ...
+    __syncthreads();                                                    // ... and so are everybody's in this block
+    if (threadIdx.x < world) {
+        volatile uint32_t* f = xchg_flags(peers.base[threadIdx.x], parity) + rank;
+        *f = step;                                                      // raise my flag at peer threadIdx.x
+        __threadfence_system();
+        // wait for peer threadIdx.x's flag in my own buffer (bounded: a dead peer must not hang the GPU)
+        volatile uint32_t* w = xchg_flags(peers.base[rank], parity) + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t)(*w - step) < 0) {
+            if (clock64() - t0 > 20000000000LL) __trap();               // ~10 s
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        unsigned long long k0 = 0ull, k1 = 0ull;
+        for (int s = 0; s < world; s++) {
+            const volatile unsigned long long* ks = xchg_keys(peers.base[rank], parity, world, nq_cap, s) + 2 * q;
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const unsigned long long k = ks[p];
+                if (k > k0) { k1 = k0; k0 = k; } else if (k > k1) k1 = k;
+            }
+        }
+        const unsigned long long kk[2] = {k0, k1};
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            if (kk[p] == 0ull) { idx_out[2 * q + p] = -1; dist_out[2 * q + p] = FLT_MAX; continue; }
+            const unsigned long long u = ~kk[p];
+            idx_out[2 * q + p] = (int64_t)(uint32_t)u;
+            dist_out[2 * q + p] = __uint_as_float((uint32_t)(u >> 32));
+        }
+    }
+}
+
 }  // namespace vsm

@@ -73,6 +73,9 @@ SYMBOLS = {
     "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_db_top2_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]),
     "vsm_merge_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsm_xchg_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vsm_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vsm_db_top2_xchg_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_merge_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32]),
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
@@ -317,6 +320,21 @@ class Matcher:
     def merge_keys_device(self, d_keys_in, nshard, nq, d_idx_out, d_dist_out, sync=False):
         self._ck(self._lib.vsm_merge_keys_device(self._h, C.c_void_p(d_keys_in), nshard, nq, C.c_void_p(d_idx_out),
                                                  C.c_void_p(d_dist_out), int(sync)))
+
+    def xchg_create(self, rank, world, nq_cap):
+        """Allocate this rank's peer-exchange buffer; returns its 64-byte CUDA IPC handle."""
+        h = (C.c_uint8 * 64)()
+        self._ck(self._lib.vsm_xchg_create(self._h, rank, world, nq_cap, h))
+        return bytes(h)
+
+    def xchg_connect(self, handles):
+        """handles: list of every rank's 64-byte IPC handle, in rank order."""
+        blob = b"".join(handles)
+        self._ck(self._lib.vsm_xchg_connect(self._h, blob))
+
+    def db_top2_xchg_device(self, d_query_ptr, nq, row_offset, d_idx_ptr, d_dist_ptr, sync=False):
+        self._ck(self._lib.vsm_db_top2_xchg_device(self._h, C.c_void_p(d_query_ptr), nq, row_offset,
+                                                   C.c_void_p(d_idx_ptr), C.c_void_p(d_dist_ptr), int(sync)))
 
     def merge_top2_device(self, d_idx_in, d_dist_in, nshard, nq, d_idx_out, d_dist_out, sync=False):
         self._ck(self._lib.vsm_merge_top2_device(self._h, C.c_void_p(d_idx_in), C.c_void_p(d_dist_in), nshard, nq,

@@ -49,12 +49,23 @@ def gather_and_merge(l_idx, l_dist, world, group, merge, g_idx=None, g_dist=None
 
 
 class ShardedDB:
-    def __init__(self, device, rank=0, world=1, group=None, engine=ENGINE_TENSOR):
+    def __init__(self, device, rank=0, world=1, group=None, engine=ENGINE_TENSOR, exchange="p2p", nq_cap=4096):
+        """exchange: "p2p"  = result keys stored straight into the peers' buffers over NVLink and merged
+                              in the same kernel (libvsm's fused exchange; CUDA IPC handles are swapped
+                              once through the process group);
+                     "nccl" = all_gather_into_tensor of the keys + merge kernel."""
         self.rank, self.world, self.group = rank, world, group
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.matcher = Matcher(device=device, engine=engine)
         self.matcher.set_stream(self.stream.cuda_stream)
+        self.exchange = exchange if world > 1 else "none"
+        if self.exchange == "p2p":
+            mine = self.matcher.xchg_create(rank, world, nq_cap)
+            handles = [None] * world
+            torch.distributed.all_gather_object(handles, mine, group=group)
+            self.matcher.xchg_connect(handles)
+            torch.distributed.barrier(group=group)          # every buffer is zeroed and mapped before first use
         self.row_offset = 0
         self.rows = 0
         self._db = None
@@ -96,6 +107,9 @@ class ShardedDB:
             if self.world == 1:
                 self.matcher.db_top2_device(d_q.data_ptr(), nq, self.row_offset, self.l_idx.data_ptr(),
                                             self.l_dist.data_ptr(), sync=False)
+            elif self.exchange == "p2p":
+                self.matcher.db_top2_xchg_device(d_q.data_ptr(), nq, self.row_offset, self.o_idx.data_ptr(),
+                                                 self.o_dist.data_ptr(), sync=False)
             else:
                 # one 16 B x nq buffer per rank: keys ~((distance bits << 32) | global index)
                 self.matcher.db_top2_keys_device(d_q.data_ptr(), nq, self.row_offset, self.l_keys.data_ptr(), sync=False)
@@ -117,7 +131,7 @@ class ShardedDB:
         return self.h_idx, self.h_dist
 
     def launches_per_search(self):
-        return self.matcher.stats()["kernel_launches"] + (1 if self.world > 1 else 0)
+        return self.matcher.stats()["kernel_launches"] + (1 if self.exchange == "nccl" else 0)
 
     def close(self):
         self.matcher.close()
