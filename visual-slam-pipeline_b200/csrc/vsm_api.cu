@@ -84,6 +84,7 @@ struct vsm_ctx {
     DevBuf<PartialRec> d_recs;
     unsigned long long* d_out_key = nullptr;     // [query][2] result keys, inside d_aux (zeroed per call)
     DevBuf<uint8_t> d_result;            // DMatch lists followed by the counts
+    bool result_on_host = false;         // small results: filter_kernel writes straight into pinned h_result
     uint8_t* h_result = nullptr;
     size_t h_result_cap = 0;
     // zeroed per call: [0] candidates, [1] flagged slices (u64), [2] rescan work count, then
@@ -240,7 +241,7 @@ int collect_stats(vsm_ctx* ctx) {
     if (ctx->timed_tc) CK(cudaEventElapsedTime(&ctx->stats.tc_ms, ctx->ev_tc0, ctx->ev_tc1));
     if (ctx->timed_sel) CK(cudaEventElapsedTime(&ctx->stats.select_ms, ctx->timed_tc ? ctx->ev_tc1 : ctx->ev_tc0, ctx->ev_sel1));
     unsigned long long c[2] = {0, 0};
-    if (ctx->d_counters) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (ctx->d_counters && ctx->profiling) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.candidates = (int64_t)c[0];
     ctx->stats.flagged_slices = (int64_t)c[1];
     return VSM_OK;
@@ -358,7 +359,11 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
     TRY(ensure(ctx, ctx->d_recs, (size_t)std::max<int64_t>(nrecs, 1)));
     const size_t result_bytes = (size_t)total_matches * sizeof(DMatch) + jobs.size() * 2 * sizeof(int32_t);
-    TRY(ensure(ctx, ctx->d_result, std::max<size_t>(result_bytes, 16)));
+    // small result lists are written by filter_kernel straight into the pinned host buffer
+    // (zero-copy over PCIe): one stream operation and ~10 us less per tracking step
+    ctx->result_on_host = !jobs.empty() && result_bytes <= ((size_t)1 << 20);
+    if (ctx->result_on_host) TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(result_bytes, 16)));
+    else TRY(ensure(ctx, ctx->d_result, std::max<size_t>(result_bytes, 16)));
 
     const size_t nout = (size_t)std::max<int64_t>(total_out, 1);
     const size_t off_keys = align16(48 + nout * sizeof(uint32_t));
@@ -454,8 +459,9 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         }
     }
     if (!jobs.empty()) {
-        DMatch* dm = reinterpret_cast<DMatch*>(ctx->d_result.p);
-        int32_t* dc = reinterpret_cast<int32_t*>(ctx->d_result.p + (size_t)total_matches * sizeof(DMatch));
+        uint8_t* rbase = ctx->result_on_host ? ctx->h_result : ctx->d_result.p;
+        DMatch* dm = reinterpret_cast<DMatch*>(rbase);
+        int32_t* dc = reinterpret_cast<int32_t*>(rbase + (size_t)total_matches * sizeof(DMatch));
         filter_kernel<<<(unsigned)jobs.size(), FILTER_THREADS, 0, ctx->stream>>>(
             reinterpret_cast<const FilterJob*>(dd + off_job), ctx->d_out_key, dm, dc);
         ctx->launches++;
@@ -473,6 +479,7 @@ int upload_scratch(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n) {
 }
 
 int fetch_result(vsm_ctx* ctx, size_t bytes) {
+    if (ctx->result_on_host) return VSM_OK;                  // already there once the stream is idle
     TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(bytes, 16)));
     if (bytes) CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return VSM_OK;
@@ -1023,20 +1030,29 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
     TRY(run_problems(ctx, probs, jobs, total_matches, total_matches, ctx->scratch.f32, 0, nq));
     const size_t mbytes = (size_t)total_matches * sizeof(DMatch);
     const size_t cbytes = jobs.size() * 2 * sizeof(int32_t);
-    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, cbytes));
-    CK(cudaMemcpyAsync(ctx->h_result, ctx->d_result.p + mbytes, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
-    if (matches) {
-        if (!eligible) {
-            CK(cudaMemcpyAsync(matches, ctx->d_result.p, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
-        } else {
-            for (size_t k = 0; k < jobs.size(); k++)       // slot k -> keyframe job_seg[k]
-                CK(cudaMemcpyAsync(matches + (size_t)job_seg[k] * nq, ctx->d_result.p + k * (size_t)nq * sizeof(DMatch),
-                                   (size_t)nq * sizeof(DMatch), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int32_t> cnt(jobs.size() * 2);
+    if (ctx->result_on_host) {
+        TRY(end_call(ctx, true));
+        memcpy(cnt.data(), ctx->h_result + mbytes, cbytes);
+        if (matches) {
+            for (size_t k = 0; k < jobs.size(); k++)
+                memcpy(matches + (size_t)job_seg[k] * nq, ctx->h_result + k * (size_t)nq * sizeof(DMatch),
+                       (size_t)cnt[2 * k] * sizeof(DMatch));
         }
+    } else {
+        CK(cudaMemcpyAsync(cnt.data(), ctx->d_result.p + mbytes, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (matches) {
+            if (!eligible) {
+                CK(cudaMemcpyAsync(matches, ctx->d_result.p, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
+            } else {
+                for (size_t k = 0; k < jobs.size(); k++)       // slot k -> keyframe job_seg[k]
+                    CK(cudaMemcpyAsync(matches + (size_t)job_seg[k] * nq, ctx->d_result.p + k * (size_t)nq * sizeof(DMatch),
+                                       (size_t)nq * sizeof(DMatch), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        }
+        TRY(end_call(ctx, true));
     }
-    TRY(end_call(ctx, true));
-    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result);
-    for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = c[2 * k];
+    for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = cnt[2 * k];
     return VSM_OK;
 }
 
