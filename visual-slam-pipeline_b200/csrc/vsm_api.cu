@@ -927,10 +927,24 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
     TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + std::max<int64_t>(n_cur, 1), ctx->store_rows));
     const int64_t row0 = ctx->store_rows;
     if (n_cur > 0) {
-        CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, cur, (size_t)n_cur * VSM_DIM * sizeof(float),
-                           cudaMemcpyHostToDevice, ctx->stream));
-        TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
-                           ctx->store.n2 + row0, n_cur, ctx->d_store_stats));
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, cur) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+                            attr.devicePointer != nullptr;
+        if (!pinned) cudaGetLastError();
+        if (pinned && n_cur <= 8192) {
+            // pinned frame: one kernel reads it over PCIe and writes fp32 master + bf16 shadow + norms
+            const int64_t blocks = std::min<int64_t>((n_cur + 7) / 8, (int64_t)ctx->num_sms * 16);
+            convert_from_host_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                static_cast<const float*>(attr.devicePointer), ctx->store.f32 + row0 * VSM_DIM,
+                ctx->store.b16 + row0 * VSM_DIM, ctx->store.n2 + row0, n_cur, ctx->d_store_stats);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, cur, (size_t)n_cur * VSM_DIM * sizeof(float),
+                               cudaMemcpyHostToDevice, ctx->stream));
+            TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
+                               ctx->store.n2 + row0, n_cur, ctx->d_store_stats));
+        }
     }
     Seg ns = {row0, n_cur, frame_id};
     ctx->segs.push_back(ns);

@@ -43,6 +43,43 @@ convert_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, f
     }
 }
 
+// Same, reading the rows straight from pinned HOST memory (zero-copy over PCIe) and also writing
+// the fp32 master copy: upload + convert of a tracking frame in one kernel instead of a DMA
+// followed by a kernel.
+__global__ void __launch_bounds__(256)
+convert_from_host_kernel(const float* __restrict__ src_host, float* __restrict__ dst_f32,
+                         __nv_bfloat16* __restrict__ dst, float* __restrict__ n2, int64_t nrows,
+                         uint32_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float lo = INFINITY, hi = 0.f;
+    for (int64_t row = warp0; row < nrows; row += nwarps) {
+        const float4* p = reinterpret_cast<const float4*>(src_host + row * VSM_DIM) + lane * 2;
+        const float4 a = p[0], b = p[1];
+        float4* o = reinterpret_cast<float4*>(dst_f32 + row * VSM_DIM) + lane * 2;
+        o[0] = a; o[1] = b;
+        float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+        __nv_bfloat162 o0 = __floats2bfloat162_rn(a.x, a.y), o1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 o2b = __floats2bfloat162_rn(b.x, b.y), o3 = __floats2bfloat162_rn(b.z, b.w);
+        uint4 packed;
+        packed.x = *reinterpret_cast<uint32_t*>(&o0);
+        packed.y = *reinterpret_cast<uint32_t*>(&o1);
+        packed.z = *reinterpret_cast<uint32_t*>(&o2b);
+        packed.w = *reinterpret_cast<uint32_t*>(&o3);
+        reinterpret_cast<uint4*>(dst + row * VSM_DIM)[lane] = packed;
+        if (lane == 0) n2[row] = s;
+        lo = fminf(lo, s);
+        hi = fmaxf(hi, s);
+    }
+    if (lane == 0 && lo <= hi) {
+        atomicMax(stats, ~__float_as_uint(lo));
+        atomicMax(stats + 1, __float_as_uint(hi));
+    }
+}
+
 // ---- select / exact re-score ---------------------------------------------------
 constexpr int SELECT_WARPS = 4;
 
