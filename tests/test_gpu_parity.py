@@ -394,3 +394,50 @@ def test_fused_exchange_single_rank(tc):
         big = torch.zeros((600, 256), device="cuda")
         m.db_top2_xchg_device(big.data_ptr(), 600, 0, oi.data_ptr(), od.data_ptr(), sync=True)   # above nq_cap
     m.close()
+
+
+def _unit_rows(rng, n):
+    x = rng.standard_normal((n, 256), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def test_baseline_config2_full_size(tc):
+    """BASELINE configs[2] at full size: 1000 queries x 500 keyframes x 1000 descriptors (500K rows),
+    global top-2, every index and every distance bit against the CPU oracle."""
+    rng = np.random.default_rng(2024)
+    db = _unit_rows(rng, 500_000)
+    q = _unit_rows(rng, 1000)
+    rows = rng.integers(0, db.shape[0], 200)
+    v = db[rows] + 0.05 * rng.standard_normal((200, 256), dtype=np.float32)      # 20 % planted re-observations
+    q[:200] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    tc.clear_store()
+    for kf in range(0, 500, 50):                                   # 10 uploads of 50 keyframes' worth
+        tc.add_keyframe(kf, db[kf * 1000:(kf + 50) * 1000])
+    idx, dist = tc.search_map_points(q)
+    oi, od = oracle.knn(q, db, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    assert np.array_equal(idx[:200, 0], rows)
+    tc.clear_store()
+
+
+def test_baseline_config4_full_size(tc):
+    """BASELINE configs[4] at full size: 64 ragged pairs, sizes U{200..2048}, mutual-NN + ratio 0.75."""
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(200, 2049, size=(64, 2))
+    qs, ts = [], []
+    for nq, nt in sizes:
+        a = _unit_rows(rng, int(nq))
+        b = _unit_rows(rng, int(nt))
+        k = int(0.6 * min(nq, nt))
+        v = a[:k] + 0.08 * rng.standard_normal((k, 256), dtype=np.float32)
+        b[:k] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        qs.append(a)
+        ts.append(b)
+    got = tc.match_batch(qs, ts, 0.75, mutual=True)
+    total = 0
+    for a, b, g in zip(qs, ts, got):
+        og, _ = oracle.match_features(a, b, 0.75, mutual=True)
+        assert g.tobytes() == og.tobytes()
+        total += len(g)
+    assert total > 64 * 50

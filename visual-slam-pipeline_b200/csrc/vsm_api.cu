@@ -258,10 +258,10 @@ int end_call(vsm_ctx* ctx, bool sync) {
     return VSM_OK;
 }
 
-// Plans, uploads and launches: tensor-core pass -> select/re-score -> filter.
-// The scratch stats slot lives at the head of the descriptor block; `conv_*` describes
-// the scratch rows that still have to be converted (after the block is uploaded, because
-// the upload re-arms the slot).
+// Plans, uploads and launches: tensor-core pass -> select/re-score (+ re-scan) -> filter.
+// `conv_*` describes the scratch rows that still have to be converted; the conversion is
+// launched here, after the per-call aux block (counters, unit queue head, scratch norm
+// statistics, hints, result keys) has been zeroed.
 int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::vector<HJob>& jobs,
                  int64_t total_out, int64_t total_matches, const float* conv_src, int64_t conv_row0,
                  int64_t conv_rows, int dump_first = 0) {
