@@ -188,6 +188,37 @@ int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
 int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8_t* mask, int64_t n_mask,
                        int64_t* idx, float* dist);
 
+/* ---- projected-window map-point tracking (Slam::track_local_map, src/Slam.cpp:380-469) ---------
+ * For every valid map point: project it with the frame pose (fp64, :417-428), take the keypoints
+ * within search_radius pixels (:452-454; the reference walks a 30-px cell grid, the same set),
+ * keep the one with the smallest descriptor distance below desc_threshold (:456-460, cv::norm in
+ * double), then assign map points to keypoints in map-point order, a later point replacing an
+ * earlier one only with a strictly smaller distance (:465-470).
+ * Distances are sqrt(sum((double)a-(double)b)^2) in fp64; OpenCV's cv::norm uses a dispatch-dependent
+ * summation order, so they agree to ~1e-15 relative, decisions except on such near-ties. */
+typedef struct {
+    double fx, fy, cx, cy;           /* Config::FX, FY, CX, CY (include/Config.h:14-17) */
+    int32_t width, height;           /* Config::IMAGE_WIDTH, IMAGE_HEIGHT (:10-11) */
+    int32_t cell_size;               /* Config::TRACK_GRID_CELL_SIZE (:108): fixes the visiting order of ties */
+    int32_t reserved;
+    double depth_min, depth_max;     /* (double)Config::DEPTH_MIN (:29), Config::TRIANG_MAX_DEPTH (:72) */
+    double search_radius;            /* Config::TRACK_SEARCH_RADIUS (:109) */
+    double desc_threshold;           /* Config::TRACK_DESC_THRESHOLD (:110) */
+} vsm_track_cfg;
+
+/* kp_xy: [nkp][2] keypoint pixel coordinates, desc: [nkp][256] the frame's descriptors;
+ * mp_pos: [nmp][3] map-point positions, mp_desc: [nmp][256] their descriptors (NULL: the first nmp
+ * rows of the keyframe store are the map-point descriptors), mp_valid: [nmp] (NULL = all valid);
+ * R_cam (row-major 3x3), t_cam: world -> camera (the reference's R.t(), -R.t()*t, :404-407).
+ * indices: [nkp] in/out = frame->map_point_indices(); obs_mp / obs_ki: [nmp] the (map point,
+ * keypoint) pairs for MapPoint::add_observation in the order the reference adds them (:468),
+ * *tracked = their count (the function's return value, :469).  best_ki / best_dist ([nmp], may be
+ * NULL): per map point the chosen keypoint (-1 = none) and its distance. */
+int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_xy, const float* desc, int32_t nkp,
+                        const double* mp_pos, const float* mp_desc, const uint8_t* mp_valid, int32_t nmp,
+                        const double* R_cam, const double* t_cam, int32_t* indices, int32_t* obs_mp,
+                        int32_t* obs_ki, int32_t* tracked, int32_t* best_ki, double* best_dist);
+
 /* LoopCloser::detect's candidate loop WITH its eligibility rules (src/LoopCloser.cpp:43-62):
  * stored keyframes are visited in store order; a keyframe is skipped when
  * cur_frame_id - frame_id < min_gap (:44, Config::LC_MIN_FRAME_GAP = 200) or it is empty (:45);

@@ -137,3 +137,68 @@ def loop_detect(q, db, seg_off, frame_ids, cur_frame_id, ratio=0.75, min_gap=200
         status[s] = len(good)
         lists[s] = good
     return status, lists
+
+
+def track_local_map(kp_xy, desc, mp_pos, mp_desc, mp_valid, R_cam, t_cam, indices, cfg=None):
+    """Slam::track_local_map (src/Slam.cpp:380-469) restated loop for loop: the 30-px cell grid
+    (:391-401), fp64 projection (:417-428), the window of cells (:431-434), the radius test
+    (:452-454), cv::norm in double (:456; here numpy float64, see include/vsm.h on its summation
+    order) and the sequential assignment (:465-470).  indices is updated in place.
+    Returns (tracked, observations, best_ki[nmp], best_dist[nmp])."""
+    c = dict(fx=525.0, fy=525.0, cx=319.5, cy=239.5, width=640, height=480, cell_size=30,
+             depth_min=float(np.float32(0.1)), depth_max=50.0, search_radius=12.0, desc_threshold=0.5)
+    c.update(cfg or {})
+    kp = np.asarray(kp_xy, np.float32).reshape(-1, 2)
+    nkp, nmp = kp.shape[0], len(mp_pos)
+    best_ki = -np.ones(nmp, np.int32)
+    best_dist = np.full(nmp, c["desc_threshold"], np.float64)
+    if nkp == 0 or nmp == 0:
+        return 0, [], best_ki, best_dist
+    CELL = c["cell_size"]
+    GW, GH = (c["width"] + CELL - 1) // CELL, (c["height"] + CELL - 1) // CELL
+    grid = [[] for _ in range(GW * GH)]
+    for ki in range(nkp):
+        gx = min(int(np.float32(kp[ki, 0]) / np.float32(CELL)), GW - 1)     # int() truncates like the C cast
+        gy = min(int(np.float32(kp[ki, 1]) / np.float32(CELL)), GH - 1)
+        if gx >= 0 and gy >= 0:
+            grid[gy * GW + gx].append(ki)
+    R = np.asarray(R_cam, np.float64).reshape(3, 3)
+    t = np.asarray(t_cam, np.float64).reshape(3)
+    RAD = c["search_radius"]
+    d64 = np.asarray(desc, np.float32).astype(np.float64)
+    best_desc_dist = np.full(nkp, 1e9)
+    tracked, obs = 0, []
+    for mp in range(nmp):
+        if mp_valid is not None and not mp_valid[mp]:
+            continue
+        X, Y, Z = (float(v) for v in mp_pos[mp])
+        px = R[0, 0] * X + R[0, 1] * Y + R[0, 2] * Z + t[0]
+        py = R[1, 0] * X + R[1, 1] * Y + R[1, 2] * Z + t[1]
+        pz = R[2, 0] * X + R[2, 1] * Y + R[2, 2] * Z + t[2]
+        if pz < c["depth_min"] or pz > c["depth_max"]:
+            continue
+        u = c["fx"] * px / pz + c["cx"]
+        v = c["fy"] * py / pz + c["cy"]
+        if u < 0 or u >= c["width"] or v < 0 or v >= c["height"]:
+            continue
+        gx0, gy0 = max(0, int((u - RAD) / CELL)), max(0, int((v - RAD) / CELL))
+        gx1, gy1 = min(GW - 1, int((u + RAD) / CELL)), min(GH - 1, int((v + RAD) / CELL))
+        bk, bd = -1, c["desc_threshold"]
+        m64 = np.asarray(mp_desc[mp], np.float32).astype(np.float64)
+        for gy in range(gy0, gy1 + 1):
+            for gx in range(gx0, gx1 + 1):
+                for ki in grid[gy * GW + gx]:
+                    dx, dy = u - float(kp[ki, 0]), v - float(kp[ki, 1])
+                    if dx * dx + dy * dy > RAD * RAD:
+                        continue
+                    dd = m64 - d64[ki]
+                    dist = float(np.sqrt(np.dot(dd, dd)))
+                    if dist < bd:
+                        bd, bk = dist, ki
+        best_ki[mp], best_dist[mp] = bk, bd
+        if bk >= 0 and bd < best_desc_dist[bk]:
+            indices[bk] = mp
+            best_desc_dist[bk] = bd
+            obs.append((mp, bk))
+            tracked += 1
+    return tracked, obs, best_ki, best_dist

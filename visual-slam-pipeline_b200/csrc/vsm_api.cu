@@ -93,6 +93,7 @@ struct vsm_ctx {
     unsigned long long* d_counters = nullptr;    // = d_aux.p
     DevBuf<WorkItem> d_work;
     DevBuf<int32_t> d_sel;                       // selected store rows of a masked search
+    DevBuf<uint8_t> d_track;                     // track_local_map: keypoints, map-point positions, results
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_tc0 = nullptr, ev_tc1 = nullptr, ev_sel1 = nullptr;
@@ -600,6 +601,7 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_aux.p) cudaFree(ctx->d_aux.p);
     if (ctx->d_work.p) cudaFree(ctx->d_work.p);
     if (ctx->d_sel.p) cudaFree(ctx->d_sel.p);
+    if (ctx->d_track.p) cudaFree(ctx->d_track.p);
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1067,6 +1069,83 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
         TRY(end_call(ctx, true));
     }
     for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = cnt[2 * k];
+    return VSM_OK;
+}
+
+int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_xy, const float* desc, int32_t nkp,
+                        const double* mp_pos, const float* mp_desc, const uint8_t* mp_valid, int32_t nmp,
+                        const double* R_cam, const double* t_cam, int32_t* indices, int32_t* obs_mp, int32_t* obs_ki,
+                        int32_t* tracked, int32_t* best_ki, double* best_dist) {
+    if (!ctx || !cfg || nkp < 0 || nmp < 0 || !tracked || !R_cam || !t_cam || cfg->cell_size <= 0 ||
+        (nkp > 0 && (!kp_xy || !desc || !indices)) || (nmp > 0 && (!mp_pos || !obs_mp || !obs_ki)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_track_local_map: bad argument") : VSM_ERR_INVALID;
+    *tracked = 0;
+    if (nkp == 0 || nmp == 0) return VSM_OK;                               // src/Slam.cpp:384
+    if (!mp_desc && ctx->store_rows < nmp)
+        return fail(ctx, VSM_ERR_INVALID, "vsm_track_local_map: the store holds fewer rows than map points");
+    // the reference's visiting order: its cell grid (:391-401), cells row-major, keypoints in push order
+    const int GW = (cfg->width + cfg->cell_size - 1) / cfg->cell_size, GH = (cfg->height + cfg->cell_size - 1) / cfg->cell_size;
+    std::vector<std::pair<int, int>> order;                                // (cell, ki)
+    order.reserve(nkp);
+    for (int ki = 0; ki < nkp; ki++) {
+        const int gx = std::min((int)(kp_xy[2 * ki] / cfg->cell_size), GW - 1);
+        const int gy = std::min((int)(kp_xy[2 * ki + 1] / cfg->cell_size), GH - 1);
+        if (gx >= 0 && gy >= 0) order.push_back({gy * GW + gx, ki});
+    }
+    std::stable_sort(order.begin(), order.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+    const int nord = (int)order.size();
+    std::vector<float> sxy((size_t)std::max(nord, 1) * 2);
+    std::vector<int32_t> sid(std::max(nord, 1));
+    for (int k = 0; k < nord; k++) { sxy[2 * k] = kp_xy[2 * order[k].second]; sxy[2 * k + 1] = kp_xy[2 * order[k].second + 1]; sid[k] = order[k].second; }
+
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nkp + (mp_desc ? nmp : 0), 0));
+    TRY(upload_scratch(ctx, desc, 0, nkp));
+    if (mp_desc) TRY(upload_scratch(ctx, mp_desc, nkp, nmp));
+    const size_t o_xy = 0, o_id = align16(o_xy + sxy.size() * 4), o_pos = align16(o_id + sid.size() * 4),
+                 o_valid = align16(o_pos + (size_t)nmp * 24), o_bk = align16(o_valid + (size_t)nmp),
+                 o_bd = align16(o_bk + (size_t)nmp * 4), total = align16(o_bd + (size_t)nmp * 8);
+    TRY(ensure(ctx, ctx->d_track, total));
+    uint8_t* d = ctx->d_track.p;
+    CK(cudaMemcpyAsync(d + o_xy, sxy.data(), sxy.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + o_id, sid.data(), sid.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + o_pos, mp_pos, (size_t)nmp * 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (mp_valid) CK(cudaMemcpyAsync(d + o_valid, mp_valid, (size_t)nmp, cudaMemcpyHostToDevice, ctx->stream));
+    TrackCfg tc;
+    tc.fx = cfg->fx; tc.fy = cfg->fy; tc.cx = cfg->cx; tc.cy = cfg->cy;
+    tc.depth_min = cfg->depth_min; tc.depth_max = cfg->depth_max;
+    tc.radius_sq = cfg->search_radius * cfg->search_radius;                // :409
+    tc.desc_threshold = cfg->desc_threshold;
+    for (int i = 0; i < 9; i++) tc.R[i] = R_cam[i];
+    for (int i = 0; i < 3; i++) tc.t[i] = t_cam[i];
+    tc.width = cfg->width; tc.height = cfg->height;
+    const float* d_mp_desc = mp_desc ? ctx->scratch.f32 + (int64_t)nkp * VSM_DIM : ctx->store.f32;
+    track_local_map_kernel<<<(unsigned)(((int64_t)nmp * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        tc, reinterpret_cast<const float2*>(d + o_xy), reinterpret_cast<const int32_t*>(d + o_id), nord, ctx->scratch.f32,
+        reinterpret_cast<const double*>(d + o_pos), d_mp_desc, mp_valid ? d + o_valid : nullptr, nmp,
+        reinterpret_cast<int32_t*>(d + o_bk), reinterpret_cast<double*>(d + o_bd));
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<int32_t> bk(nmp);
+    std::vector<double> bd(nmp);
+    CK(cudaMemcpyAsync(bk.data(), d + o_bk, (size_t)nmp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(bd.data(), d + o_bd, (size_t)nmp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(end_call(ctx, true));
+    // the sequential part (:465-470): map points in id order, strictly smaller distance replaces
+    std::vector<double> best_desc_dist(nkp, 1e9);                          // :389
+    int n = 0;
+    for (int mp = 0; mp < nmp; mp++) {
+        if (best_ki) best_ki[mp] = bk[mp];
+        if (best_dist) best_dist[mp] = bd[mp];
+        const int ki = bk[mp];
+        if (ki >= 0 && bd[mp] < best_desc_dist[ki]) {
+            indices[ki] = mp;
+            best_desc_dist[ki] = bd[mp];
+            obs_mp[n] = mp; obs_ki[n] = ki;
+            n++;
+        }
+    }
+    *tracked = n;
     return VSM_OK;
 }
 

@@ -452,6 +452,76 @@ __global__ void merge_keys_kernel(const unsigned long long* __restrict__ keys, i
     }
 }
 
+// ---- Slam::track_local_map (src/Slam.cpp:380-469): projection + windowed descriptor search -------
+struct TrackCfg {
+    double fx, fy, cx, cy, depth_min, depth_max, radius_sq, desc_threshold;
+    double R[9], t[3];
+    int32_t width, height;
+};
+
+// One warp per map point.  kp_xy / kp_id are in the reference's visiting order (cell-major), so the
+// first keypoint reaching the minimum wins, as in the reference's strict `<` (:457).
+__global__ void __launch_bounds__(256)
+track_local_map_kernel(TrackCfg cfg, const float2* __restrict__ kp_xy, const int32_t* __restrict__ kp_id, int nkp,
+                       const float* __restrict__ frame_desc, const double* __restrict__ mp_pos,
+                       const float* __restrict__ mp_desc, const uint8_t* __restrict__ mp_valid, int nmp,
+                       int32_t* __restrict__ best_ki, double* __restrict__ best_dist) {
+    const int lane = threadIdx.x & 31;
+    const int mp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (mp >= nmp) return;
+    int32_t bk = -1;
+    double bd = cfg.desc_threshold;
+    bool live = mp_valid == nullptr || mp_valid[mp] != 0;
+    double u = 0, v = 0;
+    if (live) {
+        const double X = mp_pos[3 * mp], Y = mp_pos[3 * mp + 1], Z = mp_pos[3 * mp + 2];
+        // same operation order as :417-419 (no FMA contraction: explicit rounded ops)
+        const double px = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cfg.R[0], X), __dmul_rn(cfg.R[1], Y)), __dmul_rn(cfg.R[2], Z)), cfg.t[0]);
+        const double py = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cfg.R[3], X), __dmul_rn(cfg.R[4], Y)), __dmul_rn(cfg.R[5], Z)), cfg.t[1]);
+        const double pz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(cfg.R[6], X), __dmul_rn(cfg.R[7], Y)), __dmul_rn(cfg.R[8], Z)), cfg.t[2]);
+        if (pz < cfg.depth_min || pz > cfg.depth_max) live = false;                       // :421
+        else {
+            u = __dadd_rn(__ddiv_rn(__dmul_rn(cfg.fx, px), pz), cfg.cx);                  // :423-424
+            v = __dadd_rn(__ddiv_rn(__dmul_rn(cfg.fy, py), pz), cfg.cy);
+            if (u < 0 || u >= cfg.width || v < 0 || v >= cfg.height) live = false;        // :426
+        }
+    }
+    if (live) {
+        // this map point's descriptor: 8 elements per lane, as doubles
+        double md[8];
+        const float4* mpd = reinterpret_cast<const float4*>(mp_desc + (size_t)mp * VSM_DIM) + lane * 2;
+        const float4 m0 = __ldg(mpd), m1 = __ldg(mpd + 1);
+        md[0] = m0.x; md[1] = m0.y; md[2] = m0.z; md[3] = m0.w; md[4] = m1.x; md[5] = m1.y; md[6] = m1.z; md[7] = m1.w;
+        for (int k0 = 0; k0 < nkp; k0 += 32) {
+            const int k = k0 + lane;
+            bool in = false;
+            if (k < nkp) {
+                const float2 p = __ldg(kp_xy + k);
+                const double dx = __dsub_rn(u, (double)p.x), dy = __dsub_rn(v, (double)p.y);
+                in = !(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) > cfg.radius_sq);   // :453-454
+            }
+            unsigned m = __ballot_sync(0xffffffffu, in);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const int kk = k0 + l;
+                const int32_t ki = __ldg(kp_id + kk);
+                const float4* fd = reinterpret_cast<const float4*>(frame_desc + (size_t)ki * VSM_DIM) + lane * 2;
+                const float4 f0 = __ldg(fd), f1 = __ldg(fd + 1);
+                const double fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                double s = 0.0;
+#pragma unroll
+                for (int e = 0; e < 8; e++) { const double d = md[e] - fv[e]; s = fma(d, d, s); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const double dist = sqrt(s);
+                if (dist < bd) { bd = dist; bk = ki; }                                     // :456-460
+            }
+        }
+    }
+    if (lane == 0) { best_ki[mp] = bk; best_dist[mp] = bd; }
+}
+
 // ---- fused exchange over peer memory -----------------------------------------------------------
 // Per rank one buffer: flags[2][XCHG_MAX_WORLD] (u32) then keys[2][world][nq_cap][2] (u64).
 constexpr int XCHG_MAX_WORLD = 16;

@@ -30,6 +30,20 @@ class _Opts(C.Structure):
                 ("store_rows", C.c_int64), ("reserved", C.c_int32 * 8)]
 
 
+class TrackCfg(C.Structure):
+    """vsm_track_cfg; defaults = the reference's Config.h constants."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("width", C.c_int32), ("height", C.c_int32), ("cell_size", C.c_int32), ("reserved", C.c_int32),
+                ("depth_min", C.c_double), ("depth_max", C.c_double), ("search_radius", C.c_double),
+                ("desc_threshold", C.c_double)]
+
+    def __init__(self, **kw):
+        d = dict(fx=525.0, fy=525.0, cx=319.5, cy=239.5, width=640, height=480, cell_size=30, reserved=0,
+                 depth_min=float(np.float32(0.1)), depth_max=50.0, search_radius=12.0, desc_threshold=0.5)
+        d.update(kw)
+        super().__init__(**d)
+
+
 class _Stats(C.Structure):
     _fields_ = [("candidates", C.c_int64), ("flagged_slices", C.c_int64), ("kernel_launches", C.c_int64),
                 ("device_ms", C.c_float), ("tc_ms", C.c_float), ("select_ms", C.c_float)]
@@ -66,6 +80,9 @@ SYMBOLS = {
     "vsm_track": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                             C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vsm_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vsm_track_local_map": (C.c_int, [C.c_void_p, C.POINTER(TrackCfg), C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     "vsm_db_top2_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "vsm_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
@@ -283,6 +300,31 @@ class Matcher:
         self._ck(self._lib.vsm_db_top2_masked(self._h, q.ctypes.data, q.shape[0], mask.ctypes.data, mask.shape[0],
                                               idx.ctypes.data, dist.ctypes.data))
         return idx, dist
+
+    def track_local_map(self, kp_xy, desc, mp_pos, mp_desc, mp_valid, R_cam, t_cam, indices, cfg=None):
+        """Slam::track_local_map (src/Slam.cpp:380-469).  indices is updated in place.
+        Returns (tracked, observations [(mp, ki)], best_ki[nmp], best_dist[nmp])."""
+        cfg = cfg or TrackCfg()
+        kp = np.ascontiguousarray(kp_xy, np.float32).reshape(-1, 2)
+        d = _rows(desc, "desc")
+        pos = np.ascontiguousarray(mp_pos, np.float64).reshape(-1, 3)
+        md = _rows(mp_desc, "mp_desc") if mp_desc is not None else None
+        valid = np.ascontiguousarray(mp_valid, np.uint8) if mp_valid is not None else None
+        R = np.ascontiguousarray(R_cam, np.float64).reshape(9)
+        t = np.ascontiguousarray(t_cam, np.float64).reshape(3)
+        nmp = pos.shape[0]
+        assert indices.dtype == np.int32 and indices.flags.c_contiguous and len(indices) == kp.shape[0]
+        obs_mp = np.zeros(max(nmp, 1), np.int32)
+        obs_ki = np.zeros(max(nmp, 1), np.int32)
+        bk = np.zeros(max(nmp, 1), np.int32)
+        bd = np.zeros(max(nmp, 1), np.float64)
+        n = C.c_int32(0)
+        self._ck(self._lib.vsm_track_local_map(
+            self._h, C.byref(cfg), kp.ctypes.data, d.ctypes.data, kp.shape[0], pos.ctypes.data,
+            md.ctypes.data if md is not None else None, valid.ctypes.data if valid is not None else None, nmp,
+            R.ctypes.data, t.ctypes.data, indices.ctypes.data, obs_mp.ctypes.data, obs_ki.ctypes.data, C.byref(n),
+            bk.ctypes.data, bd.ctypes.data))
+        return n.value, list(zip(obs_mp[:n.value].tolist(), obs_ki[:n.value].tolist())), bk[:nmp], bd[:nmp]
 
     def detect_candidates(self, frame_desc, ratio=0.75, want_matches=True):
         """LoopCloser::detect matching block: per stored keyframe, top-2 inside the keyframe +
