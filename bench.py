@@ -226,6 +226,21 @@ def parity_report(vsm_b200, device, q, t, cpu_result):
     return rep
 
 
+def cpp_track_latency(vsm_b200):
+    """Builds bench_cpp/track_latency.cpp against libvsm.so and runs it (2544 pairs)."""
+    import tempfile
+    try:
+        libdir = os.path.dirname(vsm_b200.lib_path())
+        exe = os.path.join(tempfile.mkdtemp(prefix="vsm_bench_"), "track_latency")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "bench_cpp", "track_latency.cpp"), "-L", libdir, "-lvsm",
+                               f"-Wl,-rpath,{libdir}", "-lpthread", "-ldl", "-o", exe], stderr=subprocess.DEVNULL)
+        res = subprocess.run([exe, "2544"], capture_output=True, text=True, timeout=120)
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:            # a missing compiler only loses this informational number
+        return {"unavailable": repr(e)[:200]}
+
+
 # ---- extra: the pair-matching configs (rank 0, N = 1) ------------------------------------------------
 def extra_pair_numbers(torch, vsm_b200, device):
     import numpy as np
@@ -304,6 +319,8 @@ def extra_pair_numbers(torch, vsm_b200, device):
               "launches_per_pair": st["kernel_launches"]})
     out["tracking_1000x1000_mutual_ratio"] = r
     mt.close()
+    # (c) the same step timed from C++ (the reference's host language) through the C ABI
+    out["tracking_1000x1000_mutual_ratio_cpp"] = cpp_track_latency(vsm_b200)
     # configs[0]: 2000 x 2000, k=2 + ratio 0.8
     a = unit(2000)
     b = planted_from(a, 0.6, 0.08)
