@@ -290,19 +290,23 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
         float qreg[16];
         load_qreg(qreg, w.q, l16);
         Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
-        for (int k = 0; k < RESCAN_ROWS / 32; k++) {
-            const int ra = w.r0 + k * 32 + hw, rb = ra + 16;
-            const int offa = ra < r1 ? slice_row(si, ra) : -1, offb = rb < r1 ? slice_row(si, rb) : -1;
-            const int32_t ja = offa >= 0 ? si.t_index0 + offa : -1, jb = offb >= 0 ? si.t_index0 + offb : -1;
-            float ta[16], tb[16];                      // issue both rows' loads before either reduction
-            const float* pa = w.t + (size_t)(ja >= 0 ? ja : 0) * VSM_DIM;
-            const float* pb = w.t + (size_t)(jb >= 0 ? jb : 0) * VSM_DIM;
+        // 16 half-warps x 4 rows per step: all 64 rows' loads of a step are in flight together
+        for (int k = 0; k < RESCAN_ROWS / 64; k++) {
+            int32_t j[4];
+            float tv[4][16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) { ta[i] = __ldg(pa + 16 * i + l16); tb[i] = __ldg(pb + 16 * i + l16); }
-            const float da = canon_l2sqr_halfwarp_regs(qreg, ta), db = canon_l2sqr_halfwarp_regs(qreg, tb);
-            if (l16 == 0) {
-                if (ja >= 0) insert2(__fsqrt_rn(da), ja, best.d0, best.i0, best.d1, best.i1);
-                if (jb >= 0) insert2(__fsqrt_rn(db), jb, best.d0, best.i0, best.d1, best.i1);
+            for (int u = 0; u < 4; u++) {
+                const int r = w.r0 + k * 64 + u * 16 + hw;
+                const int off = r < r1 ? slice_row(si, r) : -1;
+                j[u] = off >= 0 ? si.t_index0 + off : -1;
+                const float* p = w.t + (size_t)(j[u] >= 0 ? j[u] : 0) * VSM_DIM;
+#pragma unroll
+                for (int i = 0; i < 16; i++) tv[u][i] = __ldg(p + 16 * i + l16);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float d2 = canon_l2sqr_halfwarp_regs(qreg, tv[u]);
+                if (l16 == 0 && j[u] >= 0) insert2(__fsqrt_rn(d2), j[u], best.d0, best.i0, best.d1, best.i1);
             }
         }
         if (l16 == 0) part[hw] = best;
