@@ -310,7 +310,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         // stream small next to the database stream
         const int seg_pref = ctx->seg_tiles > 0 ? ctx->seg_tiles
                                                 : (ntiles > 4096 ? 64 : std::max(1, std::min(16, ntiles / 16)));
-        const int seg = std::min(tpr, seg_pref);
+        const int seg = std::min(std::min(tpr, seg_pref), 64);      // 64 tiles x 128 columns = the 13 index bits of a packed entry
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
         std::vector<int> range_slice0(nranges);
         for (int r = 0; r < nranges; r++) {
