@@ -318,15 +318,20 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         if (lane == 0) {
             int slot = 0;
             uint32_t ph = 0;
+            // the queue is read one unit ahead: the atomic and the descriptor load of unit i+1 are
+            // in flight while unit i streams, so a unit boundary costs no L2 round trips
+            int idx = (int)atomicAdd(work_counter, 1u);
+            TcUnit u;
+            if (idx < nunits) u = units[idx]; else u.t_count = 0;            // t_count 0 = no more work
             for (uint32_t ui = 0;; ui++) {
                 const int us = ui & 1;
-                const int idx = (int)atomicAdd(work_counter, 1u);
                 mbar_wait(BAR_UEMPTY + 8 * us, ((ui >> 1) & 1) ^ 1);
-                TcUnit u;
-                if (idx < nunits) u = units[idx]; else u.t_count = 0;        // t_count 0 = no more work
                 unit_ring[us] = u;
                 mbar_arrive(BAR_UFULL + 8 * us);                             // release: publishes the slot
                 if (idx >= nunits) break;
+                const int idx_next = (int)atomicAdd(work_counter, 1u);       // result first used after tile 0 is issued
+                TcUnit u_next;
+                u_next.t_count = 0;
                 const CUtensorMap* mq = (u.maps & 1) ? &map_store : &map_scratch;
                 const CUtensorMap* mt = (u.maps & 2) ? &map_store : &map_scratch;
                 const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
@@ -356,7 +361,10 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         tma_load_2d(dst + T_STAGE_BYTES / 2, mt, c * KCHUNK, row + TILE_N / 2, BAR_FULL + 8 * slot);
                         if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
+                    if (n == 0 && idx_next < nunits) u_next = units[idx_next];   // lands while the other tiles stream
                 }
+                idx = idx_next;
+                u = u_next;
             }
         }
     } else if (warp == 1) {

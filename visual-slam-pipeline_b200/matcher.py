@@ -110,7 +110,13 @@ def load_library():
     if _lib is None:
         path = lib_path()
         if not os.path.exists(path):
-            raise VsmError(f"{path} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
+            # not built yet (fresh checkout): compile it in-tree with nvcc; there is no other way to run
+            try:
+                from . import build as _build
+                _build.build_lib()
+            except Exception as e:
+                raise VsmError(f"{path} is missing and could not be built ({e}): run "
+                               "`python __graft_entry__.py build` (there is no CPU fallback)")
         lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)
