@@ -385,7 +385,7 @@ def run_gpu(args):
     total_rows = args.rows
 
     sh = vsm_b200.load_sharded()
-    db = sh.ShardedDB(local, rank, world, exchange=args.exchange)
+    db = sh.ShardedDB(local, rank, world, exchange=args.exchange, engine=args.engine)
     q, noise = make_queries(torch, device)
     shard, off, planted = make_shard(torch, device, rank, world, q, noise, total_rows)
     seg = None   # one segment per shard for the global search
@@ -476,7 +476,7 @@ def run_gpu(args):
             "e2e": {"value": flops / (per_step_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": per_step_e2e,
                     "h2d_bytes_per_step": NQ * 1024, "d2h_bytes_per_step": NQ * 2 * 12,
                     "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)"},
-            "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange,
+            "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange, "engine": args.engine,
             "roofline": {"bound": "tensor", "kernel": "tc_top3_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": args.traffic if args.traffic is not None else committed_traffic(shard.shape[0]),
@@ -525,6 +525,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=100_000, help="cpu_baseline: DB sample rows")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: fused peer-memory exchange (default) or NCCL all-gather + merge")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 tensor cores (1 CTA/SM), 3 tensor cores on CTA pairs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,

@@ -60,7 +60,8 @@ typedef struct {
 typedef enum {
     VSM_ENGINE_AUTO = 0,     /* tensor-core path (tcgen05) with exact fp32 re-score */
     VSM_ENGINE_TENSOR = 1,   /* same, forced */
-    VSM_ENGINE_SIMT = 2      /* exact fp32 CUDA-core brute force (debug / cross-check) */
+    VSM_ENGINE_SIMT = 2,     /* exact fp32 CUDA-core brute force (debug / cross-check) */
+    VSM_ENGINE_TENSOR_PAIR = 3   /* tensor-core path on CTA pairs (tcgen05 cta_group::2, clusters of 2) */
 } vsm_engine;
 
 typedef struct {

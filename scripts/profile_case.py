@@ -26,7 +26,7 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     g = torch.Generator(device="cuda")
     g.manual_seed(5)
-    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR)
+    m = vsm_b200.Matcher(engine=int(os.environ.get("VSM_ENGINE", vsm_b200.ENGINE_TENSOR)))
     if case.startswith("pair"):
         n = int(case[4:])
         a = unit(n, g)

@@ -25,6 +25,14 @@ def tc():
 
 
 @pytest.fixture(scope="module")
+def pair():
+    """tensor-core pass on CTA pairs (tcgen05 cta_group::2, clusters of two)"""
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR_PAIR)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
 def simt():
     m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_SIMT)
     yield m
@@ -51,7 +59,7 @@ def test_tensor_core_tile_is_the_bf16_dot(tc):
 
 
 @pytest.mark.parametrize("name", list(cases.PAIR_CASES))
-@pytest.mark.parametrize("engine", ["tc", "simt"])
+@pytest.mark.parametrize("engine", ["tc", "pair", "simt"])
 def test_knn_equals_oracle_and_golden(name, engine, request):
     m = request.getfixturevalue(engine)
     q, t = cases.PAIR_CASES[name]()
@@ -441,3 +449,31 @@ def test_baseline_config4_full_size(tc):
         assert g.tobytes() == og.tobytes()
         total += len(g)
     assert total > 64 * 50
+
+
+def test_pair_engine_db_batch_and_mutual(pair):
+    """The cta_group::2 engine through the other entry points: keyframe store (odd number of query
+    tiles -> a dummy partner tile), segmented search, ragged batch with mutual filter."""
+    q, db, seg_off = cases.db_case()                        # 300 queries = 3 query tiles
+    pair.clear_store()
+    for s in range(len(seg_off) - 1):
+        pair.add_keyframe(s, db[seg_off[s]:seg_off[s + 1]])
+    idx, dist = pair.search_map_points(q)
+    oi, od = oracle.knn(q, db, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    counts, lists = pair.detect_candidates(q, 0.75)
+    oc, ol = oracle.segmented(q, db, seg_off, 0.75)
+    assert np.array_equal(counts, oc)
+    for a, b in zip(lists, ol):
+        assert a.tobytes() == b.tobytes()
+    pair.clear_store()
+    qs = [gen.planted(500 + i, n, m_, 0.5, 0.08)[0] for i, (n, m_) in enumerate([(700, 900), (129, 300), (1, 1), (2048, 257)])]
+    ts = [gen.planted(500 + i, n, m_, 0.5, 0.08)[1] for i, (n, m_) in enumerate([(700, 900), (129, 300), (1, 1), (2048, 257)])]
+    got = pair.match_batch(qs, ts, 0.75, mutual=True)
+    for a, b, g in zip(qs, ts, got):
+        og, _ = oracle.match_features(a, b, 0.75, mutual=True)
+        assert g.tobytes() == og.tobytes()
+    q2, t2, _ = gen.planted(79, 1500, 40000, 0.5, 0.08)     # several 64-tile units per cluster
+    idx, dist = pair.knn_match(q2, t2)
+    oi, od = oracle.knn(q2, t2, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))

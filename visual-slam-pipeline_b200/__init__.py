@@ -6,7 +6,7 @@ The directory name carries a hyphen, so import it through the repo-root shim:
     import vsm_b200
 """
 from .matcher import (DMATCH, Matcher, TrackCfg, VsmError, lib_path, load_library,  # noqa: F401
-                      ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT)
+                      ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT, ENGINE_TENSOR_PAIR)
 
 
 def load_sharded():

@@ -17,6 +17,7 @@
 #include "vsm_common.cuh"
 #include "vsm_kernels.cuh"
 #include "vsm_tc.cuh"
+#include "vsm_tc2.cuh"
 
 using namespace vsm;
 
@@ -270,13 +271,18 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     const int P = (int)probs.size();
     std::vector<Problem> dp(P);
     std::vector<int32_t> qb(P + 1, 0);
+    const bool pairs = ctx->engine == VSM_ENGINE_TENSOR_PAIR && !dump_first;
     std::vector<TcUnit> units;
+    std::vector<TcUnit2> units2;
     std::vector<int> unit_prob;
     std::vector<SliceInfo> slices;
     int64_t nrecs = 0;
 
+    // scheduling granularity: query tiles on SMs, or pairs of query tiles on SM pairs
     int64_t total_qtiles = 0;
-    for (auto& p : probs) if (p.nq > 0 && p.nt > 0) total_qtiles += (p.nq + TILE_M - 1) / TILE_M;
+    for (auto& p : probs)
+        if (p.nq > 0 && p.nt > 0) total_qtiles += pairs ? ((p.nq + TILE_M - 1) / TILE_M + 1) / 2 : (p.nq + TILE_M - 1) / TILE_M;
+    const int64_t nworkers = pairs ? ctx->num_sms / 2 : ctx->num_sms;
 
     // device addresses inside the descriptor block are fixed up after the layout is known
     for (int i = 0; i < P; i++) {
@@ -301,7 +307,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         // waves over the SMs, so that the dynamic scheduler ends every CTA at about the same time
         int nranges = 1;
         for (int64_t k = 1; k <= 8192; k++) {
-            nranges = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (int64_t)ctx->num_sms * k / std::max<int64_t>(total_qtiles, 1)));
+            nranges = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, nworkers * k / std::max<int64_t>(total_qtiles, 1)));
             if ((ntiles + nranges - 1) / nranges <= UNIT_TILES || nranges == ntiles) break;
         }
         const int tpr = (ntiles + nranges - 1) / nranges;
@@ -325,7 +331,28 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         d.nslices = (int)slices.size() - d.slice_off;
         for (int r = 0; r < nranges; r++) {
             const int tile0 = r * tpr, tile1 = std::min(ntiles, tile0 + tpr);
-            for (int qt = 0; qt < nqt; qt++) {
+            for (int qt = 0; pairs && qt < nqt; qt += 2) {
+                TcUnit2 u;
+                memset(&u, 0, sizeof u);
+                for (int k = 0; k < 2; k++) {
+                    const bool real = qt + k < nqt;
+                    const int q = real ? qt + k : qt;                   // an odd tail pairs the last tile with a dummy
+                    u.q_n2[k] = hp.q_n2 + (int64_t)q * TILE_M;
+                    u.rec_base[k] = nrecs + (int64_t)q * TILE_M * d.nslices + range_slice0[r];
+                    u.q_row[k] = (int32_t)(hp.q_row + (int64_t)q * TILE_M);
+                    u.q_valid[k] = real ? std::min(TILE_M, hp.nq - q * TILE_M) : 0;
+                }
+                u.rec_stride = d.nslices;
+                u.t_row = (int32_t)(hp.t_row + (int64_t)tile0 * TILE_N);
+                u.t_index0 = tile0 * TILE_N;
+                u.t_count = (int32_t)std::min<int64_t>((int64_t)(tile1 - tile0) * TILE_N, hp.nt - u.t_index0);
+                u.seg_tiles = seg;
+                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0);
+                u.prefetch = (qt == 0 || qt == ((nqt / 2) & ~1)) ? 1 + std::min(tc::L2_AHEAD, ntiles - tile1) : 0;
+                units2.push_back(u);
+                unit_prob.push_back(i);
+            }
+            for (int qt = 0; !pairs && qt < nqt; qt++) {
                 TcUnit u;
                 memset(&u, 0, sizeof u);
                 u.q_n2 = hp.q_n2 + (int64_t)qt * TILE_M;
@@ -353,7 +380,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     const size_t off_prob = 0;
     const size_t off_qb = align16(off_prob + sizeof(Problem) * P);
     const size_t off_unit = align16(off_qb + sizeof(int32_t) * (P + 1));
-    const size_t off_slice = align16(off_unit + sizeof(TcUnit) * units.size());
+    const size_t off_slice = align16(off_unit + sizeof(TcUnit) * units.size() + sizeof(TcUnit2) * units2.size());
     const size_t off_job = align16(off_slice + sizeof(SliceInfo) * slices.size());
     const size_t total = align16(off_job + sizeof(FilterJob) * jobs.size());
     TRY(ensure(ctx, ctx->d_desc, total));
@@ -383,6 +410,11 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         units[k].t_stats = dp[i].t_stats;
         units[k].hint = d_hints + probs[i].out_off + (units[k].q_row - probs[i].q_row);
     }
+    for (size_t k = 0; k < units2.size(); k++) {
+        const int i = unit_prob[k];
+        units2[k].t_stats = dp[i].t_stats;
+        for (int c = 0; c < 2; c++) units2[k].hint[c] = d_hints + probs[i].out_off + (units2[k].q_row[c] - probs[i].q_row);
+    }
 
     // build the block; upload it only if it differs from what the device already holds
     // (tracking calls repeat the same shapes frame after frame)
@@ -392,6 +424,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     memcpy(h + off_prob, dp.data(), sizeof(Problem) * P);
     memcpy(h + off_qb, qb.data(), sizeof(int32_t) * (P + 1));
     if (!units.empty()) memcpy(h + off_unit, units.data(), sizeof(TcUnit) * units.size());
+    if (!units2.empty()) memcpy(h + off_unit, units2.data(), sizeof(TcUnit2) * units2.size());
     if (!slices.empty()) memcpy(h + off_slice, slices.data(), sizeof(SliceInfo) * slices.size());
     for (size_t j = 0; j < jobs.size(); j++) {
         FilterJob fj;
@@ -417,6 +450,19 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
 
     uint8_t* dd = ctx->d_desc.p;
     if (ctx->profiling) CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
+    if (!units2.empty()) {
+        const CUtensorMap& ms = ctx->scratch.map;
+        const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
+        const unsigned nclusters = (unsigned)std::min<size_t>(units2.size(), (size_t)(ctx->num_sms / 2));
+        tc2::tc_top3_pair_kernel<<<nclusters * 2, tc::THREADS, tc2::SMEM2_BYTES, ctx->stream>>>(
+            ms, mt, reinterpret_cast<const TcUnit2*>(dd + off_unit), (int)units2.size(), ctx->d_recs.p);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (ctx->profiling) {
+            CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
+            ctx->timed_tc = true;
+        }
+    }
     if (!units.empty()) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
@@ -448,7 +494,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ctx->launches++;
             CK(cudaGetLastError());
         }
-        if (!units.empty()) {
+        if (!units.empty() || !units2.empty()) {
             // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
             rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, ctx->work_cap);
             ctx->launches++;
@@ -573,6 +619,7 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
         CK(cudaFuncSetAttribute(tc::tc_top3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
         CK(cudaFuncSetAttribute(tc::tc_top3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc2::tc_top3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::SMEM2_BYTES));
         TRY(arena_reserve(ctx, ctx->scratch, o.scratch_rows > 0 ? o.scratch_rows : 8192, 0));
         if (o.store_rows > 0) TRY(arena_reserve(ctx, ctx->store, o.store_rows, 0));
         return VSM_OK;

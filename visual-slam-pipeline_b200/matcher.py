@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
-ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT = 0, 1, 2
+ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT, ENGINE_TENSOR_PAIR = 0, 1, 2, 3
 DIM = 256
 
 
