@@ -476,7 +476,7 @@ def run_gpu(args):
             "e2e": {"value": flops / (per_step_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": per_step_e2e,
                     "h2d_bytes_per_step": NQ * 1024, "d2h_bytes_per_step": NQ * 2 * 12,
                     "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)"},
-            "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange, "engine": args.engine,
+            "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange, "exchange_note": db.exchange_note, "engine": args.engine,
             "roofline": {"bound": "tensor", "kernel": "tc_top3_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": args.traffic if args.traffic is not None else committed_traffic(shard.shape[0]),

@@ -60,11 +60,29 @@ class ShardedDB:
         self.matcher = Matcher(device=device, engine=engine)
         self.matcher.set_stream(self.stream.cuda_stream)
         self.exchange = exchange if world > 1 else "none"
+        self.exchange_note = None
         if self.exchange == "p2p":
-            mine = self.matcher.xchg_create(rank, world, nq_cap)
+            # CUDA IPC between the ranks' processes; if ANY rank cannot set it up (e.g. a container
+            # without shared IPC namespaces) every rank switches to the NCCL exchange together
+            ok, err = 1, ""
+            try:
+                mine = self.matcher.xchg_create(rank, world, nq_cap)
+            except Exception as e:                          # noqa: BLE001
+                ok, err, mine = 0, repr(e), b""
             handles = [None] * world
             torch.distributed.all_gather_object(handles, mine, group=group)
-            self.matcher.xchg_connect(handles)
+            if ok and all(len(h) == 64 for h in handles):
+                try:
+                    self.matcher.xchg_connect(handles)
+                except Exception as e:                      # noqa: BLE001
+                    ok, err = 0, repr(e)
+            else:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.exchange = "nccl"
+                self.exchange_note = f"peer-memory exchange unavailable ({err or 'another rank failed'}); using NCCL all-gather"
             torch.distributed.barrier(group=group)          # every buffer is zeroed and mapped before first use
         self.row_offset = 0
         self.rows = 0
