@@ -430,9 +430,15 @@ def run_gpu(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(db.stream):
         f0.record()
+    e2e_dev, e2e_tc, e2e_wall = [], [], []
     for _ in range(args.steps):
+        tw = time.perf_counter()
         hi, hd = db.search_host(hq)
         db.stream.synchronize()                        # the caller reads the result every step
+        e2e_wall.append((time.perf_counter() - tw) * 1e3)
+        st = db.matcher.stats()                        # stream already idle: reads the call's own events
+        e2e_dev.append(st["device_ms"])
+        e2e_tc.append(st["tc_ms"])
     with torch.cuda.stream(db.stream):
         f1.record()
     barrier()
@@ -474,6 +480,8 @@ def run_gpu(args):
             "config": workload_config(world, total_rows),
             "clocks": clocks,
             "e2e": {"value": flops / (per_step_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": per_step_e2e,
+                    "breakdown_ms_rank0_median": {"host_wall": float(np.median(e2e_wall)), "library_call_on_device": float(np.median(e2e_dev)),
+                                                  "tc_top3_kernel": float(np.median(e2e_tc))},
                     "h2d_bytes_per_step": NQ * 1024, "d2h_bytes_per_step": NQ * 2 * 12,
                     "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)"},
             "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange, "exchange_note": db.exchange_note, "engine": args.engine,

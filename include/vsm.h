@@ -230,6 +230,21 @@ int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_
 int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every,
                     const float* query, int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches);
 
+/* The same loop for ONE SHARD of a keyframe list partitioned across GPUs (whole keyframes per
+ * rank, SURVEY 8e: no collective, the host concatenates the per-rank status arrays).  The
+ * every-`every`-th rule counts over the WHOLE list (src/LoopCloser.cpp:47-48), so the caller
+ * passes checked_before = the number of keyframes on earlier shards that pass the gap (:44) and
+ * non-empty (:45) tests; *checked_after (may be NULL) = checked_before + this shard's own count.
+ * vsm_loop_detect is this call with checked_before = 0. */
+int vsm_loop_detect_shard(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every,
+                          int32_t checked_before, const float* query, int32_t nq, float ratio,
+                          int32_t* status, vsm_dmatch* matches, int32_t* checked_after);
+
+/* Frame ids of the stored keyframes, in store order (n must equal the keyframe count).  For a
+ * store built by vsm_store_adopt_device, whose keyframes otherwise get ids 0..n-1
+ * (Frame::id(), include/Frame.h, read by the gap rule src/LoopCloser.cpp:44). */
+int vsm_store_set_frame_ids(vsm_ctx* ctx, const int32_t* frame_ids, int32_t n);
+
 /* ---- device-pointer variants (resident data; multi-GPU plumbing) ---------- */
 
 /* vsm_db_top2 with query and outputs already on this context's device.

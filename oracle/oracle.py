@@ -116,13 +116,15 @@ def gen_rows(seed, set_id, row0, n):
     return out
 
 
-def loop_detect(q, db, seg_off, frame_ids, cur_frame_id, ratio=0.75, min_gap=200, every=5, threads=0):
+def loop_detect(q, db, seg_off, frame_ids, cur_frame_id, ratio=0.75, min_gap=200, every=5, threads=0, checked0=0):
     """LoopCloser::detect's candidate loop (src/LoopCloser.cpp:43-62): eligibility (:44-48) then the
-    per-keyframe kNN + ratio test.  Returns status[nkf] (-1 = skipped, else survivors) and the lists."""
+    per-keyframe kNN + ratio test.  Returns status[nkf] (-1 = skipped, else survivors) and the lists.
+    checked0: value of the reference's `checked` counter on entry (0 for the whole list; the tests of
+    the partitioned search start a later shard where the earlier ones left off)."""
     nkf = len(seg_off) - 1
     status = -np.ones(nkf, np.int32)
     lists = [None] * nkf
-    checked = 0
+    checked = checked0
     for s in range(nkf):
         if cur_frame_id - frame_ids[s] < min_gap:
             continue

@@ -256,6 +256,45 @@ def test_loop_detect_eligibility_and_matches(tc):
     tc.clear_store()
 
 
+def test_loop_detect_two_shards_on_one_gpu(tc):
+    """vsm_loop_detect_shard: the keyframe list split over two contexts (as over two GPUs) gives the
+    whole list's status and match lists; the every-5th counter carries across the shard boundary."""
+    import torch
+    sh = vsm_b200.load_sharded()
+    q, db, seg_off = cases.db_case()
+    nkf = len(seg_off) - 1
+    frame_ids = [30 * s for s in range(nkf)]
+    counts = np.diff(seg_off)
+    parts = sh.partition_keyframes(seg_off, 2)
+    shards = []
+    for k0, k1, r0, r1 in parts:
+        m = vsm_b200.Matcher()
+        d = torch.from_numpy(db[r0:r1]).cuda().contiguous()
+        m.adopt_device_matrix(d.data_ptr(), r1 - r0, np.asarray(seg_off[k0:k1 + 1] - r0, np.int64))
+        m.set_frame_ids(frame_ids[k0:k1])
+        shards.append((m, d, k0))
+    for cur_id, gap, every in ((900, 200, 5), (650, 100, 3), (900, 200, 1)):
+        ost, ol = oracle.loop_detect(q, db, seg_off, frame_ids, cur_id, 0.75, gap, every)
+        got, after_prev = [], 0
+        for m, _, k0 in shards:
+            before = sh.loop_checked_before(cur_id, frame_ids, counts, gap, k0)
+            assert before == after_prev                       # the table-derived count = the chained one
+            st, lists, after_prev = m.loop_detect_shard(cur_id, q, before, 0.75, gap, every)
+            for s in range(len(st)):
+                g = k0 + s
+                assert st[s] == ost[g]
+                if ost[g] >= 0:
+                    want = ol[g].copy()
+                    want["imgIdx"] = s                        # imgIdx is the keyframe's index in ITS store
+                    assert lists[s].tobytes() == want.tobytes()
+            got.append(st)
+        assert np.array_equal(np.concatenate(got), ost)
+    for m, _, _ in shards:
+        m.close()
+    with pytest.raises(vsm_b200.VsmError):
+        tc.set_frame_ids([1, 2, 3] * 1000)
+
+
 def test_spcf_feature_cache_bulk_load(tc, tmp_path):
     """The reference's on-disk descriptor format (SPCF, src/FeatureExtractor.cpp:269-381) loads
     straight into the device store; float entries become keyframes, ORB (CV_8U) entries are skipped."""

@@ -50,6 +50,52 @@ def _worker(rank, world, port, case, out):
     dist.destroy_process_group()
 
 
+def _loop_worker(rank, world, port, out):
+    """LoopCloser::detect over a partitioned keyframe list: per-rank eligibility from the product's
+    loop_checked_before, per-keyframe matching by the oracle (standing in for libvsm), status
+    concatenation by the product's concat_keyframe_status."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = vsm_b200.load_sharded()
+    q, db, seg_off = cases.db_case()
+    nkf = len(seg_off) - 1
+    frame_ids = [30 * s for s in range(nkf)]
+    counts = np.diff(seg_off)
+    parts = sh.partition_keyframes(seg_off, world)
+    k0, k1, r0, r1 = parts[rank]
+    ok = True
+    for cur_id, gap, every in ((900, 200, 5), (900, 200, 1), (650, 100, 3), (100, 200, 5)):
+        before = sh.loop_checked_before(cur_id, frame_ids, counts, gap, k0)
+        st, _ = oracle.loop_detect(q, db[r0:r1], seg_off[k0:k1 + 1] - r0, frame_ids[k0:k1], cur_id, 0.75, gap, every,
+                                   checked0=before)
+        whole = sh.concat_keyframe_status(torch.from_numpy(st), [p[1] - p[0] for p in parts], world)
+        want, _ = oracle.loop_detect(q, db, seg_off, frame_ids, cur_id, 0.75, gap, every)
+        ok = ok and np.array_equal(whole.numpy(), want)
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_loop_detect_equals_whole():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_loop_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+
+
+def test_loop_checked_before_counts_gap_and_empty():
+    sh = vsm_b200.load_sharded()
+    ids = [0, 30, 60, 90, 120, 150]
+    counts = [10, 0, 10, 10, 10, 10]
+    # cur 200, gap 100: keyframes with id <= 100 pass the gap test -> 0, 30(empty), 60, 90
+    assert sh.loop_checked_before(200, ids, counts, 100, 0) == 0
+    assert sh.loop_checked_before(200, ids, counts, 100, 2) == 1
+    assert sh.loop_checked_before(200, ids, counts, 100, 4) == 3
+    assert sh.loop_checked_before(200, ids, counts, 100, 6) == 3
+
+
 @pytest.mark.parametrize("case", ["db", "dups"])
 def test_two_rank_search_equals_whole(case):
     world = 2

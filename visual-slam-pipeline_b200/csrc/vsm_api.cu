@@ -79,6 +79,7 @@ struct vsm_ctx {
     uint8_t* h_desc = nullptr;
     size_t h_desc_cap = 0;
     std::vector<uint8_t> desc_build, desc_last;      // descriptor block cache (skip identical uploads)
+    std::vector<uint8_t> plan_key_build;
     const uint8_t* desc_dev = nullptr;
     cudaEvent_t ev_desc = nullptr;
     bool desc_copy_pending = false;
@@ -113,6 +114,19 @@ struct vsm_ctx {
     int seg_tiles = 0;                   // 0 = automatic
     bool profiling = true;               // per-kernel events (tc_ms / select_ms)
     uint32_t work_cap = 0;               // rescan work-list capacity (0 = WORK_CAP)
+    // plan of the last run_problems call: a call with identical inputs (the loop-closure search and
+    // the tracking step repeat their shapes) reuses the descriptor block already on the device
+    struct Plan {
+        std::vector<uint8_t> key;
+        const void* p_desc = nullptr;
+        const void* p_aux = nullptr;
+        const void* p_stats = nullptr;
+        size_t off_prob = 0, off_unit = 0, off_slice = 0, off_job = 0, total = 0, nunits = 0, nunits2 = 0;
+        int64_t nrecs = 0;
+        int qb_total = 0;
+        bool valid = false;
+    } plan;
+    int64_t plan_hits = 0;
 };
 
 namespace {
@@ -187,13 +201,31 @@ int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
     want = (want + 255) / 256 * 256;
     CK(cudaStreamSynchronize(ctx->stream));
     float* f32 = nullptr; __nv_bfloat16* b16 = nullptr; float* n2 = nullptr;
-    if (a.own_f32) CK(cudaMalloc(&f32, (size_t)want * VSM_DIM * sizeof(float)));
-    CK(cudaMalloc(&b16, (size_t)want * VSM_DIM * sizeof(__nv_bfloat16)));
-    CK(cudaMalloc(&n2, (size_t)want * sizeof(float)));
-    if (keep > 0) {
-        if (a.own_f32) CK(cudaMemcpy(f32, a.f32, (size_t)keep * VSM_DIM * sizeof(float), cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(b16, a.b16, (size_t)keep * VSM_DIM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
-        CK(cudaMemcpy(n2, a.n2, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice));
+    // allocate and copy everything first: on failure (e.g. out of HBM) the old arena stays intact
+    auto grow = [&]() -> int {
+        if (a.own_f32) CK(cudaMalloc(&f32, (size_t)want * VSM_DIM * sizeof(float)));
+        CK(cudaMalloc(&b16, (size_t)want * VSM_DIM * sizeof(__nv_bfloat16)));
+        CK(cudaMalloc(&n2, (size_t)want * sizeof(float)));
+        if (keep > 0) {
+            if (a.own_f32) CK(cudaMemcpy(f32, a.f32, (size_t)keep * VSM_DIM * sizeof(float), cudaMemcpyDeviceToDevice));
+            CK(cudaMemcpy(b16, a.b16, (size_t)keep * VSM_DIM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
+            CK(cudaMemcpy(n2, a.n2, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice));
+        }
+        return VSM_OK;
+    };
+    int st = grow();
+    const int64_t tight = (rows + 255) / 256 * 256;
+    if (st != VSM_OK && want > tight) {                     // the 1.5x head-room did not fit: take exactly what is needed
+        cudaFree(f32); cudaFree(b16); cudaFree(n2);
+        cudaGetLastError();
+        f32 = nullptr; b16 = nullptr; n2 = nullptr;
+        want = tight;
+        st = grow();
+    }
+    if (st != VSM_OK) {
+        cudaFree(f32); cudaFree(b16); cudaFree(n2);
+        cudaGetLastError();
+        return st;
     }
     if (a.own_f32) { if (a.f32) CK(cudaFree(a.f32)); a.f32 = f32; }
     if (a.b16) CK(cudaFree(a.b16));
@@ -269,7 +301,19 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                  int64_t conv_rows, int dump_first = 0) {
     const bool exact = ctx->engine == VSM_ENGINE_SIMT;
     const int P = (int)probs.size();
-    std::vector<Problem> dp(P);
+    vsm_ctx::Plan& pl = ctx->plan;
+    // everything the plan depends on, byte for byte (HProblem and HJob have no padding)
+    std::vector<uint8_t>& key = ctx->plan_key_build;
+    {
+        const int64_t head[8] = {ctx->engine, ctx->seg_tiles, ctx->num_sms, P, (int64_t)jobs.size(), total_out, total_matches, 0};
+        key.resize(sizeof head + sizeof(HProblem) * probs.size() + sizeof(HJob) * jobs.size());
+        memcpy(key.data(), head, sizeof head);
+        if (P) memcpy(key.data() + sizeof head, probs.data(), sizeof(HProblem) * probs.size());
+        if (!jobs.empty()) memcpy(key.data() + sizeof head + sizeof(HProblem) * probs.size(), jobs.data(), sizeof(HJob) * jobs.size());
+    }
+    const bool hit = !dump_first && pl.valid && pl.p_desc == ctx->d_desc.p && pl.p_aux == ctx->d_aux.p &&
+                     pl.p_stats == ctx->d_store_stats && pl.key == key;
+    std::vector<Problem> dp(hit ? 0 : P);
     std::vector<int32_t> qb(P + 1, 0);
     const bool pairs = ctx->engine == VSM_ENGINE_TENSOR_PAIR && !dump_first;
     std::vector<TcUnit> units;
@@ -285,7 +329,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     const int64_t nworkers = pairs ? ctx->num_sms / 2 : ctx->num_sms;
 
     // device addresses inside the descriptor block are fixed up after the layout is known
-    for (int i = 0; i < P; i++) {
+    for (int i = 0; i < P && !hit; i++) {
         const HProblem& hp = probs[i];
         Problem& d = dp[i];
         memset(&d, 0, sizeof d);
@@ -377,12 +421,26 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     }
 
     // descriptor block: [Problem][q_block0][TcUnit][SliceInfo][FilterJob]
-    const size_t off_prob = 0;
+    if (!hit) {
+        pl.valid = false;
+        pl.off_prob = 0;
+        const size_t off_qb0 = align16(pl.off_prob + sizeof(Problem) * P);
+        pl.off_unit = align16(off_qb0 + sizeof(int32_t) * (P + 1));
+        pl.off_slice = align16(pl.off_unit + sizeof(TcUnit) * units.size() + sizeof(TcUnit2) * units2.size());
+        pl.off_job = align16(pl.off_slice + sizeof(SliceInfo) * slices.size());
+        pl.total = align16(pl.off_job + sizeof(FilterJob) * jobs.size());
+        pl.nunits = units.size();
+        pl.nunits2 = units2.size();
+        pl.nrecs = nrecs;
+        pl.qb_total = qb[P];
+    } else {
+        ctx->plan_hits++;
+    }
+    const size_t off_prob = pl.off_prob;
     const size_t off_qb = align16(off_prob + sizeof(Problem) * P);
-    const size_t off_unit = align16(off_qb + sizeof(int32_t) * (P + 1));
-    const size_t off_slice = align16(off_unit + sizeof(TcUnit) * units.size() + sizeof(TcUnit2) * units2.size());
-    const size_t off_job = align16(off_slice + sizeof(SliceInfo) * slices.size());
-    const size_t total = align16(off_job + sizeof(FilterJob) * jobs.size());
+    const size_t off_unit = pl.off_unit, off_slice = pl.off_slice, off_job = pl.off_job, total = pl.total;
+    const size_t nunits = pl.nunits, nunits2 = pl.nunits2;
+    nrecs = pl.nrecs;
     TRY(ensure(ctx, ctx->d_desc, total));
     TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
     TRY(ensure(ctx, ctx->d_recs, (size_t)std::max<int64_t>(nrecs, 1)));
@@ -404,6 +462,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     ctx->d_out_key = reinterpret_cast<unsigned long long*>(ctx->d_aux.p + off_keys);
     CK(cudaMemsetAsync(ctx->d_aux.p, 0, aux_bytes, ctx->stream));
 
+    if (!hit) {
     for (int i = 0; i < P; i++) dp[i].t_stats = probs[i].t_store ? ctx->d_store_stats : d_scratch_stats;
     for (size_t k = 0; k < units.size(); k++) {
         const int i = unit_prob[k];
@@ -443,6 +502,14 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         ctx->desc_last = blk;
         ctx->desc_dev = ctx->d_desc.p;
     }
+    if (!dump_first) {
+        pl.key = key;
+        pl.p_desc = ctx->d_desc.p;
+        pl.p_aux = ctx->d_aux.p;
+        pl.p_stats = ctx->d_store_stats;
+        pl.valid = true;
+    }
+    }   // !hit
 
     if (conv_rows > 0)
         TRY(launch_convert(ctx, conv_src, ctx->scratch.b16 + conv_row0 * VSM_DIM, ctx->scratch.n2 + conv_row0,
@@ -450,12 +517,12 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
 
     uint8_t* dd = ctx->d_desc.p;
     if (ctx->profiling) CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
-    if (!units2.empty()) {
+    if (nunits2) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
-        const unsigned nclusters = (unsigned)std::min<size_t>(units2.size(), (size_t)(ctx->num_sms / 2));
+        const unsigned nclusters = (unsigned)std::min<size_t>(nunits2, (size_t)(ctx->num_sms / 2));
         tc2::tc_top3_pair_kernel<<<nclusters * 2, tc::THREADS, tc2::SMEM2_BYTES, ctx->stream>>>(
-            ms, mt, reinterpret_cast<const TcUnit2*>(dd + off_unit), (int)units2.size(), ctx->d_recs.p);
+            ms, mt, reinterpret_cast<const TcUnit2*>(dd + off_unit), (int)nunits2, ctx->d_recs.p);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->profiling) {
@@ -463,18 +530,18 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ctx->timed_tc = true;
         }
     }
-    if (!units.empty()) {
+    if (nunits) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
-        const unsigned grid = (unsigned)std::min<size_t>(units.size(), (size_t)ctx->num_sms);
+        const unsigned grid = (unsigned)std::min<size_t>(nunits, (size_t)ctx->num_sms);
         uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
         if (dump_first)
             tc::tc_top3_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)units.size(), d_unit_counter,
+                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, d_unit_counter,
                 ctx->d_recs.p, ctx->d_dump);
         else
             tc::tc_top3_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)units.size(), d_unit_counter,
+                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, d_unit_counter,
                 ctx->d_recs.p, ctx->d_dump);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -483,7 +550,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ctx->timed_tc = true;
         }
     }
-    if (qb[P] > 0) {
+    if (pl.qb_total > 0) {
         int max_blocks = 0;
         for (int i = 0; i < P; i++) max_blocks = std::max(max_blocks, (probs[i].nq + SELECT_WARPS - 1) / SELECT_WARPS);
         for (int p0 = 0; p0 < P; p0 += 65535) {                           // gridDim.y limit
@@ -494,7 +561,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ctx->launches++;
             CK(cudaGetLastError());
         }
-        if (!units.empty() || !units2.empty()) {
+        if (nunits || nunits2) {
             // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
             rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, ctx->work_cap);
             ctx->launches++;
@@ -1324,13 +1391,14 @@ int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, 
     return segmented_impl(ctx, query, nq, ratio, nullptr, counts, matches);
 }
 
-int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
-                    int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches) {
-    if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0)
+int vsm_loop_detect_shard(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, int32_t checked_before,
+                          const float* query, int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches,
+                          int32_t* checked_after) {
+    if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || checked_before < 0)
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect: bad argument") : VSM_ERR_INVALID;
     const int nseg = (int)ctx->segs.size();
     std::vector<char> eligible(nseg, 0);
-    int checked = 0, any = 0;
+    int checked = checked_before, any = 0;
     for (int s = 0; s < nseg; s++) {                                  // src/LoopCloser.cpp:43-48
         status[s] = -1;
         if (cur_frame_id - ctx->segs[s].frame_id < min_gap) continue;
@@ -1341,8 +1409,21 @@ int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t
         status[s] = 0;
         any = 1;
     }
+    if (checked_after) *checked_after = checked;
     if (nq == 0 || !any) return VSM_OK;                               // :22 (empty current frame)
     return segmented_impl(ctx, query, nq, ratio, &eligible, status, matches);
+}
+
+int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
+                    int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches) {
+    return vsm_loop_detect_shard(ctx, cur_frame_id, min_gap, every, 0, query, nq, ratio, status, matches, nullptr);
+}
+
+int vsm_store_set_frame_ids(vsm_ctx* ctx, const int32_t* frame_ids, int32_t n) {
+    if (!ctx || !frame_ids || n != (int32_t)ctx->segs.size())
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_set_frame_ids: n must equal the keyframe count") : VSM_ERR_INVALID;
+    for (int s = 0; s < n; s++) ctx->segs[s].frame_id = frame_ids[s];
+    return VSM_OK;
 }
 
 int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_dist_in, int32_t nshard, int32_t nq,

@@ -87,6 +87,9 @@ SYMBOLS = {
     "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "vsm_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                                   C.c_void_p, C.c_void_p]),
+    "vsm_loop_detect_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                        C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "vsm_store_set_frame_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_db_top2_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]),
     "vsm_merge_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
@@ -347,14 +350,29 @@ class Matcher:
     def loop_detect(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, want_matches=True):
         """LoopCloser::detect's candidate loop with its eligibility rules (src/LoopCloser.cpp:43-62).
         Returns (status[nkf]: -1 skipped / survivor count, [DMATCH array or None per keyframe])."""
+        status, lists, _ = self.loop_detect_shard(cur_frame_id, frame_desc, 0, ratio, min_gap, every, want_matches)
+        return status, lists
+
+    def loop_detect_shard(self, cur_frame_id, frame_desc, checked_before, ratio=0.75, min_gap=200, every=5,
+                          want_matches=True):
+        """loop_detect for one shard of a partitioned keyframe list: checked_before = eligible
+        (gap + non-empty) keyframes on earlier shards.  Returns (status, lists, checked_after)."""
         q = _rows(frame_desc, "frame_desc")
         nkf = self.store_info()[1]
         status = np.zeros(max(nkf, 1), np.int32)
         m = np.zeros((max(nkf, 1), max(q.shape[0], 1)), DMATCH) if want_matches else None
-        self._ck(self._lib.vsm_loop_detect(self._h, cur_frame_id, min_gap, every, q.ctypes.data, q.shape[0], ratio,
-                                           status.ctypes.data, m.ctypes.data if want_matches else None))
+        after = C.c_int32(0)
+        self._ck(self._lib.vsm_loop_detect_shard(self._h, cur_frame_id, min_gap, every, checked_before, q.ctypes.data,
+                                                 q.shape[0], ratio, status.ctypes.data,
+                                                 m.ctypes.data if want_matches else None, C.byref(after)))
         status = status[:nkf]
-        return status, ([m[s, :status[s]] if status[s] >= 0 else None for s in range(nkf)] if want_matches else None)
+        lists = [m[s, :status[s]] if status[s] >= 0 else None for s in range(nkf)] if want_matches else None
+        return status, lists, int(after.value)
+
+    def set_frame_ids(self, frame_ids):
+        """Frame ids of the stored keyframes in store order (after adopt_device_matrix)."""
+        ids = np.ascontiguousarray(frame_ids, np.int32)
+        self._ck(self._lib.vsm_store_set_frame_ids(self._h, ids.ctypes.data, ids.shape[0]))
 
     # -- device-pointer plumbing (resident queries, sharded search) -------------------------
     def db_top2_device(self, d_query_ptr, nq, row_offset, d_idx_ptr, d_dist_ptr, sync=False):

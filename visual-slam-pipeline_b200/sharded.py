@@ -48,6 +48,36 @@ def gather_and_merge(l_idx, l_dist, world, group, merge, g_idx=None, g_dist=None
     return merge(g_idx, g_dist)
 
 
+def loop_checked_before(cur_frame_id, frame_ids, counts, min_gap, kf_begin):
+    """The `checked` counter of LoopCloser::detect (src/LoopCloser.cpp:43-48) on entry to the shard
+    that starts at keyframe kf_begin: how many EARLIER keyframes pass the gap (:44) and non-empty
+    (:45) tests.  frame_ids / counts describe the whole keyframe list (every rank holds this
+    small table), so no rank waits for another."""
+    n = 0
+    for s in range(int(kf_begin)):
+        if cur_frame_id - int(frame_ids[s]) < min_gap:
+            continue
+        if int(counts[s]) == 0:
+            continue
+        n += 1
+    return n
+
+
+def concat_keyframe_status(local_status, nkf_per_rank, world, group=None):
+    """Host concatenation of the per-rank status arrays (the per-keyframe search has
+    no data-path collective).  local_status: int32 tensor [nkf of this rank] (CPU with gloo, CUDA
+    with NCCL); returns the whole list's status on every rank, as a CPU int32 tensor."""
+    if world == 1:
+        return local_status.cpu()
+    cap = max(int(n) for n in nkf_per_rank)
+    pad = torch.full((cap,), -1, dtype=torch.int32, device=local_status.device)
+    pad[:local_status.shape[0]] = local_status
+    out = torch.empty((world * cap,), dtype=torch.int32, device=local_status.device)
+    torch.distributed.all_gather_into_tensor(out, pad, group=group)
+    out = out.cpu().view(world, cap)
+    return torch.cat([out[r, :int(nkf_per_rank[r])] for r in range(world)])
+
+
 class ShardedDB:
     def __init__(self, device, rank=0, world=1, group=None, engine=ENGINE_TENSOR, exchange="p2p", nq_cap=4096):
         """exchange: "p2p"  = result keys stored straight into the peers' buffers over NVLink and merged
@@ -89,15 +119,40 @@ class ShardedDB:
         self._db = None
         self._nq = -1
 
-    def adopt(self, db, row_offset, seg_off=None):
+    def adopt(self, db, row_offset, seg_off=None, frame_ids=None):
         """db: this rank's [rows, 256] fp32 CUDA tensor (kept alive here); row_offset: global
-        index of its first row."""
+        index of its first row; seg_off: local row offsets of its keyframes; frame_ids: their
+        Frame::id()s (for the gap rule of loop_detect)."""
         assert db.is_cuda and db.dtype == torch.float32 and db.is_contiguous() and db.shape[1] == 256
         torch.cuda.synchronize(self.device)
         self._db = db
         self.rows = db.shape[0]
         self.row_offset = int(row_offset)
         self.matcher.adopt_device_matrix(db.data_ptr(), self.rows, seg_off)
+        if frame_ids is not None:
+            self.matcher.set_frame_ids(frame_ids)
+
+    def set_keyframe_table(self, frame_ids, counts, kf_cuts):
+        """The whole keyframe list's frame ids and descriptor counts plus the partition
+        (kf_cuts[r] .. kf_cuts[r+1] = rank r's keyframes, e.g. from partition_keyframes)."""
+        self._kf_ids = [int(x) for x in frame_ids]
+        self._kf_counts = [int(x) for x in counts]
+        self._kf_cuts = [int(x) for x in kf_cuts]
+        assert len(self._kf_cuts) == self.world + 1 and self._kf_cuts[-1] == len(self._kf_ids)
+
+    def loop_detect(self, cur_frame_id, h_q, ratio=0.75, min_gap=200, every=5, want_matches=True):
+        """LoopCloser::detect's candidate loop (src/LoopCloser.cpp:43-62) over the partitioned
+        keyframe list: each rank matches its own eligible keyframes, the status arrays are
+        concatenated.  Returns (status of the WHOLE list [CPU int32], this rank's match lists
+        keyed by global keyframe index)."""
+        k0 = self._kf_cuts[self.rank]
+        before = loop_checked_before(cur_frame_id, self._kf_ids, self._kf_counts, min_gap, k0)
+        st, lists, _ = self.matcher.loop_detect_shard(cur_frame_id, h_q, before, ratio, min_gap, every, want_matches)
+        nkf = [self._kf_cuts[r + 1] - self._kf_cuts[r] for r in range(self.world)]
+        whole = concat_keyframe_status(torch.from_numpy(st).to(self.device if self.world > 1 else "cpu"), nkf,
+                                       self.world, self.group)
+        mine = {k0 + s: lists[s] for s in range(len(st)) if lists is not None and lists[s] is not None}
+        return whole, mine
 
     def _buffers(self, nq):
         if nq != self._nq:
