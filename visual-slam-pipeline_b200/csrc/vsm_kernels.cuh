@@ -123,6 +123,41 @@ __device__ __forceinline__ void score_pair(const float (&qreg)[16], const float*
     if (act && l16 == 0) insert2(__fsqrt_rn(d2), j, b.d0, b.i0, b.d1, b.i1);
 }
 
+// Each half-warp scores four train rows (j[u] < 0 = idle; j uniform over the half-warp): the
+// loads of all four rows are issued before the first distance is reduced, so one round costs one
+// memory latency instead of four.
+__device__ __forceinline__ void score4(const float (&qreg)[16], const float* __restrict__ t_f32,
+                                       const int32_t (&j)[4], int l16, Best2& b) {
+    float tv[4][16];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const float* p = t_f32 + (size_t)(j[u] >= 0 ? j[u] : 0) * VSM_DIM;
+#pragma unroll
+        for (int i = 0; i < 16; i++) tv[u][i] = __ldg(p + 16 * i + l16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const float d2 = canon_l2sqr_halfwarp_regs(qreg, tv[u]);
+        if (l16 == 0 && j[u] >= 0) insert2(__fsqrt_rn(d2), j[u], b.d0, b.i0, b.d1, b.i1);
+    }
+}
+
+// Exact scan of a whole slice by one warp, eight rows per round.
+__device__ __forceinline__ void scan_slice(const float (&qreg)[16], const float* __restrict__ t_f32,
+                                           const SliceInfo& si, int h, int l16, Best2& b) {
+    const int span = slice_span(si);
+    for (int r0 = 0; r0 < span; r0 += 8) {
+        int32_t j[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int r = r0 + h * 4 + u;
+            const int off = r < span ? slice_row(si, r) : -1;
+            j[u] = off >= 0 ? si.t_index0 + off : -1;
+        }
+        score4(qreg, t_f32, j, l16, b);
+    }
+}
+
 // An overflowing slice is re-scanned exactly by rescan_kernel, RESCAN_ROWS slice rows per
 // work item, so that one unlucky query does not serialise thousands of rows in one warp.
 constexpr int RESCAN_ROWS = 128;
@@ -147,6 +182,8 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     const int h = lane >> 4, l16 = lane & 15;
     const unsigned full = 0xffffffffu;
 
+    // per-warp list of surviving train rows: < 8 left over from earlier chunks + at most 32 x 4 new
+    __shared__ int32_t s_list[SELECT_WARPS][8 + 32 * VSM_TOPK];
     float qreg[16];
     load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
     Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
@@ -154,18 +191,12 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     const SliceInfo* sl = slices + P.slice_off;
 
     if (P.exact) {
-        for (int s = 0; s < P.nslices; s++) {
-            const SliceInfo si = sl[s];
-            const int span = slice_span(si);
-            for (int r = h; r < span + h; r += 2) {
-                int off = r < span ? slice_row(si, r) : -1;
-                score_pair(qreg, P.t_f32, off >= 0 ? si.t_index0 + off : -1, l16, best);
-            }
-        }
+        for (int s = 0; s < P.nslices; s++) scan_slice(qreg, P.t_f32, sl[s], h, l16, best);
     } else {
         const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
         // pass 1: the second largest approximate dot over every record of the query
         float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll 4
         for (int s = lane; s < P.nslices; s += 32) {
             const float4 rv = *reinterpret_cast<const float4*>(rq + s);
             const float rs[VSM_TOPK] = {rv.x, rv.y, rv.z, rv.w};
@@ -184,14 +215,37 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
         stats_read(P.t_stats, tmin2, tmax2);
         const float thr = a1 - 2.f * dot_margin(__ldg(P.q_n2 + q), tmin2, tmax2);   // -inf if < 2 entries
 
-        // pass 2: survivors -> exact distance; overflowing slices -> exact scan
+        // pass 2: survivors -> this warp's candidate list -> exact distance, eight at a time;
+        // overflowing slices -> exact scan.  The next chunk's records are loaded before the
+        // current one is processed.
+        int32_t* list = s_list[warp];
+        int cnt = 0;
+        auto drain = [&]() {                                 // score the last (up to) eight list entries
+            const int n = min(cnt, 8), base = cnt - n;
+            int32_t j[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int slot = base + h * 4 + u;
+                j[u] = slot < cnt ? list[slot] : -1;
+            }
+            score4(qreg, P.t_f32, j, l16, best);
+            cnt = base;
+            __syncwarp();
+        };
+        const float4 none = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        float4 rv_next = none;
+        SliceInfo my_next = {0, 0, 0, 0};
+        if (lane < P.nslices) {
+            rv_next = *reinterpret_cast<const float4*>(rq + lane);
+            my_next = sl[lane];
+        }
         for (int s0 = 0; s0 < P.nslices; s0 += 32) {
-            const int s = s0 + lane;
-            float4 rv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            SliceInfo my = {0, 0, 0, 0};
-            if (s < P.nslices) {
-                rv = *reinterpret_cast<const float4*>(rq + s);
-                my = sl[s];
+            const float4 rv = rv_next;
+            const SliceInfo my = my_next;
+            rv_next = none;
+            if (s0 + 32 + lane < P.nslices) {
+                rv_next = *reinterpret_cast<const float4*>(rq + s0 + 32 + lane);
+                my_next = sl[s0 + 32 + lane];
             }
             const float rs[VSM_TOPK] = {rv.x, rv.y, rv.z, rv.w};
             const bool flagged = rs[VSM_TOPK - 1] > VALID_FLOOR && rs[VSM_TOPK - 1] > thr;
@@ -205,19 +259,16 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
                 if (!flagged && rs[e] > VALID_FLOOR && rs[e] > thr) mine |= 1u << e;
             }
             n_cand += __popc(mine);
-            // two survivors per round (one per half-warp), taken from the two lowest lanes that have any
-            unsigned any = __ballot_sync(full, mine != 0);
-            while (any) {
-                const int l0 = __ffs(any) - 1;
-                const unsigned rest = any & (any - 1);
-                const int l1 = rest ? __ffs(rest) - 1 : -1;
-                const int e0 = __ffs(mine) - 1;                              // this lane's next entry
-                const int32_t pop = e0 == 0 ? cand[0] : e0 == 1 ? cand[1] : e0 == 2 ? cand[2] : cand[3];
-                const int src = h == 0 ? l0 : l1;
-                const int32_t j = __shfl_sync(full, pop, src < 0 ? 0 : src);
-                score_pair(qreg, P.t_f32, src < 0 ? -1 : j, l16, best);
-                if (lane == l0 || lane == l1) mine &= mine - 1;
-                any = __ballot_sync(full, mine != 0);
+            if (__ballot_sync(full, mine != 0)) {
+#pragma unroll
+                for (int e = 0; e < VSM_TOPK; e++) {
+                    const bool on = (mine >> e) & 1u;
+                    const unsigned bal = __ballot_sync(full, on);
+                    if (on) list[cnt + __popc(bal & ((1u << lane) - 1u))] = cand[e];
+                    cnt += __popc(bal);
+                }
+                __syncwarp();
+                while (cnt >= 8) drain();
             }
             n_flag += __popc(__ballot_sync(full, flagged));
             // hand the overflowing slices to rescan_kernel; scan inline only if its list is full
@@ -246,14 +297,10 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
             unsigned fm = __ballot_sync(full, inline_scan);
             while (fm) {
                 int l0 = __ffs(fm) - 1; fm &= fm - 1;
-                const SliceInfo si = sl[s0 + l0];
-                const int span = slice_span(si);
-                for (int r = h; r < span + h; r += 2) {
-                    int off = r < span ? slice_row(si, r) : -1;
-                    score_pair(qreg, P.t_f32, off >= 0 ? si.t_index0 + off : -1, l16, best);
-                }
+                scan_slice(qreg, P.t_f32, sl[s0 + l0], h, l16, best);
             }
         }
+        while (cnt > 0) drain();
     }
     unsigned long long n_cand_warp = n_cand;
 #pragma unroll
