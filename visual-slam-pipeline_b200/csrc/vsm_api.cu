@@ -78,9 +78,8 @@ struct vsm_ctx {
     DevBuf<uint8_t> d_desc;
     uint8_t* h_desc = nullptr;
     size_t h_desc_cap = 0;
-    std::vector<uint8_t> desc_build, desc_last;      // descriptor block cache (skip identical uploads)
+    std::vector<uint8_t> desc_build;                 // descriptor block under construction
     std::vector<uint8_t> plan_key_build;
-    const uint8_t* desc_dev = nullptr;
     cudaEvent_t ev_desc = nullptr;
     bool desc_copy_pending = false;
     DevBuf<PartialRec> d_recs;
@@ -127,6 +126,9 @@ struct vsm_ctx {
         bool valid = false;
     } plan;
     int64_t plan_hits = 0;
+    std::vector<ConvJob> pending_conv;   // conversions queued by this call, run by its prologue kernel
+    uint32_t call_seq = 0;               // run_problems calls so far: picks the scratch-statistics slot
+    const void* aux_zeroed = nullptr;    // d_aux.p at the time its slots were last known to be zero
 };
 
 namespace {
@@ -259,6 +261,7 @@ int begin_call(vsm_ctx* ctx) {
     ctx->err.clear();
     ctx->launches = 0;
     ctx->timed_tc = ctx->timed_sel = false;
+    ctx->pending_conv.clear();
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     return VSM_OK;
@@ -292,20 +295,61 @@ int end_call(vsm_ctx* ctx, bool sync) {
     return VSM_OK;
 }
 
+// Launch with programmatic stream serialization (see pdl_wait in vsm_common.cuh): the kernel may be
+// scheduled while its predecessor in the stream still runs; it orders itself with pdl_wait().
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("VSM_NO_PDL") != nullptr;         // A/B switch: plain stream order
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// Queue the conversion (bf16 shadow + norms) of scratch rows [row0, row0+n) whose fp32 values are
+// already on the device at `src` (in the scratch arena itself, or a caller's device matrix).
+void queue_convert(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n) {
+    if (n <= 0) return;
+    ConvJob j = {src, nullptr, ctx->scratch.b16 + row0 * VSM_DIM, ctx->scratch.n2 + row0, nullptr, n};
+    ctx->pending_conv.push_back(j);
+}
+
+// Runs queued conversions as stand-alone kernels until at most `keep` are left (their statistics
+// target must be set).
+int flush_conversions(vsm_ctx* ctx, size_t keep) {
+    while (ctx->pending_conv.size() > keep) {
+        const ConvJob j = ctx->pending_conv.back();
+        ctx->pending_conv.pop_back();
+        if (j.dst_f32) CK(cudaMemcpyAsync(j.dst_f32, j.src, (size_t)j.rows * VSM_DIM * sizeof(float), cudaMemcpyDefault, ctx->stream));
+        TRY(launch_convert(ctx, j.dst_f32 ? j.dst_f32 : j.src, j.dst_b16, j.n2, j.rows, j.stats));
+    }
+    return VSM_OK;
+}
+
 // Plans, uploads and launches: tensor-core pass -> select/re-score (+ re-scan) -> filter.
-// `conv_*` describes the scratch rows that still have to be converted; the conversion is
-// launched here, after the per-call aux block (counters, unit queue head, scratch norm
-// statistics, hints, result keys) has been zeroed.
+// The conversions queued by the call (ctx->pending_conv), the zeroing of the per-call aux block
+// (counters, unit queue head, hints, result keys) and the descriptor upload are one prologue kernel.
+// Scratch norm statistics live in two alternating 8-byte slots: a call accumulates into slot
+// call_seq & 1, which the PREVIOUS call's prologue zeroed, and zeroes the other one.
 int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::vector<HJob>& jobs,
-                 int64_t total_out, int64_t total_matches, const float* conv_src, int64_t conv_row0,
-                 int64_t conv_rows, int dump_first = 0) {
+                 int64_t total_out, int64_t total_matches, int dump_first = 0) {
     const bool exact = ctx->engine == VSM_ENGINE_SIMT;
     const int P = (int)probs.size();
     vsm_ctx::Plan& pl = ctx->plan;
     // everything the plan depends on, byte for byte (HProblem and HJob have no padding)
     std::vector<uint8_t>& key = ctx->plan_key_build;
     {
-        const int64_t head[8] = {ctx->engine, ctx->seg_tiles, ctx->num_sms, P, (int64_t)jobs.size(), total_out, total_matches, 0};
+        int64_t uses_slot = 0;
+        for (auto& p : probs) if (!p.t_store) uses_slot = 1 + (ctx->call_seq & 1);
+        const int64_t head[8] = {ctx->engine, ctx->seg_tiles, ctx->num_sms, P, (int64_t)jobs.size(), total_out, total_matches, uses_slot};
         key.resize(sizeof head + sizeof(HProblem) * probs.size() + sizeof(HJob) * jobs.size());
         memcpy(key.data(), head, sizeof head);
         if (P) memcpy(key.data() + sizeof head, probs.data(), sizeof(HProblem) * probs.size());
@@ -456,11 +500,16 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     const size_t aux_bytes = off_keys + nout * 2 * sizeof(unsigned long long);
     TRY(ensure(ctx, ctx->d_aux, aux_bytes));
     TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
+    if (ctx->aux_zeroed != ctx->d_aux.p) {                   // a fresh allocation: both statistics slots start at zero
+        CK(cudaMemsetAsync(ctx->d_aux.p, 0, ctx->d_aux.cap, ctx->stream));
+        ctx->aux_zeroed = ctx->d_aux.p;
+    }
+    const int stats_slot = (int)(ctx->call_seq & 1u);
     ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
-    uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32);
+    uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32 + 8 * stats_slot);
     uint32_t* d_hints = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 48);
     ctx->d_out_key = reinterpret_cast<unsigned long long*>(ctx->d_aux.p + off_keys);
-    CK(cudaMemsetAsync(ctx->d_aux.p, 0, aux_bytes, ctx->stream));
+    bool upload_desc = false;
 
     if (!hit) {
     for (int i = 0; i < P; i++) dp[i].t_stats = probs[i].t_store ? ctx->d_store_stats : d_scratch_stats;
@@ -493,15 +542,9 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         fj.nq = jobs[j].nq; fj.nt = jobs[j].nt; fj.img_idx = jobs[j].img_idx; fj.ratio = jobs[j].ratio;
         memcpy(h + off_job + j * sizeof(FilterJob), &fj, sizeof fj);
     }
-    if (ctx->desc_dev != ctx->d_desc.p || ctx->desc_last != blk) {
-        if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));   // h_desc may still be in flight
-        memcpy(ctx->h_desc, h, total);
-        CK(cudaMemcpyAsync(ctx->d_desc.p, ctx->h_desc, total, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaEventRecord(ctx->ev_desc, ctx->stream));
-        ctx->desc_copy_pending = true;
-        ctx->desc_last = blk;
-        ctx->desc_dev = ctx->d_desc.p;
-    }
+    if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));       // h_desc may still be read by the last prologue
+    memcpy(ctx->h_desc, h, total);
+    upload_desc = true;
     if (!dump_first) {
         pl.key = key;
         pl.p_desc = ctx->d_desc.p;
@@ -511,9 +554,34 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     }
     }   // !hit
 
-    if (conv_rows > 0)
-        TRY(launch_convert(ctx, conv_src, ctx->scratch.b16 + conv_row0 * VSM_DIM, ctx->scratch.n2 + conv_row0,
-                           conv_rows, d_scratch_stats));
+    // prologue: aux zeroing + descriptor block + conversions, one kernel
+    {
+        for (auto& j : ctx->pending_conv) if (!j.stats) j.stats = d_scratch_stats;
+        TRY(flush_conversions(ctx, MAX_CONV));                          // more row sets than one prologue takes
+        Prologue pr;
+        memset(&pr, 0, sizeof pr);
+        pr.aux = reinterpret_cast<uint4*>(ctx->d_aux.p);
+        pr.aux_vecs = (uint32_t)(aux_bytes / 16);
+        pr.keep_slot = stats_slot;
+        pr.desc_src = reinterpret_cast<const uint4*>(ctx->h_desc);      // pinned, mapped (unified addressing)
+        pr.desc_dst = reinterpret_cast<uint4*>(ctx->d_desc.p);
+        pr.desc_vecs = upload_desc ? (uint32_t)(total / 16) : 0u;
+        int64_t max_rows = 0;
+        for (auto& j : ctx->pending_conv) {
+            pr.conv[pr.nconv++] = j;
+            max_rows = std::max(max_rows, j.rows);
+        }
+        ctx->pending_conv.clear();
+        const int64_t want = std::max<int64_t>((max_rows + 7) / 8, ((int64_t)pr.aux_vecs + pr.desc_vecs + 1023) / 1024);
+        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * 16));
+        CK(launch_pdl(prologue_kernel, dim3(blocks), dim3(256), 0, ctx->stream, pr));
+        ctx->launches++;
+        if (upload_desc) {
+            CK(cudaEventRecord(ctx->ev_desc, ctx->stream));
+            ctx->desc_copy_pending = true;
+        }
+        ctx->call_seq++;
+    }
 
     uint8_t* dd = ctx->d_desc.p;
     if (ctx->profiling) CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
@@ -535,16 +603,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
         const unsigned grid = (unsigned)std::min<size_t>(nunits, (size_t)ctx->num_sms);
         uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
-        if (dump_first)
-            tc::tc_top3_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, d_unit_counter,
-                ctx->d_recs.p, ctx->d_dump);
-        else
-            tc::tc_top3_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, ctx->stream>>>(
-                ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, d_unit_counter,
-                ctx->d_recs.p, ctx->d_dump);
+        CK(launch_pdl(dump_first ? tc::tc_top3_kernel<true> : tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS),
+                      tc::SMEM_BYTES, ctx->stream, ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits,
+                      d_unit_counter, ctx->d_recs.p, ctx->d_dump));
         ctx->launches++;
-        CK(cudaGetLastError());
         if (ctx->profiling) {
             CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
             ctx->timed_tc = true;
@@ -555,17 +617,17 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         for (int i = 0; i < P; i++) max_blocks = std::max(max_blocks, (probs[i].nq + SELECT_WARPS - 1) / SELECT_WARPS);
         for (int p0 = 0; p0 < P; p0 += 65535) {                           // gridDim.y limit
             const int np = std::min(65535, P - p0);
-            select_kernel<<<dim3((unsigned)max_blocks, (unsigned)np), SELECT_WARPS * 32, 0, ctx->stream>>>(
-                reinterpret_cast<const Problem*>(dd + off_prob), p0, ctx->d_recs.p,
-                reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters, ctx->d_work.p, ctx->work_cap);
+            CK(launch_pdl(select_kernel, dim3((unsigned)max_blocks, (unsigned)np), dim3(SELECT_WARPS * 32), 0, ctx->stream,
+                          reinterpret_cast<const Problem*>(dd + off_prob), p0, (const PartialRec*)ctx->d_recs.p,
+                          reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters,
+                          ctx->d_work.p, ctx->work_cap));
             ctx->launches++;
-            CK(cudaGetLastError());
         }
         if (nunits || nunits2) {
             // exact re-scan of the slices whose top-3 overflowed (usually none: the blocks exit at once)
-            rescan_kernel<<<(unsigned)ctx->num_sms * 2, 256, 0, ctx->stream>>>(ctx->d_work.p, ctx->d_counters, ctx->work_cap);
+            CK(launch_pdl(rescan_kernel, dim3((unsigned)ctx->num_sms * 2), dim3(256), 0, ctx->stream,
+                          (const WorkItem*)ctx->d_work.p, (const unsigned long long*)ctx->d_counters, ctx->work_cap));
             ctx->launches++;
-            CK(cudaGetLastError());
         }
         if (ctx->profiling) {
             CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
@@ -576,16 +638,41 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         uint8_t* rbase = ctx->result_on_host ? ctx->h_result : ctx->d_result.p;
         DMatch* dm = reinterpret_cast<DMatch*>(rbase);
         int32_t* dc = reinterpret_cast<int32_t*>(rbase + (size_t)total_matches * sizeof(DMatch));
-        filter_kernel<<<(unsigned)jobs.size(), FILTER_THREADS, 0, ctx->stream>>>(
-            reinterpret_cast<const FilterJob*>(dd + off_job), ctx->d_out_key, dm, dc);
+        CK(launch_pdl(filter_kernel, dim3((unsigned)jobs.size()), dim3(FILTER_THREADS), 0, ctx->stream,
+                      reinterpret_cast<const FilterJob*>(dd + off_job), (const unsigned long long*)ctx->d_out_key, dm, dc));
         ctx->launches++;
-        CK(cudaGetLastError());
     }
     return VSM_OK;
 }
 
-// Host rows -> scratch fp32 rows [row0, row0+n).
+// Host-mapped device address of a pinned host buffer, or nullptr if `p` is pageable memory.
+const float* host_mapped(const float* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+    return static_cast<const float*>(attr.devicePointer);
+}
+
+// up to this many rows (1 KB each) the prologue reads a pinned buffer straight over PCIe
+// (VSM_ZERO_COPY_ROWS overrides it, for tuning)
+static const int64_t ZERO_COPY_ROWS = getenv("VSM_ZERO_COPY_ROWS") ? atoll(getenv("VSM_ZERO_COPY_ROWS")) : 2048;
+
+// Host rows -> scratch rows [row0, row0+n): fp32 master + queued conversion.  A small pinned buffer
+// is not copied here at all: the call's prologue kernel reads it over PCIe (one launch for upload,
+// conversion and norms).  Otherwise a DMA now, conversion in the prologue.
 int upload_scratch(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n) {
+    if (n <= 0) return VSM_OK;
+    float* dst = ctx->scratch.f32 + row0 * VSM_DIM;
+    const float* mapped = n <= ZERO_COPY_ROWS ? host_mapped(src) : nullptr;
+    ConvJob j = {mapped ? mapped : dst, mapped ? dst : nullptr, ctx->scratch.b16 + row0 * VSM_DIM, ctx->scratch.n2 + row0,
+                 nullptr, n};
+    if (!mapped) CK(cudaMemcpyAsync(dst, src, (size_t)n * VSM_DIM * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->pending_conv.push_back(j);
+    return VSM_OK;
+}
+
+// Host rows -> scratch fp32 rows only (no bf16 shadow: track_local_map scores in fp64 from these).
+int upload_plain(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n) {
     if (n <= 0) return VSM_OK;
     CK(cudaMemcpyAsync(ctx->scratch.f32 + row0 * VSM_DIM, src, (size_t)n * VSM_DIM * sizeof(float),
                        cudaMemcpyHostToDevice, ctx->stream));
@@ -777,7 +864,7 @@ int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, i
     TRY(upload_scratch(ctx, query, 0, nq));
     TRY(upload_scratch(ctx, train, nq, nt));
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
-    TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + nt));
+    TRY(run_problems(ctx, probs, {}, nq, 0));
     TRY(fetch_keys(ctx, nq));
     TRY(end_call(ctx, true));
     const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
@@ -790,14 +877,13 @@ int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, i
 }
 
 static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int nt, float ratio, int mutual,
-                        vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw,
-                        const float* conv_src, int64_t conv_row0, int64_t conv_rows) {
+                        vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
     const bool want_raw = raw && n_raw;
     HJob j;
     j.fwd_off = 0; j.back_off = mutual ? nq : -1; j.good_off = 0; j.raw_off = want_raw ? nq : -1;
     j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
     const int64_t total_matches = (int64_t)nq * (want_raw ? 2 : 1);
-    TRY(run_problems(ctx, probs, {j}, (int64_t)nq + (mutual ? nt : 0), total_matches, conv_src, conv_row0, conv_rows));
+    TRY(run_problems(ctx, probs, {j}, (int64_t)nq + (mutual ? nt : 0), total_matches));
     const size_t bytes = (size_t)total_matches * sizeof(DMatch) + 2 * sizeof(int32_t);
     TRY(fetch_result(ctx, bytes));
     TRY(end_call(ctx, true));
@@ -824,8 +910,7 @@ int vsm_match_pair(vsm_ctx* ctx, const float* query, int32_t nq, const float* tr
     TRY(upload_scratch(ctx, train, nq, nt));
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
     if (mutual) probs.push_back(scratch_vs_scratch(ctx, nq, nt, 0, nq, nq));
-    return match_common(ctx, probs, nq, nt, ratio, mutual, good, n_good, raw, n_raw, ctx->scratch.f32, 0,
-                        (int64_t)nq + nt);
+    return match_common(ctx, probs, nq, nt, ratio, mutual, good, n_good, raw, n_raw);
 }
 
 int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int32_t* q_off, const float* train,
@@ -856,7 +941,7 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int
         j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
         jobs.push_back(j);
     }
-    TRY(run_problems(ctx, probs, jobs, NQ + (mutual ? NT : 0), NQ, ctx->scratch.f32, 0, NQ + NT));
+    TRY(run_problems(ctx, probs, jobs, NQ + (mutual ? NT : 0), NQ));
     const size_t bytes = (size_t)NQ * sizeof(DMatch) + (size_t)n_pairs * 2 * sizeof(int32_t);
     TRY(fetch_result(ctx, bytes));
     TRY(end_call(ctx, true));
@@ -1028,7 +1113,7 @@ int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t 
         b.t_f32 = f.q_f32; b.t_row = sg.row0; b.t_store = 1; b.nt = sg.count; b.out_off = sg.count;
         probs.push_back(b);
     }
-    return match_common(ctx, probs, sg.count, n_cur, ratio, mutual, good, n_good, raw, n_raw, ctx->scratch.f32, 0, n_cur);
+    return match_common(ctx, probs, sg.count, n_cur, ratio, mutual, good, n_good, raw, n_raw);
 }
 
 int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* cur, int32_t n_cur, float ratio,
@@ -1037,30 +1122,22 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_track: bad argument") : VSM_ERR_INVALID;
     if (ref_handle >= (int)ctx->segs.size()) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown keyframe handle");
     if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it first");
+    if (!good && ref_handle >= 0 && n_cur > 0 && ctx->segs[ref_handle].count > 0)
+        return fail(ctx, VSM_ERR_INVALID, "vsm_track: null output");
     *n_good = 0;
     if (n_raw) *n_raw = 0;
     TRY(begin_call(ctx));
     TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + std::max<int64_t>(n_cur, 1), ctx->store_rows));
     const int64_t row0 = ctx->store_rows;
     if (n_cur > 0) {
-        cudaPointerAttributes attr;
-        const bool pinned = cudaPointerGetAttributes(&attr, cur) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-                            attr.devicePointer != nullptr;
-        if (!pinned) cudaGetLastError();
-        if (pinned && n_cur <= 8192) {
-            // pinned frame: one kernel reads it over PCIe and writes fp32 master + bf16 shadow + norms
-            const int64_t blocks = std::min<int64_t>((n_cur + 7) / 8, (int64_t)ctx->num_sms * 16);
-            convert_from_host_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(
-                static_cast<const float*>(attr.devicePointer), ctx->store.f32 + row0 * VSM_DIM,
-                ctx->store.b16 + row0 * VSM_DIM, ctx->store.n2 + row0, n_cur, ctx->d_store_stats);
-            ctx->launches++;
-            CK(cudaGetLastError());
-        } else {
-            CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, cur, (size_t)n_cur * VSM_DIM * sizeof(float),
-                               cudaMemcpyHostToDevice, ctx->stream));
-            TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
-                               ctx->store.n2 + row0, n_cur, ctx->d_store_stats));
-        }
+        // the frame goes straight into the keyframe store; a small pinned frame is read over PCIe by
+        // the call's prologue kernel (fp32 master + bf16 shadow + norms in one launch)
+        float* dst = ctx->store.f32 + row0 * VSM_DIM;
+        const float* mapped = n_cur <= ZERO_COPY_ROWS ? host_mapped(cur) : nullptr;
+        if (!mapped) CK(cudaMemcpyAsync(dst, cur, (size_t)n_cur * VSM_DIM * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ConvJob j = {mapped ? mapped : dst, mapped ? dst : nullptr, ctx->store.b16 + row0 * VSM_DIM, ctx->store.n2 + row0,
+                     ctx->d_store_stats, n_cur};
+        ctx->pending_conv.push_back(j);
     }
     Seg ns = {row0, n_cur, frame_id};
     ctx->segs.push_back(ns);
@@ -1068,10 +1145,10 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
     *cur_handle = (int32_t)ctx->segs.size() - 1;
     const Seg ref = ref_handle >= 0 ? ctx->segs[ref_handle] : Seg{0, 0, 0};
     if (ref_handle < 0 || ref.count == 0 || n_cur == 0) {
+        TRY(flush_conversions(ctx, 0));                                  // no matching step: convert the frame on its own
         CK(cudaStreamSynchronize(ctx->stream));                          // the caller may reuse `cur`
         return end_call(ctx, true);
     }
-    if (!good) return fail(ctx, VSM_ERR_INVALID, "vsm_track: null output");
     HProblem f;
     f.q_f32 = ctx->store.f32 + ref.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + ref.row0; f.q_row = ref.row0;
     f.q_store = 1; f.nq = ref.count;
@@ -1083,7 +1160,7 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
         b.t_f32 = f.q_f32; b.t_row = ref.row0; b.t_store = 1; b.nt = ref.count; b.out_off = ref.count;
         probs.push_back(b);
     }
-    return match_common(ctx, probs, ref.count, n_cur, ratio, mutual, good, n_good, raw, n_raw, nullptr, 0, 0);
+    return match_common(ctx, probs, ref.count, n_cur, ratio, mutual, good, n_good, raw, n_raw);
 }
 
 // ---- database search -------------------------------------------------------------------
@@ -1102,7 +1179,7 @@ int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset
     TRY(upload_scratch(ctx, query, 0, nq));
     HProblem p;
     db_problem(ctx, ctx->scratch.f32, nq, p);
-    TRY(run_problems(ctx, {p}, {}, nq, 0, ctx->scratch.f32, 0, nq));
+    TRY(run_problems(ctx, {p}, {}, nq, 0));
     TRY(fetch_keys(ctx, nq));
     TRY(end_call(ctx, true));
     const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
@@ -1123,7 +1200,8 @@ int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t r
     HProblem p;
     db_problem(ctx, d_query, nq, p);
     static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? std::max(2, atoi(getenv("VSM_DEBUG_TIMELINE"))) : 0;
-    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
+    queue_convert(ctx, d_query, 0, nq);
+    TRY(run_problems(ctx, {p}, {}, nq, 0, timeline));
     widen_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_key, nq * 2, row_offset, d_idx, d_dist);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -1157,7 +1235,7 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
     }
     if (jobs.empty()) return end_call(ctx, true);
     const int64_t total_matches = (int64_t)jobs.size() * nq;
-    TRY(run_problems(ctx, probs, jobs, total_matches, total_matches, ctx->scratch.f32, 0, nq));
+    TRY(run_problems(ctx, probs, jobs, total_matches, total_matches));
     const size_t mbytes = (size_t)total_matches * sizeof(DMatch);
     const size_t cbytes = jobs.size() * 2 * sizeof(int32_t);
     std::vector<int32_t> cnt(jobs.size() * 2);
@@ -1214,8 +1292,8 @@ int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_
 
     TRY(begin_call(ctx));
     TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nkp + (mp_desc ? nmp : 0), 0));
-    TRY(upload_scratch(ctx, desc, 0, nkp));
-    if (mp_desc) TRY(upload_scratch(ctx, mp_desc, nkp, nmp));
+    TRY(upload_plain(ctx, desc, 0, nkp));
+    if (mp_desc) TRY(upload_plain(ctx, mp_desc, nkp, nmp));
     const size_t o_xy = 0, o_id = align16(o_xy + sxy.size() * 4), o_pos = align16(o_id + sid.size() * 4),
                  o_valid = align16(o_pos + (size_t)nmp * 24), o_bk = align16(o_valid + (size_t)nmp),
                  o_bd = align16(o_bk + (size_t)nmp * 4), total = align16(o_bd + (size_t)nmp * 8);
@@ -1285,7 +1363,8 @@ int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8
         CK(cudaGetLastError());
     }
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, (int)ns, 0)};
-    TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + ns));
+    queue_convert(ctx, ctx->scratch.f32 + (int64_t)nq * VSM_DIM, nq, ns);        // the gathered rows
+    TRY(run_problems(ctx, probs, {}, nq, 0));
     TRY(fetch_keys(ctx, nq));
     TRY(end_call(ctx, true));                                            // also keeps `sel` alive past the H2D
     const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
@@ -1307,7 +1386,8 @@ int vsm_db_top2_keys_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int6
     HProblem p;
     db_problem(ctx, d_query, nq, p);
     static const int timeline = getenv("VSM_DEBUG_TIMELINE") ? std::max(2, atoi(getenv("VSM_DEBUG_TIMELINE"))) : 0;
-    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq, timeline));
+    queue_convert(ctx, d_query, 0, nq);
+    TRY(run_problems(ctx, {p}, {}, nq, 0, timeline));
     globalize_keys_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(
         ctx->d_out_key, nq * 2, (uint32_t)row_offset, reinterpret_cast<unsigned long long*>(d_keys));
     ctx->launches++;
@@ -1359,7 +1439,8 @@ int vsm_db_top2_xchg_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int6
     TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
     HProblem p;
     db_problem(ctx, d_query, nq, p);
-    TRY(run_problems(ctx, {p}, {}, nq, 0, d_query, 0, nq));
+    queue_convert(ctx, d_query, 0, nq);
+    TRY(run_problems(ctx, {p}, {}, nq, 0));
     ctx->xchg_step++;
     xchg_publish_merge_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_out_key, nq, (uint32_t)row_offset, ctx->xchg_peers,
                                                           ctx->xchg_rank, ctx->xchg_world, ctx->xchg_nq_cap, ctx->xchg_step,
@@ -1455,7 +1536,7 @@ int vsm_debug_tile_scores(vsm_ctx* ctx, const float* query, int32_t nq, const fl
     TRY(upload_scratch(ctx, query, 0, nq));
     TRY(upload_scratch(ctx, train, nq, nt));
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
-    TRY(run_problems(ctx, probs, {}, nq, 0, ctx->scratch.f32, 0, (int64_t)nq + nt, 1));
+    TRY(run_problems(ctx, probs, {}, nq, 0, 1));
     CK(cudaMemcpyAsync(out, ctx->d_dump, TILE_M * TILE_N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     return end_call(ctx, true);
 }

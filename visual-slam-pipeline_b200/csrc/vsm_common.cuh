@@ -19,6 +19,15 @@
 
 namespace vsm {
 
+// Programmatic dependent launch: the kernels of one call (prologue -> tensor-core pass -> select ->
+// re-scan -> filter) are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each
+// one lets its successor be scheduled at once (pdl_launch_dependents: the successor's launch
+// latency, block scheduling and set-up overlap this kernel) and touches global memory only after
+// pdl_wait(), which returns when the predecessor grid has completed and its writes are visible.
+// Without a programmatic predecessor both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Geometry of the tensor-core kernel (vsm_tc.cuh).
 constexpr int TILE_M = 128;        // queries per CTA (TMEM lanes)
 constexpr int TILE_N = 256;        // train rows per MMA tile (TMEM columns of one stage)

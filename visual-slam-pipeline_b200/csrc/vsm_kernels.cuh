@@ -1,5 +1,6 @@
 // vsm_kernels.cuh -- the CUDA-core kernels around the tensor-core pass:
 //   convert_kernel  fp32 rows -> bf16 shadow + squared norms (+ min/max norm of the set)
+//   prologue_kernel first kernel of a matching call: aux zeroing + descriptor upload + conversions
 //   select_kernel   per query: threshold the approximate records, re-score the survivors
 //                   with the canonical fp32 distance, keep the exact top-2
 //   filter_kernel   Slam::match_features' loop (src/Slam.cpp:1151-1158) + mutual-NN,
@@ -43,40 +44,76 @@ convert_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, f
     }
 }
 
-// Same, reading the rows straight from pinned HOST memory (zero-copy over PCIe) and also writing
-// the fp32 master copy: upload + convert of a tracking frame in one kernel instead of a DMA
-// followed by a kernel.
+// First kernel of every matching call.  One launch instead of a memset, a descriptor upload and
+// one conversion per input:
+//   * zeroes the per-call aux block (counters, unit queue head, hints, result keys) -- except the
+//     scratch-statistics slot this call accumulates into (zeroed by the previous call, see
+//     run_problems: the two slots alternate);
+//   * copies the call's descriptor block from pinned host memory (read over PCIe);
+//   * converts up to MAX_CONV row sets to bf16 + squared norms.  A set whose source is pinned HOST
+//     memory (mapped into the device) is read straight over PCIe and its fp32 master copy is
+//     written as well: upload + convert of a tracking frame without a DMA in front.
+struct ConvJob {
+    const float* src;          // fp32 rows: device memory, or pinned host memory mapped into the device
+    float* dst_f32;            // fp32 master copy to write (zero-copy upload) or nullptr (src IS the master)
+    __nv_bfloat16* dst_b16;
+    float* n2;
+    uint32_t* stats;           // norm statistics of the set the rows belong to (see stats_read)
+    int64_t rows;
+};
+constexpr int MAX_CONV = 2;
+struct Prologue {
+    uint4* aux;
+    const uint4* desc_src;
+    uint4* desc_dst;
+    uint32_t aux_vecs, desc_vecs;      // 16-byte vectors
+    int32_t keep_slot, nconv;
+    ConvJob conv[MAX_CONV];
+};
+
 __global__ void __launch_bounds__(256)
-convert_from_host_kernel(const float* __restrict__ src_host, float* __restrict__ dst_f32,
-                         __nv_bfloat16* __restrict__ dst, float* __restrict__ n2, int64_t nrows,
-                         uint32_t* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    float lo = INFINITY, hi = 0.f;
-    for (int64_t row = warp0; row < nrows; row += nwarps) {
-        const float4* p = reinterpret_cast<const float4*>(src_host + row * VSM_DIM) + lane * 2;
-        const float4 a = p[0], b = p[1];
-        float4* o = reinterpret_cast<float4*>(dst_f32 + row * VSM_DIM) + lane * 2;
-        o[0] = a; o[1] = b;
-        float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
-#pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-        __nv_bfloat162 o0 = __floats2bfloat162_rn(a.x, a.y), o1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 o2b = __floats2bfloat162_rn(b.x, b.y), o3 = __floats2bfloat162_rn(b.z, b.w);
-        uint4 packed;
-        packed.x = *reinterpret_cast<uint32_t*>(&o0);
-        packed.y = *reinterpret_cast<uint32_t*>(&o1);
-        packed.z = *reinterpret_cast<uint32_t*>(&o2b);
-        packed.w = *reinterpret_cast<uint32_t*>(&o3);
-        reinterpret_cast<uint4*>(dst + row * VSM_DIM)[lane] = packed;
-        if (lane == 0) n2[row] = s;
-        lo = fminf(lo, s);
-        hi = fmaxf(hi, s);
+prologue_kernel(const Prologue pr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t v = tid; v < pr.aux_vecs; v += nth) {
+        // vector 2 = bytes 32..47 = the two statistics slots of 8 bytes each
+        if (v == 2) reinterpret_cast<uint2*>(pr.aux)[4 + (1 - pr.keep_slot)] = make_uint2(0u, 0u);
+        else pr.aux[v] = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (lane == 0 && lo <= hi) {
-        atomicMax(stats, ~__float_as_uint(lo));
-        atomicMax(stats + 1, __float_as_uint(hi));
+    for (uint32_t v = tid; v < pr.desc_vecs; v += nth) pr.desc_dst[v] = pr.desc_src[v];
+
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)(tid >> 5), nwarps = (int64_t)(nth >> 5);
+    for (int c = 0; c < pr.nconv; c++) {
+        const ConvJob& J = pr.conv[c];
+        float lo = INFINITY, hi = 0.f;
+        for (int64_t row = warp0; row < J.rows; row += nwarps) {
+            const float4* p = reinterpret_cast<const float4*>(J.src + row * VSM_DIM) + lane * 2;
+            const float4 a = p[0], b = p[1];
+            if (J.dst_f32) {
+                float4* o = reinterpret_cast<float4*>(J.dst_f32 + row * VSM_DIM) + lane * 2;
+                o[0] = a; o[1] = b;
+            }
+            float s = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(a.x, a.y), o1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 o2b = __floats2bfloat162_rn(b.x, b.y), o3 = __floats2bfloat162_rn(b.z, b.w);
+            uint4 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&o0);
+            packed.y = *reinterpret_cast<uint32_t*>(&o1);
+            packed.z = *reinterpret_cast<uint32_t*>(&o2b);
+            packed.w = *reinterpret_cast<uint32_t*>(&o3);
+            reinterpret_cast<uint4*>(J.dst_b16 + row * VSM_DIM)[lane] = packed;
+            if (lane == 0) J.n2[row] = s;
+            lo = fminf(lo, s);
+            hi = fmaxf(hi, s);
+        }
+        if (lane == 0 && lo <= hi) {
+            atomicMax(J.stats, ~__float_as_uint(lo));          // see stats_read
+            atomicMax(J.stats + 1, __float_as_uint(hi));
+        }
     }
 }
 
@@ -175,6 +212,8 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
               unsigned long long* __restrict__ out_key,
               unsigned long long* __restrict__ counters, WorkItem* __restrict__ work, uint32_t work_cap) {
     // grid: x = block of SELECT_WARPS queries, y = problem (ragged problems: surplus blocks exit)
+    pdl_launch_dependents();
+    pdl_wait();
     const Problem P = problems[problem0 + blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = (int)blockIdx.x * SELECT_WARPS + warp;
@@ -325,6 +364,8 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
 // scoring two rows per step (both rows' loads are in flight together).
 __global__ void __launch_bounds__(256)
 rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __restrict__ counters, uint32_t work_cap) {
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t nwork = min(*reinterpret_cast<const uint32_t*>(counters + 2), work_cap);
     __shared__ Best2 part[16];
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
@@ -378,6 +419,8 @@ constexpr int FILTER_THREADS = 1024;
 __global__ void __launch_bounds__(FILTER_THREADS)
 filter_kernel(const FilterJob* __restrict__ jobs, const unsigned long long* __restrict__ out_key,
               DMatch* __restrict__ matches, int32_t* __restrict__ counts) {
+    pdl_launch_dependents();
+    pdl_wait();
     const FilterJob J = jobs[blockIdx.x];
     __shared__ int wsum[2][FILTER_THREADS / 32];
     __shared__ int base[2];

@@ -283,6 +283,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&map_scratch);
         prefetch_tensormap(&map_store);
@@ -309,6 +310,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                 // barriers, TMEM and tensor maps are set up; now the inputs must be complete
 
     // Persistent CTA: units are handed out by an atomic counter in launch order (range-major,
     // query-tile-minor), so the CTAs running together always work on neighbouring train rows:
