@@ -287,7 +287,8 @@ void* vsm_stream(vsm_ctx* ctx);
 /* Run on a caller-owned stream (e.g. the stream an NCCL collective is enqueued on). */
 int   vsm_set_stream(vsm_ctx* ctx, void* cuda_stream);
 int   vsm_sync(vsm_ctx* ctx);
-/* Per-kernel CUDA events (tc_ms / select_ms in vsm_stats); on by default, a few microseconds per call. */
+/* CUDA events and counters behind vsm_stats (device_ms, tc_ms, select_ms, candidates, flagged_slices);
+ * on by default.  Off: those fields read 0 and a call is a few microseconds shorter. */
 int   vsm_set_profiling(vsm_ctx* ctx, int32_t on);
 
 /* Debug / bring-up: the raw tensor-core accumulators (bf16 dot products q.t) of the

@@ -236,6 +236,52 @@ def test_track_sequence(tc):
     tc.clear_store()
 
 
+def _pinned(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+
+def test_pinned_inputs_take_the_zero_copy_path(tc):
+    """Pinned host inputs of up to 2048 rows are read over PCIe by the call's prologue kernel (no
+    DMA); larger or pageable ones are copied first.  Same answers either way, on every entry point."""
+    q, t = cases.PAIR_CASES["pair_777x1301"]()
+    pq, pt = _pinned(q), _pinned(t)
+    oi, od = oracle.knn(q, t, 2)
+    for a, b in ((pq, pt), (pq, t), (q, pt)):                  # pinned/pinned, pinned/pageable, pageable/pinned
+        gi, gd = tc.knn_match(a, b)
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+        good, raw = tc.match_features(a, b, 0.75, mutual=True)
+        og, orw = oracle.match_features(q, t, 0.75, mutual=True)
+        assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+    # above the zero-copy limit (2048 rows) a pinned buffer goes through the DMA path
+    q2, t2 = gen.planted(8, 2100, 2500, 0.6, 0.08)[:2]
+    gi, gd = tc.knn_match(_pinned(q2), _pinned(t2))
+    oi, od = oracle.knn(q2, t2, 2)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    # tracking: pinned frames; the first call has no reference frame (stand-alone conversion)
+    frames = gen.video(11, 4, 500)
+    tc.clear_store()
+    prev = -1
+    for f, d in enumerate(frames):
+        good, _, h = tc.track(prev, f, _pinned(d), 0.75, mutual=True)
+        if f > 0:
+            og, _ = oracle.match_features(frames[f - 1], d, 0.75, mutual=True)
+            assert good.tobytes() == og.tobytes()
+        prev = h
+    # keyframe DB search with pinned queries (both the per-keyframe and the global form)
+    qd, db, seg_off = cases.db_case()
+    tc.clear_store()
+    for s in range(len(seg_off) - 1):
+        tc.add_keyframe(s, db[seg_off[s]:seg_off[s + 1]])
+    gi, gd = tc.search_map_points(_pinned(qd))
+    oi, od = oracle.knn(qd, db, 2)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    counts, lists = tc.detect_candidates(_pinned(qd), 0.75)
+    oc, ol = oracle.segmented(qd, db, seg_off, 0.75)
+    assert np.array_equal(counts, oc)
+    tc.clear_store()
+
+
 def test_loop_detect_eligibility_and_matches(tc):
     """vsm_loop_detect = LoopCloser::detect's loop incl. the gap >= 200 / every-5th rules."""
     q, db, seg_off = cases.db_case()

@@ -98,7 +98,7 @@ struct vsm_ctx {
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_tc0 = nullptr, ev_tc1 = nullptr, ev_sel1 = nullptr;
-    bool timed_tc = false, timed_sel = false, pending_stats = false;
+    bool timed_tc = false, timed_sel = false, timed_call = false, pending_stats = false;
     vsm_stats stats{};
     int launches = 0;
     std::string err;
@@ -263,7 +263,8 @@ int begin_call(vsm_ctx* ctx) {
     ctx->timed_tc = ctx->timed_sel = false;
     ctx->pending_conv.clear();
     CK(cudaSetDevice(ctx->device));
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ctx->timed_call = ctx->profiling;
+    if (ctx->timed_call) CK(cudaEventRecord(ctx->ev0, ctx->stream));
     return VSM_OK;
 }
 
@@ -272,7 +273,7 @@ int collect_stats(vsm_ctx* ctx) {
     if (!ctx->pending_stats) return VSM_OK;
     ctx->pending_stats = false;
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ctx->timed_call) CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.device_ms = ms;
     ctx->stats.tc_ms = ctx->stats.select_ms = 0.f;
     if (ctx->timed_tc) CK(cudaEventElapsedTime(&ctx->stats.tc_ms, ctx->ev_tc0, ctx->ev_tc1));
@@ -285,7 +286,7 @@ int collect_stats(vsm_ctx* ctx) {
 }
 
 int end_call(vsm_ctx* ctx, bool sync) {
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (ctx->timed_call) CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->stats.kernel_launches = ctx->launches;
     ctx->pending_stats = true;
     if (sync) {

@@ -361,7 +361,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
 
 // One block per work item: exact top-2 over RESCAN_ROWS rows of one slice for one query,
 // pushed into the query's result slots with the atomicMax cascade.  16 half-warps, each
-// scoring two rows per step (both rows' loads are in flight together).
+// scoring eight rows (all loads in flight together).
 __global__ void __launch_bounds__(256)
 rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __restrict__ counters, uint32_t work_cap) {
     pdl_launch_dependents();
@@ -378,13 +378,13 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
         float qreg[16];
         load_qreg(qreg, w.q, l16);
         Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
-        // 16 half-warps x 4 rows per step: all 64 rows' loads of a step are in flight together
-        for (int k = 0; k < RESCAN_ROWS / 64; k++) {
-            int32_t j[4];
-            float tv[4][16];
+        // 16 half-warps x 8 rows: the loads of all 128 rows of the item are in flight together
+        for (int k = 0; k < RESCAN_ROWS / 128; k++) {
+            int32_t j[8];
+            float tv[8][16];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int r = w.r0 + k * 64 + u * 16 + hw;
+            for (int u = 0; u < 8; u++) {
+                const int r = w.r0 + k * 128 + u * 16 + hw;
                 const int off = r < r1 ? slice_row(si, r) : -1;
                 j[u] = off >= 0 ? si.t_index0 + off : -1;
                 const float* p = w.t + (size_t)(j[u] >= 0 ? j[u] : 0) * VSM_DIM;
@@ -392,7 +392,7 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
                 for (int i = 0; i < 16; i++) tv[u][i] = __ldg(p + 16 * i + l16);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const float d2 = canon_l2sqr_halfwarp_regs(qreg, tv[u]);
                 if (l16 == 0 && j[u] >= 0) insert2(__fsqrt_rn(d2), j[u], best.d0, best.i0, best.d1, best.i1);
             }
