@@ -2,6 +2,7 @@
 event timings.  Usage: python scripts/profile_case.py <case> [reps]
   pair1000   1000x1000 match_features, mutual + ratio (BASELINE configs[1])
   pair2000   2000x2000 knn + ratio 0.8 (configs[0])
+  ragged64   64 ragged pairs in one call (configs[4])
   seg:<nkf>:<rows>:<nq>  LoopCloser block: per-keyframe top-2 + ratio over nkf stored keyframes
   db:<rows>:<nq>   global top-2 of nq queries over a <rows>-row resident DB (configs[2]/[3])
 """
@@ -41,6 +42,28 @@ def main():
             good, _ = m.match_features(ha, hb, 0.75, mutual=True, want_raw=False)
             dt = time.perf_counter() - t0
             print(case, "wall_us", round(dt * 1e6, 1), "matches", len(good), m.stats())
+    elif case == "ragged64":
+        # BASELINE configs[4]: 64 pairs, sizes U{200..2048}, mutual + ratio, one launch sequence
+        rng = np.random.default_rng(0)
+        sizes = rng.integers(200, 2049, size=(64, 2))
+        qs, tsets = [], []
+        for nq, nt in sizes:
+            base = unit(int(max(nq, nt)), g)
+            k = int(0.6 * len(base))
+            nxt = unit(len(base), g)
+            v = base[:k] + 0.08 * torch.randn((k, 256), generator=g, device="cuda")
+            nxt[:k] = v / v.norm(dim=1, keepdim=True)
+            qs.append(base[:nq].cpu().numpy())
+            tsets.append(nxt[:nt].cpu().numpy())
+        q_off = np.zeros(65, np.int32); t_off = np.zeros(65, np.int32)
+        q_off[1:] = np.cumsum(sizes[:, 0]); t_off[1:] = np.cumsum(sizes[:, 1])
+        qa = torch.from_numpy(np.concatenate(qs)).pin_memory().numpy()
+        ta = torch.from_numpy(np.concatenate(tsets)).pin_memory().numpy()
+        for r in range(reps + 3):
+            t0 = time.perf_counter()
+            res = m.match_batch_packed(qa, q_off, ta, t_off, 0.75, True)
+            dt = time.perf_counter() - t0
+            print(case, "wall_ms", round(dt * 1e3, 3), "matches", int(sum(len(x) for x in res)), m.stats())
     elif case.startswith("seg"):
         _, nkf, rows, nq = case.split(":")
         nkf, rows, nq = int(nkf), int(rows), int(nq)

@@ -137,10 +137,16 @@ __device__ __forceinline__ void key_decode(unsigned long long k, int32_t& i, flo
     i = (int32_t)(uint32_t)k;
     d = __uint_as_float((uint32_t)(k >> 32));
 }
-__device__ __forceinline__ void key_push(unsigned long long* slot2, unsigned long long k) {
-    const unsigned long long old = atomicMax(slot2, k);
-    const unsigned long long loser = old < k ? old : k;
-    if (loser != 0ull) atomicMax(slot2 + 1, loser);
+
+// Push a partial top-2 (k0 >= k1, k1 may be 0 = none) into a query's two slots: the larger of
+// (old slot 0, k0) stays in slot 0, the loser competes with k1 (which can only ever be second)
+// for slot 1.  Every key is either kept or re-offered one slot down, so concurrent pushes from
+// several blocks leave the two largest keys -- no lock.
+__device__ __forceinline__ void key_push2(unsigned long long* slot2, unsigned long long k0, unsigned long long k1) {
+    const unsigned long long old = atomicMax(slot2, k0);
+    const unsigned long long loser = old < k0 ? old : k0;
+    const unsigned long long second = loser > k1 ? loser : k1;
+    if (second != 0ull) atomicMax(slot2 + 1, second);
 }
 
 __device__ __forceinline__ int32_t slice_row(const SliceInfo& si, int r) {
@@ -160,38 +166,45 @@ __device__ __forceinline__ void score_pair(const float (&qreg)[16], const float*
     if (act && l16 == 0) insert2(__fsqrt_rn(d2), j, b.d0, b.i0, b.d1, b.i1);
 }
 
-// Each half-warp scores four train rows (j[u] < 0 = idle; j uniform over the half-warp): the
-// loads of all four rows are issued before the first distance is reduced, so one round costs one
-// memory latency instead of four.
-__device__ __forceinline__ void score4(const float (&qreg)[16], const float* __restrict__ t_f32,
-                                       const int32_t (&j)[4], int l16, Best2& b) {
-    float tv[4][16];
+// Each half-warp scores U train rows (j[u] < 0 = idle; j uniform over the half-warp): the loads of
+// all U rows are issued before the first distance is reduced, so one round costs one memory
+// latency instead of U.  Measured (B200): in select_kernel U = 1 (64 registers, 32 warps per SM)
+// beats U = 2 (78) and U = 4 (127) by 6 % / 50 % when there are many queries (500 keyframes x 1000
+// queries) and ties with them on a single tracking step, where a query has ~3 survivors -- so
+// SELECT_U = 1; rescan_kernel, whose items are 128 rows long, uses RESCAN_U = 4.
+constexpr int SELECT_U = 1;
+constexpr int RESCAN_U = 4;
+template <int U>
+__device__ __forceinline__ void score_n(const float (&qreg)[16], const float* __restrict__ t_f32,
+                                        const int32_t (&j)[U], int l16, Best2& b) {
+    float tv[U][16];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < U; u++) {
         const float* p = t_f32 + (size_t)(j[u] >= 0 ? j[u] : 0) * VSM_DIM;
 #pragma unroll
         for (int i = 0; i < 16; i++) tv[u][i] = __ldg(p + 16 * i + l16);
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < U; u++) {
         const float d2 = canon_l2sqr_halfwarp_regs(qreg, tv[u]);
         if (l16 == 0 && j[u] >= 0) insert2(__fsqrt_rn(d2), j[u], b.d0, b.i0, b.d1, b.i1);
     }
 }
 
-// Exact scan of a whole slice by one warp, eight rows per round.
+// Exact scan of a whole slice by one warp, 2U rows per round.
+template <int U>
 __device__ __forceinline__ void scan_slice(const float (&qreg)[16], const float* __restrict__ t_f32,
                                            const SliceInfo& si, int h, int l16, Best2& b) {
     const int span = slice_span(si);
-    for (int r0 = 0; r0 < span; r0 += 8) {
-        int32_t j[4];
+    for (int r0 = 0; r0 < span; r0 += 2 * U) {
+        int32_t j[U];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int r = r0 + h * 4 + u;
+        for (int u = 0; u < U; u++) {
+            const int r = r0 + h * U + u;
             const int off = r < span ? slice_row(si, r) : -1;
             j[u] = off >= 0 ? si.t_index0 + off : -1;
         }
-        score4(qreg, t_f32, j, l16, b);
+        score_n<U>(qreg, t_f32, j, l16, b);
     }
 }
 
@@ -221,8 +234,8 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     const int h = lane >> 4, l16 = lane & 15;
     const unsigned full = 0xffffffffu;
 
-    // per-warp list of surviving train rows: < 8 left over from earlier chunks + at most 32 x 4 new
-    __shared__ int32_t s_list[SELECT_WARPS][8 + 32 * VSM_TOPK];
+    // per-warp list of surviving train rows: < 2 x SELECT_U left over from earlier chunks + at most 32 x 4 new
+    __shared__ int32_t s_list[SELECT_WARPS][2 * SELECT_U + 32 * VSM_TOPK];
     float qreg[16];
     load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
     Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
@@ -230,7 +243,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     const SliceInfo* sl = slices + P.slice_off;
 
     if (P.exact) {
-        for (int s = 0; s < P.nslices; s++) scan_slice(qreg, P.t_f32, sl[s], h, l16, best);
+        for (int s = 0; s < P.nslices; s++) scan_slice<SELECT_U>(qreg, P.t_f32, sl[s], h, l16, best);
     } else {
         const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
         // pass 1: the second largest approximate dot over every record of the query
@@ -254,20 +267,20 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
         stats_read(P.t_stats, tmin2, tmax2);
         const float thr = a1 - 2.f * dot_margin(__ldg(P.q_n2 + q), tmin2, tmax2);   // -inf if < 2 entries
 
-        // pass 2: survivors -> this warp's candidate list -> exact distance, eight at a time;
+        // pass 2: survivors -> this warp's candidate list -> exact distance, 2 x SELECT_U at a time;
         // overflowing slices -> exact scan.  The next chunk's records are loaded before the
         // current one is processed.
         int32_t* list = s_list[warp];
         int cnt = 0;
-        auto drain = [&]() {                                 // score the last (up to) eight list entries
-            const int n = min(cnt, 8), base = cnt - n;
-            int32_t j[4];
+        auto drain = [&]() {                                 // score the last (up to) 2 x SELECT_U list entries
+            const int n = min(cnt, 2 * SELECT_U), base = cnt - n;
+            int32_t j[SELECT_U];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int slot = base + h * 4 + u;
+            for (int u = 0; u < SELECT_U; u++) {
+                const int slot = base + h * SELECT_U + u;
                 j[u] = slot < cnt ? list[slot] : -1;
             }
-            score4(qreg, P.t_f32, j, l16, best);
+            score_n<SELECT_U>(qreg, P.t_f32, j, l16, best);
             cnt = base;
             __syncwarp();
         };
@@ -307,7 +320,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
                     cnt += __popc(bal);
                 }
                 __syncwarp();
-                while (cnt >= 8) drain();
+                while (cnt >= 2 * SELECT_U) drain();
             }
             n_flag += __popc(__ballot_sync(full, flagged));
             // hand the overflowing slices to rescan_kernel; scan inline only if its list is full
@@ -336,7 +349,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
             unsigned fm = __ballot_sync(full, inline_scan);
             while (fm) {
                 int l0 = __ffs(fm) - 1; fm &= fm - 1;
-                scan_slice(qreg, P.t_f32, sl[s0 + l0], h, l16, best);
+                scan_slice<SELECT_U>(qreg, P.t_f32, sl[s0 + l0], h, l16, best);
             }
         }
         while (cnt > 0) drain();
@@ -378,13 +391,13 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
         float qreg[16];
         load_qreg(qreg, w.q, l16);
         Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
-        // 16 half-warps x 8 rows: the loads of all 128 rows of the item are in flight together
-        for (int k = 0; k < RESCAN_ROWS / 128; k++) {
-            int32_t j[8];
-            float tv[8][16];
+        // 16 half-warps x RESCAN_U rows per step, all loads of a step in flight together
+        for (int k = 0; k < RESCAN_ROWS / (16 * RESCAN_U); k++) {
+            int32_t j[RESCAN_U];
+            float tv[RESCAN_U][16];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int r = w.r0 + k * 128 + u * 16 + hw;
+            for (int u = 0; u < RESCAN_U; u++) {
+                const int r = w.r0 + k * 16 * RESCAN_U + u * 16 + hw;
                 const int off = r < r1 ? slice_row(si, r) : -1;
                 j[u] = off >= 0 ? si.t_index0 + off : -1;
                 const float* p = w.t + (size_t)(j[u] >= 0 ? j[u] : 0) * VSM_DIM;
@@ -392,7 +405,7 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
                 for (int i = 0; i < 16; i++) tv[u][i] = __ldg(p + 16 * i + l16);
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
+            for (int u = 0; u < RESCAN_U; u++) {
                 const float d2 = canon_l2sqr_halfwarp_regs(qreg, tv[u]);
                 if (l16 == 0 && j[u] >= 0) insert2(__fsqrt_rn(d2), j[u], best.d0, best.i0, best.d1, best.i1);
             }
@@ -404,8 +417,7 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
                 if (part[k].i0 >= 0) insert2(part[k].d0, part[k].i0, best.d0, best.i0, best.d1, best.i1);
                 if (part[k].i1 >= 0) insert2(part[k].d1, part[k].i1, best.d0, best.i0, best.d1, best.i1);
             }
-            if (best.i0 >= 0) key_push(w.key, result_key(best.d0, best.i0));
-            if (best.i1 >= 0) key_push(w.key, result_key(best.d1, best.i1));
+            if (best.i0 >= 0) key_push2(w.key, result_key(best.d0, best.i0), best.i1 >= 0 ? result_key(best.d1, best.i1) : 0ull);
         }
         __syncthreads();
     }
