@@ -290,6 +290,11 @@ int   vsm_sync(vsm_ctx* ctx);
 /* CUDA events and counters behind vsm_stats (device_ms, tc_ms, select_ms, candidates, flagged_slices);
  * on by default.  Off: those fields read 0 and a call is a few microseconds shorter. */
 int   vsm_set_profiling(vsm_ctx* ctx, int32_t on);
+/* Device time of the tensor-core kernel in each of the last calls (oldest first, at most the last
+ * 64 calls made with profiling on; 0 for a call that did not run it).  Waits for the stream.  Lets
+ * a caller that enqueues a loop of asynchronous searches read every launch's duration afterwards
+ * without synchronising inside the loop.  ms: [n], *n_out = entries written. */
+int   vsm_tc_history(vsm_ctx* ctx, float* ms, int32_t n, int32_t* n_out);
 
 /* Debug / bring-up: the raw tensor-core accumulators (bf16 dot products q.t) of the
  * first 128 queries x first 256 train rows, written to out[128*256] (host). */

@@ -97,6 +97,12 @@ struct vsm_ctx {
     DevBuf<uint8_t> d_track;                     // track_local_map: keypoints, map-point positions, results
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // event pairs around the tensor-core kernel of the last TC_RING calls (ev_tc0/ev_tc1 = the current
+    // call's pair): asynchronous callers read a whole timed loop afterwards (vsm_tc_history)
+    static constexpr int TC_RING = 64;
+    cudaEvent_t tc_ring0[TC_RING] = {}, tc_ring1[TC_RING] = {};
+    bool tc_ring_valid[TC_RING] = {};
+    uint32_t tc_ring_head = 0;               // slot of the next timed call
     cudaEvent_t ev_tc0 = nullptr, ev_tc1 = nullptr, ev_sel1 = nullptr;
     bool timed_tc = false, timed_sel = false, timed_call = false, pending_stats = false;
     vsm_stats stats{};
@@ -585,7 +591,13 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     }
 
     uint8_t* dd = ctx->d_desc.p;
-    if (ctx->profiling) CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
+    if (ctx->profiling) {
+        const uint32_t slot = ctx->tc_ring_head++ % vsm_ctx::TC_RING;
+        ctx->ev_tc0 = ctx->tc_ring0[slot];
+        ctx->ev_tc1 = ctx->tc_ring1[slot];
+        ctx->tc_ring_valid[slot] = nunits || nunits2;
+        CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
+    }
     if (nunits2) {
         const CUtensorMap& ms = ctx->scratch.map;
         const CUtensorMap& mt = ctx->store.b16 ? ctx->store.map : ctx->scratch.map;
@@ -760,8 +772,12 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ctx->ev0));
         CK(cudaEventCreate(&ctx->ev1));
-        CK(cudaEventCreate(&ctx->ev_tc0));
-        CK(cudaEventCreate(&ctx->ev_tc1));
+        for (int i = 0; i < vsm_ctx::TC_RING; i++) {
+            CK(cudaEventCreate(&ctx->tc_ring0[i]));
+            CK(cudaEventCreate(&ctx->tc_ring1[i]));
+        }
+        ctx->ev_tc0 = ctx->tc_ring0[0];
+        ctx->ev_tc1 = ctx->tc_ring1[0];
         CK(cudaEventCreate(&ctx->ev_sel1));
         CK(cudaEventCreateWithFlags(&ctx->ev_desc, cudaEventDisableTiming));
         void* fn = nullptr;
@@ -807,8 +823,10 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev_tc0) cudaEventDestroy(ctx->ev_tc0);
-    if (ctx->ev_tc1) cudaEventDestroy(ctx->ev_tc1);
+    for (int i = 0; i < vsm_ctx::TC_RING; i++) {
+        if (ctx->tc_ring0[i]) cudaEventDestroy(ctx->tc_ring0[i]);
+        if (ctx->tc_ring1[i]) cudaEventDestroy(ctx->tc_ring1[i]);
+    }
     if (ctx->ev_sel1) cudaEventDestroy(ctx->ev_sel1);
     if (ctx->ev_desc) cudaEventDestroy(ctx->ev_desc);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -822,6 +840,23 @@ int vsm_get_stats(vsm_ctx* ctx, vsm_stats* out) {
         TRY(collect_stats(ctx));
     }
     *out = ctx->stats;
+    return VSM_OK;
+}
+
+int vsm_tc_history(vsm_ctx* ctx, float* ms, int32_t n, int32_t* n_out) {
+    if (!ctx || !ms || n < 0 || !n_out) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_tc_history: bad argument") : VSM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t have = std::min<uint32_t>(ctx->tc_ring_head, (uint32_t)vsm_ctx::TC_RING);
+    const uint32_t take = std::min<uint32_t>(have, (uint32_t)n);
+    int32_t k = 0;
+    for (uint32_t i = ctx->tc_ring_head - take; i != ctx->tc_ring_head; i++) {      // oldest first
+        const uint32_t slot = i % vsm_ctx::TC_RING;
+        float t = 0.f;
+        if (ctx->tc_ring_valid[slot]) CK(cudaEventElapsedTime(&t, ctx->tc_ring0[slot], ctx->tc_ring1[slot]));
+        ms[k++] = t;
+    }
+    *n_out = k;
     return VSM_OK;
 }
 

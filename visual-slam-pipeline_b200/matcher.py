@@ -90,6 +90,7 @@ SYMBOLS = {
     "vsm_loop_detect_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                         C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "vsm_store_set_frame_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsm_tc_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_db_top2_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]),
     "vsm_merge_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
@@ -408,6 +409,13 @@ class Matcher:
 
     def set_stream(self, cuda_stream):
         self._ck(self._lib.vsm_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def tc_history(self, n=64):
+        """Device milliseconds of the tensor-core kernel in each of the last n calls (oldest first)."""
+        ms = np.zeros(max(n, 1), np.float32)
+        k = C.c_int32(0)
+        self._ck(self._lib.vsm_tc_history(self._h, ms.ctypes.data, n, C.byref(k)))
+        return ms[:k.value].copy()
 
     def set_profiling(self, on):
         self._ck(self._lib.vsm_set_profiling(self._h, int(on)))
