@@ -42,9 +42,10 @@ def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)"
+        return (float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)",
+                float(p.get("bf16_tflops_burst", p["bf16_tflops_sustained"])))
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)", 1400.0
 
 
 class ClockSampler:
@@ -495,7 +496,7 @@ def run_gpu(args):
     per_step_e2e = ms_e2e / args.steps
     if rank == 0:
         import numpy as np
-        peak_tf, peak_hbm, peak_src = peaks()
+        peak_tf, peak_hbm, peak_src, peak_burst = peaks()
         # sanity: every planted query must find its DB row as the nearest neighbour
         got = hi.numpy()[:N_PLANTED, 0]
         recovered = int((got == np.array(planted)).sum())
@@ -506,6 +507,11 @@ def run_gpu(args):
         tc_avg = sum(tc_ms) / len(tc_ms)
         shard_flops = 2.0 * NQ * shard.shape[0] * 256
         achieved = shard_flops / (tc_avg * 1e-3) / 1e12
+        # the sustained peak is what a long power-capped step can reach (N = 1: 16 ms steps at ~1.4 GHz);
+        # a short shard step that runs at boost clocks is compared with the burst figure instead
+        unthrottled = bool(clocks and clocks.get("sm_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
+        if (unthrottled or achieved > peak_tf) and peak_burst > peak_tf:
+            peak_tf, peak_src = peak_burst, "measured (MEASURED_PEAKS.json, burst: the kernel ran above the sustained-clock regime)"
         line = {
             "metric": METRIC, "value": flops / (per_step * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True,
