@@ -175,6 +175,47 @@ public:
             good_matches[s].assign(flat.begin() + (size_t)s * cur.rows, flat.begin() + (size_t)s * cur.rows + counts[s]);
     }
 
+    /* The same block INCLUDING the reference's eligibility rules (src/LoopCloser.cpp:44-48): a stored
+     * keyframe is skipped when cur_frame_id - its frame id < min_gap (Config::LC_MIN_FRAME_GAP) or it
+     * is empty, and of the rest only every `every`-th is matched (the reference: 5).  status[s] = -1
+     * for a skipped keyframe, otherwise its number of survivors; only eligible keyframes are matched. */
+    void detect_loop_candidates(int cur_frame_id, const Mat& cur, float ratio, int min_gap, int every,
+                                std::vector<int>& status, std::vector<std::vector<DMatch>>& good_matches) {
+        int64_t rows = 0;
+        int32_t nkf = 0;
+        check(vsm_store_info(ctx_, &rows, &nkf));
+        status.assign(nkf, -1);
+        good_matches.assign(nkf, std::vector<DMatch>());
+        if (nkf == 0) return;
+        std::vector<float> b;
+        std::vector<int32_t> st(nkf, -1);
+        std::vector<DMatch> flat(cur.empty() ? 1 : (size_t)nkf * cur.rows);
+        check(vsm_loop_detect(ctx_, cur_frame_id, min_gap, every, cur.empty() ? nullptr : rows_of(cur, b),
+                              cur.empty() ? 0 : cur.rows, ratio, st.data(), reinterpret_cast<vsm_dmatch*>(flat.data())));
+        for (int s = 0; s < nkf; s++) {
+            status[s] = st[s];
+            if (st[s] > 0)
+                good_matches[s].assign(flat.begin() + (size_t)s * cur.rows, flat.begin() + (size_t)s * cur.rows + st[s]);
+        }
+    }
+
+    /* knnMatch(frame_desc, stack of the stored rows with valid[row] != 0, knn, 2): the map-point searches
+     * that re-stack a subset per call (valid points src/Slam.cpp:552-557; points seen near the loop
+     * keyframe :748-759).  trainIdx is the ORIGINAL store row (the reference's mp_ids_vec[trainIdx], :768). */
+    void search_store(const Mat& frame_desc, const std::vector<unsigned char>& valid,
+                      std::vector<std::vector<DMatch>>& knn) {
+        knn.assign(frame_desc.rows, std::vector<DMatch>());
+        if (frame_desc.empty()) return;
+        std::vector<float> b;
+        std::vector<int64_t> idx((size_t)frame_desc.rows * 2);
+        std::vector<float> dist((size_t)frame_desc.rows * 2);
+        check(vsm_db_top2_masked(ctx_, rows_of(frame_desc, b), frame_desc.rows, valid.data(), (int64_t)valid.size(),
+                                 idx.data(), dist.data()));
+        for (int i = 0; i < frame_desc.rows; i++)
+            for (int p = 0; p < 2; p++)
+                if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, (int)idx[2 * i + p], 0, dist[2 * i + p]));
+    }
+
     /* knnMatch(frame_desc, all_descs, knn, 2) over every stored row (src/Slam.cpp:567, :764). */
     void search_store(const Mat& frame_desc, std::vector<std::vector<DMatch>>& knn) {
         knn.assign(frame_desc.rows, std::vector<DMatch>());

@@ -100,6 +100,55 @@ int main() {
         }
         EXPECT(counts[0] >= 30);                      // the loop-closure gate at LoopCloser.cpp:62 would pass
     }
+    // LoopCloser::detect with its eligibility rules (LoopCloser.cpp:43-48), restated here as the caller's
+    // loop; and the map-point search over a re-stacked subset (Slam.cpp:546-574)
+    {
+        matcher.clear_keyframes();
+        const int nkf = 12, kf_rows = 150;
+        std::vector<float> db = rows(7, 1, nkf * kf_rows);
+        for (int s = 0; s < nkf; s++) matcher.add_keyframe(30 * s, Mat(kf_rows, 256, &db[(size_t)s * kf_rows * 256]));
+        const int nq = 90;
+        std::vector<float> q = rows(7, 2, nq);
+        std::memcpy(q.data(), &db[(size_t)(5 * kf_rows + 3) * 256], 40 * 1024);        // re-observe 40 rows of keyframe 5
+        Mat cur(nq, 256, q.data());
+        std::vector<int64_t> seg(nkf + 1);
+        for (int s = 0; s <= nkf; s++) seg[s] = (int64_t)s * kf_rows;
+        std::vector<int32_t> counts(nkf);
+        std::vector<vsm_oracle_dmatch> om((size_t)nkf * nq);
+        vsm_oracle_segmented(q.data(), nq, db.data(), seg.data(), nkf, 0.75f, counts.data(), om.data(), 0);
+        const int cur_id = 400, min_gap = 200, every = 2;
+        std::vector<int> status;
+        std::vector<std::vector<DMatch>> per_kf;
+        matcher.detect_loop_candidates(cur_id, cur, 0.75f, min_gap, every, status, per_kf);
+        int checked = 0, matched = 0;
+        for (int s = 0; s < nkf; s++) {
+            bool eligible = false;
+            if (!(cur_id - 30 * s < min_gap)) { checked++; eligible = checked % every == 0; }
+            if (!eligible) { EXPECT(status[s] == -1 && per_kf[s].empty()); continue; }
+            matched++;
+            std::vector<vsm_oracle_dmatch> os(om.begin() + (size_t)s * nq, om.begin() + (size_t)s * nq + counts[s]);
+            EXPECT(status[s] == counts[s]);
+            EXPECT(same(per_kf[s], os, counts[s]));
+        }
+        EXPECT(matched == 3);                                   // keyframes 0..6 pass the gap rule, every 2nd of them
+        // subset search: every third row is a valid map point
+        std::vector<unsigned char> valid((size_t)nkf * kf_rows, 0);
+        std::vector<float> sub;
+        std::vector<int> ids;
+        for (int r = 0; r < nkf * kf_rows; r += 3) { valid[r] = 1; ids.push_back(r); sub.insert(sub.end(), &db[(size_t)r * 256], &db[(size_t)r * 256 + 256]); }
+        std::vector<std::vector<DMatch>> knn2;
+        matcher.search_store(cur, valid, knn2);
+        std::vector<int64_t> oi((size_t)nq * 2);
+        std::vector<float> od((size_t)nq * 2);
+        vsm_oracle_knn(q.data(), nq, 256, sub.data(), (int64_t)ids.size(), 256, 2, oi.data(), od.data(), 0);
+        for (int i = 0; i < nq; i++) {
+            EXPECT(knn2[i].size() == 2);
+            for (int k = 0; k < 2 && knn2[i].size() == 2; k++) {
+                EXPECT(knn2[i][k].trainIdx == ids[(size_t)oi[2 * i + k]]);
+                EXPECT(std::memcmp(&knn2[i][k].distance, &od[2 * i + k], 4) == 0);
+            }
+        }
+    }
     std::printf(fails ? "adaptor test: %d FAILURES\n" : "adaptor test: OK\n", fails);
     return fails ? 1 : 0;
 }
