@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle import cases, gen, oracle
+from oracle import cases, oracle
 import vsm_b200
 
 
