@@ -214,6 +214,9 @@ struct Top3Core {
 };
 __device__ __noinline__ Top3Core top3_push8(Top3Core c, float v0, float v1, float v2, float v3, float v4, float v5,
                                             float v6, float v7, uint32_t scol) {
+    // all eight values are inserted, unconditionally: measured, an `if (v > thr)` around each insert
+    // (skipped by the warp when no lane needs that position) is 50 % SLOWER on small problems --
+    // the divergence bookkeeping costs more than the seven FMNMX it saves
     const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
 #pragma unroll
     for (int e = 0; e < 8; e++) {
@@ -436,11 +439,13 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
             top3_update_thr(s);
             volatile uint32_t* hint = u.hint + (row_valid ? row : 0);
             int seg = 0, seg_tile = 0;
+            // bound published by the other CTAs / warps working on the same query (a second-best
+            // of any subset of the train set is a lower bound on the global second-best); the load
+            // for tile n+1 is issued during tile n's last scan, so its latency is never exposed
+            uint32_t h_next = *hint;
             for (int n = 0; n < ntiles; n++, tile_it++) {
                 const int st = tile_it & 1;
-                // bound published by the other CTAs / warps working on the same query (a second-best
-                // of any subset of the train set is a lower bound on the global second-best)
-                const uint32_t h = *hint;
+                const uint32_t h = h_next;
                 mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
                 tcgen05_fence_after();
                 if (DEBUG && u.dump >= 2 && threadIdx.x == EPI_WARP0 * 32 && n < 4096)
@@ -476,6 +481,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+                h_next = *hint;
                 if (DEBUG && u.dump == 1 && n == 0)
                     for (int e = 0; e < 32; e++) dump[row * TILE_N + half * HALF_N + 96 + e] = __uint_as_float(rb[e]);
                 if (!full_tile) mask32(rb, ucol + 96, u.t_count);
