@@ -367,6 +367,27 @@ def extra_pair_numbers(torch, vsm_b200, device):
                               "matches": int(sum(len(r) for r in res)), "device_ms": st["device_ms"],
                               "h2d_mbytes": (qa.nbytes + ta.nbytes) / 1e6, "select_ms": st["select_ms"],
                               "tc_ms": st["tc_ms"], "tc_useful_tflops": flops / (st["tc_ms"] * 1e-3) / 1e12 if st["tc_ms"] else None}
+    # the same 64 pairs with every frame already resident in the keyframe store (nothing uploaded):
+    # what the batch costs inside a SLAM process that keeps its keyframes on the device
+    m.clear_store()
+    qh = [m.add_keyframe(2 * p, qs[p]) for p in range(64)]
+    th = [m.add_keyframe(2 * p + 1, tsets[p]) for p in range(64)]
+    cap = int(sizes[:, 0].sum())
+    for _ in range(3):
+        m.match_batch_stored(qh, th, 0.75, True, capacity=cap)
+    tb = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        res2 = m.match_batch_stored(qh, th, 0.75, True, capacity=cap)
+        tb.append(time.perf_counter() - t0)
+    tb.sort()
+    st = m.stats()
+    out["ragged_batch_64_resident"] = {"p50_ms": tb[len(tb) // 2] * 1e3, "useful_gflop": flops / 1e9,
+                                       "matches": int(sum(len(r) for r in res2)), "same_matches_as_from_host": bool(
+                                           all(a.tobytes() == b.tobytes() for a, b in zip(res, res2))),
+                                       "device_ms": st["device_ms"], "tc_ms": st["tc_ms"], "select_ms": st["select_ms"],
+                                       "useful_tflops_e2e": flops / tb[len(tb) // 2] / 1e12}
+    m.clear_store()
     # configs[2]: 1000 queries vs a 500-keyframe database (500K rows), both forms the reference uses:
     # the stacked global top-2 (src/Slam.cpp:546-574) and LoopCloser::detect's per-keyframe kNN +
     # ratio test (src/LoopCloser.cpp:43-62); queries come from pinned host memory, results go back

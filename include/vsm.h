@@ -220,6 +220,18 @@ int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_
                         const double* R_cam, const double* t_cam, int32_t* indices, int32_t* obs_mp,
                         int32_t* obs_ki, int32_t* tracked, int32_t* best_ki, double* best_dist);
 
+/* Slam::match_features for n_pairs pairs of STORED keyframes in one launch sequence -- the ragged
+ * batch of BASELINE configs[4] with every frame already resident (handles from vsm_store_add /
+ * vsm_track), e.g. the keyframe-to-keyframe matches before triangulation (src/Slam.cpp:926) for a
+ * window of keyframes.  Nothing is uploaded.  queryIdx indexes keyframe q_handle[p], trainIdx
+ * keyframe t_handle[p].  good_off: [n_pairs+1] (out) = prefix sums of the query keyframes' row
+ * counts; pair p's survivors are good[good_off[p] .. good_off[p] + n_good[p]); good_cap (entries)
+ * must be >= good_off[n_pairs] or the call fails with VSM_ERR_INVALID.  good == NULL with
+ * good_cap == 0 is a size query: only good_off is filled. */
+int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handle, const int32_t* t_handle,
+                           float ratio, int32_t mutual, vsm_dmatch* good, int64_t good_cap,
+                           int32_t* n_good, int64_t* good_off);
+
 /* LoopCloser::detect's candidate loop WITH its eligibility rules (src/LoopCloser.cpp:43-62):
  * stored keyframes are visited in store order; a keyframe is skipped when
  * cur_frame_id - frame_id < min_gap (:44, Config::LC_MIN_FRAME_GAP = 200) or it is empty (:45);

@@ -282,6 +282,27 @@ def test_pinned_inputs_take_the_zero_copy_path(tc):
     tc.clear_store()
 
 
+def test_batch_of_stored_keyframe_pairs(tc):
+    """vsm_match_batch_stored: the ragged batch with every frame resident in the store (nothing
+    uploaded) equals match_features on the same pairs, incl. an empty keyframe and a repeated one."""
+    frames = gen.video(21, 7, 350)
+    sizes = [350, 200, 0, 333, 350, 1, 129]
+    frames = [f[:n] for f, n in zip(frames, sizes)]
+    tc.clear_store()
+    handles = [tc.add_keyframe(10 * i, f) for i, f in enumerate(frames)]
+    pairs = [(0, 1), (1, 0), (3, 4), (2, 3), (3, 2), (5, 6), (6, 5), (4, 4), (0, 6)]
+    for mutual in (False, True):
+        res = tc.match_batch_stored([handles[a] for a, _ in pairs], [handles[b] for _, b in pairs], 0.75, mutual=mutual)
+        assert len(res) == len(pairs)
+        for (a, b), got in zip(pairs, res):
+            og, _ = oracle.match_features(frames[a], frames[b], 0.75, mutual=mutual)
+            assert got.tobytes() == og.tobytes(), (a, b, mutual)
+    assert tc.match_batch_stored([], []) == []
+    with pytest.raises(vsm_b200.VsmError):
+        tc.match_batch_stored([0], [99])
+    tc.clear_store()
+
+
 def test_loop_detect_eligibility_and_matches(tc):
     """vsm_loop_detect = LoopCloser::detect's loop incl. the gap >= 200 / every-5th rules."""
     q, db, seg_off = cases.db_case()

@@ -1152,6 +1152,60 @@ int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t 
     return match_common(ctx, probs, sg.count, n_cur, ratio, mutual, good, n_good, raw, n_raw);
 }
 
+int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handle, const int32_t* t_handle, float ratio,
+                           int32_t mutual, vsm_dmatch* good, int64_t good_cap, int32_t* n_good, int64_t* good_off) {
+    if (!ctx || n_pairs < 0 || (n_pairs > 0 && (!q_handle || !t_handle || !n_good || !good_off)))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_batch_stored: bad argument") : VSM_ERR_INVALID;
+    if (n_pairs == 0) return VSM_OK;
+    const int nseg = (int)ctx->segs.size();
+    int64_t NQ = 0, NT = 0;
+    std::vector<int64_t> t_off(n_pairs + 1, 0);
+    for (int p = 0; p < n_pairs; p++) {
+        if (q_handle[p] < 0 || q_handle[p] >= nseg || t_handle[p] < 0 || t_handle[p] >= nseg)
+            return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_match_batch_stored: unknown keyframe handle");
+        good_off[p] = NQ;
+        t_off[p] = NT;
+        NQ += ctx->segs[q_handle[p]].count;
+        NT += ctx->segs[t_handle[p]].count;
+        n_good[p] = 0;
+    }
+    good_off[n_pairs] = NQ;
+    t_off[n_pairs] = NT;
+    if (NQ == 0 || (!good && good_cap == 0)) return VSM_OK;               // size query: good_off is filled
+    if (!good || good_cap < NQ) return fail(ctx, VSM_ERR_INVALID, "vsm_match_batch_stored: good_cap is smaller than the query rows");
+    TRY(begin_call(ctx));
+    std::vector<HProblem> probs;
+    std::vector<HJob> jobs;
+    for (int p = 0; p < n_pairs; p++) {
+        const Seg& a = ctx->segs[q_handle[p]];
+        const Seg& b = ctx->segs[t_handle[p]];
+        HProblem f;
+        f.q_f32 = ctx->store.f32 + a.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + a.row0; f.q_row = a.row0; f.q_store = 1; f.nq = a.count;
+        f.t_f32 = ctx->store.f32 + b.row0 * VSM_DIM; f.t_row = b.row0; f.t_store = 1; f.nt = b.count; f.out_off = good_off[p];
+        probs.push_back(f);
+        if (mutual) {
+            HProblem r;
+            r.q_f32 = f.t_f32; r.q_n2 = ctx->store.n2 + b.row0; r.q_row = b.row0; r.q_store = 1; r.nq = b.count;
+            r.t_f32 = f.q_f32; r.t_row = a.row0; r.t_store = 1; r.nt = a.count; r.out_off = NQ + t_off[p];
+            probs.push_back(r);
+        }
+        HJob j;
+        j.fwd_off = good_off[p]; j.back_off = mutual ? NQ + t_off[p] : -1; j.good_off = good_off[p]; j.raw_off = -1;
+        j.nq = a.count; j.nt = b.count; j.img_idx = 0; j.ratio = ratio;
+        jobs.push_back(j);
+    }
+    TRY(run_problems(ctx, probs, jobs, NQ + (mutual ? NT : 0), NQ));
+    const size_t bytes = (size_t)NQ * sizeof(DMatch) + (size_t)n_pairs * 2 * sizeof(int32_t);
+    TRY(fetch_result(ctx, bytes));
+    TRY(end_call(ctx, true));
+    const int32_t* c = reinterpret_cast<const int32_t*>(ctx->h_result + (size_t)NQ * sizeof(DMatch));
+    for (int p = 0; p < n_pairs; p++) {
+        n_good[p] = c[2 * p];
+        memcpy(good + good_off[p], ctx->h_result + (size_t)good_off[p] * sizeof(DMatch), (size_t)c[2 * p] * sizeof(DMatch));
+    }
+    return VSM_OK;
+}
+
 int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* cur, int32_t n_cur, float ratio,
               int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw, int32_t* cur_handle) {
     if (!ctx || n_cur < 0 || !n_good || (n_cur > 0 && !cur) || !cur_handle)

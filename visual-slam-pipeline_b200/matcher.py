@@ -90,6 +90,8 @@ SYMBOLS = {
     "vsm_loop_detect_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                         C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "vsm_store_set_frame_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsm_match_batch_stored": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_tc_history": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "vsm_db_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_db_top2_keys_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]),
@@ -228,6 +230,27 @@ class Matcher:
                                            t_off.ctypes.data, ratio, int(mutual), good.ctypes.data,
                                            n_good.ctypes.data))
         return [good[q_off[p]:q_off[p] + n_good[p]] for p in range(n)]
+
+    def match_batch_stored(self, q_handles, t_handles, ratio=0.75, mutual=False, capacity=None):
+        """match_features for pairs of STORED keyframes (no upload).  Returns a list of DMATCH arrays.
+        capacity: the sum of the query keyframes' rows if the caller knows it (saves the size query)."""
+        qh = np.ascontiguousarray(q_handles, np.int32)
+        th = np.ascontiguousarray(t_handles, np.int32)
+        n = len(qh)
+        assert len(th) == n
+        n_good = np.zeros(max(n, 1), np.int32)
+        off = np.zeros(n + 1, np.int64)
+        if capacity is None:
+            self._ck(self._lib.vsm_match_batch_stored(self._h, n, qh.ctypes.data, th.ctypes.data, ratio, int(mutual),
+                                                      None, 0, n_good.ctypes.data, off.ctypes.data))
+            capacity = int(off[n])
+        cap = max(int(capacity), 1)
+        if not hasattr(self, "_mbs") or len(self._mbs) < cap:
+            self._mbs = np.zeros(cap, DMATCH)
+        good = self._mbs
+        self._ck(self._lib.vsm_match_batch_stored(self._h, n, qh.ctypes.data, th.ctypes.data, ratio, int(mutual),
+                                                  good.ctypes.data, cap, n_good.ctypes.data, off.ctypes.data))
+        return [good[off[p]:off[p] + n_good[p]].copy() for p in range(n)]
 
     # -- device-resident keyframe store -----------------------------------------------------
     def add_keyframe(self, frame_id, desc):
