@@ -141,6 +141,24 @@ public:
         return good;
     }
 
+    /* match_features for many pairs of stored keyframes in one launch sequence (nothing is uploaded):
+     * result[p] = match_features(descriptors of q_handles[p], descriptors of t_handles[p]). */
+    std::vector<std::vector<DMatch>> match_features_batch(const std::vector<int>& q_handles, const std::vector<int>& t_handles,
+                                                          float ratio = 0.75f, bool mutual = false) {
+        if (q_handles.size() != t_handles.size()) throw std::runtime_error("vsm_cv: handle lists differ in length");
+        const int n = (int)q_handles.size();
+        std::vector<std::vector<DMatch>> out(n);
+        if (n == 0) return out;
+        std::vector<int32_t> qh(q_handles.begin(), q_handles.end()), th(t_handles.begin(), t_handles.end()), ng(n, 0);
+        std::vector<int64_t> off(n + 1, 0);
+        check(vsm_match_batch_stored(ctx_, n, qh.data(), th.data(), ratio, mutual ? 1 : 0, nullptr, 0, ng.data(), off.data()));
+        std::vector<DMatch> flat((size_t)(off[n] > 0 ? off[n] : 1));
+        check(vsm_match_batch_stored(ctx_, n, qh.data(), th.data(), ratio, mutual ? 1 : 0,
+                                     reinterpret_cast<vsm_dmatch*>(flat.data()), (int64_t)flat.size(), ng.data(), off.data()));
+        for (int p = 0; p < n; p++) out[p].assign(flat.begin() + off[p], flat.begin() + off[p] + ng[p]);
+        return out;
+    }
+
     /* The tracking match of Slam::process_frame (src/Slam.cpp:838-842) for a sequence: the current
      * frame goes to the device once and becomes keyframe *cur_handle; ref_handle < 0 = first frame. */
     std::vector<DMatch> track(int ref_handle, int ref_rows, int frame_id, const Mat& cur, int* cur_handle,

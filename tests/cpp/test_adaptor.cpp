@@ -131,6 +131,21 @@ int main() {
             EXPECT(same(per_kf[s], os, counts[s]));
         }
         EXPECT(matched == 3);                                   // keyframes 0..6 pass the gap rule, every 2nd of them
+        // pairs of stored keyframes in one call = the per-pair calls
+        {
+            std::vector<int> qh = {0, 5, 11, 3}, th = {1, 0, 11, 7};
+            for (int mutual = 0; mutual < 2; mutual++) {
+                std::vector<std::vector<DMatch>> batch = matcher.match_features_batch(qh, th, 0.75f, mutual != 0);
+                EXPECT(batch.size() == 4);
+                for (size_t p = 0; p < qh.size(); p++) {
+                    std::vector<vsm_oracle_dmatch> og(kf_rows);
+                    int ng = 0;
+                    vsm_oracle_match_features(&db[(size_t)qh[p] * kf_rows * 256], kf_rows, &db[(size_t)th[p] * kf_rows * 256], kf_rows,
+                                              0.75f, mutual, og.data(), &ng, nullptr, nullptr, 0);
+                    EXPECT(same(batch[p], og, ng));
+                }
+            }
+        }
         // subset search: every third row is a valid map point
         std::vector<unsigned char> valid((size_t)nkf * kf_rows, 0);
         std::vector<float> sub;
