@@ -88,6 +88,27 @@ def test_match_features_equals_golden(name, ratio, tc):
         assert np.array_equal(raw["trainIdx"], g["idx"][has2, 0])
         og, orw = oracle.match_features(q, t, ratio, mutual=mutual)
         assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
+    # ratio-only form (no raw list, no mutual test): queries whose approximate top-2 already prove
+    # that the ratio test fails are answered without an exact re-score -- same survivors
+    good, _ = tc.match_features(q, t, ratio, mutual=False, want_raw=False)
+    og, _ = oracle.match_features(q, t, ratio, mutual=False)
+    assert good.tobytes() == og.tobytes()
+
+
+def test_ratio_only_early_out_on_borderline_ratios(tc):
+    """Planted pairs with noise levels that put d0/d1 on both sides of the ratio, scaled rows
+    (non-unit norms) and extreme ratios: the ratio-only early-out never changes a decision."""
+    rng = np.random.default_rng(3)
+    for it, sigma in enumerate((0.07, 0.09, 0.11, 0.13)):
+        q, t, _ = gen.planted(300 + it, 900, 1100, 0.7, sigma)
+        if it & 1:
+            t = np.ascontiguousarray(t * rng.uniform(0.7, 1.3, size=(t.shape[0], 1)).astype(np.float32))
+        for ratio in (0.6, 0.75, 0.9, 0.999, 1.0, 1.2):
+            good, _ = tc.match_features(q, t, ratio, mutual=False, want_raw=False)
+            og, _ = oracle.match_features(q, t, ratio, mutual=False)
+            assert good.tobytes() == og.tobytes(), (sigma, ratio)
+            res = tc.match_batch([q, q[:100]], [t, t[:50]], ratio, mutual=False)
+            assert res[0].tobytes() == og.tobytes(), (sigma, ratio)
 
 
 def test_empty_inputs(tc):

@@ -49,7 +49,12 @@ struct HProblem {
     const float* q_f32;  const float* q_n2;  int64_t q_row;  int q_store;  int nq;
     const float* t_f32;  int64_t t_row;  int t_store;  int nt;
     int64_t out_off;
+    float skip_ratio2 = 0.f;     // see Problem::skip_ratio2
+    int32_t pad_ = 0;            // keeps the struct free of padding: plans are compared byte-wise
 };
+
+// ratio^2 with slack for a caller that only keeps ratio-test survivors; 0 = never skip
+inline float skip_r2(float ratio) { return (ratio > 0.f && ratio <= 1.5f) ? ratio * ratio * 1.001f : 0.f; }
 
 struct HJob {
     int64_t fwd_off, back_off, good_off, raw_off;
@@ -389,6 +394,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         d.slice_off = (int32_t)slices.size();
         d.partial_off = nrecs;
         d.exact = (exact || hp.nt == 0) ? 1 : 0;
+        d.skip_ratio2 = hp.skip_ratio2;
         qb[i + 1] = qb[i] + (hp.nq + SELECT_WARPS - 1) / SELECT_WARPS;
         if (hp.nq <= 0 || hp.nt <= 0) { d.nslices = 0; continue; }
         if (d.exact) {
@@ -915,6 +921,7 @@ int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, i
 static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int nt, float ratio, int mutual,
                         vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
     const bool want_raw = raw && n_raw;
+    if (!mutual && !want_raw) probs[0].skip_ratio2 = skip_r2(ratio);
     HJob j;
     j.fwd_off = 0; j.back_off = mutual ? nq : -1; j.good_off = 0; j.raw_off = want_raw ? nq : -1;
     j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
@@ -971,6 +978,7 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int
     for (int p = 0; p < n_pairs; p++) {
         const int nq = q_off[p + 1] - q_off[p], nt = t_off[p + 1] - t_off[p];
         probs.push_back(scratch_vs_scratch(ctx, q_off[p], nq, NQ + t_off[p], nt, q_off[p]));
+        if (!mutual) probs.back().skip_ratio2 = skip_r2(ratio);
         if (mutual) probs.push_back(scratch_vs_scratch(ctx, NQ + t_off[p], nt, q_off[p], nq, NQ + t_off[p]));
         HJob j;
         j.fwd_off = q_off[p]; j.back_off = mutual ? NQ + t_off[p] : -1; j.good_off = q_off[p]; j.raw_off = -1;
@@ -1182,6 +1190,7 @@ int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handl
         HProblem f;
         f.q_f32 = ctx->store.f32 + a.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + a.row0; f.q_row = a.row0; f.q_store = 1; f.nq = a.count;
         f.t_f32 = ctx->store.f32 + b.row0 * VSM_DIM; f.t_row = b.row0; f.t_store = 1; f.nt = b.count; f.out_off = good_off[p];
+        if (!mutual) f.skip_ratio2 = skip_r2(ratio);
         probs.push_back(f);
         if (mutual) {
             HProblem r;
@@ -1316,6 +1325,7 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
         p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
         p.t_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; p.t_row = sg.row0; p.t_store = 1; p.nt = sg.count;
         p.out_off = slot * nq;
+        p.skip_ratio2 = skip_r2(ratio);                 // only ratio-test survivors are returned
         probs.push_back(p);
         HJob j;
         j.fwd_off = p.out_off; j.back_off = -1; j.good_off = slot * nq; j.raw_off = -1;

@@ -94,7 +94,10 @@ struct Problem {
     int32_t nslices;
     int32_t slice_off;             // first SliceInfo of this problem
     int32_t exact;                 // 1: no tensor-core records, scan every slice exactly
-    int32_t pad;
+    // > 0: the caller only wants ratio-test survivors (no raw list, no mutual test) with this
+    // ratio^2 * 1.001: a query whose approximate top-2 already PROVES the ratio test fails is
+    // answered "no match" without any exact re-score (select_kernel)
+    float skip_ratio2;
 };
 
 // One pair for the filter kernel (match_features semantics).

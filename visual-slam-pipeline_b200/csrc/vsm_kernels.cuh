@@ -237,12 +237,12 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     // per-warp list of surviving train rows: < 2 x SELECT_U left over from earlier chunks + at most 32 x 4 new
     __shared__ int32_t s_list[SELECT_WARPS][2 * SELECT_U + 32 * VSM_TOPK];
     float qreg[16];
-    load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
     Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
     unsigned long long n_cand = 0, n_flag = 0;      // n_cand is per lane (summed at the end)
     const SliceInfo* sl = slices + P.slice_off;
 
     if (P.exact) {
+        load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
         for (int s = 0; s < P.nslices; s++) scan_slice<SELECT_U>(qreg, P.t_f32, sl[s], h, l16, best);
     } else {
         const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
@@ -265,7 +265,30 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
         }
         float tmin2, tmax2;
         stats_read(P.t_stats, tmin2, tmax2);
-        const float thr = a1 - 2.f * dot_margin(__ldg(P.q_n2 + q), tmin2, tmax2);   // -inf if < 2 entries
+        const float qn2 = __ldg(P.q_n2 + q);
+        const float margin = dot_margin(qn2, tmin2, tmax2);
+        const float thr = a1 - 2.f * margin;                                         // -inf if < 2 entries
+
+        // Ratio-only callers (LoopCloser::detect's loop, match_features without raw list / mutual):
+        // a0 is the largest approximate dot of the whole train set (a slice's maximum is always
+        // recorded), so every exact squared distance is >= lo0; the row behind a1 exists, so the
+        // exact SECOND-best squared distance is <= hi1.  If lo0 >= ratio^2 * hi1 (with 0.1 % slack for
+        // the fp32 rounding of the distances and of the reference's `d0 < ratio * d1`), the ratio
+        // test fails whatever the exact top-2 is: no match, no re-score.  Most (query, keyframe)
+        // pairs of a loop-closure search end here.
+        if (P.skip_ratio2 > 0.f && a1 > -INFINITY) {
+            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
+            const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
+            if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) {
+                if (lane == 0) {
+                    unsigned long long* o = out_key + (P.out_off + q) * 2;
+                    o[0] = 0ull;
+                    o[1] = 0ull;
+                }
+                return;
+            }
+        }
+        load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
 
         // pass 2: survivors -> this warp's candidate list -> exact distance, 2 x SELECT_U at a time;
         // overflowing slices -> exact scan.  The next chunk's records are loaded before the
