@@ -109,6 +109,10 @@ def test_ratio_only_early_out_on_borderline_ratios(tc):
             assert good.tobytes() == og.tobytes(), (sigma, ratio)
             res = tc.match_batch([q, q[:100]], [t, t[:50]], ratio, mutual=False)
             assert res[0].tobytes() == og.tobytes(), (sigma, ratio)
+            # with the mutual test on top (the forward problem still ends early, the reverse one never does)
+            good, _ = tc.match_features(q, t, ratio, mutual=True, want_raw=False)
+            ogm, _ = oracle.match_features(q, t, ratio, mutual=True)
+            assert good.tobytes() == ogm.tobytes(), (sigma, ratio, "mutual")
 
 
 def test_empty_inputs(tc):

@@ -921,7 +921,7 @@ int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, i
 static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int nt, float ratio, int mutual,
                         vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
     const bool want_raw = raw && n_raw;
-    if (!mutual && !want_raw) probs[0].skip_ratio2 = skip_r2(ratio);
+    if (!want_raw) probs[0].skip_ratio2 = skip_r2(ratio);        // forward problem: a survivor must pass the ratio test
     HJob j;
     j.fwd_off = 0; j.back_off = mutual ? nq : -1; j.good_off = 0; j.raw_off = want_raw ? nq : -1;
     j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
@@ -978,7 +978,7 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int
     for (int p = 0; p < n_pairs; p++) {
         const int nq = q_off[p + 1] - q_off[p], nt = t_off[p + 1] - t_off[p];
         probs.push_back(scratch_vs_scratch(ctx, q_off[p], nq, NQ + t_off[p], nt, q_off[p]));
-        if (!mutual) probs.back().skip_ratio2 = skip_r2(ratio);
+        probs.back().skip_ratio2 = skip_r2(ratio);               // forward problem only; the reverse one feeds the mutual test
         if (mutual) probs.push_back(scratch_vs_scratch(ctx, NQ + t_off[p], nt, q_off[p], nq, NQ + t_off[p]));
         HJob j;
         j.fwd_off = q_off[p]; j.back_off = mutual ? NQ + t_off[p] : -1; j.good_off = q_off[p]; j.raw_off = -1;
@@ -1190,7 +1190,7 @@ int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handl
         HProblem f;
         f.q_f32 = ctx->store.f32 + a.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + a.row0; f.q_row = a.row0; f.q_store = 1; f.nq = a.count;
         f.t_f32 = ctx->store.f32 + b.row0 * VSM_DIM; f.t_row = b.row0; f.t_store = 1; f.nt = b.count; f.out_off = good_off[p];
-        if (!mutual) f.skip_ratio2 = skip_r2(ratio);
+        f.skip_ratio2 = skip_r2(ratio);
         probs.push_back(f);
         if (mutual) {
             HProblem r;

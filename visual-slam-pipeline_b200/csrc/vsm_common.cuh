@@ -94,8 +94,8 @@ struct Problem {
     int32_t nslices;
     int32_t slice_off;             // first SliceInfo of this problem
     int32_t exact;                 // 1: no tensor-core records, scan every slice exactly
-    // > 0: the caller only wants ratio-test survivors (no raw list, no mutual test) with this
-    // ratio^2 * 1.001: a query whose approximate top-2 already PROVES the ratio test fails is
+    // > 0: the caller only wants ratio-test survivors of this problem (no raw list; a mutual test, if
+    // any, is applied on top by filter_kernel) with this ratio^2 * 1.001: a query whose approximate top-2 already PROVES the ratio test fails is
     // answered "no match" without any exact re-score (select_kernel)
     float skip_ratio2;
 };
