@@ -50,7 +50,7 @@ struct HProblem {
     const float* t_f32;  int64_t t_row;  int t_store;  int nt;
     int64_t out_off;
     float skip_ratio2 = 0.f;     // see Problem::skip_ratio2
-    int32_t pad_ = 0;            // keeps the struct free of padding: plans are compared byte-wise
+    int32_t maxima_only = 0;     // with skip_ratio2: records = slice maxima only (matches are rare: LoopCloser's loop)
 };
 
 // ratio^2 with slack for a caller that only keeps ratio-test survivors; 0 = never skip
@@ -395,9 +395,11 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         d.partial_off = nrecs;
         d.exact = (exact || hp.nt == 0) ? 1 : 0;
         d.skip_ratio2 = hp.skip_ratio2;
+        const bool maxima = hp.maxima_only && hp.skip_ratio2 > 0.f && !d.exact && !pairs;
+        if (maxima) d.exact |= 2;
         qb[i + 1] = qb[i] + (hp.nq + SELECT_WARPS - 1) / SELECT_WARPS;
         if (hp.nq <= 0 || hp.nt <= 0) { d.nslices = 0; continue; }
-        if (d.exact) {
+        if (d.exact & 1) {
             SliceInfo si = {0, hp.nt, -1, 0};
             slices.push_back(si);
             d.nslices = 1;
@@ -466,7 +468,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 u.t_count = (int32_t)std::min<int64_t>((int64_t)(tile1 - tile0) * TILE_N, hp.nt - u.t_index0);
                 u.q_valid = std::min(TILE_M, hp.nq - qt * TILE_M);
                 u.seg_tiles = seg;
-                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0);
+                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0) | (maxima ? 4 : 0);
                 u.dump = (dump_first && units.empty()) ? dump_first : 0;
                 // 1 + the number of tiles past this unit's end that may be prefetched as well
                 u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 + std::min(tc::L2_AHEAD, ntiles - tile1) : 0;
@@ -1325,7 +1327,8 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
         p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
         p.t_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; p.t_row = sg.row0; p.t_store = 1; p.nt = sg.count;
         p.out_off = slot * nq;
-        p.skip_ratio2 = skip_r2(ratio);                 // only ratio-test survivors are returned
+        p.skip_ratio2 = skip_r2(ratio);                 // only ratio-test survivors are returned ...
+        p.maxima_only = 1;                              // ... and they are rare: most keyframes are not the loop
         probs.push_back(p);
         HJob j;
         j.fwd_off = p.out_off; j.back_off = -1; j.good_off = slot * nq; j.raw_off = -1;

@@ -56,7 +56,8 @@ struct TcUnit {
     int32_t t_index0;              // logical train index of the range's first row
     int32_t q_valid;               // valid query rows in the tile (1..128)
     int32_t seg_tiles;             // tiles per slice segment (records flushed every seg_tiles tiles)
-    int32_t maps;                  // bit0: query rows in store map, bit1: train rows in store map
+    int32_t maps;                  // bit0: query rows in store map, bit1: train rows in store map,
+                                   // bit2: maxima-only records (see scan32_max2)
     int32_t dump;                  // debug: 1 = raw accumulators of tile 0, 2 = clock64 timeline
     int32_t prefetch;              // this CTA issues the L2 prefetches for its train range
     uint32_t* hint;                // per query row: shared lower bound on the global second-best dot
@@ -93,7 +94,9 @@ struct Problem {
     int32_t nq, nt;
     int32_t nslices;
     int32_t slice_off;             // first SliceInfo of this problem
-    int32_t exact;                 // 1: no tensor-core records, scan every slice exactly
+    int32_t exact;                 // bit0: no tensor-core records, scan every slice exactly;
+                                   // bit1: the records hold slice maxima only (TcUnit maps bit2): a query
+                                   //       that the ratio-only test cannot dismiss is re-scanned exactly
     // > 0: the caller only wants ratio-test survivors of this problem (no raw list; a mutual test, if
     // any, is applied on top by filter_kernel) with this ratio^2 * 1.001: a query whose approximate top-2 already PROVES the ratio test fails is
     // answered "no match" without any exact re-score (select_kernel)

@@ -241,7 +241,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     unsigned long long n_cand = 0, n_flag = 0;      // n_cand is per lane (summed at the end)
     const SliceInfo* sl = slices + P.slice_off;
 
-    if (P.exact) {
+    if (P.exact & 1) {
         load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
         for (int s = 0; s < P.nslices; s++) scan_slice<SELECT_U>(qreg, P.t_f32, sl[s], h, l16, best);
     } else {
@@ -323,7 +323,9 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
                 my_next = sl[s0 + 32 + lane];
             }
             const float rs[VSM_TOPK] = {rv.x, rv.y, rv.z, rv.w};
-            const bool flagged = rs[VSM_TOPK - 1] > VALID_FLOOR && rs[VSM_TOPK - 1] > thr;
+            // maxima-only records carry no candidates: every slice of a query that got here is re-scanned
+            const bool flagged = (P.exact & 2) ? (s0 + lane < P.nslices)
+                                               : (rs[VSM_TOPK - 1] > VALID_FLOOR && rs[VSM_TOPK - 1] > thr);
             // this lane's surviving entries (a bit per entry) and their logical train indices
             int32_t cand[VSM_TOPK];
             unsigned mine = 0;

@@ -254,6 +254,19 @@ __device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], uint32_
     }
 }
 
+// Maxima-only form (units with maps bit 2): the running top-2 of the GROUP MAXIMA of a slice --
+// g0 is the slice's exact maximum, g1 a value of another row (a lower bound on the slice's second
+// largest).  No insert path at all: 28 instructions per 32 values whatever the data.
+__device__ __forceinline__ void scan32_max2(float& g0, float& g1, const uint32_t (&r)[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const float* v = reinterpret_cast<const float*>(&r[8 * g]);
+        const float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        g1 = fmaxf(g1, fminf(g0, m));
+        g0 = fmaxf(g0, m);
+    }
+}
+
 // A partial last tile: columns at or past the end of the train range become MASKED_VALUE.
 __device__ __forceinline__ void mask32(uint32_t (&r)[32], int32_t ucol0, int32_t t_count) {
 #pragma unroll
@@ -427,6 +440,51 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
             if (u.t_count == 0) break;
             const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
             const bool row_valid = row < u.q_valid;
+            if (u.maps & 4) {
+                // ----- maxima-only unit (per-keyframe ratio search): the record of a slice is
+                // (max, second of the group maxima, -inf, -inf); select_kernel either proves from
+                // them that the ratio test fails or has the slice re-scanned exactly
+                float g0 = -INFINITY, g1 = -INFINITY;
+                int seg = 0, seg_tile = 0;
+                for (int n = 0; n < ntiles; n++, tile_it++) {
+                    const int st = tile_it & 1;
+                    mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t taddr = lane_addr + st * TILE_N;
+                    const int32_t ucol = n * TILE_N + half * HALF_N;
+                    const bool full_tile = (n + 1) * TILE_N <= u.t_count;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr, ra);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 32, rb);
+                    if (!full_tile) mask32(ra, ucol, u.t_count);
+                    scan32_max2(g0, g1, ra);
+                    tmem_ld_wait(rb);
+                    tmem_ld32(taddr + 64, ra);
+                    if (!full_tile) mask32(rb, ucol + 32, u.t_count);
+                    scan32_max2(g0, g1, rb);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 96, rb);
+                    if (!full_tile) mask32(ra, ucol + 64, u.t_count);
+                    scan32_max2(g0, g1, ra);
+                    tmem_ld_wait(rb);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+                    if (!full_tile) mask32(rb, ucol + 96, u.t_count);
+                    scan32_max2(g0, g1, rb);
+                    if (++seg_tile == u.seg_tiles || n == ntiles - 1) {
+                        if (row_valid) {
+                            const float4 rec = make_float4(g0, g1, -INFINITY, -INFINITY);
+                            *reinterpret_cast<float4*>(recs + u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half) = rec;
+                        }
+                        seg++;
+                        seg_tile = 0;
+                        g0 = g1 = -INFINITY;
+                    }
+                }
+                continue;
+            }
             Top3 s;
             s.b0 = s.b1 = s.b2 = s.b3 = -INFINITY;
             s.G = s.published = -INFINITY;
