@@ -43,7 +43,7 @@ def peaks():
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
         return (float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained)",
-                float(p.get("bf16_tflops_burst", p["bf16_tflops_sustained"])))
+                float(p.get("bf16_tflops", p["bf16_tflops_sustained"])))        # "bf16_tflops" = best of 10 (burst)
     except Exception:
         return 1400.0, 6650.0, "fallback (B200_PROFILING.md)", 1400.0
 
