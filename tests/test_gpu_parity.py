@@ -328,6 +328,39 @@ def test_batch_of_stored_keyframe_pairs(tc):
     tc.clear_store()
 
 
+def test_per_keyframe_search_adapts_its_epilogue():
+    """vsm_db_segmented measures how many (query, keyframe) pairs its ratio-only test could not dismiss
+    and picks the next call's tensor-core epilogue from it: maxima-only records while matches are rare
+    (a pair that stays open is then re-scanned exactly), top-4 records otherwise.  Same answers."""
+    q, db, seg_off = cases.db_case()                       # 30 % of the queries re-observe two keyframes
+    nkf = len(seg_off) - 1
+    q_none = gen.rows(77, 0, 0, 300)                       # a frame that matches nothing
+    m = vsm_b200.Matcher()
+    for s in range(nkf):
+        m.add_keyframe(s, db[seg_off[s]:seg_off[s + 1]])
+
+    def run(qq):
+        c, lists = m.detect_candidates(qq, 0.75)
+        oc, ol = oracle.segmented(qq, db, seg_off, 0.75)
+        assert np.array_equal(c, oc)
+        for s in range(nkf):
+            assert lists[s].tobytes() == ol[s].tobytes()
+        return m.stats(), int(c.max())
+
+    st, best = run(q)                                      # first call: pessimistic -> top-4 records
+    assert best > 10 and st["candidates"] > 0
+    st, best = run(q_none)                                 # nothing stays open ...
+    assert best == 0
+    st, best = run(q)                                      # ... so this one runs maxima-only: no candidates,
+    assert best > 10 and st["candidates"] == 0 and st["flagged_slices"] > 0       # the open pairs are re-scanned
+    st, best = run(q)                                      # many pairs stayed open -> back to top-4 records
+    assert best > 10 and st["candidates"] > 0
+    status, _ = m.loop_detect(900, q, 0.75, min_gap=200, every=1)
+    ost, _ = oracle.loop_detect(q, db, seg_off, list(range(nkf)), 900, 0.75, 200, 1)
+    assert np.array_equal(status, ost)
+    m.close()
+
+
 def test_loop_detect_eligibility_and_matches(tc):
     """vsm_loop_detect = LoopCloser::detect's loop incl. the gap >= 200 / every-5th rules."""
     q, db, seg_off = cases.db_case()

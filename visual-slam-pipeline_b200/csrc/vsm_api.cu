@@ -93,7 +93,8 @@ struct vsm_ctx {
     bool result_on_host = false;         // small results: filter_kernel writes straight into pinned h_result
     uint8_t* h_result = nullptr;
     size_t h_result_cap = 0;
-    // zeroed per call: [0] candidates, [1] flagged slices (u64), [2] rescan work count, then
+    // zeroed per call: [0] candidates, [1] flagged slices (u64), [2] rescan work count (u32) and the
+    // number of ratio-only queries that were not dismissed (u32), unit queue head, statistics slots, then
     // per output query the shared second-best hint (u32) and the two result keys (u64)
     DevBuf<uint8_t> d_aux;
     unsigned long long* d_counters = nullptr;    // = d_aux.p
@@ -140,6 +141,9 @@ struct vsm_ctx {
     std::vector<ConvJob> pending_conv;   // conversions queued by this call, run by its prologue kernel
     uint32_t call_seq = 0;               // run_problems calls so far: picks the scratch-statistics slot
     const void* aux_zeroed = nullptr;    // d_aux.p at the time its slots were last known to be zero
+    // share of the (query, keyframe) problems of the last per-keyframe search that the ratio-only test
+    // could NOT dismiss; starts pessimistic.  Decides the epilogue of the next one (segmented_impl).
+    float seg_open_rate = 1.f;
 };
 
 namespace {
@@ -1327,8 +1331,12 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
         p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
         p.t_f32 = ctx->store.f32 + sg.row0 * VSM_DIM; p.t_row = sg.row0; p.t_store = 1; p.nt = sg.count;
         p.out_off = slot * nq;
-        p.skip_ratio2 = skip_r2(ratio);                 // only ratio-test survivors are returned ...
-        p.maxima_only = 1;                              // ... and they are rare: most keyframes are not the loop
+        p.skip_ratio2 = skip_r2(ratio);                 // only ratio-test survivors are returned
+        // Maxima-only records pay off while matches are rare: a query the ratio test cannot dismiss costs
+        // an exact scan of the whole keyframe instead of ~4 re-scores.  The share of such (query, keyframe)
+        // pairs is measured by every per-keyframe search (either epilogue); the next search uses the
+        // maxima-only epilogue only if it was below 0.1 % (no loop in sight: the usual case).
+        p.maxima_only = ctx->seg_open_rate < 1e-3f ? 1 : 0;
         probs.push_back(p);
         HJob j;
         j.fwd_off = p.out_off; j.back_off = -1; j.good_off = slot * nq; j.raw_off = -1;
@@ -1364,6 +1372,9 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
         TRY(end_call(ctx, true));
     }
     for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = cnt[2 * k];
+    uint32_t open_pairs = 0;                                      // stream is idle: a 4-byte read
+    CK(cudaMemcpy(&open_pairs, reinterpret_cast<const uint8_t*>(ctx->d_counters) + 20, sizeof open_pairs, cudaMemcpyDeviceToHost));
+    ctx->seg_open_rate = (float)open_pairs / (float)std::max<int64_t>(total_matches, 1);
     return VSM_OK;
 }
 

@@ -276,7 +276,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
         // the fp32 rounding of the distances and of the reference's `d0 < ratio * d1`), the ratio
         // test fails whatever the exact top-2 is: no match, no re-score.  Most (query, keyframe)
         // pairs of a loop-closure search end here.
-        if (P.skip_ratio2 > 0.f && a1 > -INFINITY) {
+        if (P.skip_ratio2 > 0.f && a1 > VALID_FLOOR) {       // a1 below the floor: fewer than two rows seen (or masked columns)
             const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
             const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
             if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) {
@@ -287,6 +287,8 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
                 }
                 return;
             }
+            // not dismissed: counted, so that the host can tell how rare matches are (see segmented_impl)
+            if (lane == 0) atomicAdd(reinterpret_cast<uint32_t*>(counters + 2) + 1, 1u);
         }
         load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
 
