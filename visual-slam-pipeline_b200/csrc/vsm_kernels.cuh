@@ -401,7 +401,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
 
 // One block per work item: exact top-2 over RESCAN_ROWS rows of one slice for one query,
 // pushed into the query's result slots with the atomicMax cascade.  16 half-warps, each
-// scoring eight rows (all loads in flight together).
+// scoring RESCAN_U rows per step (their loads in flight together).
 __global__ void __launch_bounds__(256)
 rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __restrict__ counters, uint32_t work_cap) {
     pdl_launch_dependents();
