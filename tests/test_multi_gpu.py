@@ -83,6 +83,19 @@ def _worker(rank, world, port, exchange, out):
                     fails.append(f"loop_detect list of keyframe {g} differs")
             elif g in mine:
                 fails.append(f"keyframe {g} should have been skipped")
+    # more ranks than keyframes: one rank holds an empty shard and still takes part in the exchange
+    one = np.array([0, int(seg_off[7 + 1] - seg_off[7])], np.int64)
+    db1 = db[seg_off[7]:seg_off[8]]
+    p1 = sh.partition_keyframes(one, world)
+    a0, a1, b0, b1 = p1[rank]
+    sdb.adopt(torch.from_numpy(db1[b0:b1]).cuda().contiguous(), b0, np.asarray(one[a0:a1 + 1] - b0, np.int64))
+    w1i, w1d = oracle.knn(q, db1, 2)
+    hi, hd = sdb.search_host(hq)
+    sdb.stream.synchronize()
+    if not (np.array_equal(hi.numpy(), w1i.astype(np.int64)) and np.array_equal(hd.numpy().view(np.uint32), w1d.view(np.uint32))):
+        fails.append("single-keyframe database over two ranks differs")
+    if sorted(b1 - b0 for _, _, b0, b1 in p1)[0] != 0:
+        fails.append("expected one empty shard")
     out[rank] = fails
     dist.barrier()
     sdb.close()

@@ -128,6 +128,11 @@ class ShardedDB:
         self._db = db
         self.rows = db.shape[0]
         self.row_offset = int(row_offset)
+        if self.rows == 0:
+            # more ranks than keyframes: this rank holds nothing and answers "no neighbour" to every
+            # query; it still takes part in the exchange
+            self.matcher.clear_store()
+            return
         self.matcher.adopt_device_matrix(db.data_ptr(), self.rows, seg_off)
         if frame_ids is not None:
             self.matcher.set_frame_ids(frame_ids)
