@@ -230,6 +230,59 @@ def parity_report(vsm_b200, device, q, t, cpu_result):
     return rep
 
 
+def oracle_parity(torch, dist, shard, off, q_host, sample, got_idx, got_dist, rank, world, device):
+    """The answer of the timed search against the CPU oracle over the WHOLE database, at every N:
+    each rank runs oracle.knn(q[sample], its own shard copied to the host chunk by chunk), the per-rank
+    top-2 lists are gathered and rank 0 merges them with oracle.merge_top2 -- no GPU kernel of the
+    product takes part -- and compares indices and fp32 distance bits (first and second neighbour)
+    with what the GPU path returned for those queries."""
+    import numpy as np
+    from oracle import oracle
+    t0 = time.perf_counter()
+    qs = np.ascontiguousarray(q_host[sample])
+    threads = max(1, (os.cpu_count() or 1) // world)
+    S = len(sample)
+    parts_i, parts_d = [], []
+    chunk = 1 << 20
+    for c0 in range(0, shard.shape[0], chunk):
+        c1 = min(shard.shape[0], c0 + chunk)
+        host = shard[c0:c1].cpu().numpy()
+        oi, od = oracle.knn(qs, host, 2, threads=threads)
+        parts_i.append(np.where(oi >= 0, oi + off + c0, -1))
+        parts_d.append(od)
+    if parts_i:
+        li, ld = oracle.merge_top2(np.stack(parts_i), np.stack(parts_d))
+    else:
+        li = -np.ones((S, 2), np.int64)
+        ld = np.full((S, 2), np.finfo(np.float32).max, np.float32)
+    if world > 1:
+        gi = torch.empty((world, S, 2), dtype=torch.int64, device=device)
+        gd = torch.empty((world, S, 2), dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(gi.view(-1, 2), torch.from_numpy(li).to(device))
+        dist.all_gather_into_tensor(gd.view(-1, 2), torch.from_numpy(ld).to(device))
+        gi, gd = gi.cpu().numpy(), gd.cpu().numpy()
+    else:
+        gi, gd = li[None], ld[None]
+    if rank != 0:
+        return None
+    wi, wd = oracle.merge_top2(gi, gd)
+    hi, hd = got_idx[sample], got_dist[sample]
+    same_idx = (hi == wi).all(axis=1)
+    same_bits = (hd.view(np.uint32) == wd.view(np.uint32)).all(axis=1)
+    bad = ~(same_idx & same_bits)
+    ties = bad & (wd[:, 0] == wd[:, 1])
+    rep = {"oracle": "oracle/vsm_oracle.c knn (CPU) over every row of the database, per rank on its shard, merged by oracle.merge_top2",
+           "queries": int(S), "planted_queries": int((sample < N_PLANTED).sum()),
+           "identical_indices_both_neighbours": int(same_idx.sum()), "identical_distance_bits": int(same_bits.sum())}
+    for r in (0.70, 0.75, 0.80):
+        rr = np.float32(r)
+        rep[f"ratio_{int(r * 100)}_decisions_identical"] = int(((hd[:, 0] < rr * hd[:, 1]) == (wd[:, 0] < rr * wd[:, 1])).sum())
+    rep["exempt_exact_ties"] = int(ties.sum())
+    rep["unexplained_mismatches"] = int((bad & ~ties).sum())
+    rep["seconds"] = round(time.perf_counter() - t0, 1)
+    return rep
+
+
 def cpp_track_latency(vsm_b200):
     """Builds bench_cpp/track_latency.cpp against libvsm.so and runs it (2544 pairs)."""
     import tempfile
@@ -243,6 +296,69 @@ def cpp_track_latency(vsm_b200):
         return json.loads(res.stdout.strip().splitlines()[-1])
     except Exception as e:            # a missing compiler only loses this informational number
         return {"unavailable": repr(e)[:200]}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_pair_baselines():
+    """The reference's CPU matchers on the pair-matching configs (BASELINE configs[0], [1], [4]), on this
+    box's host: cv::BFMatcher(NORM_L2).knnMatch (the exact matcher BASELINE names) with all threads and
+    with one, and cv::FlannBasedMatcher -- what the reference actually calls for float descriptors
+    (src/Slam.cpp:23, src/LoopCloser.cpp:31), approximate and not reproducible run to run.
+    Times are per pair (per batch for configs[4]), best of a few repetitions; mutual = both directions."""
+    import numpy as np
+    try:
+        import cv2
+    except Exception as e:
+        return {"unavailable": repr(e)[:120]}
+    rng = np.random.default_rng(5)
+
+    def unit(n):
+        x = rng.standard_normal((n, 256)).astype(np.float32)
+        return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+    def best(fn, reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e3
+
+    nthreads = cv2.getNumThreads()
+    out = {"cpu_model": cpu_model(), "host_threads": nthreads, "opencv": cv2.__version__,
+           "flann_note": "cv::FlannBasedMatcher (default KD-tree index, rebuilt per call like the reference's 2-argument knnMatch): "
+                         "approximate, shown for reference only"}
+    sizes4 = np.random.default_rng(0).integers(200, 2049, size=(64, 2))
+    cases = {"configs0_2000x2000_ratio": ([(2000, 2000)], False),
+             "configs1_1000x1000_mutual_ratio": ([(1000, 1000)], True),
+             "configs4_ragged64_mutual_ratio": ([(int(a), int(b)) for a, b in sizes4], True)}
+    for name, (shapes, mutual) in cases.items():
+        mats = [(unit(a), unit(b)) for a, b in shapes]
+
+        def run(m):
+            for a, b in mats:
+                m.knnMatch(a, b, k=2)
+                if mutual:
+                    m.knnMatch(b, a, k=1)
+
+        r = {}
+        cv2.setNumThreads(nthreads)
+        r["bfmatcher_all_threads_ms"] = best(lambda: run(cv2.BFMatcher(cv2.NORM_L2)), 3)
+        r["flann_all_threads_ms"] = best(lambda: run(cv2.FlannBasedMatcher()), 2)
+        cv2.setNumThreads(1)
+        r["bfmatcher_1_thread_ms"] = best(lambda: run(cv2.BFMatcher(cv2.NORM_L2)), 2 if len(shapes) == 1 else 1)
+        cv2.setNumThreads(nthreads)
+        out[name] = r
+    return out
 
 
 # ---- extra: the pair-matching configs (rank 0, N = 1) ------------------------------------------------
@@ -425,6 +541,60 @@ def extra_pair_numbers(torch, vsm_b200, device):
     return out
 
 
+def sharded_configs2(torch, dist, db, rank, world, device, barrier, steps=50):
+    """BASELINE configs[2] at this N: 1000 query descriptors against a 500-keyframe database (500K rows)
+    partitioned like the headline database; device-timed with resident queries, and end to end through
+    the host-buffer C-ABI call.  Max over ranks."""
+    import numpy as np
+    nq, rows_total = 1000, 500_000
+    g = torch.Generator(device=device)
+    g.manual_seed(4321)
+    full = torch.randn((rows_total, 256), generator=g, device=device)
+    full = full / full.norm(dim=1, keepdim=True)
+    q = torch.randn((nq, 256), generator=g, device=device)
+    q = q / q.norm(dim=1, keepdim=True)
+    v = full[123_000:123_200] + 0.06 * torch.randn((200, 256), generator=g, device=device)
+    q[:200] = v / v.norm(dim=1, keepdim=True)
+    rows = rows_total // world
+    off = rank * rows
+    if rank == world - 1:
+        rows = rows_total - off
+    shard = full[off:off + rows].contiguous()
+    del full
+    db.adopt(shard, off, None)
+    hq = q.cpu().pin_memory().numpy()
+    for _ in range(5):
+        db.search_device(q)
+        db.search_host_abi(hq)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(db.stream):
+        e0.record()
+    for _ in range(steps):
+        db.search_device(q)
+    with torch.cuda.stream(db.stream):
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    tc_ms = float(np.mean(db.matcher.tc_history(min(steps, 64))))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hi, hd = db.search_host_abi(hq)
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, tc_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, tc_ms = (float(x) for x in t)
+    fl = 2.0 * nq * rows_total * 256
+    return {"workload": "1000 queries x 500K-row keyframe DB, exact global top-2, sharded over the GPUs (BASELINE configs[2])",
+            "ms_per_search_device": ms, "tflops_device": fl / (ms * 1e-3) / 1e12,
+            "ms_per_search_e2e_host_buffers": ms_e2e, "tflops_e2e": fl / (ms_e2e * 1e-3) / 1e12,
+            "tc_kernel_ms_max_rank": tc_ms, "planted_recovered": int(((hi[:200, 0] >= 123_000) & (hi[:200, 0] < 123_200)).sum()),
+            "note": "e2e timed by host wall clock between barriers (synchronous calls), max over ranks"}
+
+
 # ---- main arm -----------------------------------------------------------------------------------
 def run_gpu(args):
     import torch
@@ -449,6 +619,7 @@ def run_gpu(args):
     seg = None   # one segment per shard for the global search
     db.adopt(shard, off, seg)
     hq = q.cpu().pin_memory()
+    hq_np = hq.numpy()
 
     def barrier():
         torch.cuda.synchronize()
@@ -459,7 +630,7 @@ def run_gpu(args):
     # warm-up (also sizes every buffer and the NCCL communicator)
     for _ in range(max(args.warmup, 3)):
         db.search_device(q)
-        db.search_host(hq)
+        db.search_host_abi(hq_np)
     db.stream.synchronize()
     launches_per_step = db.launches_per_search()
 
@@ -493,7 +664,7 @@ def run_gpu(args):
     barrier()
     time.sleep(1.0)
     for _ in range(max(args.warmup, 3)):
-        db.search_host(hq)
+        db.search_host_abi(hq_np)
     db.stream.synchronize()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -502,8 +673,7 @@ def run_gpu(args):
     e2e_dev, e2e_tc, e2e_wall = [], [], []
     for _ in range(args.steps):
         tw = time.perf_counter()
-        hi, hd = db.search_host(hq)
-        db.stream.synchronize()                        # the caller reads the result every step
+        hi, hd = db.search_host_abi(hq_np)             # ONE synchronous C-ABI call per rank: host queries in, host top-2 out
         e2e_wall.append((time.perf_counter() - tw) * 1e3)
         st = db.matcher.stats()                        # stream already idle: reads the call's own events
         e2e_dev.append(st["device_ms"])
@@ -526,6 +696,22 @@ def run_gpu(args):
     if sampler:
         sampler.stop()
 
+    # parity of the timed search's answer against the CPU oracle over the whole database (all ranks take part)
+    import numpy as _np
+    parity = None
+    if args.parity_queries > 0:
+        half = max(1, args.parity_queries // 2)
+        sample = _np.unique(_np.concatenate([_np.arange(0, N_PLANTED, max(1, N_PLANTED // half)),
+                                             _np.arange(N_PLANTED, NQ, max(1, (NQ - N_PLANTED) // half))]))
+        parity = oracle_parity(torch, dist, shard, off, hq_np, sample, hi, hd, rank, world, device)
+    shard_rows_main = shard.shape[0]
+    cfg2 = None
+    if not args.no_extra:
+        # BASELINE configs[2] (1000 queries x 500 keyframes x 1000 descriptors) sharded the same way, at this N
+        del shard
+        torch.cuda.empty_cache()
+        cfg2 = sharded_configs2(torch, dist, db, rank, world, device, barrier)
+
     flops = 2.0 * NQ * total_rows * 256
     per_step = ms / args.steps
     per_step_e2e = ms_e2e / args.steps
@@ -533,14 +719,14 @@ def run_gpu(args):
         import numpy as np
         peak_tf, peak_hbm, peak_src, peak_burst = peaks()
         # sanity: every planted query must find its DB row as the nearest neighbour
-        got = hi.numpy()[:N_PLANTED, 0]
+        got = hi[:N_PLANTED, 0]
         recovered = int((got == np.array(planted)).sum())
         # the same seeded database gives the same answer for every N: compare this across runs
-        chk = (int((hi.numpy().astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
-               ^ int(hd.numpy().view(np.uint32).astype(np.uint64).sum()))
+        chk = (int((hi.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
+               ^ int(hd.view(np.uint32).astype(np.uint64).sum()))
         st = db.matcher.stats()
         tc_avg = sum(tc_ms) / len(tc_ms)
-        shard_flops = 2.0 * NQ * shard.shape[0] * 256
+        shard_flops = 2.0 * NQ * shard_rows_main * 256
         achieved = shard_flops / (tc_avg * 1e-3) / 1e12
         # the sustained peak is what a long power-capped step can reach (N = 1: 16 ms steps at ~1.4 GHz);
         # a short shard step that runs at boost clocks is compared with the burst figure instead
@@ -552,23 +738,27 @@ def run_gpu(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(world, total_rows),
+            "parity": parity,
+            "check": {"planted_recovered": f"{recovered}/{N_PLANTED}", "result_checksum": f"{chk:016x}", "candidates_rescored": st["candidates"],
+                      "flagged_slices": st["flagged_slices"], "select_ms": st["select_ms"]},
             "clocks": clocks,
             "e2e": {"value": flops / (per_step_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": per_step_e2e,
                     "breakdown_ms_rank0_median": {"host_wall": float(np.median(e2e_wall)), "library_call_on_device": float(np.median(e2e_dev)),
                                                   "tc_top3_kernel": float(np.median(e2e_tc))},
                     "h2d_bytes_per_step": NQ * 1024, "d2h_bytes_per_step": NQ * 2 * 12,
-                    "api": "ShardedDB.search_host (pinned host queries in, pinned host top-2 out)",
+                    "api": ("vsm_db_top2 (C ABI: host queries in, host top-2 out, synchronous)" if world == 1 else
+                            ("vsm_db_top2_xchg (C ABI, one call per rank: host queries in, merged host top-2 out, fused peer-memory exchange)"
+                             if db.exchange == "p2p" else "ShardedDB.search_host (torch H2D/D2H + NCCL all-gather + merge kernel)")),
                     "conditions": "each timed loop (this one and the `value` one) is preceded by 1 s idle + its own warm-up steps"},
             "gpu_launches": launches_per_step * args.steps, "exchange": db.exchange, "exchange_note": db.exchange_note, "engine": args.engine,
             "roofline": {"bound": "tensor", "kernel": "tc_top3_kernel", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": args.traffic if args.traffic is not None else committed_traffic(shard.shape[0]),
+                         "traffic": args.traffic if args.traffic is not None else committed_traffic(shard_rows_main),
                          "peak_source": peak_src, "kernel_ms": tc_avg,
                          "algorithmic": "2*nq*shard_rows*256 FLOP per launch",
-                         "hbm_gbs": (shard.shape[0] * 512 + NQ * 512) / (tc_avg * 1e-3) / 1e9, "hbm_peak": peak_hbm},
-            "check": {"planted_recovered": f"{recovered}/{N_PLANTED}", "result_checksum": f"{chk:016x}", "candidates_rescored": st["candidates"],
-                      "flagged_slices": st["flagged_slices"], "select_ms": st["select_ms"]},
+                         "hbm_gbs": (shard_rows_main * 512 + NQ * 512) / (tc_avg * 1e-3) / 1e9, "hbm_peak": peak_hbm},
             "matches_per_s": NQ / (per_step * 1e-3),
+            "configs2_sharded": cfg2,
         }
         if world == 1 and not args.no_cpu:
             fn, cores, kind, what = cpu_matcher()
@@ -584,12 +774,14 @@ def run_gpu(args):
                     break
             dt = (time.perf_counter() - t0) / reps
             # parity on the same sample: the CUDA path against what the CPU matcher just returned
-            line["parity"] = parity_report(vsm_b200, local, cq, ct, fn(cq, ct))
+            line["parity_vs_cpu_matcher_sample"] = parity_report(vsm_b200, local, cq, ct, fn(cq, ct))
             line["cpu_baseline"] = {"value": 2.0 * NQ * n * 256 / dt / 1e12, "unit": "TFLOP/s", "cores": cores,
                                     "kind": kind, "sample": f"{what}; {NQ} queries x {n}-row sample of the DB, {reps} repetitions"}
         if world == 1 and not args.no_extra:
             # free the big shard first: the pair configs need little memory
             line["extra"] = extra_pair_numbers(torch, vsm_b200, local)
+            if not args.no_cpu:
+                line["extra"]["cpu_pair_baselines"] = cpu_pair_baselines()
         print(json.dumps(line))
     db.close()
     if world > 1:
@@ -609,6 +801,8 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: fused peer-memory exchange (default) or NCCL all-gather + merge")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 tensor cores (1 CTA/SM), 3 tensor cores on CTA pairs")
+    ap.add_argument("--parity-queries", type=int, default=64,
+                    help="queries whose answer is checked against the CPU oracle over the whole database (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,

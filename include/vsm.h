@@ -45,7 +45,8 @@ typedef enum {
     VSM_ERR_NO_DEVICE = 2,   /* no usable CUDA device / not sm_100 */
     VSM_ERR_CUDA = 3,        /* CUDA runtime/driver failure (message in vsm_last_error) */
     VSM_ERR_CAPACITY = 4,    /* store / scratch capacity exceeded */
-    VSM_ERR_NOT_FOUND = 5    /* unknown keyframe handle */
+    VSM_ERR_NOT_FOUND = 5,   /* unknown keyframe handle */
+    VSM_ERR_TIMEOUT = 6      /* fused peer-memory exchange: a peer rank never made the matching call */
 } vsm_status;
 
 /* Mirror of cv::DMatch {int queryIdx; int trainIdx; int imgIdx; float distance;}
@@ -72,7 +73,8 @@ typedef struct {
     int64_t store_rows;          /* initial capacity of the keyframe store in rows; it grows
                                     on demand; 0 = allocate at the first add */
     int32_t reserved[8];         /* [0]: tiles per slice segment (0 = automatic);
-                                    [1]: rescan work-list capacity (0 = default; tests shrink it) */
+                                    [1]: rescan work-list capacity (0 = default; tests shrink it);
+                                    [2]: plain frames vsm_track keeps before recycling (0 = 2) */
 } vsm_opts;
 
 typedef struct vsm_ctx vsm_ctx;
@@ -128,12 +130,40 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs,
                     const float* train, const int32_t* t_off,
                     float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good);
 
-/* ---- device-resident keyframe store (Frame::descriptors_, Map::frames_) ---- */
+/* ---- device-resident frame store (Frame::descriptors_, Map::frames_) ----------------------------
+ * The store mirrors Map::frames_ (src/Map.cpp:7-10): every stored frame has a handle, a frame id and
+ * the reference's is_keyframe flag (include/Frame.h; false until Frame::set_keyframe(true)).
+ *   - vsm_store_add* adds a KEYFRAME; vsm_track adds the frame being tracked as a PLAIN frame, which the
+ *     caller promotes (vsm_store_promote) when the reference calls set_keyframe(true)
+ *     (src/Slam.cpp:590, :660, :828, :852, :919, :1065, :1076).
+ *   - "the keyframes" below always means Map::get_keyframes() (src/Map.cpp:40-47): the live frames
+ *     with the flag set, in insertion order.  Per-keyframe outputs (counts / status arrays) are
+ *     indexed by position in that list; vsm_store_keyframes returns its handles.  While frames are
+ *     only added with vsm_store_add and never removed, position == handle.
+ *   - plain frames are transient: only last_frame_ and the current frame are ever matched again
+ *     (src/Slam.cpp:838, :848), so vsm_track keeps the newest `ring` (default 2) plain frames and
+ *     recycles the rows of older ones; a tracking sequence does not grow the store.
+ *   - vsm_store_remove frees a frame's rows for reuse; its handle value is reused by a later add.
+ *   - the arrays grow in place (CUDA virtual memory management: a reserved address range into which
+ *     physical chunks are mapped), so adding a keyframe never copies or moves existing rows.
+ *   - VSM_ERR_CAPACITY: the device is out of memory (the store is left as it was). */
 
 /* Mirrors Map::add_frame for a keyframe (src/Map.cpp, include/Frame.h:37,61):
  * uploads the N x 256 descriptor matrix once; fp32 master + bf16 shadow live on
- * the device.  Rows are appended; *handle identifies the keyframe (segment). */
+ * the device.  *handle identifies the frame. */
 int vsm_store_add(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int32_t* handle);
+/* Frame::set_keyframe(true) for a frame stored by vsm_track: it joins the keyframes at its own
+ * position in insertion order (a bridge keyframe promoted late, src/Slam.cpp:851-863, included). */
+int vsm_store_promote(vsm_ctx* ctx, int32_t handle);
+/* Drops a stored frame (keyframe or plain); its rows and its handle value are reused. */
+int vsm_store_remove(vsm_ctx* ctx, int32_t handle);
+/* First store row, row count, frame id and keyframe flag of a live handle (any pointer may be NULL):
+ * what a caller needs to size the good / raw buffers of vsm_match_to_stored and vsm_track, and to turn
+ * a store row returned by vsm_db_top2 into (frame, keypoint index = row - row0). */
+int vsm_store_frame_info(const vsm_ctx* ctx, int32_t handle, int64_t* row0, int32_t* n_rows, int32_t* frame_id,
+                         int32_t* is_keyframe);
+/* Handles of the keyframes in Map::get_keyframes() order; *n = their number (also when cap is smaller). */
+int vsm_store_keyframes(const vsm_ctx* ctx, int32_t* handles, int32_t cap, int32_t* n);
 /* Same, from a device pointer (bulk loads; no host round trip). */
 int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, int64_t n, int32_t* handle);
 /* Adopt an externally owned device fp32 matrix as the whole store (no copy of the
@@ -149,6 +179,8 @@ int vsm_store_adopt_device(vsm_ctx* ctx, const float* d_desc, int64_t n_rows,
 int vsm_store_load_spcf(vsm_ctx* ctx, const char* path, int32_t* n_loaded, int32_t* n_skipped,
                         int32_t* first_handle);
 int vsm_store_clear(vsm_ctx* ctx);
+/* n_rows = rows in use up to the high-water mark (removed ranges inside it included: the length a
+ * vsm_db_top2_masked mask must have); n_keyframes = live keyframes. */
 int vsm_store_info(const vsm_ctx* ctx, int64_t* n_rows, int32_t* n_keyframes);
 
 /* Slam::match_features(ref_kf->descriptors(), cur->descriptors()) with the reference
@@ -159,17 +191,18 @@ int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t 
 
 /* The tracking step of Slam::process_frame (src/Slam.cpp:838-842: ref = last keyframe or last
  * frame; matches = match_features(ref->descriptors(), frame->descriptors(), &raw)) for a
- * sequence: uploads the current frame ONCE, straight into the store as a new keyframe
- * (*cur_handle), and matches the resident reference `ref_handle` against it (query = reference,
- * train = current).  ref_handle < 0: only store the frame (first frame of a sequence).
- * good / raw must hold as many entries as the reference keyframe has rows. */
+ * sequence: uploads the current frame ONCE, straight into the store as a PLAIN frame
+ * (*cur_handle; see vsm_store_promote), and matches the resident reference `ref_handle` -- a keyframe
+ * or the previous plain frame -- against it (query = reference, train = current).
+ * ref_handle < 0: only store the frame (first frame of a sequence).
+ * good / raw must hold as many entries as the reference frame has rows (vsm_store_frame_info). */
 int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* cur, int32_t n_cur,
               float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw,
               int32_t* cur_handle);
 
-/* Global top-2 per query over every row of the store -- the stacked-matrix search of
- * src/Slam.cpp:546-574 and :744-774 (knnMatch(frame, all_descs, 2)).
- * idx: [nq][2] store row (+ row_offset, for sharded stores), dist: [nq][2]. */
+/* Global top-2 per query over the rows of every KEYFRAME of the store -- the stacked-matrix search of
+ * src/Slam.cpp:546-574 and :744-774 (knnMatch(frame, all_descs, 2)).  Rows of plain or removed
+ * frames are skipped.  idx: [nq][2] store row (+ row_offset, for sharded stores), dist: [nq][2]. */
 int vsm_db_top2(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset,
                 int64_t* idx, float* dist);
 
@@ -287,6 +320,13 @@ int vsm_xchg_create(vsm_ctx* ctx, int32_t rank, int32_t world, int32_t nq_cap, u
 int vsm_xchg_connect(vsm_ctx* ctx, const uint8_t* handles /* [world][64] */);
 int vsm_db_top2_xchg_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset,
                             int64_t* d_idx_out, float* d_dist_out, int32_t sync);
+/* The same collective search with HOST buffers in and out (the reference-facing form of one rank of a
+ * partitioned loop-closure search): queries are read from host memory, the merged global top-2 is
+ * written straight into pinned host memory by the exchange kernel and copied to idx / dist.
+ * Synchronous.  Every rank must make the same sequence of exchange calls with the same nq; a peer
+ * that is more than VSM_XCHG_TIMEOUT_S (default 10) seconds late makes the call fail with
+ * VSM_ERR_TIMEOUT on the ranks that waited for it -- the context stays usable. */
+int vsm_db_top2_xchg(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset, int64_t* idx, float* dist);
 
 /* Merge per-shard top-2 lists (e.g. after an NCCL all-gather) by (distance, index).
  * d_idx_in/d_dist_in: [nshard][nq][2] with GLOBAL indices (-1 = empty). */

@@ -125,10 +125,20 @@ public:
         return h;
     }
     void clear_keyframes() { check(vsm_store_clear(ctx_)); }
+    /* Frame::set_keyframe(true) (src/Slam.cpp:1065, :1076, :852) / dropping a frame from the device store. */
+    void promote(int handle) { check(vsm_store_promote(ctx_, handle)); }
+    void remove_frame(int handle) { check(vsm_store_remove(ctx_, handle)); }
+    int frame_rows(int handle) {
+        int32_t n = 0;
+        if (vsm_store_frame_info(ctx_, handle, nullptr, &n, nullptr, nullptr) != VSM_OK)
+            throw std::runtime_error("vsm_cv: unknown frame handle");
+        return n;
+    }
 
     /* match_features(ref_kf->descriptors(), cur->descriptors(), raw) with ref_kf resident (src/Slam.cpp:841). */
-    std::vector<DMatch> match_features(int keyframe_handle, int keyframe_rows, const Mat& cur,
+    std::vector<DMatch> match_features(int keyframe_handle, const Mat& cur,
                                        std::vector<DMatch>* raw_out = nullptr, float ratio = 0.75f, bool mutual = false) {
+        const int keyframe_rows = frame_rows(keyframe_handle);        /* the library's own count sizes the buffers */
         std::vector<DMatch> good(keyframe_rows > 0 ? keyframe_rows : 1);
         if (raw_out) raw_out->assign(good.size(), DMatch());
         std::vector<float> b;
@@ -160,9 +170,11 @@ public:
     }
 
     /* The tracking match of Slam::process_frame (src/Slam.cpp:838-842) for a sequence: the current
-     * frame goes to the device once and becomes keyframe *cur_handle; ref_handle < 0 = first frame. */
-    std::vector<DMatch> track(int ref_handle, int ref_rows, int frame_id, const Mat& cur, int* cur_handle,
+     * frame goes to the device once, as a plain frame *cur_handle (promote() it when the reference
+     * calls frame->set_keyframe(true)); ref_handle = last_keyframe_ or last_frame_, < 0 = first frame. */
+    std::vector<DMatch> track(int ref_handle, int frame_id, const Mat& cur, int* cur_handle,
                               std::vector<DMatch>* raw_out = nullptr, float ratio = 0.75f, bool mutual = false) {
+        const int ref_rows = ref_handle >= 0 ? frame_rows(ref_handle) : 0;
         std::vector<DMatch> good(ref_rows > 0 ? ref_rows : 1);
         if (raw_out) raw_out->assign(good.size(), DMatch());
         std::vector<float> b;

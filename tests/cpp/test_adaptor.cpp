@@ -80,7 +80,7 @@ int main() {
     int h1 = matcher.add_keyframe(20, Mat(333, 256, c.data()));
     EXPECT(h0 == 0 && h1 == 1);
     {
-        std::vector<DMatch> good = matcher.match_features(h0, n1, desc2);
+        std::vector<DMatch> good = matcher.match_features(h0, desc2);
         std::vector<vsm_oracle_dmatch> og(n1);
         int ng = 0;
         vsm_oracle_match_features(a.data(), n1, b.data(), n2, 0.75f, 0, og.data(), &ng, nullptr, nullptr, 0);

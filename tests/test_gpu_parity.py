@@ -257,7 +257,91 @@ def test_track_sequence(tc):
         assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes()
         assert len(good) > 100
         h = h2
-    assert tc.store_info() == (2000, 5)
+    # tracked frames are PLAIN frames (Frame::is_keyframe_ false): only the newest two stay resident
+    assert tc.store_info()[1] == 0 and tc.store_info()[0] <= 3 * 400
+    tc.clear_store()
+
+
+def test_track_promote_remove_interleaved_with_loop_detect(tc):
+    """One context used like the reference's Slam + LoopCloser together: every frame is tracked
+    (vsm_track: plain frame, src/Slam.cpp:838-842), some are promoted afterwards (set_keyframe(true),
+    :1065/:1076 -- one of them LATE, as the bridge keyframe of :851-863), one keyframe is removed, and
+    the loop search (src/LoopCloser.cpp:43-62) and the stacked search must see Map::get_keyframes()
+    only (src/Map.cpp:40-47): live keyframes in insertion order, never the plain frames."""
+    nfr, n = 40, 220
+    frames = gen.video(77, nfr, n)
+    tc.clear_store()
+    handles, kf_frames = {}, []
+    prev, ref_f = -1, -1
+    for f in range(nfr):
+        good, _, h = tc.track(prev, 10 * f, frames[f], 0.75, mutual=False)
+        if f > 0:
+            og, _ = oracle.match_features(frames[ref_f], frames[f], 0.75)
+            assert good.tobytes() == og.tobytes(), f
+        handles[f] = h
+        if f % 4 == 0:                                   # keyframe decision after matching
+            tc.promote(h)
+            kf_frames.append(f)
+        if f == 10:                                      # bridge: last_frame_ (frame 9) is promoted after frame 10 was tracked
+            tc.promote(handles[9])
+            kf_frames.append(9)
+            kf_frames.sort()
+        prev, ref_f = h, f
+    # only the two newest plain frames stay resident: the store holds the keyframes + 2 frames, not all 40
+    assert tc.store_info() == ((len(kf_frames) + 2) * n, len(kf_frames))
+    # drop a keyframe in the middle; its rows are reused by later frames
+    tc.remove_frame(handles[12])
+    kf_frames.remove(12)
+    extra = gen.rows(79, 0, 0, 150)
+    tc.add_keyframe(10 * nfr, extra)
+    order = tc.keyframes()
+    assert [tc.frame_info(int(h))[1] for h in order] == [10 * f for f in kf_frames] + [10 * nfr]
+    assert all(tc.frame_info(int(h))[2] for h in order)
+    kf_mats = [frames[f] for f in kf_frames] + [extra]
+    db = np.concatenate(kf_mats)
+    seg_off = np.concatenate([[0], np.cumsum([len(k) for k in kf_mats])]).astype(np.int64)
+    ids = np.array([10 * f for f in kf_frames] + [10 * nfr], np.int32)
+    # the query frame re-observes 150 rows of frame 0 (a keyframe far enough back): a loop candidate
+    vq = gen.int_rows(80, 0, 0, n).copy()
+    f0 = np.rint(frames[0][:150].astype(np.float64) * 3300).astype(np.int64)
+    vq[:150] = 1000 * f0 + 900 * gen.int_rows(81, 0, 0, 150)
+    q = gen._normalize_int(vq)
+    cur_id = 10 * nfr + 50
+    st, lists = tc.loop_detect(cur_id, q, 0.75, min_gap=200, every=2)
+    ost, ol = oracle.loop_detect(q, db, seg_off, ids, cur_id, 0.75, min_gap=200, every=2)
+    assert np.array_equal(st, ost)
+    for s in range(len(ids)):
+        if ost[s] >= 0:
+            assert lists[s].tobytes() == ol[s].tobytes(), s
+    # stacked search over the keyframes only: store rows map back through frame_info
+    gi, gd = tc.search_map_points(q)
+    oi, od = oracle.knn(q, db, 2)
+    row0 = np.array([tc.frame_info(int(h))[3] for h in order], np.int64)
+    seg_of = np.searchsorted(seg_off, oi, side="right") - 1
+    want = row0[seg_of] + (oi - seg_off[seg_of])
+    assert np.array_equal(gi, want) and np.array_equal(bits(gd), bits(od))
+    # per-keyframe search without the eligibility rules sees the same list
+    c, _ = tc.detect_candidates(q, 0.75, want_matches=False)
+    oc, _ = oracle.segmented(q, db, seg_off, 0.75)
+    assert np.array_equal(c, oc) and (oc >= 30).any()
+    tc.clear_store()
+
+
+def test_store_grows_in_place_without_copies(tc):
+    """Keyframes added one by one past several growth steps: earlier rows keep their place and content
+    (global top-2 equals the oracle over the concatenation) -- the arena maps new chunks, it never
+    re-allocates (vsm_store_info's row count is the only thing that changes)."""
+    tc.clear_store()
+    mats = []
+    for k in range(12):
+        mats.append(gen.rows(300 + k, 0, 0, 30000))
+        tc.add_keyframe(k, mats[-1])
+    db = np.concatenate(mats)
+    q = gen._normalize_int(1000 * gen.int_rows(300, 0, 100, 64) + 700 * gen.int_rows(299, 0, 0, 64))
+    gi, gd = tc.search_map_points(q)
+    oi, od = oracle.knn(q, db, 2)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    assert (gi[:, 0] == 100 + np.arange(64)).all()
     tc.clear_store()
 
 

@@ -33,12 +33,28 @@ def _scaled(t, rng):
 def test_random_call_sequence():
     rng = np.random.default_rng(2026)
     m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, scratch_rows=256)
-    kf, prev_handle, prev_frame = [], -1, None
+    # model of the store: keyframes in Map::get_keyframes() order as (handle, matrix); the reference frame
+    kf, prev_handle, prev_frame, prev_is_kf = [], -1, None, False
     counts = {}
-    for it in range(140):
+
+    def layout():
+        """concatenated keyframe matrix, its offsets, and each keyframe's first store row"""
+        order = m.keyframes()
+        assert [int(h) for h in order] == [h for h, _ in kf]
+        db = np.concatenate([d for _, d in kf])
+        seg = np.concatenate([[0], np.cumsum([len(d) for _, d in kf])]).astype(np.int64)
+        row0 = np.array([m.frame_info(h)[3] for h, _ in kf], np.int64)
+        return db, seg, row0
+
+    def to_store_rows(oi, seg, row0):
+        s_ = np.clip(np.searchsorted(seg, np.maximum(oi, 0), side="right") - 1, 0, len(row0) - 1)
+        return np.where(oi >= 0, row0[s_] + (oi - seg[s_]), -1)
+
+    for it in range(160):
         if rng.random() < 0.15:
             m.set_profiling(bool(rng.integers(0, 2)))
-        op = rng.choice(["knn", "match", "match", "track", "add", "global", "segmented", "masked", "batch", "repeat"])
+        op = rng.choice(["knn", "match", "match", "track", "track", "add", "global", "segmented", "masked", "batch",
+                         "repeat", "remove"])
         counts[op] = counts.get(op, 0) + 1
         nq, nt = int(rng.integers(1, 700)), int(rng.integers(1, 1100))
         q, t, _ = gen.planted(1000 + it, nq, nt, 0.5, 0.09)
@@ -62,31 +78,47 @@ def test_random_call_sequence():
             if prev_frame is not None:
                 og, orw = oracle.match_features(prev_frame, d, 0.75, mutual=mutual)
                 assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes(), (it, op)
-            kf.append(d)
+            # the frame is a plain frame until the "keyframe decision" (src/Slam.cpp:1065/:1076)
+            prev_is_kf = bool(rng.random() < 0.4)
+            if prev_is_kf:
+                m.promote(h)
+                kf.append((h, d))
             prev_handle, prev_frame = h, d
         elif op == "add":
             h = m.add_keyframe(it, t)
-            kf.append(t)
-            prev_handle, prev_frame = h, t
+            kf.append((h, t))
+            prev_handle, prev_frame, prev_is_kf = h, t, True
+        elif op == "remove" and len(kf) > 2:
+            k = int(rng.integers(0, len(kf)))
+            h, _ = kf.pop(k)
+            m.remove_frame(h)
+            if h == prev_handle:
+                prev_handle, prev_frame = -1, None
         elif kf and op == "global":
-            db = np.concatenate(kf)
+            db, seg, row0 = layout()
             gi, gd = m.search_map_points(_maybe_pinned(q, rng))
             oi, od = oracle.knn(q, db, 2)
-            assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od)), (it, op)
+            assert np.array_equal(gi, to_store_rows(oi, seg, row0)) and np.array_equal(bits(gd), bits(od)), (it, op)
         elif kf and op == "segmented":
-            db = np.concatenate(kf)
-            seg = np.concatenate([[0], np.cumsum([len(k) for k in kf])]).astype(np.int64)
+            db, seg, _ = layout()
             c, lists = m.detect_candidates(_maybe_pinned(q, rng), 0.75)
             oc, ol = oracle.segmented(q, db, seg, 0.75)
             assert np.array_equal(c, oc), (it, op)
             for s in range(len(kf)):
                 assert lists[s].tobytes() == ol[s].tobytes(), (it, op, s)
         elif kf and op == "masked":
-            db = np.concatenate(kf)
-            mask = (rng.random(db.shape[0]) < 0.4).astype(np.uint8)
-            ids = np.nonzero(mask)[0]
+            # the mask runs over store rows; only rows of live keyframes are offered here
+            db, seg, row0 = layout()
+            nrows = m.store_info()[0]
+            pick = rng.random(db.shape[0]) < 0.4
+            rows_of_db = to_store_rows(np.arange(db.shape[0]), seg, row0)
+            mask = np.zeros(nrows, np.uint8)
+            mask[rows_of_db[pick]] = 1
+            ids = np.nonzero(mask)[0]                                 # ascending store row = the compacted order
+            phys = np.zeros((nrows, 256), np.float32)
+            phys[rows_of_db] = db
             gi, gd = m.search_map_points_masked(q, mask)
-            oi, od = oracle.knn(q, db[ids], 2)
+            oi, od = oracle.knn(q, phys[ids], 2)
             want = np.where(oi >= 0, ids[np.maximum(oi, 0)] if len(ids) else -1, -1)
             assert np.array_equal(gi, want) and np.array_equal(bits(gd), bits(od)), (it, op)
         elif op == "batch":
@@ -105,4 +137,4 @@ def test_random_call_sequence():
             m.clear_store()
             kf, prev_handle, prev_frame = [], -1, None
     m.close()
-    assert len(counts) >= 8
+    assert len(counts) >= 9

@@ -26,8 +26,26 @@ namespace {
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// virtual memory management (driver API, resolved through cudaGetDriverEntryPoint like the tensor-map encoder)
+typedef CUresult (*PFN_cuMemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+typedef CUresult (*PFN_cuMemAddressFree)(CUdeviceptr, size_t);
+typedef CUresult (*PFN_cuMemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+typedef CUresult (*PFN_cuMemRelease)(CUmemGenericAllocationHandle);
+typedef CUresult (*PFN_cuMemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+typedef CUresult (*PFN_cuMemUnmap)(CUdeviceptr, size_t);
+typedef CUresult (*PFN_cuMemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+typedef CUresult (*PFN_cuMemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
 
 thread_local std::string g_create_error;
+
+// One array of an arena that grows IN PLACE: a virtual address range reserved once
+// (cuMemAddressReserve) into which physical chunks are mapped as the row count grows
+// (cuMemCreate + cuMemMap + cuMemSetAccess).  Growth never moves a row and never copies.
+struct VmmRange {
+    CUdeviceptr base = 0;
+    size_t reserved = 0, mapped = 0;
+    std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;    // (handle, bytes), in address order
+};
 
 struct Arena {
     float* f32 = nullptr;            // fp32 master rows (exact re-score reads these)
@@ -35,13 +53,25 @@ struct Arena {
     float* n2 = nullptr;             // squared norms
     int64_t cap = 0;                 // rows
     bool own_f32 = true;
+    bool vmm = false;                // arrays live in VmmRanges (growth maps chunks, no copy)
+    VmmRange r_f32, r_b16, r_n2;
     CUtensorMap map;
 };
 
+// One stored frame = a contiguous row range of the store (Frame::descriptors_, include/Frame.h:61).
+// Handles index `segs`; the slot of a removed frame is reused.
 struct Seg {
     int64_t row0;
     int32_t count;
     int32_t frame_id;
+    int64_t seq;                     // insertion order (Map::frames_ order, src/Map.cpp:7-10)
+    uint8_t live;                    // 0 = removed (slot waits in free_handles)
+    uint8_t is_kf;                   // Frame::is_keyframe() (Map::get_keyframes filters on it, src/Map.cpp:40-47)
+};
+
+// A run of consecutive store rows that belong to live keyframes (global search skips the rest).
+struct Run {
+    int64_t row0, count;
 };
 
 // Host description of one kNN problem before planning.
@@ -51,6 +81,9 @@ struct HProblem {
     int64_t out_off;
     float skip_ratio2 = 0.f;     // see Problem::skip_ratio2
     int32_t maxima_only = 0;     // with skip_ratio2: records = slice maxima only (matches are rare: LoopCloser's loop)
+    // train rows = these runs of STORE rows (logical train index = store row; t_row = 0, nt = the store's
+    // high-water mark); nullptr = the one contiguous range [t_row, t_row + nt)
+    const std::vector<Run>* runs = nullptr;
 };
 
 // ratio^2 with slack for a caller that only keeps ratio-test survivors; 0 = never skip
@@ -77,8 +110,28 @@ struct vsm_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     Arena scratch, store;
-    int64_t store_rows = 0;
-    std::vector<Seg> segs;
+    int64_t store_rows = 0;              // high-water mark: rows [0, store_rows) have been handed out
+    std::vector<Seg> segs;               // indexed by handle
+    std::vector<int32_t> free_handles;   // slots of removed frames
+    std::vector<Run> free_rows;          // row ranges of removed frames, sorted by row0, coalesced
+    std::vector<int32_t> kf_order;       // live keyframes in insertion order = Map::get_keyframes() (src/Map.cpp:40-47)
+    std::vector<int32_t> plain_ring;     // live NON-keyframe frames, oldest first (last_frame_ and the current one)
+    int ring_depth = 2;                  // plain frames kept: a new one evicts the oldest (src/Slam.cpp:838 needs last_frame_)
+    int64_t next_seq = 0;
+    std::vector<Run> kf_runs;            // merged row runs of the live keyframes (global search), see store_runs()
+    bool kf_runs_valid = false;
+    bool vmm_ok = false;                 // driver entry points below resolved and the device supports them
+    size_t vmm_gran = 0;
+    PFN_cuMemAddressReserve p_reserve = nullptr;
+    PFN_cuMemAddressFree p_addr_free = nullptr;
+    PFN_cuMemCreate p_create = nullptr;
+    PFN_cuMemRelease p_release = nullptr;
+    PFN_cuMemMap p_map = nullptr;
+    PFN_cuMemUnmap p_unmap = nullptr;
+    PFN_cuMemSetAccess p_set_access = nullptr;
+    PFN_cuMemGetAllocationGranularity p_gran = nullptr;
+    int64_t arena_grow_copies = 0;       // growth events that had to copy (non-VMM fall-back path); tests read it
+    uint32_t* h_status = nullptr;        // pinned, device-visible: kernels report soft failures here (exchange timeout)
     uint32_t* d_store_stats = nullptr;   // {min, max} squared norm over the store
     DevBuf<uint8_t> d_desc;
     uint8_t* h_desc = nullptr;
@@ -211,9 +264,110 @@ int encode_map(vsm_ctx* ctx, Arena& a) {
     return VSM_OK;
 }
 
-// Grow an arena to hold `rows`; keeps the first `keep` rows.
+#define CKU(call)                                                                                    \
+    do {                                                                                             \
+        CUresult r_ = (call);                                                                        \
+        if (r_ != CUDA_SUCCESS) {                                                                    \
+            char b_[512];                                                                            \
+            snprintf(b_, sizeof b_, "%s failed: CUresult %d (%s:%d)", #call, (int)r_, __FILE__, __LINE__); \
+            ctx->err = b_;                                                                           \
+            return r_ == CUDA_ERROR_OUT_OF_MEMORY ? VSM_ERR_CAPACITY : VSM_ERR_CUDA;                 \
+        }                                                                                            \
+    } while (0)
+
+// ---- arenas that grow in place (virtual memory management) ------------------------------------
+int vmm_reserve(vsm_ctx* ctx, VmmRange& r, size_t bytes) {
+    bytes = (bytes + ctx->vmm_gran - 1) / ctx->vmm_gran * ctx->vmm_gran;
+    CKU(ctx->p_reserve(&r.base, bytes, 0, 0, 0));
+    r.reserved = bytes;
+    r.mapped = 0;
+    return VSM_OK;
+}
+
+// Map physical memory so that [base, base + need) is backed; existing mappings are untouched.
+int vmm_back(vsm_ctx* ctx, VmmRange& r, size_t need) {
+    need = (need + ctx->vmm_gran - 1) / ctx->vmm_gran * ctx->vmm_gran;
+    if (need <= r.mapped) return VSM_OK;
+    if (need > r.reserved) return fail(ctx, VSM_ERR_CAPACITY, "descriptor arena: beyond the reserved address range");
+    const size_t bytes = need - r.mapped;
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = ctx->device;
+    CUmemGenericAllocationHandle h;
+    CKU(ctx->p_create(&h, bytes, &prop, 0));
+    CUresult rc = ctx->p_map(r.base + r.mapped, bytes, 0, h, 0);
+    if (rc == CUDA_SUCCESS) {
+        CUmemAccessDesc acc;
+        memset(&acc, 0, sizeof acc);
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        rc = ctx->p_set_access(r.base + r.mapped, bytes, &acc, 1);
+        if (rc != CUDA_SUCCESS) ctx->p_unmap(r.base + r.mapped, bytes);
+    }
+    if (rc != CUDA_SUCCESS) {
+        ctx->p_release(h);
+        char b[160];
+        snprintf(b, sizeof b, "descriptor arena: mapping %zu bytes failed (CUresult %d)", bytes, (int)rc);
+        return fail(ctx, rc == CUDA_ERROR_OUT_OF_MEMORY ? VSM_ERR_CAPACITY : VSM_ERR_CUDA, b);
+    }
+    r.chunks.push_back({h, bytes});
+    r.mapped = need;
+    return VSM_OK;
+}
+
+void vmm_release(vsm_ctx* ctx, VmmRange& r) {
+    size_t off = 0;
+    for (auto& c : r.chunks) {
+        ctx->p_unmap(r.base + off, c.second);
+        ctx->p_release(c.first);
+        off += c.second;
+    }
+    if (r.base) ctx->p_addr_free(r.base, r.reserved);
+    r = VmmRange();
+}
+
+// Grow an arena to hold `rows`; the first `keep` rows survive.  With virtual memory management
+// (the normal case) growth maps more chunks behind the same addresses: nothing is copied, nothing
+// moves, no stream is synchronised.  The cudaMalloc path below is only taken when the driver has no
+// VMM support or for an adopted matrix (whose fp32 master is the caller's).
 int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
     if (rows <= a.cap && a.b16) return VSM_OK;
+    if (ctx->vmm_ok && a.own_f32 && (a.vmm || !a.b16)) {
+        if (!a.vmm) {
+            // address space for as many rows as the device could ever hold (fp32 + bf16 + norm = 1540 B per row)
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t max_rows = total_b / 1536 + (1u << 20);
+            TRY(vmm_reserve(ctx, a.r_f32, max_rows * VSM_DIM * sizeof(float)));
+            int st = vmm_reserve(ctx, a.r_b16, max_rows * VSM_DIM * sizeof(__nv_bfloat16));
+            if (st == VSM_OK) st = vmm_reserve(ctx, a.r_n2, max_rows * sizeof(float));
+            if (st != VSM_OK) { vmm_release(ctx, a.r_f32); vmm_release(ctx, a.r_b16); vmm_release(ctx, a.r_n2); return st; }
+            a.vmm = true;
+            a.f32 = reinterpret_cast<float*>(a.r_f32.base);
+            a.b16 = reinterpret_cast<__nv_bfloat16*>(a.r_b16.base);
+            a.n2 = reinterpret_cast<float*>(a.r_n2.base);
+            a.cap = 0;
+        }
+        auto back = [&](int64_t want) -> int {
+            TRY(vmm_back(ctx, a.r_f32, (size_t)want * VSM_DIM * sizeof(float)));
+            TRY(vmm_back(ctx, a.r_b16, (size_t)want * VSM_DIM * sizeof(__nv_bfloat16)));
+            TRY(vmm_back(ctx, a.r_n2, (size_t)want * sizeof(float)));
+            return VSM_OK;
+        };
+        // head-room: a quarter of the arena, at least 64K rows (96 MB), so that growth is rare
+        int64_t want = std::max<int64_t>(rows, a.cap + std::max<int64_t>(a.cap / 4, 65536));
+        want = (want + 255) / 256 * 256;
+        int st = back(want);
+        if (st != VSM_OK) {                                  // the head-room did not fit: exactly what is needed
+            want = (rows + 255) / 256 * 256;
+            st = back(want);                                 // chunks mapped by the failed attempt are kept and reused
+        }
+        if (st != VSM_OK) return st;
+        a.cap = want;
+        return encode_map(ctx, a);
+    }
     int64_t want = std::max<int64_t>(rows, a.cap + a.cap / 2);
     want = (want + 255) / 256 * 256;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -227,6 +381,7 @@ int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
             if (a.own_f32) CK(cudaMemcpy(f32, a.f32, (size_t)keep * VSM_DIM * sizeof(float), cudaMemcpyDeviceToDevice));
             CK(cudaMemcpy(b16, a.b16, (size_t)keep * VSM_DIM * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice));
             CK(cudaMemcpy(n2, a.n2, (size_t)keep * sizeof(float), cudaMemcpyDeviceToDevice));
+            ctx->arena_grow_copies++;
         }
         return VSM_OK;
     };
@@ -242,7 +397,8 @@ int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
     if (st != VSM_OK) {
         cudaFree(f32); cudaFree(b16); cudaFree(n2);
         cudaGetLastError();
-        return st;
+        ctx->err = "descriptor arena: out of device memory (" + ctx->err + ")";
+        return VSM_ERR_CAPACITY;
     }
     if (a.own_f32) { if (a.f32) CK(cudaFree(a.f32)); a.f32 = f32; }
     if (a.b16) CK(cudaFree(a.b16));
@@ -251,10 +407,14 @@ int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
     return encode_map(ctx, a);
 }
 
-void arena_free(Arena& a) {
-    if (a.own_f32 && a.f32) cudaFree(a.f32);
-    if (a.b16) cudaFree(a.b16);
-    if (a.n2) cudaFree(a.n2);
+void arena_free(vsm_ctx* ctx, Arena& a) {
+    if (a.vmm) {
+        vmm_release(ctx, a.r_f32); vmm_release(ctx, a.r_b16); vmm_release(ctx, a.r_n2);
+    } else {
+        if (a.own_f32 && a.f32) cudaFree(a.f32);
+        if (a.b16) cudaFree(a.b16);
+        if (a.n2) cudaFree(a.n2);
+    }
     a = Arena();
 }
 
@@ -370,6 +530,11 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         memcpy(key.data(), head, sizeof head);
         if (P) memcpy(key.data() + sizeof head, probs.data(), sizeof(HProblem) * probs.size());
         if (!jobs.empty()) memcpy(key.data() + sizeof head + sizeof(HProblem) * probs.size(), jobs.data(), sizeof(HJob) * jobs.size());
+        for (auto& p : probs)                                // a run list is part of the plan, not only its address
+            if (p.runs && !p.runs->empty()) {
+                const uint8_t* b = reinterpret_cast<const uint8_t*>(p.runs->data());
+                key.insert(key.end(), b, b + p.runs->size() * sizeof(Run));
+            }
     }
     const bool hit = !dump_first && pl.valid && pl.p_desc == ctx->d_desc.p && pl.p_aux == ctx->d_aux.p &&
                      pl.p_stats == ctx->d_store_stats && pl.key == key;
@@ -404,40 +569,59 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         qb[i + 1] = qb[i] + (hp.nq + SELECT_WARPS - 1) / SELECT_WARPS;
         if (hp.nq <= 0 || hp.nt <= 0) { d.nslices = 0; continue; }
         if (d.exact & 1) {
-            SliceInfo si = {0, hp.nt, -1, 0};
-            slices.push_back(si);
-            d.nslices = 1;
+            if (hp.runs) {
+                for (const Run& rn : *hp.runs) { SliceInfo si = {(int32_t)rn.row0, (int32_t)rn.count, -1, 0}; slices.push_back(si); }
+            } else {
+                SliceInfo si = {0, hp.nt, -1, 0};
+                slices.push_back(si);
+            }
+            d.nslices = (int)slices.size() - d.slice_off;
             continue;
         }
-        const int ntiles = (hp.nt + TILE_N - 1) / TILE_N;
+        // the train rows as runs of consecutive rows (one run unless the store has holes); idx0 = logical
+        // index of a run's first row, its tensor-map row is hp.t_row + idx0
+        std::vector<Run> one{Run{0, hp.nt}};
+        const std::vector<Run>& runs = hp.runs ? *hp.runs : one;
+        int64_t ntiles = 0;
+        for (const Run& rn : runs) ntiles += (rn.count + TILE_N - 1) / TILE_N;
         // ranges: units of at most UNIT_TILES tiles whose count is (close to) a whole number of
         // waves over the SMs, so that the dynamic scheduler ends every CTA at about the same time
-        int nranges = 1;
+        int64_t nranges = 1;
         for (int64_t k = 1; k <= 8192; k++) {
-            nranges = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, nworkers * k / std::max<int64_t>(total_qtiles, 1)));
+            nranges = std::min<int64_t>(ntiles, std::max<int64_t>(1, nworkers * k / std::max<int64_t>(total_qtiles, 1)));
             if ((ntiles + nranges - 1) / nranges <= UNIT_TILES || nranges == ntiles) break;
         }
-        const int tpr = (ntiles + nranges - 1) / nranges;
-        nranges = (ntiles + tpr - 1) / tpr;
+        const int tpr_all = (int)((ntiles + nranges - 1) / nranges);
         // slice length: short slices keep an overflow re-scan cheap, long ones keep the record
         // stream small next to the database stream
         const int seg_pref = ctx->seg_tiles > 0 ? ctx->seg_tiles
-                                                : (ntiles > 4096 ? 64 : std::max(1, std::min(16, ntiles / 16)));
-        const int seg = std::min(std::min(tpr, seg_pref), 64);      // 64 tiles x 128 columns = the 13 index bits of a packed entry
+                                                : (ntiles > 4096 ? 64 : (int)std::max<int64_t>(1, std::min<int64_t>(16, ntiles / 16)));
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
-        std::vector<int> range_slice0(nranges);
-        for (int r = 0; r < nranges; r++) {
-            range_slice0[r] = (int)slices.size() - d.slice_off;
-            const int tile0 = r * tpr, tile1 = std::min(ntiles, tile0 + tpr);
-            for (int t0 = tile0; t0 < tile1; t0 += seg) {
-                const int32_t i0 = t0 * TILE_N;
-                const int32_t cnt = std::min<int64_t>((int64_t)std::min(seg, tile1 - t0) * TILE_N, hp.nt - i0);
-                for (int h = 0; h < 2; h++) { SliceInfo si = {i0, cnt, h, 0}; slices.push_back(si); }
+        struct Range { int64_t idx0, count; int tiles_after; int slice0; int seg; };
+        std::vector<Range> ranges;
+        for (const Run& rn : runs) {
+            const int rt = (int)((rn.count + TILE_N - 1) / TILE_N);
+            if (rt == 0) continue;
+            const int nr = (rt + tpr_all - 1) / tpr_all;
+            const int tpr = (rt + nr - 1) / nr;
+            const int seg = std::min(std::min(tpr, seg_pref), 64);  // 64 tiles x 128 columns = the 13 index bits of a packed entry
+            for (int tile0 = 0; tile0 < rt; tile0 += tpr) {
+                const int tile1 = std::min(rt, tile0 + tpr);
+                Range g;
+                g.idx0 = rn.row0 + (int64_t)tile0 * TILE_N;
+                g.count = std::min<int64_t>((int64_t)(tile1 - tile0) * TILE_N, rn.row0 + rn.count - g.idx0);
+                g.tiles_after = rt - tile1;
+                g.slice0 = (int)slices.size() - d.slice_off;
+                g.seg = seg;
+                for (int64_t i0 = 0; i0 < g.count; i0 += (int64_t)seg * TILE_N) {
+                    const int32_t cnt = (int32_t)std::min<int64_t>((int64_t)seg * TILE_N, g.count - i0);
+                    for (int h = 0; h < 2; h++) { SliceInfo si = {(int32_t)(g.idx0 + i0), cnt, h, 0}; slices.push_back(si); }
+                }
+                ranges.push_back(g);
             }
         }
         d.nslices = (int)slices.size() - d.slice_off;
-        for (int r = 0; r < nranges; r++) {
-            const int tile0 = r * tpr, tile1 = std::min(ntiles, tile0 + tpr);
+        for (const Range& g : ranges) {
             for (int qt = 0; pairs && qt < nqt; qt += 2) {
                 TcUnit2 u;
                 memset(&u, 0, sizeof u);
@@ -445,17 +629,17 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                     const bool real = qt + k < nqt;
                     const int q = real ? qt + k : qt;                   // an odd tail pairs the last tile with a dummy
                     u.q_n2[k] = hp.q_n2 + (int64_t)q * TILE_M;
-                    u.rec_base[k] = nrecs + (int64_t)q * TILE_M * d.nslices + range_slice0[r];
+                    u.rec_base[k] = nrecs + (int64_t)q * TILE_M * d.nslices + g.slice0;
                     u.q_row[k] = (int32_t)(hp.q_row + (int64_t)q * TILE_M);
                     u.q_valid[k] = real ? std::min(TILE_M, hp.nq - q * TILE_M) : 0;
                 }
                 u.rec_stride = d.nslices;
-                u.t_row = (int32_t)(hp.t_row + (int64_t)tile0 * TILE_N);
-                u.t_index0 = tile0 * TILE_N;
-                u.t_count = (int32_t)std::min<int64_t>((int64_t)(tile1 - tile0) * TILE_N, hp.nt - u.t_index0);
-                u.seg_tiles = seg;
+                u.t_row = (int32_t)(hp.t_row + g.idx0);
+                u.t_index0 = (int32_t)g.idx0;
+                u.t_count = (int32_t)g.count;
+                u.seg_tiles = g.seg;
                 u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0);
-                u.prefetch = (qt == 0 || qt == ((nqt / 2) & ~1)) ? 1 + std::min(tc::L2_AHEAD, ntiles - tile1) : 0;
+                u.prefetch = (qt == 0 || qt == ((nqt / 2) & ~1)) ? 1 + std::min(tc::L2_AHEAD, g.tiles_after) : 0;
                 units2.push_back(u);
                 unit_prob.push_back(i);
             }
@@ -464,18 +648,18 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 memset(&u, 0, sizeof u);
                 u.q_n2 = hp.q_n2 + (int64_t)qt * TILE_M;
                 u.t_stats = nullptr;                                    // fixed up below
-                u.rec_base = nrecs + (int64_t)qt * TILE_M * d.nslices + range_slice0[r];
+                u.rec_base = nrecs + (int64_t)qt * TILE_M * d.nslices + g.slice0;
                 u.rec_stride = d.nslices;
                 u.q_row = (int32_t)(hp.q_row + (int64_t)qt * TILE_M);
-                u.t_row = (int32_t)(hp.t_row + (int64_t)tile0 * TILE_N);
-                u.t_index0 = tile0 * TILE_N;
-                u.t_count = (int32_t)std::min<int64_t>((int64_t)(tile1 - tile0) * TILE_N, hp.nt - u.t_index0);
+                u.t_row = (int32_t)(hp.t_row + g.idx0);
+                u.t_index0 = (int32_t)g.idx0;
+                u.t_count = (int32_t)g.count;
                 u.q_valid = std::min(TILE_M, hp.nq - qt * TILE_M);
-                u.seg_tiles = seg;
+                u.seg_tiles = g.seg;
                 u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0) | (maxima ? 4 : 0);
                 u.dump = (dump_first && units.empty()) ? dump_first : 0;
                 // 1 + the number of tiles past this unit's end that may be prefetched as well
-                u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 + std::min(tc::L2_AHEAD, ntiles - tile1) : 0;
+                u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 + std::min(tc::L2_AHEAD, g.tiles_after) : 0;
                 units.push_back(u);
                 unit_prob.push_back(i);
             }
@@ -797,6 +981,42 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
         if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, VSM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
         ctx->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+        // virtual memory management: arenas grow by mapping chunks (VSM_NO_VMM=1 forces the copying path, for A/B tests)
+        {
+            auto sym = [&](const char* name) -> void* {
+                void* f = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+                    cudaGetLastError();
+                    return nullptr;
+                }
+                return f;
+            };
+            ctx->p_reserve = reinterpret_cast<PFN_cuMemAddressReserve>(sym("cuMemAddressReserve"));
+            ctx->p_addr_free = reinterpret_cast<PFN_cuMemAddressFree>(sym("cuMemAddressFree"));
+            ctx->p_create = reinterpret_cast<PFN_cuMemCreate>(sym("cuMemCreate"));
+            ctx->p_release = reinterpret_cast<PFN_cuMemRelease>(sym("cuMemRelease"));
+            ctx->p_map = reinterpret_cast<PFN_cuMemMap>(sym("cuMemMap"));
+            ctx->p_unmap = reinterpret_cast<PFN_cuMemUnmap>(sym("cuMemUnmap"));
+            ctx->p_set_access = reinterpret_cast<PFN_cuMemSetAccess>(sym("cuMemSetAccess"));
+            ctx->p_gran = reinterpret_cast<PFN_cuMemGetAllocationGranularity>(sym("cuMemGetAllocationGranularity"));
+            if (ctx->p_reserve && ctx->p_addr_free && ctx->p_create && ctx->p_release && ctx->p_map && ctx->p_unmap &&
+                ctx->p_set_access && ctx->p_gran && !getenv("VSM_NO_VMM")) {
+                CUmemAllocationProp prop;
+                memset(&prop, 0, sizeof prop);
+                prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+                prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+                prop.location.id = ctx->device;
+                size_t g = 0;
+                if (ctx->p_gran(&g, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && g > 0) {
+                    ctx->vmm_gran = g;
+                    ctx->vmm_ok = true;
+                }
+            }
+        }
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status), 64, cudaHostAllocMapped));
+        memset(ctx->h_status, 0, 64);
+        if (o.reserved[2] > 0) ctx->ring_depth = o.reserved[2];
         CK(cudaMalloc(&ctx->d_store_stats, 16));
         CK(cudaMemset(ctx->d_store_stats, 0, 16));
         CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
@@ -817,12 +1037,13 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    arena_free(ctx->scratch);
-    arena_free(ctx->store);
+    arena_free(ctx, ctx->scratch);
+    arena_free(ctx, ctx->store);
     for (int r = 0; r < ctx->xchg_world; r++)
         if (r != ctx->xchg_rank && ctx->xchg_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->xchg_peer_ptr[r]);
     if (ctx->xchg_buf) cudaFree(ctx->xchg_buf);
     if (ctx->d_store_stats) cudaFree(ctx->d_store_stats);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->d_desc.p) cudaFree(ctx->d_desc.p);
     if (ctx->h_desc) cudaFreeHost(ctx->h_desc);
     if (ctx->d_recs.p) cudaFree(ctx->d_recs.p);
@@ -898,6 +1119,11 @@ int vsm_set_profiling(vsm_ctx* ctx, int32_t on) {
 int vsm_sync(vsm_ctx* ctx) {
     if (!ctx) return VSM_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_status && ctx->h_status[0] == 0x7100u) {          // XCHG_TIMEOUT of an asynchronous exchange
+        ctx->h_status[0] = 0;
+        ctx->err = "peer-memory exchange timed out waiting for a peer rank";
+        return VSM_ERR_TIMEOUT;
+    }
     return VSM_OK;
 }
 
@@ -1004,21 +1230,106 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int
 }
 
 // ---- keyframe store ------------------------------------------------------------------
+// Rows for a new frame: the first removed range that is large enough, else the end of the store.
+static int store_alloc_rows(vsm_ctx* ctx, int64_t n, int64_t* row0) {
+    if (n <= 0) { *row0 = ctx->store_rows; return VSM_OK; }
+    for (size_t k = 0; k < ctx->free_rows.size(); k++) {
+        Run& f = ctx->free_rows[k];
+        if (f.count < n) continue;
+        *row0 = f.row0;
+        f.row0 += n; f.count -= n;
+        if (f.count == 0) ctx->free_rows.erase(ctx->free_rows.begin() + (long)k);
+        return VSM_OK;
+    }
+    TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + n, ctx->store_rows));
+    *row0 = ctx->store_rows;
+    ctx->store_rows += n;
+    return VSM_OK;
+}
+
+static void store_free_rows(vsm_ctx* ctx, int64_t row0, int64_t n) {
+    if (n <= 0) return;
+    if (row0 + n == ctx->store_rows) {                       // the tail: lower the high-water mark instead
+        ctx->store_rows = row0;
+        while (!ctx->free_rows.empty() && ctx->free_rows.back().row0 + ctx->free_rows.back().count == ctx->store_rows) {
+            ctx->store_rows = ctx->free_rows.back().row0;
+            ctx->free_rows.pop_back();
+        }
+        return;
+    }
+    auto it = std::lower_bound(ctx->free_rows.begin(), ctx->free_rows.end(), row0,
+                               [](const Run& r, int64_t v) { return r.row0 < v; });
+    it = ctx->free_rows.insert(it, Run{row0, n});
+    if (it + 1 != ctx->free_rows.end() && it->row0 + it->count == (it + 1)->row0) {      // merge with the next range
+        it->count += (it + 1)->count;
+        ctx->free_rows.erase(it + 1);
+    }
+    if (it != ctx->free_rows.begin() && (it - 1)->row0 + (it - 1)->count == it->row0) {  // and with the previous one
+        (it - 1)->count += it->count;
+        ctx->free_rows.erase(it);
+    }
+}
+
+static int32_t store_new_seg(vsm_ctx* ctx, int64_t row0, int32_t n, int32_t frame_id, bool is_kf) {
+    Seg s = {row0, n, frame_id, ctx->next_seq++, 1, (uint8_t)(is_kf ? 1 : 0)};
+    int32_t h;
+    if (!ctx->free_handles.empty()) { h = ctx->free_handles.back(); ctx->free_handles.pop_back(); ctx->segs[h] = s; }
+    else { h = (int32_t)ctx->segs.size(); ctx->segs.push_back(s); }
+    if (is_kf) ctx->kf_order.push_back(h);                   // seq is the largest so far: stays sorted
+    else ctx->plain_ring.push_back(h);
+    ctx->kf_runs_valid = false;
+    return h;
+}
+
+static bool seg_live(const vsm_ctx* ctx, int32_t h) { return h >= 0 && h < (int32_t)ctx->segs.size() && ctx->segs[h].live; }
+
+static void store_remove_seg(vsm_ctx* ctx, int32_t h) {
+    Seg& s = ctx->segs[h];
+    auto& list = s.is_kf ? ctx->kf_order : ctx->plain_ring;
+    list.erase(std::find(list.begin(), list.end(), h));
+    store_free_rows(ctx, s.row0, s.count);
+    s.live = 0;
+    ctx->free_handles.push_back(h);
+    ctx->kf_runs_valid = false;
+}
+
+// Merged row runs of the live keyframes, ascending: what a global search over the store scans.
+static const std::vector<Run>& store_runs(vsm_ctx* ctx) {
+    if (!ctx->kf_runs_valid) {
+        std::vector<Run> r;
+        for (int32_t h : ctx->kf_order) if (ctx->segs[h].count > 0) r.push_back(Run{ctx->segs[h].row0, ctx->segs[h].count});
+        std::sort(r.begin(), r.end(), [](const Run& a, const Run& b) { return a.row0 < b.row0; });
+        ctx->kf_runs.clear();
+        for (const Run& x : r) {
+            if (!ctx->kf_runs.empty() && ctx->kf_runs.back().row0 + ctx->kf_runs.back().count == x.row0) ctx->kf_runs.back().count += x.count;
+            else ctx->kf_runs.push_back(x);
+        }
+        ctx->kf_runs_valid = true;
+    }
+    return ctx->kf_runs;
+}
+
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 static int store_append(vsm_ctx* ctx, int32_t frame_id, const float* src, int64_t n, cudaMemcpyKind kind,
-                        int32_t* handle) {
+                        bool is_kf, int32_t* handle) {
     if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it first");
-    TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + std::max<int64_t>(n, 1), ctx->store_rows));
-    const int64_t row0 = ctx->store_rows;
+    int64_t row0 = 0;
+    TRY(store_alloc_rows(ctx, n, &row0));
     if (n > 0) {
         CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, src, (size_t)n * VSM_DIM * sizeof(float), kind, ctx->stream));
         TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
                            ctx->store.n2 + row0, n, ctx->d_store_stats));
-        if (kind == cudaMemcpyHostToDevice) CK(cudaStreamSynchronize(ctx->stream));   // caller may reuse src
+        // a pageable source has been staged when cudaMemcpyAsync returns; only a pinned one is still
+        // being read by the DMA engine, and the caller may reuse it right after this call
+        if (kind == cudaMemcpyHostToDevice && host_pinned(src)) CK(cudaStreamSynchronize(ctx->stream));
     }
-    Seg s = {row0, (int32_t)n, frame_id};
-    ctx->segs.push_back(s);
-    ctx->store_rows += n;
-    if (handle) *handle = (int32_t)ctx->segs.size() - 1;
+    const int32_t h = store_new_seg(ctx, row0, (int32_t)n, frame_id, is_kf);
+    if (handle) *handle = h;
     return VSM_OK;
 }
 
@@ -1026,7 +1337,7 @@ int vsm_store_add(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, 
     if (!ctx || n < 0 || (n > 0 && !desc)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_add: bad argument") : VSM_ERR_INVALID;
     ctx->err.clear();
     CK(cudaSetDevice(ctx->device));
-    return store_append(ctx, frame_id, desc, n, cudaMemcpyHostToDevice, handle);
+    return store_append(ctx, frame_id, desc, n, cudaMemcpyHostToDevice, true, handle);
 }
 
 int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, int64_t n, int32_t* handle) {
@@ -1034,7 +1345,54 @@ int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, in
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_add_device: bad argument") : VSM_ERR_INVALID;
     ctx->err.clear();
     CK(cudaSetDevice(ctx->device));
-    return store_append(ctx, frame_id, d_desc, n, cudaMemcpyDeviceToDevice, handle);
+    return store_append(ctx, frame_id, d_desc, n, cudaMemcpyDeviceToDevice, true, handle);
+}
+
+int vsm_store_remove(vsm_ctx* ctx, int32_t handle) {
+    if (!ctx) return VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (!seg_live(ctx, handle)) return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_store_remove: unknown frame handle");
+    if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it instead");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));                  // an asynchronous search may still read the rows
+    store_remove_seg(ctx, handle);
+    return VSM_OK;
+}
+
+int vsm_store_promote(vsm_ctx* ctx, int32_t handle) {
+    if (!ctx) return VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (!seg_live(ctx, handle)) return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_store_promote: unknown frame handle");
+    Seg& s = ctx->segs[handle];
+    if (s.is_kf) return VSM_OK;                              // Frame::set_keyframe(true) twice is harmless
+    ctx->plain_ring.erase(std::find(ctx->plain_ring.begin(), ctx->plain_ring.end(), handle));
+    s.is_kf = 1;
+    // Map::get_keyframes walks frames_ in insertion order (src/Map.cpp:40-47): a frame promoted late
+    // (the bridge keyframe of src/Slam.cpp:851-863) still sits at its own position in that order
+    auto it = std::lower_bound(ctx->kf_order.begin(), ctx->kf_order.end(), s.seq,
+                               [&](int32_t h, int64_t seq) { return ctx->segs[h].seq < seq; });
+    ctx->kf_order.insert(it, handle);
+    ctx->kf_runs_valid = false;
+    return VSM_OK;
+}
+
+int vsm_store_frame_info(const vsm_ctx* ctx, int32_t handle, int64_t* row0, int32_t* n_rows, int32_t* frame_id,
+                         int32_t* is_keyframe) {
+    if (!ctx) return VSM_ERR_INVALID;
+    if (!seg_live(ctx, handle)) return VSM_ERR_NOT_FOUND;
+    const Seg& s = ctx->segs[handle];
+    if (row0) *row0 = s.row0;
+    if (n_rows) *n_rows = s.count;
+    if (frame_id) *frame_id = s.frame_id;
+    if (is_keyframe) *is_keyframe = s.is_kf;
+    return VSM_OK;
+}
+
+int vsm_store_keyframes(const vsm_ctx* ctx, int32_t* handles, int32_t cap, int32_t* n) {
+    if (!ctx || !n || cap < 0 || (cap > 0 && !handles)) return VSM_ERR_INVALID;
+    *n = (int32_t)ctx->kf_order.size();
+    for (int32_t k = 0; k < *n && k < cap; k++) handles[k] = ctx->kf_order[k];
+    return VSM_OK;
 }
 
 int vsm_store_load_spcf(vsm_ctx* ctx, const char* path, int32_t* n_loaded, int32_t* n_skipped, int32_t* first_handle) {
@@ -1082,7 +1440,7 @@ int vsm_store_load_spcf(vsm_ctx* ctx, const char* path, int32_t* n_loaded, int32
             // file offsets are only 4-byte aligned by construction, which is all the copy needs
             int32_t h = -1;
             TRY(store_append(ctx, (int32_t)frame_idx, reinterpret_cast<const float*>(buf.data() + pos), rows,
-                             cudaMemcpyHostToDevice, &h));
+                             cudaMemcpyHostToDevice, true, &h));
             if (loaded == 0 && first_handle) *first_handle = h;
             loaded++;
         } else {
@@ -1095,39 +1453,52 @@ int vsm_store_load_spcf(vsm_ctx* ctx, const char* path, int32_t* n_loaded, int32
     return VSM_OK;
 }
 
+static void store_reset_tables(vsm_ctx* ctx) {
+    ctx->store_rows = 0;
+    ctx->segs.clear();
+    ctx->free_handles.clear();
+    ctx->free_rows.clear();
+    ctx->kf_order.clear();
+    ctx->plain_ring.clear();
+    ctx->kf_runs.clear();
+    ctx->kf_runs_valid = false;
+    ctx->next_seq = 0;
+}
+
 int vsm_store_clear(vsm_ctx* ctx) {
     if (!ctx) return VSM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->store.own_f32) arena_free(ctx->store);
-    ctx->store_rows = 0;
-    ctx->segs.clear();
-    CK(cudaMemset(ctx->d_store_stats, 0, 16));
+    if (!ctx->store.own_f32) arena_free(ctx, ctx->store);
+    store_reset_tables(ctx);
+    // on the context's own stream: ordered before the next conversion's atomicMax into the slot
+    CK(cudaMemsetAsync(ctx->d_store_stats, 0, 16, ctx->stream));
     return VSM_OK;
 }
 
 int vsm_store_adopt_device(vsm_ctx* ctx, const float* d_desc, int64_t n_rows, const int64_t* seg_off, int32_t nseg) {
     if (!ctx || !d_desc || n_rows <= 0 || n_rows > INT32_MAX || (seg_off && nseg <= 0))
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_adopt_device: bad argument") : VSM_ERR_INVALID;
+    if (seg_off) {                                           // validate before anything is changed
+        if (seg_off[0] < 0) return fail(ctx, VSM_ERR_INVALID, "vsm_store_adopt_device: bad segment offsets");
+        for (int s = 0; s < nseg; s++)
+            if (seg_off[s + 1] < seg_off[s] || seg_off[s + 1] > n_rows)
+                return fail(ctx, VSM_ERR_INVALID, "vsm_store_adopt_device: bad segment offsets");
+    }
     TRY(vsm_store_clear(ctx));
-    arena_free(ctx->store);
+    arena_free(ctx, ctx->store);
     ctx->store.own_f32 = false;
     ctx->store.f32 = const_cast<float*>(d_desc);
-    TRY(arena_reserve(ctx, ctx->store, n_rows, 0));
+    int st = arena_reserve(ctx, ctx->store, n_rows, 0);
+    if (st != VSM_OK) { ctx->store = Arena(); return st; }
     ctx->launches = 0;
     TRY(launch_convert(ctx, d_desc, ctx->store.b16, ctx->store.n2, n_rows, ctx->d_store_stats));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->store_rows = n_rows;
     if (seg_off) {
-        for (int s = 0; s < nseg; s++) {
-            if (seg_off[s + 1] < seg_off[s] || seg_off[s + 1] > n_rows)
-                return fail(ctx, VSM_ERR_INVALID, "vsm_store_adopt_device: bad segment offsets");
-            Seg g = {seg_off[s], (int32_t)(seg_off[s + 1] - seg_off[s]), s};
-            ctx->segs.push_back(g);
-        }
+        for (int s = 0; s < nseg; s++) store_new_seg(ctx, seg_off[s], (int32_t)(seg_off[s + 1] - seg_off[s]), s, true);
     } else {
-        Seg g = {0, (int32_t)n_rows, 0};
-        ctx->segs.push_back(g);
+        store_new_seg(ctx, 0, (int32_t)n_rows, 0, true);
     }
     return VSM_OK;
 }
@@ -1135,7 +1506,7 @@ int vsm_store_adopt_device(vsm_ctx* ctx, const float* d_desc, int64_t n_rows, co
 int vsm_store_info(const vsm_ctx* ctx, int64_t* n_rows, int32_t* n_keyframes) {
     if (!ctx) return VSM_ERR_INVALID;
     if (n_rows) *n_rows = ctx->store_rows;
-    if (n_keyframes) *n_keyframes = (int32_t)ctx->segs.size();
+    if (n_keyframes) *n_keyframes = (int32_t)ctx->kf_order.size();
     return VSM_OK;
 }
 
@@ -1143,7 +1514,7 @@ int vsm_match_to_stored(vsm_ctx* ctx, int32_t handle, const float* cur, int32_t 
                         vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
     if (!ctx || n_cur < 0 || !n_good || (n_cur > 0 && !cur))
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_to_stored: bad argument") : VSM_ERR_INVALID;
-    if (handle < 0 || handle >= (int)ctx->segs.size()) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown keyframe handle");
+    if (!seg_live(ctx, handle)) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown keyframe handle");
     const Seg sg = ctx->segs[handle];
     *n_good = 0;
     if (n_raw) *n_raw = 0;
@@ -1171,11 +1542,10 @@ int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handl
     if (!ctx || n_pairs < 0 || (n_pairs > 0 && (!q_handle || !t_handle || !n_good || !good_off)))
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_batch_stored: bad argument") : VSM_ERR_INVALID;
     if (n_pairs == 0) return VSM_OK;
-    const int nseg = (int)ctx->segs.size();
     int64_t NQ = 0, NT = 0;
     std::vector<int64_t> t_off(n_pairs + 1, 0);
     for (int p = 0; p < n_pairs; p++) {
-        if (q_handle[p] < 0 || q_handle[p] >= nseg || t_handle[p] < 0 || t_handle[p] >= nseg)
+        if (!seg_live(ctx, q_handle[p]) || !seg_live(ctx, t_handle[p]))
             return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_match_batch_stored: unknown keyframe handle");
         good_off[p] = NQ;
         t_off[p] = NT;
@@ -1225,18 +1595,28 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
               int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw, int32_t* cur_handle) {
     if (!ctx || n_cur < 0 || !n_good || (n_cur > 0 && !cur) || !cur_handle)
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_track: bad argument") : VSM_ERR_INVALID;
-    if (ref_handle >= (int)ctx->segs.size()) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown keyframe handle");
+    if (ref_handle >= 0 && !seg_live(ctx, ref_handle)) return fail(ctx, VSM_ERR_NOT_FOUND, "unknown frame handle");
     if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it first");
     if (!good && ref_handle >= 0 && n_cur > 0 && ctx->segs[ref_handle].count > 0)
         return fail(ctx, VSM_ERR_INVALID, "vsm_track: null output");
     *n_good = 0;
     if (n_raw) *n_raw = 0;
     TRY(begin_call(ctx));
-    TRY(arena_reserve(ctx, ctx->store, ctx->store_rows + std::max<int64_t>(n_cur, 1), ctx->store_rows));
-    const int64_t row0 = ctx->store_rows;
+    // The frame enters the store as a PLAIN frame (Frame::is_keyframe_ = false, src/Frame.cpp:13); the
+    // caller promotes it once the reference decides so (src/Slam.cpp:1065, :1076; vsm_store_promote).
+    // Only last_frame_ and the frame being processed are ever matched again (src/Slam.cpp:838, :848),
+    // so older plain frames are evicted here and their rows reused: tracking does not grow the store.
+    while ((int)ctx->plain_ring.size() >= ctx->ring_depth) {
+        int32_t victim = -1;
+        for (int32_t h : ctx->plain_ring) if (h != ref_handle) { victim = h; break; }     // oldest first; never the reference
+        if (victim < 0) break;
+        store_remove_seg(ctx, victim);          // stream order protects the rows: every later use is enqueued after this call's
+    }
+    int64_t row0 = 0;
+    TRY(store_alloc_rows(ctx, n_cur, &row0));
     if (n_cur > 0) {
-        // the frame goes straight into the keyframe store; a small pinned frame is read over PCIe by
-        // the call's prologue kernel (fp32 master + bf16 shadow + norms in one launch)
+        // a small pinned frame is read over PCIe by the call's prologue kernel (fp32 master + bf16
+        // shadow + norms in one launch); otherwise one DMA, conversion in the prologue
         float* dst = ctx->store.f32 + row0 * VSM_DIM;
         const float* mapped = n_cur <= ZERO_COPY_ROWS ? host_mapped(cur) : nullptr;
         if (!mapped) CK(cudaMemcpyAsync(dst, cur, (size_t)n_cur * VSM_DIM * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1244,11 +1624,8 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
                      ctx->d_store_stats, n_cur};
         ctx->pending_conv.push_back(j);
     }
-    Seg ns = {row0, n_cur, frame_id};
-    ctx->segs.push_back(ns);
-    ctx->store_rows += n_cur;
-    *cur_handle = (int32_t)ctx->segs.size() - 1;
-    const Seg ref = ref_handle >= 0 ? ctx->segs[ref_handle] : Seg{0, 0, 0};
+    *cur_handle = store_new_seg(ctx, row0, n_cur, frame_id, false);
+    const Seg ref = ref_handle >= 0 ? ctx->segs[ref_handle] : Seg{0, 0, 0, 0, 0, 0};
     if (ref_handle < 0 || ref.count == 0 || n_cur == 0) {
         TRY(flush_conversions(ctx, 0));                                  // no matching step: convert the frame on its own
         CK(cudaStreamSynchronize(ctx->stream));                          // the caller may reuse `cur`
@@ -1269,9 +1646,16 @@ int vsm_track(vsm_ctx* ctx, int32_t ref_handle, int32_t frame_id, const float* c
 }
 
 // ---- database search -------------------------------------------------------------------
+// The stacked-matrix search scans the rows of the live keyframes: one contiguous range while nothing
+// has been removed and no plain frame sits between keyframes, otherwise the merged runs (the logical
+// train index is the store row either way).
 static int db_problem(vsm_ctx* ctx, const float* q_f32, int nq, HProblem& p) {
     p.q_f32 = q_f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
     p.t_f32 = ctx->store.f32; p.t_row = 0; p.t_store = 1; p.nt = (int)ctx->store_rows; p.out_off = 0;
+    const std::vector<Run>& runs = store_runs(ctx);
+    if (runs.empty()) p.nt = 0;
+    else if (runs.size() == 1 && runs[0].row0 == 0) p.nt = (int)runs[0].count;
+    else p.runs = &runs;
     return VSM_OK;
 }
 
@@ -1313,19 +1697,20 @@ int vsm_db_top2_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t r
     return end_call(ctx, sync != 0);
 }
 
-// Per-keyframe top-2 + ratio test for the keyframes with eligible[s] != 0 (all if NULL).
+// Per-keyframe top-2 + ratio test for the keyframes with eligible[k] != 0 (all if NULL); k = position
+// in Map::get_keyframes() order (ctx->kf_order).
 static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, const std::vector<char>* eligible,
                           int32_t* counts, vsm_dmatch* matches) {
-    const int nseg = (int)ctx->segs.size();
+    const int nkf = (int)ctx->kf_order.size();
     TRY(begin_call(ctx));
     TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
     TRY(upload_scratch(ctx, query, 0, nq));
     std::vector<HProblem> probs;
     std::vector<HJob> jobs;
     std::vector<int> job_seg;
-    for (int s = 0; s < nseg; s++) {
+    for (int s = 0; s < nkf; s++) {
         if (eligible && !(*eligible)[s]) continue;
-        const Seg& sg = ctx->segs[s];
+        const Seg& sg = ctx->segs[ctx->kf_order[s]];
         const int64_t slot = (int64_t)jobs.size();
         HProblem p;
         p.q_f32 = ctx->scratch.f32; p.q_n2 = ctx->scratch.n2; p.q_row = 0; p.q_store = 0; p.nq = nq;
@@ -1349,28 +1734,17 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
     TRY(run_problems(ctx, probs, jobs, total_matches, total_matches));
     const size_t mbytes = (size_t)total_matches * sizeof(DMatch);
     const size_t cbytes = jobs.size() * 2 * sizeof(int32_t);
+    // one copy of the whole result block (lists + counts) into the pinned buffer, scattered on the host
+    if (!ctx->result_on_host) TRY(fetch_result(ctx, matches ? mbytes + cbytes : 0));
     std::vector<int32_t> cnt(jobs.size() * 2);
-    if (ctx->result_on_host) {
-        TRY(end_call(ctx, true));
-        memcpy(cnt.data(), ctx->h_result + mbytes, cbytes);
-        if (matches) {
-            for (size_t k = 0; k < jobs.size(); k++)
-                memcpy(matches + (size_t)job_seg[k] * nq, ctx->h_result + k * (size_t)nq * sizeof(DMatch),
-                       (size_t)cnt[2 * k] * sizeof(DMatch));
-        }
-    } else {
+    if (!ctx->result_on_host && !matches)
         CK(cudaMemcpyAsync(cnt.data(), ctx->d_result.p + mbytes, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (matches) {
-            if (!eligible) {
-                CK(cudaMemcpyAsync(matches, ctx->d_result.p, mbytes, cudaMemcpyDeviceToHost, ctx->stream));
-            } else {
-                for (size_t k = 0; k < jobs.size(); k++)       // slot k -> keyframe job_seg[k]
-                    CK(cudaMemcpyAsync(matches + (size_t)job_seg[k] * nq, ctx->d_result.p + k * (size_t)nq * sizeof(DMatch),
-                                       (size_t)nq * sizeof(DMatch), cudaMemcpyDeviceToHost, ctx->stream));
-            }
-        }
-        TRY(end_call(ctx, true));
-    }
+    TRY(end_call(ctx, true));
+    if (ctx->result_on_host || matches) memcpy(cnt.data(), ctx->h_result + mbytes, cbytes);
+    if (matches)
+        for (size_t k = 0; k < jobs.size(); k++)       // slot k -> keyframe job_seg[k]
+            memcpy(matches + (size_t)job_seg[k] * nq, ctx->h_result + k * (size_t)nq * sizeof(DMatch),
+                   (size_t)cnt[2 * k] * sizeof(DMatch));
     for (size_t k = 0; k < jobs.size(); k++) counts[job_seg[k]] = cnt[2 * k];
     uint32_t open_pairs = 0;                                      // stream is idle: a 4-byte read
     CK(cudaMemcpy(&open_pairs, reinterpret_cast<const uint8_t*>(ctx->d_counters) + 20, sizeof open_pairs, cudaMemcpyDeviceToHost));
@@ -1542,6 +1916,36 @@ int vsm_xchg_connect(vsm_ctx* ctx, const uint8_t* handles) {
     return VSM_OK;
 }
 
+// Soft failures reported by kernels through the pinned status word (stream must be idle).
+static int check_status(vsm_ctx* ctx) {
+    if (ctx->h_status && ctx->h_status[0] == XCHG_TIMEOUT) {
+        char b[160];
+        snprintf(b, sizeof b, "peer-memory exchange timed out waiting for rank %u (it did not make the matching call)",
+                 ctx->h_status[1]);
+        ctx->h_status[0] = 0;
+        ctx->err = b;
+        return VSM_ERR_TIMEOUT;
+    }
+    return VSM_OK;
+}
+
+static int xchg_search(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset, int64_t* d_idx_out,
+                       float* d_dist_out) {
+    HProblem p;
+    db_problem(ctx, d_query, nq, p);
+    TRY(run_problems(ctx, {p}, {}, nq, 0));
+    static const double timeout_s = getenv("VSM_XCHG_TIMEOUT_S") ? atof(getenv("VSM_XCHG_TIMEOUT_S")) : 10.0;
+    const uint32_t step = ctx->xchg_step + 1;
+    xchg_publish_merge_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_out_key, nq, (uint32_t)row_offset, ctx->xchg_peers,
+                                                          ctx->xchg_rank, ctx->xchg_world, ctx->xchg_nq_cap, step,
+                                                          d_idx_out, d_dist_out, (long long)(timeout_s * 2.0e9),
+                                                          ctx->h_status);
+    CK(cudaGetLastError());
+    ctx->xchg_step = step;                       // only once the kernel is enqueued: a failed call does not desynchronise the ranks
+    ctx->launches++;
+    return VSM_OK;
+}
+
 int vsm_db_top2_xchg_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset, int64_t* d_idx_out,
                             float* d_dist_out, int32_t sync) {
     if (!ctx || nq <= 0 || !d_query || !d_idx_out || !d_dist_out || row_offset < 0 ||
@@ -1551,17 +1955,31 @@ int vsm_db_top2_xchg_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int6
         return fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_xchg_device: exchange not connected or nq above its capacity");
     TRY(begin_call(ctx));
     TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
-    HProblem p;
-    db_problem(ctx, d_query, nq, p);
     queue_convert(ctx, d_query, 0, nq);
-    TRY(run_problems(ctx, {p}, {}, nq, 0));
-    ctx->xchg_step++;
-    xchg_publish_merge_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_out_key, nq, (uint32_t)row_offset, ctx->xchg_peers,
-                                                          ctx->xchg_rank, ctx->xchg_world, ctx->xchg_nq_cap, ctx->xchg_step,
-                                                          d_idx_out, d_dist_out);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return end_call(ctx, sync != 0);
+    TRY(xchg_search(ctx, d_query, nq, row_offset, d_idx_out, d_dist_out));
+    TRY(end_call(ctx, sync != 0));
+    return sync ? check_status(ctx) : VSM_OK;
+}
+
+int vsm_db_top2_xchg(vsm_ctx* ctx, const float* query, int32_t nq, int64_t row_offset, int64_t* idx, float* dist) {
+    if (!ctx || nq <= 0 || !query || !idx || !dist || row_offset < 0 || row_offset + ctx->store_rows > 0xFFFFFFFFll)
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_xchg: bad argument") : VSM_ERR_INVALID;
+    if (!ctx->xchg_connected || nq > ctx->xchg_nq_cap)
+        return fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_xchg: exchange not connected or nq above its capacity");
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    // the merged result goes straight into pinned host memory (zero-copy stores of 24 B per query)
+    const size_t nb = (size_t)nq * 2 * (sizeof(int64_t) + sizeof(float));
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(nb, 16)));
+    int64_t* h_idx = reinterpret_cast<int64_t*>(ctx->h_result);
+    float* h_dist = reinterpret_cast<float*>(ctx->h_result + (size_t)nq * 2 * sizeof(int64_t));
+    TRY(xchg_search(ctx, ctx->scratch.f32, nq, row_offset, h_idx, h_dist));
+    TRY(end_call(ctx, true));
+    TRY(check_status(ctx));
+    memcpy(idx, h_idx, (size_t)nq * 2 * sizeof(int64_t));
+    memcpy(dist, h_dist, (size_t)nq * 2 * sizeof(float));
+    return VSM_OK;
 }
 
 int vsm_merge_keys_device(vsm_ctx* ctx, const uint64_t* d_keys_in, int32_t nshard, int32_t nq, int64_t* d_idx_out,
@@ -1580,7 +1998,7 @@ int vsm_merge_keys_device(vsm_ctx* ctx, const uint64_t* d_keys_in, int32_t nshar
 int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, int32_t* counts, vsm_dmatch* matches) {
     if (!ctx || nq < 0 || (nq > 0 && !query) || !counts)
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_segmented: bad argument") : VSM_ERR_INVALID;
-    const int nseg = (int)ctx->segs.size();
+    const int nseg = (int)ctx->kf_order.size();
     for (int s = 0; s < nseg; s++) counts[s] = 0;
     if (nq == 0 || nseg == 0) return VSM_OK;
     return segmented_impl(ctx, query, nq, ratio, nullptr, counts, matches);
@@ -1591,13 +2009,14 @@ int vsm_loop_detect_shard(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, i
                           int32_t* checked_after) {
     if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || checked_before < 0)
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect: bad argument") : VSM_ERR_INVALID;
-    const int nseg = (int)ctx->segs.size();
+    const int nseg = (int)ctx->kf_order.size();                       // keyframes only, in Map::get_keyframes() order
     std::vector<char> eligible(nseg, 0);
     int checked = checked_before, any = 0;
     for (int s = 0; s < nseg; s++) {                                  // src/LoopCloser.cpp:43-48
+        const Seg& sg = ctx->segs[ctx->kf_order[s]];
         status[s] = -1;
-        if (cur_frame_id - ctx->segs[s].frame_id < min_gap) continue;
-        if (ctx->segs[s].count == 0) continue;
+        if (cur_frame_id - sg.frame_id < min_gap) continue;
+        if (sg.count == 0) continue;
         checked++;
         if (checked % every != 0) continue;
         eligible[s] = 1;
@@ -1615,9 +2034,9 @@ int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t
 }
 
 int vsm_store_set_frame_ids(vsm_ctx* ctx, const int32_t* frame_ids, int32_t n) {
-    if (!ctx || !frame_ids || n != (int32_t)ctx->segs.size())
+    if (!ctx || !frame_ids || n != (int32_t)ctx->kf_order.size())
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_set_frame_ids: n must equal the keyframe count") : VSM_ERR_INVALID;
-    for (int s = 0; s < n; s++) ctx->segs[s].frame_id = frame_ids[s];
+    for (int s = 0; s < n; s++) ctx->segs[ctx->kf_order[s]].frame_id = frame_ids[s];
     return VSM_OK;
 }
 

@@ -675,12 +675,18 @@ __device__ __forceinline__ unsigned long long* xchg_keys(unsigned long long base
 // -- peer stores travel over NVLink; (2) one flag per peer says "rank `rank`'s keys of step `step`
 // are complete"; (3) wait for every peer's flag in the OWN buffer; (4) merge the world x 2 keys per
 // query.  Two parities: a rank may publish step k+1 while a slower peer still merges step k.
+// A peer that does not show up within `timeout_clocks` is a SOFT failure: the kernel writes
+// XCHG_TIMEOUT (and the peer's rank) to the pinned status word, skips the merge and exits, so the
+// host returns VSM_ERR_TIMEOUT instead of losing its CUDA context to a trap.
+constexpr uint32_t XCHG_TIMEOUT = 0x7100u;
 __global__ void __launch_bounds__(1024)
 xchg_publish_merge_kernel(const unsigned long long* __restrict__ out_key, int nq, uint32_t row_offset, XchgPeers peers,
                           int rank, int world, int nq_cap, uint32_t step, int64_t* __restrict__ idx_out,
-                          float* __restrict__ dist_out) {
+                          float* __restrict__ dist_out, long long timeout_clocks, volatile uint32_t* status) {
     const int parity = step & 1;
     const int n = nq * 2;
+    __shared__ int s_timed_out;
+    if (threadIdx.x == 0) s_timed_out = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned long long k = out_key[i];
         const unsigned long long g = k == 0ull ? 0ull : ~((~k) + row_offset);
@@ -699,12 +705,19 @@ xchg_publish_merge_kernel(const unsigned long long* __restrict__ out_key, int nq
         volatile uint32_t* w = xchg_flags(peers.base[rank], parity) + threadIdx.x;
         const long long t0 = clock64();
         while ((int32_t)(*w - step) < 0) {
-            if (clock64() - t0 > 20000000000LL) __trap();               // ~10 s
+            if (clock64() - t0 > timeout_clocks) {
+                s_timed_out = 1;
+                status[0] = XCHG_TIMEOUT;
+                status[1] = (uint32_t)threadIdx.x;
+                __threadfence_system();
+                break;
+            }
             __nanosleep(200);
         }
         __threadfence_system();
     }
     __syncthreads();
+    if (s_timed_out) return;
     for (int q = threadIdx.x; q < nq; q += blockDim.x) {
         unsigned long long k0 = 0ull, k1 = 0ull;
         for (int s = 0; s < world; s++) {

@@ -74,6 +74,11 @@ SYMBOLS = {
     "vsm_store_load_spcf": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32)]),
     "vsm_store_clear": (C.c_int, [C.c_void_p]),
+    "vsm_store_promote": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsm_store_remove": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsm_store_frame_info": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vsm_store_keyframes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "vsm_store_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "vsm_match_to_stored": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]),
@@ -99,6 +104,7 @@ SYMBOLS = {
     "vsm_xchg_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "vsm_xchg_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsm_db_top2_xchg_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    "vsm_db_top2_xchg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_merge_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32]),
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
@@ -142,13 +148,14 @@ def _rows(a, name):
 class Matcher:
     """One matching context on one GPU (single caller, synchronous calls)."""
 
-    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0):
+    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0, ring=0):
         self._lib = load_library()
         o = _Opts()
         self._lib.vsm_default_opts(C.byref(o))
         o.device, o.engine, o.scratch_rows, o.store_rows = device, engine, scratch_rows, store_rows
         o.reserved[0] = seg_tiles
         o.reserved[1] = work_cap
+        o.reserved[2] = ring
         h = C.c_void_p()
         st = self._lib.vsm_create(C.byref(o), C.byref(h))
         if st != 0:
@@ -282,6 +289,27 @@ class Matcher:
     def clear_store(self):
         self._ck(self._lib.vsm_store_clear(self._h))
 
+    def promote(self, handle):
+        """Frame::set_keyframe(true) for a frame stored by track()."""
+        self._ck(self._lib.vsm_store_promote(self._h, handle))
+
+    def remove_frame(self, handle):
+        self._ck(self._lib.vsm_store_remove(self._h, handle))
+
+    def frame_info(self, handle):
+        """(rows, frame id, is_keyframe, first store row) of a live handle."""
+        r0, n, f, k = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self._lib.vsm_store_frame_info(self._h, handle, C.byref(r0), C.byref(n), C.byref(f), C.byref(k)))
+        return n.value, f.value, bool(k.value), r0.value
+
+    def keyframes(self):
+        """Handles of the keyframes in Map::get_keyframes() order."""
+        n = C.c_int32(0)
+        self._ck(self._lib.vsm_store_keyframes(self._h, None, 0, C.byref(n)))
+        h = np.zeros(max(n.value, 1), np.int32)
+        self._ck(self._lib.vsm_store_keyframes(self._h, h.ctypes.data, n.value, C.byref(n)))
+        return h[:n.value]
+
     def store_info(self):
         r, k = C.c_int64(0), C.c_int32(0)
         self._ck(self._lib.vsm_store_info(self._h, C.byref(r), C.byref(k)))
@@ -290,7 +318,7 @@ class Matcher:
     def match_to_keyframe(self, handle, cur_desc, ratio=0.75, mutual=False, want_raw=False):
         """Slam::match_features(ref_kf->descriptors(), cur->descriptors()) with the keyframe resident."""
         t = _rows(cur_desc, "cur_desc")
-        cap = max(self.store_info()[0], 1)
+        cap = max(self.frame_info(handle)[0], 1)
         good = np.zeros(cap, DMATCH)
         raw = np.zeros(cap, DMATCH) if want_raw else None
         ng, nr = C.c_int32(0), C.c_int32(0)
@@ -304,7 +332,9 @@ class Matcher:
         """Slam::process_frame's tracking match (src/Slam.cpp:838-842) for a sequence: the current
         frame is uploaded once, into the store; returns (good, raw, handle of the current frame)."""
         t = _rows(cur_desc, "cur_desc")
-        cap = max(ref_rows if ref_rows is not None else self.store_info()[0], 1)
+        if ref_rows is None:
+            ref_rows = self.frame_info(ref_handle)[0] if ref_handle >= 0 else 0
+        cap = max(ref_rows, 1)
         if not hasattr(self, "_trk") or len(self._trk[0]) < cap:
             self._trk = (np.zeros(cap, DMATCH), np.zeros(cap, DMATCH))
         good, raw = self._trk
@@ -425,6 +455,15 @@ class Matcher:
     def db_top2_xchg_device(self, d_query_ptr, nq, row_offset, d_idx_ptr, d_dist_ptr, sync=False):
         self._ck(self._lib.vsm_db_top2_xchg_device(self._h, C.c_void_p(d_query_ptr), nq, row_offset,
                                                    C.c_void_p(d_idx_ptr), C.c_void_p(d_dist_ptr), int(sync)))
+
+    def db_top2_xchg(self, query, row_offset):
+        """One rank's call of the collective search with host buffers in and out (vsm_db_top2_xchg)."""
+        q = _rows(query, "query")
+        idx = np.empty((q.shape[0], 2), np.int64)
+        dist = np.empty((q.shape[0], 2), np.float32)
+        self._ck(self._lib.vsm_db_top2_xchg(self._h, q.ctypes.data, q.shape[0], row_offset, idx.ctypes.data,
+                                            dist.ctypes.data))
+        return idx, dist
 
     def merge_top2_device(self, d_idx_in, d_dist_in, nshard, nq, d_idx_out, d_dist_out, sync=False):
         self._ck(self._lib.vsm_merge_top2_device(self._h, C.c_void_p(d_idx_in), C.c_void_p(d_dist_in), nshard, nq,

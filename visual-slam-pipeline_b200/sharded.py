@@ -160,20 +160,31 @@ class ShardedDB:
         return whole, mine
 
     def _buffers(self, nq):
+        """Per-batch-size device and pinned buffers.  They are only ever used on self.stream through raw
+        pointers, so they are allocated under that stream (the caching allocator then orders any reuse
+        of their memory after the kernels enqueued there) and kept per nq instead of being freed."""
         if nq != self._nq:
-            dev = self.device
-            self.l_idx = torch.empty((nq, 2), dtype=torch.int64, device=dev)
-            self.l_dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
-            if self.world > 1:
-                self.l_keys = torch.empty((nq, 2), dtype=torch.int64, device=dev)         # u64 bit patterns
-                self.g_keys = torch.empty((self.world * nq, 2), dtype=torch.int64, device=dev)
-                self.o_idx = torch.empty((nq, 2), dtype=torch.int64, device=dev)
-                self.o_dist = torch.empty((nq, 2), dtype=torch.float32, device=dev)
-            else:
-                self.o_idx, self.o_dist = self.l_idx, self.l_dist
-            self.h_idx = torch.empty((nq, 2), dtype=torch.int64).pin_memory()
-            self.h_dist = torch.empty((nq, 2), dtype=torch.float32).pin_memory()
-            self.d_q = torch.empty((nq, 256), dtype=torch.float32, device=dev)
+            if not hasattr(self, "_bufs"):
+                self._bufs = {}
+            if nq not in self._bufs:
+                dev = self.device
+                b = {}
+                with torch.cuda.stream(self.stream):
+                    b["l_idx"] = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+                    b["l_dist"] = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+                    if self.world > 1:
+                        b["l_keys"] = torch.empty((nq, 2), dtype=torch.int64, device=dev)         # u64 bit patterns
+                        b["g_keys"] = torch.empty((self.world * nq, 2), dtype=torch.int64, device=dev)
+                        b["o_idx"] = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+                        b["o_dist"] = torch.empty((nq, 2), dtype=torch.float32, device=dev)
+                    else:
+                        b["o_idx"], b["o_dist"] = b["l_idx"], b["l_dist"]
+                    b["d_q"] = torch.empty((nq, 256), dtype=torch.float32, device=dev)
+                b["h_idx"] = torch.empty((nq, 2), dtype=torch.int64).pin_memory()
+                b["h_dist"] = torch.empty((nq, 2), dtype=torch.float32).pin_memory()
+                self._bufs[nq] = b
+            for k, v in self._bufs[nq].items():
+                setattr(self, k, v)
             self._nq = nq
 
     def search_device(self, d_q):
@@ -207,6 +218,18 @@ class ShardedDB:
             self.h_idx.copy_(oi, non_blocking=True)
             self.h_dist.copy_(od, non_blocking=True)
         return self.h_idx, self.h_dist
+
+    def search_host_abi(self, q):
+        """The reference-facing call: q is a host [nq,256] fp32 numpy array (pinned or pageable); returns
+        host (idx, dist) numpy arrays holding the GLOBAL top-2.  One synchronous C-ABI call per rank
+        (vsm_db_top2 on one GPU; vsm_db_top2_xchg, the collective form, with the fused exchange)."""
+        if self.world == 1:
+            return self.matcher.search_map_points(q, self.row_offset)
+        if self.exchange == "p2p":
+            return self.matcher.db_top2_xchg(q, self.row_offset)
+        hi, hd = self.search_host(torch.from_numpy(q))
+        self.stream.synchronize()
+        return hi.numpy(), hd.numpy()
 
     def launches_per_search(self):
         return self.matcher.stats()["kernel_launches"] + (1 if self.exchange == "nccl" else 0)
