@@ -81,3 +81,40 @@ def db_case(seed=0, nq=300, nkf=24, lo=40, hi=700, planted_frac=0.3):
         rows = seg_off[kf] + gen._perm(seed, 60 + kf, int(sizes[kf]))[:cnt]
         vq[sl.start:sl.start + len(rows)] = 1000 * vdb[rows] + 1100 * gen.int_rows(seed, 70 + kf, 0, len(rows))
     return gen._normalize_int(vq), gen._normalize_int(vdb), seg_off
+
+
+# ---- Slam::track_local_map scenes (src/Slam.cpp:380-469), shared by make_golden.py and the tests ----
+def track_scene(seed, nmp=3000, nkp=800, drop=0.3, dup=True):
+    rng = np.random.default_rng(seed)
+    # camera pose: small rotation about y + translation (world -> camera)
+    a = 0.05
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    t = np.array([0.1, -0.05, 0.2])
+    pos = np.stack([rng.uniform(-6, 6, nmp), rng.uniform(-4, 4, nmp), rng.uniform(-1, 12, nmp)], axis=1)
+    mp_desc = gen.rows(seed, 0, 0, nmp)
+    valid = (rng.random(nmp) > 0.1).astype(np.uint8)
+    cam = (R @ pos.T).T + t
+    z = cam[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = 525.0 * cam[:, 0] / z + 319.5
+        v = 525.0 * cam[:, 1] / z + 239.5
+    vis = np.nonzero((z > 0.2) & (u >= 0) & (u < 640) & (v >= 0) & (v < 480))[0]
+    pick = rng.permutation(vis)[:int(nkp * (1 - drop))]
+    kp = np.zeros((nkp, 2), np.float32)
+    desc = gen.rows(seed, 1, 0, nkp).copy()
+    k = len(pick)
+    kp[:k, 0] = (u[pick] + rng.normal(0, 3.0, k)).astype(np.float32)
+    kp[:k, 1] = (v[pick] + rng.normal(0, 3.0, k)).astype(np.float32)
+    noisy = mp_desc[pick] + 0.02 * rng.standard_normal((k, 256)).astype(np.float32)
+    desc[:k] = noisy / np.linalg.norm(noisy, axis=1, keepdims=True)
+    kp[k:, 0] = rng.uniform(0, 640, nkp - k)
+    kp[k:, 1] = rng.uniform(0, 480, nkp - k)
+    if dup and k > 40:
+        # two map points at the same place with the same descriptor: the later one must NOT replace
+        pos[pick[1]] = pos[pick[0]]
+        mp_desc[pick[1]] = mp_desc[pick[0]]
+        # a keypoint duplicated in a neighbouring cell position: visiting order decides the tie
+        kp[k] = kp[5] + np.float32(0.25)
+        desc[k] = desc[5]
+    kp = np.clip(kp, 0, [639.5, 479.5]).astype(np.float32)
+    return kp, desc, pos, mp_desc, valid, R, t

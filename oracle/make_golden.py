@@ -7,6 +7,7 @@ own filter loops restated in Python:
   good lists at ratio 0.70 / 0.75 / 0.80     (src/Slam.cpp:1151-1158)
   mutual-NN lists                             (knnMatch(t, q, 1) composition)
   per-keyframe survivor counts                (src/LoopCloser.cpp:54-62)
+  Slam::track_local_map decisions with cv2.norm as the distance (src/Slam.cpp:380-469, :451)
 """
 import os
 import sys
@@ -62,6 +63,18 @@ def main():
                         seg_off=seg_off, seg_idx=seg_idx, seg_dist=seg_dist,
                         counts=np.array(counts, np.int32), cv2=cv2.__version__)
     print("db_small", q.shape, db.shape, "counts@0.75 max", np.array(counts)[:, 1].max())
+    # Slam::track_local_map (src/Slam.cpp:380-469) with OpenCV's own cv::norm at :451
+    from oracle import oracle
+    for seed in (1, 2, 3):
+        kp, desc, pos, mp_desc, valid, R, t = cases.track_scene(seed)
+        ind = -np.ones(len(kp), np.int32)
+        ind[7] = 123456
+        norm = lambda a, b: cv2.norm(np.ascontiguousarray(a).reshape(1, -1), np.ascontiguousarray(b).reshape(1, -1), cv2.NORM_L2)
+        tracked, obs, bk, bd = oracle.track_local_map(kp, desc, pos, mp_desc, valid, R, t, ind, norm_fn=norm)
+        np.savez_compressed(os.path.join(OUT, f"track_local_map_s{seed}.npz"), tracked=tracked,
+                            obs=np.array(obs, np.int32).reshape(-1, 2), best_ki=bk, best_dist=bd, indices=ind,
+                            cv2=cv2.__version__)
+        print("track_local_map", seed, "tracked", tracked)
 
 
 if __name__ == "__main__":

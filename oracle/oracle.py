@@ -141,11 +141,12 @@ def loop_detect(q, db, seg_off, frame_ids, cur_frame_id, ratio=0.75, min_gap=200
     return status, lists
 
 
-def track_local_map(kp_xy, desc, mp_pos, mp_desc, mp_valid, R_cam, t_cam, indices, cfg=None):
+def track_local_map(kp_xy, desc, mp_pos, mp_desc, mp_valid, R_cam, t_cam, indices, cfg=None, norm_fn=None):
     """Slam::track_local_map (src/Slam.cpp:380-469) restated loop for loop: the 30-px cell grid
     (:391-401), fp64 projection (:417-428), the window of cells (:431-434), the radius test
     (:452-454), cv::norm in double (:456; here numpy float64, see include/vsm.h on its summation
-    order) and the sequential assignment (:465-470).  indices is updated in place.
+    order -- or norm_fn(mp_desc_row, desc_row), e.g. cv2.norm itself, which is how the golden
+    vectors are made) and the sequential assignment (:465-470).  indices is updated in place.
     Returns (tracked, observations, best_ki[nmp], best_dist[nmp])."""
     c = dict(fx=525.0, fy=525.0, cx=319.5, cy=239.5, width=640, height=480, cell_size=30,
              depth_min=float(np.float32(0.1)), depth_max=50.0, search_radius=12.0, desc_threshold=0.5)
@@ -193,8 +194,11 @@ def track_local_map(kp_xy, desc, mp_pos, mp_desc, mp_valid, R_cam, t_cam, indice
                     dx, dy = u - float(kp[ki, 0]), v - float(kp[ki, 1])
                     if dx * dx + dy * dy > RAD * RAD:
                         continue
-                    dd = m64 - d64[ki]
-                    dist = float(np.sqrt(np.dot(dd, dd)))
+                    if norm_fn is not None:
+                        dist = float(norm_fn(mp_desc[mp], desc[ki]))
+                    else:
+                        dd = m64 - d64[ki]
+                        dist = float(np.sqrt(np.dot(dd, dd)))
                     if dist < bd:
                         bd, bk = dist, ki
         best_ki[mp], best_dist[mp] = bk, bd

@@ -44,7 +44,7 @@ def big_db():
     # contiguous: both column halves of its slice see > 4 entries above any threshold
     centre = db[1_000_000].clone()
     v = centre[None, :] + 6e-4 * torch.randn((400, 256), generator=g, device="cuda")
-    db[1_200_000:1_200_400] = v / v.norm(dim=1, keepdim=True)
+    db[1_203_000:1_203_400] = v / v.norm(dim=1, keepdim=True)      # between two planted rows
     v = centre[None, :] + 1e-3 * torch.randn((32, 256), generator=g, device="cuda")
     q[400:432] = v / v.norm(dim=1, keepdim=True)
     torch.cuda.synchronize()
@@ -70,7 +70,7 @@ def test_one_shard_of_the_20m_search_equals_oracle(big_db, seg_tiles):
     assert np.array_equal(bits(gd[SAMPLE]), bits(od)), "fp32 distance bits differ from the oracle"
     # the cluster queries' answers lie inside the cluster (or its centre row)
     c = gi[400:432]
-    assert (((c >= 1_200_000) & (c < 1_200_400)) | (c == 1_000_000)).all()
+    assert (((c >= 1_203_000) & (c < 1_203_400)) | (c == 1_000_000)).all()
 
 
 def test_sharded_merge_of_two_half_databases_equals_oracle(big_db):
