@@ -334,6 +334,45 @@ int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_
                           int32_t nshard, int32_t nq, int64_t* d_idx_out, float* d_dist_out,
                           int32_t sync);
 
+/* ---- several GPUs behind one caller thread ---------------------------------------------------------
+ * The reference matches on ONE thread of ONE process (src/main.cpp:1520; LoopCloser::detect,
+ * src/LoopCloser.cpp:16-18, runs inside it), so the drop-in for a box of GPUs is a group: one context
+ * per device and one worker thread per context inside the library.  A group call fans out on the
+ * workers, joins, and merges on the first device -- every member stores its exact local top-2 (keys with
+ * the STACKED row index of the whole database) straight into the first device's gather buffer over
+ * NVLink (peer access; pinned host memory if there is no peer path) and the first device's stream
+ * waits for the members' events before it merges: no CUDA IPC, no process group, no spinning kernel.
+ * Keyframes are dealt to the members whole, each to the member that holds the fewest rows.
+ * A device may be listed more than once (several contexts on one GPU; how the 1-GPU tests run it).
+ * Group keyframe handles are 0, 1, 2 ... in insertion order and are never reused. */
+typedef struct vsm_group vsm_group;
+int         vsm_group_create(const int32_t* devices, int32_t n, const vsm_opts* opts, vsm_group** out);
+void        vsm_group_destroy(vsm_group* g);
+const char* vsm_group_last_error(const vsm_group* g);       /* g may be NULL: create() errors */
+int         vsm_group_size(const vsm_group* g);
+/* Member context (pair matching, statistics): calls on it follow the single-caller rule. */
+vsm_ctx*    vsm_group_ctx(vsm_group* g, int32_t member);
+/* Map::add_frame for a keyframe (src/Map.cpp:7-10): uploaded to ONE member. */
+int vsm_group_store_add(vsm_group* g, int32_t frame_id, const float* desc, int32_t n, int32_t* handle);
+int vsm_group_store_remove(vsm_group* g, int32_t handle);
+int vsm_group_store_clear(vsm_group* g);
+/* rows_per_member: [vsm_group_size] live keyframe rows on each member (may be NULL). */
+int vsm_group_store_info(const vsm_group* g, int64_t* n_rows, int32_t* n_keyframes, int64_t* rows_per_member);
+/* Bulk load: member `member` adopts a device matrix that lives on ITS device (vsm_store_adopt_device);
+ * members must adopt in ascending order on an empty group, which makes stacked row = position in the
+ * concatenation of the members' matrices. */
+int vsm_group_adopt_device(vsm_group* g, int32_t member, const float* d_desc, int64_t n_rows, const int64_t* seg_off,
+                           int32_t nseg);
+/* knnMatch(frame, all_descs, 2) over every keyframe row of every member (src/Slam.cpp:546-574, :744-774):
+ * host queries in, host result out.  idx: [nq][2] stacked row (-1 = none), dist: [nq][2];
+ * kf_handle / kf_row ([nq][2], may be NULL): the keyframe holding the row and the row inside it. */
+int vsm_group_db_top2(vsm_group* g, const float* query, int32_t nq, int64_t* idx, float* dist, int32_t* kf_handle,
+                      int32_t* kf_row);
+/* vsm_loop_detect over the group's keyframe list: status / matches are indexed by position among the
+ * live keyframes in insertion order (= handle while nothing has been removed). */
+int vsm_group_loop_detect(vsm_group* g, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
+                          int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches);
+
 /* Raw CUDA stream of the context (cudaStream_t as void*), for event timing. */
 void* vsm_stream(vsm_ctx* ctx);
 /* Run on a caller-owned stream (e.g. the stream an NCCL collective is enqueued on). */
@@ -347,6 +386,11 @@ int   vsm_set_profiling(vsm_ctx* ctx, int32_t on);
  * a caller that enqueues a loop of asynchronous searches read every launch's duration afterwards
  * without synchronising inside the loop.  ms: [n], *n_out = entries written. */
 int   vsm_tc_history(vsm_ctx* ctx, float* ms, int32_t n, int32_t* n_out);
+
+/* Synthetic SuperPoint-shaped descriptors written straight into device memory (benchmarks in C++):
+ * rows row0 .. row0+n of stream `seed`, 256 standard normals scaled to unit length
+ * (the shape of src/FeatureExtractor.cpp:170-205's output).  d_dst must live on the context's device. */
+int vsm_synth_rows_device(vsm_ctx* ctx, float* d_dst, int64_t row0, int64_t n, uint64_t seed);
 
 /* Debug / bring-up: the raw tensor-core accumulators (bf16 dot products q.t) of the
  * first 128 queries x first 256 train rows, written to out[128*256] (host). */

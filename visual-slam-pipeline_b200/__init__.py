@@ -5,7 +5,7 @@ search) over the C ABI of libvsm.so.  See include/vsm.h and DESIGN.md.
 The directory name carries a hyphen, so import it through the repo-root shim:
     import vsm_b200
 """
-from .matcher import (DMATCH, Matcher, TrackCfg, VsmError, lib_path, load_library,  # noqa: F401
+from .matcher import (DMATCH, Group, Matcher, TrackCfg, VsmError, lib_path, load_library,  # noqa: F401
                       ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT, ENGINE_TENSOR_PAIR)
 
 

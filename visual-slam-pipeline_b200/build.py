@@ -10,9 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libvsm.so")
 SOURCES = ["vsm_api.cu"]
-DEPS = ["vsm_api.cu", "vsm_tc.cuh", "vsm_tc2.cuh", "vsm_kernels.cuh", "vsm_common.cuh", os.path.join("..", "..", "include", "vsm.h")]
+DEPS = ["vsm_api.cu", "vsm_group.inl", "vsm_tc.cuh", "vsm_tc2.cuh", "vsm_kernels.cuh", "vsm_common.cuh", os.path.join("..", "..", "include", "vsm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 def stale():

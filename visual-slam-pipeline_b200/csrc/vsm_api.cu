@@ -7,7 +7,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -2052,6 +2057,17 @@ int vsm_merge_top2_device(vsm_ctx* ctx, const int64_t* d_idx_in, const float* d_
     return VSM_OK;
 }
 
+int vsm_synth_rows_device(vsm_ctx* ctx, float* d_dst, int64_t row0, int64_t n, uint64_t seed) {
+    if (!ctx || n < 0 || (n > 0 && !d_dst)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_synth_rows_device: bad argument") : VSM_ERR_INVALID;
+    if (n == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)ctx->num_sms * 16);
+    synth_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_dst, row0, n, seed);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VSM_OK;
+}
+
 int vsm_debug_fetch_dump(vsm_ctx* ctx, void* out, int64_t bytes) {
     if (!ctx || !out || bytes <= 0 || bytes > (int64_t)(TILE_M * TILE_N * sizeof(float))) return VSM_ERR_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2073,5 +2089,7 @@ int vsm_debug_tile_scores(vsm_ctx* ctx, const float* query, int32_t nq, const fl
     CK(cudaMemcpyAsync(out, ctx->d_dump, TILE_M * TILE_N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     return end_call(ctx, true);
 }
+
+#include "vsm_group.inl"
 
 }  // extern "C"

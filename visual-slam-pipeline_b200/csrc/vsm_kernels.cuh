@@ -562,6 +562,29 @@ __global__ void globalize_keys_kernel(const unsigned long long* __restrict__ out
     keys[i] = k == 0ull ? 0ull : ~((~k) + row_offset);        // index lives in the low 32 bits of ~k
 }
 
+// local result keys -> keys carrying the STACKED row index of a database whose keyframes are dealt to
+// several devices (vsm_group): tab = (local row0, count, stacked row0) triples sorted by local row0;
+// the key's row is looked up by binary search.  `keys` may point into a peer device's memory.
+__global__ void stacked_keys_kernel(const unsigned long long* __restrict__ out_key, int n, const int64_t* __restrict__ tab,
+                                    int ntab, unsigned long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = out_key[i];
+    unsigned long long g = 0ull;
+    if (k != 0ull && ntab > 0) {
+        const unsigned long long u = ~k;
+        const int64_t row = (int64_t)(uint32_t)u;
+        int lo = 0, hi = ntab;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (tab[3 * mid] <= row) lo = mid; else hi = mid;
+        }
+        const int64_t grow = tab[3 * lo + 2] + (row - tab[3 * lo]);
+        g = ~((u & 0xFFFFFFFF00000000ull) | (unsigned long long)(uint32_t)grow);
+    }
+    keys[i] = g;
+}
+
 // gathered keys [nshard][nq][2] -> global top-2: the largest two keys per query
 __global__ void merge_keys_kernel(const unsigned long long* __restrict__ keys, int nshard, int nq,
                                   int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
@@ -582,6 +605,44 @@ __global__ void merge_keys_kernel(const unsigned long long* __restrict__ keys, i
         const unsigned long long u = ~kk[p];
         idx_out[2 * q + p] = (int64_t)(uint32_t)u;
         dist_out[2 * q + p] = __uint_as_float((uint32_t)(u >> 32));
+    }
+}
+
+// ---- synthetic descriptors (benchmarks written in C++ have no torch to make them) -------------------
+// Row r of stream `seed`: 256 standard normals (counter-based hash + Box-Muller) scaled to unit length,
+// the shape of FeatureExtractor's output (src/FeatureExtractor.cpp:170-205).  One warp per row.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256)
+synth_rows_kernel(float* __restrict__ dst, int64_t row0, int64_t n, uint64_t seed) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < n; r += nwarps) {
+        float v[8];
+        float s = 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const uint64_t h = mix64(mix64(seed) ^ (uint64_t)((row0 + r) * 128 + lane * 4 + p));
+            const float u1 = ((uint32_t)(h >> 40) + 1u) * (1.0f / 16777217.0f);      // (0, 1]
+            const float u2 = (uint32_t)(h & 0xFFFFFFu) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * __logf(u1));
+            float sn, cs;
+            __sincosf(6.28318530718f * u2, &sn, &cs);
+            v[2 * p] = rad * cs;
+            v[2 * p + 1] = rad * sn;
+            s += v[2 * p] * v[2 * p] + v[2 * p + 1] * v[2 * p + 1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float inv = rsqrtf(s);
+        float4* o4 = reinterpret_cast<float4*>(dst + r * VSM_DIM) + lane * 2;
+        o4[0] = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+        o4[1] = make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
     }
 }
 

@@ -107,10 +107,24 @@ SYMBOLS = {
     "vsm_db_top2_xchg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "vsm_merge_top2_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32]),
+    "vsm_group_create": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(_Opts), C.POINTER(C.c_void_p)]),
+    "vsm_group_destroy": (None, [C.c_void_p]),
+    "vsm_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "vsm_group_size": (C.c_int, [C.c_void_p]),
+    "vsm_group_ctx": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "vsm_group_store_add": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "vsm_group_store_remove": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsm_group_store_clear": (C.c_int, [C.c_void_p]),
+    "vsm_group_store_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p]),
+    "vsm_group_adopt_device": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "vsm_group_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vsm_group_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
+                                        C.c_void_p, C.c_void_p]),
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
     "vsm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsm_sync": (C.c_int, [C.c_void_p]),
     "vsm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vsm_synth_rows_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]),
     "vsm_debug_fetch_dump": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vsm_debug_tile_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
 }
@@ -148,6 +162,15 @@ def _rows(a, name):
 class Matcher:
     """One matching context on one GPU (single caller, synchronous calls)."""
 
+    @classmethod
+    def _borrowed(cls, handle):
+        """A view of a context owned by someone else (a group member): never destroyed here."""
+        m = cls.__new__(cls)
+        m._lib = load_library()
+        m._h = C.c_void_p(handle)
+        m._owned = False
+        return m
+
     def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0, ring=0):
         self._lib = load_library()
         o = _Opts()
@@ -164,7 +187,8 @@ class Matcher:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.vsm_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._lib.vsm_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -499,3 +523,93 @@ class Matcher:
         self._ck(self._lib.vsm_debug_tile_scores(self._h, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
                                                  out.ctypes.data))
         return out
+
+
+class Group:
+    """Several GPUs behind one caller (vsm_group_*): the keyframe database is dealt to the devices by
+    whole keyframes; a search fans out on the library's worker threads and merges on the first device.
+    Mirrors what a single-threaded C++ caller (the reference's slam_thread) gets."""
+
+    def __init__(self, devices, engine=ENGINE_AUTO, seg_tiles=0):
+        self._lib = load_library()
+        o = _Opts()
+        self._lib.vsm_default_opts(C.byref(o))
+        o.engine = engine
+        o.reserved[0] = seg_tiles
+        devs = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        st = self._lib.vsm_group_create(devs.ctypes.data, len(devs), C.byref(o), C.byref(h))
+        if st != 0:
+            raise VsmError(f"vsm_group_create failed ({st}): {self._lib.vsm_group_last_error(None).decode()}")
+        self._g = h
+        self.n = len(devs)
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.vsm_group_destroy(self._g)
+            self._g = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st != 0:
+            raise VsmError(f"libvsm group error {st}: {self._lib.vsm_group_last_error(self._g).decode()}")
+
+    def member(self, r):
+        return Matcher._borrowed(self._lib.vsm_group_ctx(self._g, r))
+
+    def add_keyframe(self, frame_id, desc):
+        d = _rows(desc, "desc")
+        h = C.c_int32(-1)
+        self._ck(self._lib.vsm_group_store_add(self._g, frame_id, d.ctypes.data, d.shape[0], C.byref(h)))
+        return h.value
+
+    def remove_keyframe(self, handle):
+        self._ck(self._lib.vsm_group_store_remove(self._g, handle))
+
+    def clear_store(self):
+        self._ck(self._lib.vsm_group_store_clear(self._g))
+
+    def store_info(self):
+        r, k = C.c_int64(0), C.c_int32(0)
+        per = np.zeros(self.n, np.int64)
+        self._ck(self._lib.vsm_group_store_info(self._g, C.byref(r), C.byref(k), per.ctypes.data))
+        return r.value, k.value, per
+
+    def adopt_device_matrix(self, member, dev_ptr, n_rows, seg_off=None):
+        if seg_off is not None:
+            seg_off = np.ascontiguousarray(seg_off, np.int64)
+            self._ck(self._lib.vsm_group_adopt_device(self._g, member, C.c_void_p(dev_ptr), n_rows, seg_off.ctypes.data,
+                                                      len(seg_off) - 1))
+        else:
+            self._ck(self._lib.vsm_group_adopt_device(self._g, member, C.c_void_p(dev_ptr), n_rows, None, 0))
+
+    def search_map_points(self, frame_desc, want_keyframes=False):
+        """Global top-2 over every member's keyframe rows: (idx [stacked rows], dist[, kf_handle, kf_row])."""
+        q = _rows(frame_desc, "frame_desc")
+        nq = q.shape[0]
+        idx = np.empty((nq, 2), np.int64)
+        dist = np.empty((nq, 2), np.float32)
+        kh = np.empty((nq, 2), np.int32) if want_keyframes else None
+        kr = np.empty((nq, 2), np.int32) if want_keyframes else None
+        self._ck(self._lib.vsm_group_db_top2(self._g, q.ctypes.data, nq, idx.ctypes.data, dist.ctypes.data,
+                                             kh.ctypes.data if want_keyframes else None,
+                                             kr.ctypes.data if want_keyframes else None))
+        return (idx, dist, kh, kr) if want_keyframes else (idx, dist)
+
+    def loop_detect(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, want_matches=True):
+        q = _rows(frame_desc, "frame_desc")
+        nkf = self.store_info()[1]
+        status = np.zeros(max(nkf, 1), np.int32)
+        m = np.zeros((max(nkf, 1), max(q.shape[0], 1)), DMATCH) if want_matches else None
+        self._ck(self._lib.vsm_group_loop_detect(self._g, cur_frame_id, min_gap, every, q.ctypes.data, q.shape[0], ratio,
+                                                 status.ctypes.data, m.ctypes.data if want_matches else None))
+        status = status[:nkf]
+        lists = [m[s, :status[s]] if status[s] >= 0 else None for s in range(nkf)] if want_matches else None
+        return status, lists
