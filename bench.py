@@ -535,6 +535,63 @@ def extra_pair_numbers(torch, vsm_b200, device):
                      "tc_tflops": fl / (st["tc_ms"] * 1e-3) / 1e12 if st["tc_ms"] else None,
                      "candidates_rescored": st["candidates"], "rescanned_slices": st["flagged_slices"]}
     out["loop_closure_500kf_per_keyframe_ratio"]["keyframes_with_30_or_more_survivors"] = int((res[0] >= 30).sum())
+    out["loop_closure_500kf_per_keyframe_ratio"]["api"] = "vsm_db_segmented (record-based, returns counts for every keyframe)"
+    # the same search in LoopCloser::detect's own shape: gate (>= 30 survivors) and packing on the device,
+    # only the surviving keyframes' lists come back (vsm_loop_detect_compact)
+    call = lambda: m.loop_detect_compact(10**6, hq2, 0.75, min_gap=0, every=1, min_matches=30)
+    for _ in range(3):
+        call()
+    tl = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        res = call()
+        tl.append(time.perf_counter() - t0)
+    tl.sort()
+    st = m.stats()
+    out["loop_closure_500kf_compact"] = {"p50_ms": tl[len(tl) // 2] * 1e3, "device_ms": st["device_ms"], "tc_ms": st["tc_ms"],
+                                         "after_tc_ms": st["select_ms"], "tflops_e2e": fl / tl[len(tl) // 2] / 1e12,
+                                         "tc_tflops": fl / (st["tc_ms"] * 1e-3) / 1e12 if st["tc_ms"] else None,
+                                         "launches": st["kernel_launches"], "candidate_keyframes": sorted(res[1]),
+                                         "survivors_returned": int(sum(len(v) for v in res[1].values())),
+                                         "api": "vsm_loop_detect_compact (fused dismissal, O(open pairs) after the tensor pass)"}
+    m.clear_store()
+    del db
+    # BASELINE configs[3] in LoopCloser's form: 10K keyframes x 2000 descriptors, 2000 queries, the reference's
+    # eligibility (gap >= 200 frames, every 5th keyframe): 2000 keyframes matched per search
+    try:
+        nkf3, rows3, nq3 = 10_000, 2000, 2000
+        db3 = torch.empty((nkf3 * rows3, 256), device="cuda")
+        for k0 in range(0, nkf3 * rows3, 500_000):
+            db3[k0:k0 + 500_000] = unit(500_000)
+        q3 = unit(nq3)
+        src = 5004 * rows3 + torch.randperm(rows3, generator=g, device="cuda")[:400]   # keyframe 5004 is every-5th eligible
+        v = db3[src] + 0.06 * torch.randn((400, 256), generator=g, device="cuda")
+        q3[:400] = v / v.norm(dim=1, keepdim=True)
+        hq3 = q3.cpu().pin_memory().numpy()
+        torch.cuda.synchronize()
+        m.adopt_device_matrix(db3.data_ptr(), nkf3 * rows3, np.arange(nkf3 + 1, dtype=np.int64) * rows3)
+        m.set_frame_ids(np.arange(nkf3, dtype=np.int32))
+        call = lambda: m.loop_detect_compact(nkf3 + 500, hq3, 0.75, min_gap=200, every=5, min_matches=30)
+        for _ in range(3):
+            call()
+        tl = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            res = call()
+            tl.append(time.perf_counter() - t0)
+        tl.sort()
+        st = m.stats()
+        matched = int((res[0] >= 0).sum())
+        fl3 = 2.0 * nq3 * matched * rows3 * 256
+        out["loop_closure_10k_kf_every5_compact"] = {
+            "keyframes": nkf3, "keyframes_matched": matched, "p50_ms": tl[len(tl) // 2] * 1e3, "device_ms": st["device_ms"],
+            "tc_ms": st["tc_ms"], "after_tc_ms": st["select_ms"], "tflops_e2e": fl3 / tl[len(tl) // 2] / 1e12,
+            "tc_tflops": fl3 / (st["tc_ms"] * 1e-3) / 1e12 if st["tc_ms"] else None,
+            "candidate_keyframes": sorted(res[1]), "survivors_returned": int(sum(len(v) for v in res[1].values()))}
+        m.clear_store()
+        del db3
+    except Exception as e:                       # informational line: never lose the bench to it
+        out["loop_closure_10k_kf_every5_compact"] = {"error": repr(e)[:300]}
     m.clear_store()
     del db
     m.close()

@@ -74,7 +74,8 @@ typedef struct {
                                     on demand; 0 = allocate at the first add */
     int32_t reserved[8];         /* [0]: tiles per slice segment (0 = automatic);
                                     [1]: rescan work-list capacity (0 = default; tests shrink it);
-                                    [2]: plain frames vsm_track keeps before recycling (0 = 2) */
+                                    [2]: plain frames vsm_track keeps before recycling (0 = 2);
+                                    [3]: open (query, keyframe) pairs vsm_loop_detect_compact can hold (0 = 262144; tests shrink it) */
 } vsm_opts;
 
 typedef struct vsm_ctx vsm_ctx;
@@ -284,6 +285,29 @@ int vsm_loop_detect(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t
 int vsm_loop_detect_shard(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every,
                           int32_t checked_before, const float* query, int32_t nq, float ratio,
                           int32_t* status, vsm_dmatch* matches, int32_t* checked_after);
+
+/* LoopCloser::detect's candidate loop in COMPACT form (src/LoopCloser.cpp:43-62, gate at :62 included):
+ * the reference only ever uses the good_matches of keyframes with at least Config::MIN_MATCHES (30)
+ * survivors, so only those come back.  Same eligibility rules and shard arguments as
+ * vsm_loop_detect_shard (checked_before = 0 / checked_after = NULL for a whole list).
+ *   status  [n_keyframes]: -1 skipped, else the number of ratio-test survivors
+ *   cands   up to cand_cap entries, ascending keyframe position: the keyframes with
+ *           count >= max(min_matches, 1); entry k's survivors are matches[offset .. offset + count),
+ *           in query order, trainIdx keyframe-local, imgIdx = keyframe position
+ *   *n_cands / *n_matches: totals (if one exceeds its capacity the arrays hold the first part: call again
+ *           with larger ones)
+ * On the device the ratio test is dismissed inside the tensor-core epilogue for almost every (query,
+ * keyframe) pair; exact scans, the gate and the packing touch the remaining OPEN pairs only -- no buffer of
+ * size keyframes x queries exists anywhere. */
+typedef struct {
+    int32_t keyframe;            /* position in Map::get_keyframes() order */
+    int32_t count;               /* survivors (>= min_matches) */
+    int64_t offset;              /* of its list in `matches` */
+} vsm_loop_candidate;
+int vsm_loop_detect_compact(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, int32_t checked_before,
+                            const float* query, int32_t nq, float ratio, int32_t min_matches, int32_t* status,
+                            vsm_loop_candidate* cands, int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches,
+                            int64_t match_cap, int64_t* n_matches, int32_t* checked_after);
 
 /* Frame ids of the stored keyframes, in store order (n must equal the keyframe count).  For a
  * store built by vsm_store_adopt_device, whose keyframes otherwise get ids 0..n-1

@@ -725,3 +725,91 @@ def test_pair_engine_db_batch_and_mutual(pair):
     idx, dist = pair.knn_match(q2, t2)
     oi, od = oracle.knn(q2, t2, 2)
     assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+
+
+def _check_compact(m, q, db, seg_off, frame_ids, cur_id, ratio, min_gap, every, min_matches):
+    st, lists, _ = m.loop_detect_compact(cur_id, q, ratio, min_gap=min_gap, every=every, min_matches=min_matches)
+    ost, ol = oracle.loop_detect(q, db, seg_off, frame_ids, cur_id, ratio, min_gap=min_gap, every=every)
+    assert np.array_equal(st, ost)
+    want = {s for s in range(len(ost)) if ost[s] >= max(min_matches, 1)}
+    assert set(lists) == want
+    for s in want:
+        assert lists[s].tobytes() == ol[s].tobytes(), s
+    return ost
+
+
+def test_loop_detect_compact_equals_reference_loop(tc):
+    """vsm_loop_detect_compact (fused ratio dismissal in the tensor-core epilogue, exact scans of the open
+    pairs, >= MIN_MATCHES gate and packing on the device) against LoopCloser::detect's loop restated
+    (src/LoopCloser.cpp:43-62): status of every keyframe, and the good_matches of every keyframe that
+    passes the gate, byte for byte."""
+    q, db, seg_off = cases.db_case()
+    nkf = len(seg_off) - 1
+    frame_ids = np.arange(nkf, dtype=np.int32) * 40
+    tc.clear_store()
+    for s in range(nkf):
+        tc.add_keyframe(int(frame_ids[s]), db[seg_off[s]:seg_off[s + 1]])
+    cur_id = int(frame_ids[-1]) + 100
+    for every in (1, 2, 5):
+        for min_matches in (30, 1, 0, 45, 1000):
+            ost = _check_compact(tc, q, db, seg_off, frame_ids, cur_id, 0.75, 200, every, min_matches)
+    assert (ost >= 30).any()
+    for ratio in (0.6, 0.9, 1.0):
+        _check_compact(tc, q, db, seg_off, frame_ids, cur_id, ratio, 0, 1, 10)
+    # ragged query counts (not a multiple of 32 / 128), one query, scaled rows
+    _check_compact(tc, q[:131], db, seg_off, frame_ids, cur_id, 0.75, 0, 1, 5)
+    _check_compact(tc, q[:1], db, seg_off, frame_ids, cur_id, 0.75, 0, 1, 0)
+    _check_compact(tc, np.ascontiguousarray(q * np.float32(1.7)), db, seg_off, frame_ids, cur_id, 0.75, 0, 1, 5)
+    # repeated call (descriptor block reused), then a changed store
+    _check_compact(tc, q, db, seg_off, frame_ids, cur_id, 0.75, 0, 1, 30)
+    _check_compact(tc, q, db, seg_off, frame_ids, cur_id, 0.75, 0, 1, 30)
+    tc.remove_frame(int(tc.keyframes()[2]))
+    keep = np.ones(db.shape[0], bool)
+    keep[seg_off[2]:seg_off[3]] = False
+    seg2 = np.concatenate([[0], np.cumsum(np.delete(np.diff(seg_off), 2))]).astype(np.int64)
+    _check_compact(tc, q, db[keep], seg2, np.delete(frame_ids, 2), cur_id, 0.75, 0, 1, 30)
+    tc.clear_store()
+
+
+def test_loop_detect_compact_overflow_takes_the_record_path():
+    """More open pairs than the compact buffers hold (a scene full of matches; here the capacity is
+    shrunk): the call falls back to the record-based search and returns the same answer."""
+    q, db, seg_off = cases.db_case()
+    nkf = len(seg_off) - 1
+    frame_ids = np.arange(nkf, dtype=np.int32)
+    with vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, pair_cap=16) as m:
+        for s in range(nkf):
+            m.add_keyframe(int(frame_ids[s]), db[seg_off[s]:seg_off[s + 1]])
+        _check_compact(m, q, db, seg_off, frame_ids, 1000, 0.75, 0, 1, 30)
+    with vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, work_cap=64) as m:
+        for s in range(nkf):
+            m.add_keyframe(int(frame_ids[s]), db[seg_off[s]:seg_off[s + 1]])
+        _check_compact(m, q, db, seg_off, frame_ids, 1000, 0.75, 0, 1, 30)
+
+
+def test_loop_detect_compact_at_baseline_config2_size(tc):
+    """BASELINE configs[2] in LoopCloser's own form, FULL size: 1000 queries against 500 keyframes x 1000
+    descriptors, every keyframe eligible; 3 keyframes are re-observed (loop candidates), a few more share
+    a handful of rows.  Status of all 500 keyframes and every surviving list against the oracle."""
+    import torch
+    nkf, rows_kf, nq = 500, 1000, 1000
+    db = np.concatenate([gen.rows(600 + k // 50, k % 50, 0, rows_kf) for k in range(nkf)])
+    vq = gen.int_rows(611, 0, 0, nq).copy()
+    vdb = lambda kf, n: np.rint(db[kf * rows_kf: kf * rows_kf + n].astype(np.float64) * 3300).astype(np.int64)
+    vq[0:300] = 1000 * vdb(123, 300) + 1000 * gen.int_rows(612, 0, 0, 300)
+    vq[300:500] = 1000 * vdb(124, 200) + 1100 * gen.int_rows(613, 0, 0, 200)
+    vq[500:540] = 1000 * vdb(400, 40) + 900 * gen.int_rows(614, 0, 0, 40)
+    vq[540:552] = 1000 * vdb(77, 12) + 900 * gen.int_rows(615, 0, 0, 12)
+    q = gen._normalize_int(vq)
+    seg_off = np.arange(nkf + 1, dtype=np.int64) * rows_kf
+    d_db = torch.from_numpy(db).cuda()
+    tc.clear_store()
+    tc.adopt_device_matrix(d_db.data_ptr(), db.shape[0], seg_off)
+    frame_ids = np.arange(nkf, dtype=np.int32)
+    ost = _check_compact(tc, q, db, seg_off, frame_ids, 10_000, 0.75, 200, 1, 30)
+    assert (ost >= 30).sum() >= 3 and ((ost > 0) & (ost < 30)).any()
+    st = tc.stats()
+    assert st["kernel_launches"] == 6
+    # the reference's every-5th rule over the same list
+    _check_compact(tc, q, db, seg_off, frame_ids, 10_000, 0.75, 200, 5, 30)
+    tc.clear_store()

@@ -159,6 +159,11 @@ struct vsm_ctx {
     DevBuf<WorkItem> d_work;
     DevBuf<int32_t> d_sel;                       // selected store rows of a masked search
     DevBuf<uint8_t> d_track;                     // track_local_map: keypoints, map-point positions, results
+    DevBuf<uint8_t> d_loop;                      // compact loop search: masks, word bases, pair keys, staged matches, offsets
+    std::vector<uint8_t> loop_key;               // plan key of the last compact loop search (descriptor block reuse)
+    const void* loop_p_desc = nullptr;
+    const void* loop_p_loop = nullptr;
+    uint32_t pair_cap = 0;                       // open (query, keyframe) pairs the compact loop search can hold (0 = PAIR_CAP)
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // event pairs around the tensor-core kernel of the last TC_RING calls (ev_tc0/ev_tc1 = the current
@@ -515,6 +520,43 @@ int flush_conversions(vsm_ctx* ctx, size_t keep) {
     return VSM_OK;
 }
 
+// First kernel of a matching call: zeroes the per-call aux block (keeping the scratch-statistics slot
+// this call accumulates into), copies the descriptor block from pinned host memory and runs the
+// conversions queued by the call.  Scratch norm statistics live in two alternating 8-byte slots: a call
+// accumulates into slot call_seq & 1, which the PREVIOUS call's prologue zeroed, and zeroes the other one.
+int launch_prologue(vsm_ctx* ctx, size_t aux_bytes, size_t desc_bytes, bool upload_desc) {
+    const int stats_slot = (int)(ctx->call_seq & 1u);
+    uint32_t* d_scratch_stats = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 32 + 8 * stats_slot);
+    for (auto& j : ctx->pending_conv) if (!j.stats) j.stats = d_scratch_stats;
+    TRY(flush_conversions(ctx, MAX_CONV));                          // more row sets than one prologue takes
+    Prologue pr;
+    memset(&pr, 0, sizeof pr);
+    pr.aux = reinterpret_cast<uint4*>(ctx->d_aux.p);
+    pr.aux_vecs = (uint32_t)(aux_bytes / 16);
+    pr.keep_slot = stats_slot;
+    pr.desc_src = reinterpret_cast<const uint4*>(ctx->h_desc);      // pinned, mapped (unified addressing)
+    pr.desc_dst = reinterpret_cast<uint4*>(ctx->d_desc.p);
+    pr.desc_vecs = upload_desc ? (uint32_t)(desc_bytes / 16) : 0u;
+    int64_t max_rows = 0;
+    for (auto& j : ctx->pending_conv) {
+        pr.conv[pr.nconv++] = j;
+        max_rows = std::max(max_rows, j.rows);
+    }
+    ctx->pending_conv.clear();
+    const int64_t want = std::max<int64_t>((max_rows + 7) / 8, ((int64_t)pr.aux_vecs + pr.desc_vecs + 1023) / 1024);
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * 16));
+    CK(launch_pdl(prologue_kernel, dim3(blocks), dim3(256), 0, ctx->stream, pr));
+    ctx->launches++;
+    if (upload_desc) {
+        CK(cudaEventRecord(ctx->ev_desc, ctx->stream));
+        ctx->desc_copy_pending = true;
+    }
+    ctx->call_seq++;
+    return VSM_OK;
+}
+
+inline uint32_t __float_as_uint_host(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
 // Plans, uploads and launches: tensor-core pass -> select/re-score (+ re-scan) -> filter.
 // The conversions queued by the call (ctx->pending_conv), the zeroing of the per-call aux block
 // (counters, unit queue head, hints, result keys) and the descriptor upload are one prologue kernel.
@@ -753,6 +795,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));       // h_desc may still be read by the last prologue
     memcpy(ctx->h_desc, h, total);
     upload_desc = true;
+    ctx->loop_p_desc = nullptr;                              // the compact loop search's block is gone
     if (!dump_first) {
         pl.key = key;
         pl.p_desc = ctx->d_desc.p;
@@ -762,34 +805,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     }
     }   // !hit
 
-    // prologue: aux zeroing + descriptor block + conversions, one kernel
-    {
-        for (auto& j : ctx->pending_conv) if (!j.stats) j.stats = d_scratch_stats;
-        TRY(flush_conversions(ctx, MAX_CONV));                          // more row sets than one prologue takes
-        Prologue pr;
-        memset(&pr, 0, sizeof pr);
-        pr.aux = reinterpret_cast<uint4*>(ctx->d_aux.p);
-        pr.aux_vecs = (uint32_t)(aux_bytes / 16);
-        pr.keep_slot = stats_slot;
-        pr.desc_src = reinterpret_cast<const uint4*>(ctx->h_desc);      // pinned, mapped (unified addressing)
-        pr.desc_dst = reinterpret_cast<uint4*>(ctx->d_desc.p);
-        pr.desc_vecs = upload_desc ? (uint32_t)(total / 16) : 0u;
-        int64_t max_rows = 0;
-        for (auto& j : ctx->pending_conv) {
-            pr.conv[pr.nconv++] = j;
-            max_rows = std::max(max_rows, j.rows);
-        }
-        ctx->pending_conv.clear();
-        const int64_t want = std::max<int64_t>((max_rows + 7) / 8, ((int64_t)pr.aux_vecs + pr.desc_vecs + 1023) / 1024);
-        const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * 16));
-        CK(launch_pdl(prologue_kernel, dim3(blocks), dim3(256), 0, ctx->stream, pr));
-        ctx->launches++;
-        if (upload_desc) {
-            CK(cudaEventRecord(ctx->ev_desc, ctx->stream));
-            ctx->desc_copy_pending = true;
-        }
-        ctx->call_seq++;
-    }
+    TRY(launch_prologue(ctx, aux_bytes, total, upload_desc));
 
     uint8_t* dd = ctx->d_desc.p;
     if (ctx->profiling) {
@@ -1022,6 +1038,7 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status), 64, cudaHostAllocMapped));
         memset(ctx->h_status, 0, 64);
         if (o.reserved[2] > 0) ctx->ring_depth = o.reserved[2];
+        if (o.reserved[3] > 0) ctx->pair_cap = (uint32_t)o.reserved[3];
         CK(cudaMalloc(&ctx->d_store_stats, 16));
         CK(cudaMemset(ctx->d_store_stats, 0, 16));
         CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
@@ -1058,6 +1075,7 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_work.p) cudaFree(ctx->d_work.p);
     if (ctx->d_sel.p) cudaFree(ctx->d_sel.p);
     if (ctx->d_track.p) cudaFree(ctx->d_track.p);
+    if (ctx->d_loop.p) cudaFree(ctx->d_loop.p);
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1757,6 +1775,240 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
     return VSM_OK;
 }
 
+// ---- LoopCloser::detect, compact form ------------------------------------------------------------
+constexpr uint32_t PAIR_CAP = 1u << 18;          // open (query, keyframe) pairs per search: 4 MB of keys + 4 MB of staged matches
+
+// The eligible keyframes (positions in get_keyframes() order) against the query frame: fused ratio
+// dismissal in the tensor-core epilogue, exact scans for the open pairs only, gate and packed lists on
+// the device.  *overflow: the open pairs did not fit (a scene full of matches): nothing was returned and
+// the caller takes the record-based path.
+static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ratio, int32_t min_matches,
+                             const std::vector<int32_t>& elig_pos, int32_t* status, vsm_loop_candidate* cands,
+                             int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches, int64_t match_cap,
+                             int64_t* n_matches, bool* overflow) {
+    *overflow = false;
+    const int nslots = (int)elig_pos.size();
+    const int nqt = (nq + TILE_M - 1) / TILE_M;
+    const int wps = nqt * 4;
+    const uint32_t pair_cap = ctx->pair_cap ? ctx->pair_cap : PAIR_CAP;
+    TRY(begin_call(ctx));
+    TRY(arena_reserve(ctx, ctx->scratch, nq, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+
+    // device layout
+    const size_t nwords = (size_t)nslots * wps;
+    const size_t o_mask = 0, o_base = align16(o_mask + nwords * 4), o_keys = align16(o_base + nwords * 4),
+                 o_stage = align16(o_keys + (size_t)pair_cap * 16), o_off = align16(o_stage + (size_t)pair_cap * sizeof(DMatch)),
+                 loop_bytes = align16(o_off + (size_t)nslots * 8);
+    TRY(ensure(ctx, ctx->d_loop, loop_bytes));
+    const size_t off_slot = 0, off_unit = align16(off_slot + sizeof(LoopSlot) * nslots),
+                 total = align16(off_unit + sizeof(TcUnit) * (size_t)nslots * nqt);
+    TRY(ensure(ctx, ctx->d_desc, total));
+    TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
+    TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
+    const size_t aux_bytes = align16(48 + (size_t)nslots * 4);                 // header + survivors per slot, zeroed per call
+    TRY(ensure(ctx, ctx->d_aux, aux_bytes));
+    if (ctx->aux_zeroed != ctx->d_aux.p) {
+        CK(cudaMemsetAsync(ctx->d_aux.p, 0, ctx->d_aux.cap, ctx->stream));
+        ctx->aux_zeroed = ctx->d_aux.p;
+    }
+    // outputs in pinned host memory, written by the last kernel: head | survivors per slot | candidates | matches
+    const size_t h_head = 0, h_good = 16, h_cand = align16(h_good + (size_t)nslots * 4),
+                 h_match = align16(h_cand + (size_t)nslots * sizeof(LoopCand)),
+                 h_total = h_match + (size_t)pair_cap * sizeof(DMatch);
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, h_total));
+    ctx->plan.valid = false;                                               // the descriptor block is overwritten
+
+    // descriptor block: rebuilt only when the eligible list (or a buffer) changed since the last search
+    std::vector<uint8_t>& key = ctx->plan_key_build;
+    {
+        const int64_t head[6] = {nq, nslots, (int64_t)__float_as_uint_host(ratio), (int64_t)(uintptr_t)ctx->store.f32,
+                                 (int64_t)(uintptr_t)ctx->scratch.n2, (int64_t)(uintptr_t)ctx->d_store_stats};
+        key.resize(sizeof head + (size_t)nslots * sizeof(LoopSlot));
+        memcpy(key.data(), head, sizeof head);
+    }
+    std::vector<LoopSlot> slots(nslots);
+    for (int s = 0; s < nslots; s++) {
+        const Seg& sg = ctx->segs[ctx->kf_order[elig_pos[s]]];
+        slots[s] = LoopSlot{sg.row0, sg.count, elig_pos[s]};
+    }
+    if (nslots) memcpy(key.data() + 48, slots.data(), (size_t)nslots * sizeof(LoopSlot));
+    const bool hit = ctx->loop_p_desc == ctx->d_desc.p && ctx->loop_p_loop == ctx->d_loop.p && ctx->loop_key == key;
+    uint8_t* dl = ctx->d_loop.p;
+    if (!hit) {
+        std::vector<uint8_t>& blk = ctx->desc_build;
+        blk.assign(total, 0);
+        memcpy(blk.data() + off_slot, slots.data(), sizeof(LoopSlot) * nslots);
+        TcUnit* units = reinterpret_cast<TcUnit*>(blk.data() + off_unit);
+        const float r2 = skip_r2(ratio);
+        for (int s = 0; s < nslots; s++)
+            for (int qt = 0; qt < nqt; qt++) {
+                TcUnit& u = units[(size_t)s * nqt + qt];
+                u.q_n2 = ctx->scratch.n2 + (int64_t)qt * TILE_M;
+                u.t_stats = ctx->d_store_stats;
+                u.rec_base = ((int64_t)s * nqt + qt) * 4;                    // first mask word of the unit
+                u.rec_stride = 0;
+                u.q_row = qt * TILE_M;
+                u.t_row = (int32_t)slots[s].row0;
+                u.t_count = slots[s].count;
+                u.t_index0 = 0;
+                u.q_valid = std::min(TILE_M, nq - qt * TILE_M);
+                u.seg_tiles = UNIT_TILES;
+                u.maps = 2 | 4 | 8;                                         // train rows in the store; maxima only; fused dismissal
+                u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 : 0;
+                u.skip_ratio2 = r2;
+                u.hint = reinterpret_cast<uint32_t*>(dl + o_mask);
+            }
+        if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));
+        memcpy(ctx->h_desc, blk.data(), total);
+        ctx->loop_key = key;
+        ctx->loop_p_desc = ctx->d_desc.p;
+        ctx->loop_p_loop = ctx->d_loop.p;
+    }
+    TRY(launch_prologue(ctx, aux_bytes, total, !hit));
+    uint8_t* dd = ctx->d_desc.p;
+    const size_t nunits = (size_t)nslots * nqt;
+    if (ctx->profiling) {
+        const uint32_t slot = ctx->tc_ring_head++ % vsm_ctx::TC_RING;
+        ctx->ev_tc0 = ctx->tc_ring0[slot];
+        ctx->ev_tc1 = ctx->tc_ring1[slot];
+        ctx->tc_ring_valid[slot] = nunits > 0;
+        CK(cudaEventRecord(ctx->ev_tc0, ctx->stream));
+    }
+    {
+        const unsigned grid = (unsigned)std::min<size_t>(nunits, (size_t)ctx->num_sms);
+        uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
+        CK(launch_pdl(tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, ctx->stream, ctx->scratch.map,
+                      ctx->store.map, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, d_unit_counter,
+                      ctx->d_recs.p, ctx->d_dump));
+        ctx->launches++;
+        if (ctx->profiling) {
+            CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
+            ctx->timed_tc = true;
+        }
+    }
+    LoopParams P;
+    memset(&P, 0, sizeof P);
+    P.slots = reinterpret_cast<const LoopSlot*>(dd + off_slot);
+    P.nslots = nslots; P.nq = nq; P.words_per_slot = wps;
+    P.q_f32 = ctx->scratch.f32;
+    P.store_f32 = ctx->store.f32;
+    P.masks = reinterpret_cast<const uint32_t*>(dl + o_mask);
+    P.word_base = reinterpret_cast<uint32_t*>(dl + o_base);
+    P.pair_keys = reinterpret_cast<unsigned long long*>(dl + o_keys);
+    P.stage = reinterpret_cast<DMatch*>(dl + o_stage);
+    P.pair_cap = pair_cap;
+    P.counters = reinterpret_cast<uint32_t*>(ctx->d_aux.p);
+    P.work = ctx->d_work.p;
+    P.work_cap = ctx->work_cap;
+    P.slot_good = reinterpret_cast<int32_t*>(ctx->d_aux.p + 48);
+    P.slot_off = reinterpret_cast<int64_t*>(dl + o_off);
+    P.ratio = ratio;
+    P.min_matches = min_matches;
+    P.out_head = reinterpret_cast<int32_t*>(ctx->h_result + h_head);
+    P.out_cands = reinterpret_cast<LoopCand*>(ctx->h_result + h_cand);
+    P.cand_cap = nslots;
+    P.out_matches = reinterpret_cast<DMatch*>(ctx->h_result + h_match);
+    P.match_cap = pair_cap;
+    const unsigned wblocks = (unsigned)std::max<size_t>(1, std::min<size_t>((nwords + 7) / 8, (size_t)ctx->num_sms * 8));
+    ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
+    CK(launch_pdl(loop_open_plan_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));
+    CK(launch_pdl(rescan_kernel, dim3((unsigned)ctx->num_sms * 2), dim3(256), 0, ctx->stream, (const WorkItem*)ctx->d_work.p,
+                  (const unsigned long long*)ctx->d_counters, ctx->work_cap));
+    CK(launch_pdl(loop_finish_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));
+    CK(launch_pdl(loop_emit_kernel, dim3(1), dim3(1024), 0, ctx->stream, P));
+    ctx->launches += 4;
+    if (ctx->profiling) {
+        CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
+        ctx->timed_sel = true;
+    }
+    if (nslots) CK(cudaMemcpyAsync(ctx->h_result + h_good, P.slot_good, (size_t)nslots * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(end_call(ctx, true));
+    const int32_t* head = reinterpret_cast<const int32_t*>(ctx->h_result + h_head);
+    ctx->seg_open_rate = (float)(uint32_t)head[3] / (float)std::max<int64_t>((int64_t)nslots * nq, 1);
+    if (head[2]) { *overflow = true; return VSM_OK; }
+    const int32_t* good = reinterpret_cast<const int32_t*>(ctx->h_result + h_good);
+    for (int s = 0; s < nslots; s++) status[elig_pos[s]] = good[s];
+    const int nc = head[0];
+    const int64_t nm = head[1];
+    if (n_cands) *n_cands = nc;
+    if (n_matches) *n_matches = nm;
+    if (cands) memcpy(cands, ctx->h_result + h_cand, (size_t)std::min(nc, cand_cap) * sizeof(LoopCand));
+    if (matches) memcpy(matches, ctx->h_result + h_match, (size_t)std::min<int64_t>(nm, match_cap) * sizeof(DMatch));
+    return VSM_OK;
+}
+
+static int loop_eligible(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, int32_t checked_before,
+                         std::vector<char>& eligible, int32_t* status, int32_t* checked_after) {
+    const int nseg = (int)ctx->kf_order.size();                       // keyframes only, in Map::get_keyframes() order
+    eligible.assign(nseg, 0);
+    int checked = checked_before, any = 0;
+    for (int s = 0; s < nseg; s++) {                                  // src/LoopCloser.cpp:43-48
+        const Seg& sg = ctx->segs[ctx->kf_order[s]];
+        status[s] = -1;
+        if (cur_frame_id - sg.frame_id < min_gap) continue;
+        if (sg.count == 0) continue;
+        checked++;
+        if (checked % every != 0) continue;
+        eligible[s] = 1;
+        status[s] = 0;
+        any = 1;
+    }
+    if (checked_after) *checked_after = checked;
+    return any;
+}
+
+int vsm_loop_detect_compact(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, int32_t checked_before,
+                            const float* query, int32_t nq, float ratio, int32_t min_matches, int32_t* status,
+                            vsm_loop_candidate* cands, int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches,
+                            int64_t match_cap, int64_t* n_matches, int32_t* checked_after) {
+    if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || checked_before < 0 || cand_cap < 0 || match_cap < 0 ||
+        !n_cands || !n_matches || (cand_cap > 0 && !cands) || (match_cap > 0 && !matches))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect_compact: bad argument") : VSM_ERR_INVALID;
+    static_assert(sizeof(vsm_loop_candidate) == sizeof(LoopCand), "vsm_loop_candidate layout");
+    *n_cands = 0;
+    *n_matches = 0;
+    std::vector<char> eligible;
+    const int any = loop_eligible(ctx, cur_frame_id, min_gap, every, checked_before, eligible, status, checked_after);
+    if (nq == 0 || !any) return VSM_OK;                               // :22 (empty current frame)
+    std::vector<int32_t> pos;
+    bool fits = ctx->engine != VSM_ENGINE_SIMT && ctx->engine != VSM_ENGINE_TENSOR_PAIR;
+    for (int s = 0; s < (int)eligible.size(); s++) {
+        if (!eligible[s]) continue;
+        const int32_t cnt = ctx->segs[ctx->kf_order[s]].count;
+        if (cnt < 2) continue;                                        // no two-entry list, no survivor (:57): status stays 0
+        if (cnt > UNIT_TILES * TILE_N) fits = false;                  // a keyframe must be one work unit
+        pos.push_back(s);
+    }
+    if (pos.empty()) return VSM_OK;
+    bool overflow = !fits;
+    if (fits)
+        TRY(loop_compact_impl(ctx, query, nq, ratio, min_matches, pos, status, cands, cand_cap, n_cands, matches, match_cap,
+                              n_matches, &overflow));
+    if (!overflow) return VSM_OK;
+    // too many open pairs for the compact buffers (or an engine / keyframe size the fused units do not
+    // cover): the record-based per-keyframe search, packed on the host
+    const int nkf = (int)eligible.size();
+    std::vector<int32_t> cnt(nkf, 0);
+    std::vector<vsm_dmatch> slab((size_t)nkf * nq);
+    TRY(segmented_impl(ctx, query, nq, ratio, &eligible, cnt.data(), slab.data()));
+    int nc = 0;
+    int64_t nm = 0;
+    for (int s = 0; s < nkf; s++) {
+        if (!eligible[s]) continue;
+        status[s] = cnt[s];
+        if (cnt[s] < min_matches || cnt[s] == 0) continue;
+        if (nc < cand_cap) cands[nc] = vsm_loop_candidate{s, cnt[s], nm};
+        for (int i = 0; i < cnt[s]; i++)
+            if (nm + i < match_cap) matches[nm + i] = slab[(size_t)s * nq + i];
+        nc++;
+        nm += cnt[s];
+    }
+    *n_cands = nc;
+    *n_matches = nm;
+    return VSM_OK;
+}
+
 int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_xy, const float* desc, int32_t nkp,
                         const double* mp_pos, const float* mp_desc, const uint8_t* mp_valid, int32_t nmp,
                         const double* R_cam, const double* t_cam, int32_t* indices, int32_t* obs_mp, int32_t* obs_ki,
@@ -2014,21 +2266,8 @@ int vsm_loop_detect_shard(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, i
                           int32_t* checked_after) {
     if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || checked_before < 0)
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect: bad argument") : VSM_ERR_INVALID;
-    const int nseg = (int)ctx->kf_order.size();                       // keyframes only, in Map::get_keyframes() order
-    std::vector<char> eligible(nseg, 0);
-    int checked = checked_before, any = 0;
-    for (int s = 0; s < nseg; s++) {                                  // src/LoopCloser.cpp:43-48
-        const Seg& sg = ctx->segs[ctx->kf_order[s]];
-        status[s] = -1;
-        if (cur_frame_id - sg.frame_id < min_gap) continue;
-        if (sg.count == 0) continue;
-        checked++;
-        if (checked % every != 0) continue;
-        eligible[s] = 1;
-        status[s] = 0;
-        any = 1;
-    }
-    if (checked_after) *checked_after = checked;
+    std::vector<char> eligible;
+    const int any = loop_eligible(ctx, cur_frame_id, min_gap, every, checked_before, eligible, status, checked_after);
     if (nq == 0 || !any) return VSM_OK;                               // :22 (empty current frame)
     return segmented_impl(ctx, query, nq, ratio, &eligible, status, matches);
 }

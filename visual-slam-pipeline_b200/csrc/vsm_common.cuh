@@ -57,10 +57,15 @@ struct TcUnit {
     int32_t q_valid;               // valid query rows in the tile (1..128)
     int32_t seg_tiles;             // tiles per slice segment (records flushed every seg_tiles tiles)
     int32_t maps;                  // bit0: query rows in store map, bit1: train rows in store map,
-                                   // bit2: maxima-only records (see scan32_max2)
+                                   // bit2: maxima-only records (see scan32_max2),
+                                   // bit3 (with bit2): FUSED ratio dismissal -- the unit covers one whole keyframe;
+                                   //       no record is written, only a 128-bit mask of the queries the
+                                   //       ratio test could not dismiss (rec_base = first mask word of the unit)
     int32_t dump;                  // debug: 1 = raw accumulators of tile 0, 2 = clock64 timeline
     int32_t prefetch;              // this CTA issues the L2 prefetches for its train range
+    float skip_ratio2;             // bit3 units: ratio^2 * 1.001 of the caller's ratio test (Problem::skip_ratio2)
     uint32_t* hint;                // per query row: shared lower bound on the global second-best dot
+                                   // (bit3 units: the open-pair mask words, uint32 [units][4])
 };
 
 // A slice = the train rows one epilogue thread scanned for one record:

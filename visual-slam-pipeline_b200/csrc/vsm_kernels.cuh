@@ -450,6 +450,199 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
     }
 }
 
+// ---- LoopCloser::detect, compact form (src/LoopCloser.cpp:43-62) ---------------------------------
+// The tensor-core pass (fused units, TcUnit maps bit 3) leaves one bit per (eligible keyframe, query):
+// "the ratio test could not be dismissed" = an OPEN pair.  Everything after it is O(open pairs):
+//   loop_open_plan_kernel  numbers the open pairs, zeroes their result keys, queues exact scans
+//   rescan_kernel          exact top-2 of the query inside the keyframe (canonical fp32 distances)
+//   loop_finish_kernel     ratio test per open pair (src/LoopCloser.cpp:55-60), survivors per keyframe
+//   loop_emit_kernel       the >= MIN_MATCHES gate (:62) and the surviving keyframes' lists, in query
+//                          order, packed -- nothing of size keyframes x queries ever exists
+struct LoopSlot {                      // one eligible keyframe
+    int64_t row0;                      // first store row
+    int32_t count;                     // rows (>= 2)
+    int32_t kf_pos;                    // position in Map::get_keyframes() order (DMatch::imgIdx)
+};
+struct LoopCand {                      // mirrors vsm_loop_candidate
+    int32_t keyframe;
+    int32_t count;
+    int64_t offset;
+};
+struct LoopParams {
+    const LoopSlot* slots;
+    int32_t nslots, nq, words_per_slot;        // words_per_slot = 4 * query tiles
+    const float* q_f32;                        // query rows (scratch arena)
+    const float* store_f32;
+    const uint32_t* masks;                     // [nslots][words_per_slot]
+    uint32_t* word_base;                       // [nslots][words_per_slot]: pair index of a word's first open bit
+    unsigned long long* pair_keys;             // [pair_cap][2]
+    DMatch* stage;                             // [pair_cap]: the pair's match, trainIdx = -1 if it fails the ratio test
+    uint32_t pair_cap;
+    uint32_t* counters;                        // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag
+    WorkItem* work;
+    uint32_t work_cap;
+    int32_t* slot_good;                        // [nslots] survivors per eligible keyframe
+    int64_t* slot_off;                         // [nslots] offset of its list in the output, -1 = below the gate
+    float ratio;
+    int32_t min_matches;
+    // outputs (pinned host memory for small results, else device)
+    int32_t* out_head;                         // [0] candidates, [1] survivors emitted, [2] overflow, [3] open pairs
+    LoopCand* out_cands;
+    int32_t cand_cap;
+    DMatch* out_matches;
+    int64_t match_cap;
+};
+
+__global__ void __launch_bounds__(256)
+loop_open_plan_kernel(const LoopParams P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwords = (int64_t)P.nslots * P.words_per_slot;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += nwarps) {
+        const uint32_t m = P.masks[w];
+        if (m == 0u) continue;                                   // the usual case: no loop in sight
+        const int slot = (int)(w / P.words_per_slot);
+        const int q = (int)(w % P.words_per_slot) * 32 + lane;
+        uint32_t base = 0;
+        if (lane == 0) {
+            base = atomicAdd(P.counters + 5, (uint32_t)__popc(m));
+            P.word_base[w] = base;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!((m >> lane) & 1u)) continue;
+        const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+        if (p >= P.pair_cap) { P.counters[7] = 1u; continue; }
+        P.pair_keys[2 * (size_t)p] = 0ull;
+        P.pair_keys[2 * (size_t)p + 1] = 0ull;
+        const LoopSlot sl = P.slots[slot];
+        const uint32_t nitem = (uint32_t)((sl.count + RESCAN_ROWS - 1) / RESCAN_ROWS);
+        const uint32_t wb = atomicAdd(P.counters + 4, nitem);
+        if (wb + nitem > P.work_cap) {
+            P.counters[7] = 1u;
+            for (uint32_t k = wb; k < P.work_cap && k < wb + nitem; k++) {       // void what this reservation still owns
+                WorkItem v = {nullptr, nullptr, nullptr, {0, 0, -1, 0}, 0, 0};
+                P.work[k] = v;
+            }
+            continue;
+        }
+        for (uint32_t k = 0; k < nitem; k++) {
+            WorkItem it = {P.q_f32 + (size_t)q * VSM_DIM, P.store_f32 + (size_t)sl.row0 * VSM_DIM, P.pair_keys + 2 * (size_t)p,
+                           {0, sl.count, -1, 0}, (int32_t)(k * RESCAN_ROWS), 0};
+            P.work[wb + k] = it;
+        }
+    }
+}
+
+// One warp per mask word: the reference's test on the pair's exact top-2, survivors counted per keyframe.
+__global__ void __launch_bounds__(256)
+loop_finish_kernel(const LoopParams P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwords = (int64_t)P.nslots * P.words_per_slot;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += nwarps) {
+        const uint32_t m = P.masks[w];
+        if (m == 0u) continue;
+        const int slot = (int)(w / P.words_per_slot);
+        const int q = (int)(w % P.words_per_slot) * 32 + lane;
+        const uint32_t base = P.word_base[w];
+        bool good = false;
+        if ((m >> lane) & 1u) {
+            const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+            if (p < P.pair_cap) {
+                int32_t i0, i1;
+                float d0, d1;
+                key_decode(P.pair_keys[2 * (size_t)p], i0, d0);
+                key_decode(P.pair_keys[2 * (size_t)p + 1], i1, d1);
+                good = i1 >= 0 && d0 < __fmul_rn(P.ratio, d1);           // m.size() >= 2 && m[0].distance < ratio * m[1].distance
+                DMatch dm = {q, good ? i0 : -1, P.slots[slot].kf_pos, d0};
+                P.stage[p] = dm;
+            }
+        }
+        const int n = __popc(__ballot_sync(0xffffffffu, good));
+        if (lane == 0 && n) atomicAdd(P.slot_good + slot, n);
+    }
+}
+
+// One block: the >= min_matches gate over the eligible keyframes (in list order), then the surviving
+// keyframes' lists packed one after the other, each in query order.
+__global__ void __launch_bounds__(1024)
+loop_emit_kernel(const LoopParams P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ long long s_off;                 // running survivor offset
+    __shared__ int s_cand;                      // running candidate count
+    __shared__ int wcnt[32];
+    __shared__ long long wsum[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_off = 0; s_cand = 0; }
+    __syncthreads();
+    for (int s0 = 0; s0 < P.nslots; s0 += 1024) {
+        const int s = s0 + threadIdx.x;
+        const int g = s < P.nslots ? P.slot_good[s] : 0;
+        const bool cand = s < P.nslots && g >= P.min_matches && g > 0;
+        // block-wide exclusive scan of (cand, g) in slot order
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        long long v = cand ? g : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) { wsum[warp] = incl; wcnt[warp] = __popc(bal); }
+        __syncthreads();
+        long long off = s_off;
+        int ci = s_cand;
+        for (int w2 = 0; w2 < warp; w2++) { off += wsum[w2]; ci += wcnt[w2]; }
+        off += incl - v;
+        ci += __popc(bal & ((1u << lane) - 1u));
+        if (s < P.nslots) P.slot_off[s] = cand ? off : -1;
+        if (cand && ci < P.cand_cap) {
+            LoopCand c = {P.slots[s].kf_pos, g, off};
+            P.out_cands[ci] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = 0;
+            int c = 0;
+            for (int w2 = 0; w2 < 32; w2++) { t += wsum[w2]; c += wcnt[w2]; }
+            s_off += t;
+            s_cand += c;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        P.out_head[0] = s_cand;
+        P.out_head[1] = (int32_t)(s_off < 0x7fffffffLL ? s_off : 0x7fffffffLL);
+        P.out_head[2] = (int32_t)P.counters[7];
+        P.out_head[3] = (int32_t)P.counters[5];
+    }
+    // lists: one warp per surviving keyframe, words in query order
+    for (int s = warp; s < P.nslots; s += 32) {
+        long long off = P.slot_off[s];
+        if (off < 0) continue;
+        for (int w = 0; w < P.words_per_slot; w++) {
+            const int64_t wi = (int64_t)s * P.words_per_slot + w;
+            const uint32_t m = P.masks[wi];
+            if (m == 0u) continue;
+            const uint32_t base = P.word_base[wi];
+            DMatch dm = {0, -1, 0, 0.f};
+            if ((m >> lane) & 1u) {
+                const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+                if (p < P.pair_cap) dm = P.stage[p];
+            }
+            const unsigned gb = __ballot_sync(0xffffffffu, dm.trainIdx >= 0);
+            const long long pos = off + __popc(gb & ((1u << lane) - 1u));
+            if (dm.trainIdx >= 0 && pos < P.match_cap) P.out_matches[pos] = dm;
+            off += __popc(gb);
+        }
+    }
+}
+
 // ---- match_features filter loop --------------------------------------------------
 // One block per pair.  good = lists with two entries whose best passes the fp32 ratio
 // test (and, if asked, the mutual-NN test); raw = every list with two entries.

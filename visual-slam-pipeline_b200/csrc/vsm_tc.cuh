@@ -38,7 +38,8 @@ constexpr uint32_t T_STAGE_BYTES = TILE_N * 128; // 32 KB: 256 rows x 64 bf16
 constexpr uint32_t SMEM_Q = 0;
 constexpr uint32_t SMEM_T = NCHUNK * Q_SUB_BYTES;                 // 65536
 constexpr uint32_t SMEM_BAR = SMEM_T + STAGES * T_STAGE_BYTES;    // 196608
-constexpr uint32_t SMEM_BYTES = SMEM_BAR + 512 + 1024;            // barriers + unit ring + alignment slack
+constexpr uint32_t SMEM_XCHG = SMEM_BAR + 512;                    // [2][128] float2: column-half exchange of fused units
+constexpr uint32_t SMEM_BYTES = SMEM_BAR + 512 + 2048 + 1024;     // barriers + unit ring, exchange, alignment slack
 constexpr int THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr uint32_t TMEM_COLS = 512;
@@ -446,6 +447,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                 // them that the ratio test fails or has the slice re-scanned exactly
                 float g0 = -INFINITY, g1 = -INFINITY;
                 int seg = 0, seg_tile = 0;
+                const bool fused = (u.maps & 8) != 0;
                 for (int n = 0; n < ntiles; n++, tile_it++) {
                     const int st = tile_it & 1;
                     mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
@@ -473,7 +475,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
                     if (!full_tile) mask32(rb, ucol + 96, u.t_count);
                     scan32_max2(g0, g1, rb);
-                    if (++seg_tile == u.seg_tiles || n == ntiles - 1) {
+                    if (!fused && (++seg_tile == u.seg_tiles || n == ntiles - 1)) {
                         if (row_valid) {
                             const float4 rec = make_float4(g0, g1, -INFINITY, -INFINITY);
                             *reinterpret_cast<float4*>(recs + u.rec_base + (int64_t)row * u.rec_stride + seg * 2 + half) = rec;
@@ -481,6 +483,32 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         seg++;
                         seg_tile = 0;
                         g0 = g1 = -INFINITY;
+                    }
+                }
+                if (fused) {
+                    // ----- the unit was one whole keyframe: decide here whether the ratio test can pass at all.
+                    // The two warps that own a row's column halves meet through shared memory (one named
+                    // barrier per quarter, two buffers alternating by unit); g0 is the exact maximum of the
+                    // keyframe, g1 a value of ANOTHER row -- the a0 / a1 of select_kernel's ratio-only test.
+                    float2* xb = reinterpret_cast<float2*>(smem_gen + SMEM_XCHG) + (ui & 1) * TILE_M;
+                    if (half == 1) xb[row] = make_float2(g0, g1);
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                    if (half == 0) {
+                        const float2 o = xb[row];
+                        const float a0 = fmaxf(g0, o.x);
+                        const float a1 = fmaxf(fminf(g0, o.x), fmaxf(g1, o.y));
+                        bool open = row_valid;
+                        if (row_valid && a1 > VALID_FLOOR) {
+                            const float qn2 = __ldg(u.q_n2 + row);
+                            float tmin2, tmax2;
+                            stats_read(u.t_stats, tmin2, tmax2);
+                            const float margin = dot_margin(qn2, tmin2, tmax2);
+                            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
+                            const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
+                            if (hi1 > 0.f && lo0 >= u.skip_ratio2 * hi1) open = false;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, open);
+                        if (lane == 0) u.hint[u.rec_base + quarter] = m;
                     }
                 }
                 continue;

@@ -94,6 +94,9 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p]),
     "vsm_loop_detect_shard": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                         C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "vsm_loop_detect_compact": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                          C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
+                                          C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "vsm_store_set_frame_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "vsm_match_batch_stored": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]),
@@ -171,7 +174,8 @@ class Matcher:
         m._owned = False
         return m
 
-    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0, ring=0):
+    def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0, ring=0,
+                 pair_cap=0):
         self._lib = load_library()
         o = _Opts()
         self._lib.vsm_default_opts(C.byref(o))
@@ -179,6 +183,7 @@ class Matcher:
         o.reserved[0] = seg_tiles
         o.reserved[1] = work_cap
         o.reserved[2] = ring
+        o.reserved[3] = pair_cap
         h = C.c_void_p()
         st = self._lib.vsm_create(C.byref(o), C.byref(h))
         if st != 0:
@@ -446,6 +451,30 @@ class Matcher:
         status = status[:nkf]
         lists = [m[s, :status[s]] if status[s] >= 0 else None for s in range(nkf)] if want_matches else None
         return status, lists, int(after.value)
+
+    def loop_detect_compact(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, min_matches=30,
+                            checked_before=0):
+        """LoopCloser::detect's candidate loop with the >= MIN_MATCHES gate on the device
+        (src/LoopCloser.cpp:43-62).  Returns (status[nkf], {keyframe position: DMATCH list} for the
+        keyframes that pass the gate, checked_after)."""
+        q = _rows(frame_desc, "frame_desc")
+        nkf = self.store_info()[1]
+        status = np.zeros(max(nkf, 1), np.int32)
+        cand_dt = np.dtype([("keyframe", "<i4"), ("count", "<i4"), ("offset", "<i8")])
+        cap_c, cap_m = 64, 64 * max(q.shape[0], 1)
+        while True:
+            cands = np.zeros(cap_c, cand_dt)
+            matches = np.zeros(cap_m, DMATCH)
+            nc, nm, after = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+            self._ck(self._lib.vsm_loop_detect_compact(self._h, cur_frame_id, min_gap, every, checked_before, q.ctypes.data,
+                                                       q.shape[0], ratio, min_matches, status.ctypes.data, cands.ctypes.data,
+                                                       cap_c, C.byref(nc), matches.ctypes.data, cap_m, C.byref(nm),
+                                                       C.byref(after)))
+            if nc.value <= cap_c and nm.value <= cap_m:
+                break
+            cap_c, cap_m = max(cap_c, nc.value), max(cap_m, nm.value)
+        out = {int(c["keyframe"]): matches[c["offset"]:c["offset"] + c["count"]].copy() for c in cands[:nc.value]}
+        return status[:nkf], out, int(after.value)
 
     def set_frame_ids(self, frame_ids):
         """Frame ids of the stored keyframes in store order (after adopt_device_matrix)."""
