@@ -593,7 +593,6 @@ def extra_pair_numbers(torch, vsm_b200, device):
     except Exception as e:                       # informational line: never lose the bench to it
         out["loop_closure_10k_kf_every5_compact"] = {"error": repr(e)[:300]}
     m.clear_store()
-    del db
     m.close()
     return out
 
@@ -836,7 +835,10 @@ def run_gpu(args):
                                     "kind": kind, "sample": f"{what}; {NQ} queries x {n}-row sample of the DB, {reps} repetitions"}
         if world == 1 and not args.no_extra:
             # free the big shard first: the pair configs need little memory
-            line["extra"] = extra_pair_numbers(torch, vsm_b200, local)
+            try:
+                line["extra"] = extra_pair_numbers(torch, vsm_b200, local)
+            except Exception as e:                       # informational numbers: the headline line is printed regardless
+                line["extra"] = {"error": repr(e)[:400]}
             if not args.no_cpu:
                 line["extra"]["cpu_pair_baselines"] = cpu_pair_baselines()
         print(json.dumps(line))

@@ -835,7 +835,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
         CK(launch_pdl(dump_first ? tc::tc_top3_kernel<true> : tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS),
                       tc::SMEM_BYTES, ctx->stream, ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits,
-                      d_unit_counter, ctx->d_recs.p, ctx->d_dump));
+                      (const uint32_t*)nullptr, d_unit_counter, ctx->d_recs.p, ctx->d_dump));
         ctx->launches++;
         if (ctx->profiling) {
             CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
@@ -1776,7 +1776,8 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
 }
 
 // ---- LoopCloser::detect, compact form ------------------------------------------------------------
-constexpr uint32_t PAIR_CAP = 1u << 18;          // open (query, keyframe) pairs per search: 4 MB of keys + 4 MB of staged matches
+constexpr uint32_t PAIR_CAP = 1u << 18;          // open (query, keyframe) pairs per search: 4 MB each of keys, references, staged matches
+constexpr uint32_t UNIT2_CAP = 8192;             // (keyframe, query tile) units of the second pass: 32 MB of records
 
 // The eligible keyframes (positions in get_keyframes() order) against the query frame: fused ratio
 // dismissal in the tensor-core epilogue, exact scans for the open pairs only, gate and packed lists on
@@ -1796,17 +1797,21 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     TRY(upload_scratch(ctx, query, 0, nq));
 
     // device layout
+    const uint32_t unit2_cap = UNIT2_CAP;
     const size_t nwords = (size_t)nslots * wps;
     const size_t o_mask = 0, o_base = align16(o_mask + nwords * 4), o_keys = align16(o_base + nwords * 4),
-                 o_stage = align16(o_keys + (size_t)pair_cap * 16), o_off = align16(o_stage + (size_t)pair_cap * sizeof(DMatch)),
-                 loop_bytes = align16(o_off + (size_t)nslots * 8);
+                 o_ref = align16(o_keys + (size_t)pair_cap * 16), o_stage = align16(o_ref + (size_t)pair_cap * sizeof(PairRef)),
+                 o_off = align16(o_stage + (size_t)pair_cap * sizeof(DMatch)), o_unit2 = align16(o_off + (size_t)nslots * 8),
+                 o_hint2 = align16(o_unit2 + (size_t)unit2_cap * sizeof(TcUnit)),
+                 loop_bytes = align16(o_hint2 + (size_t)unit2_cap * TILE_M * 4);
     TRY(ensure(ctx, ctx->d_loop, loop_bytes));
+    TRY(ensure(ctx, ctx->d_recs, (size_t)unit2_cap * TILE_M * 2));
     const size_t off_slot = 0, off_unit = align16(off_slot + sizeof(LoopSlot) * nslots),
                  total = align16(off_unit + sizeof(TcUnit) * (size_t)nslots * nqt);
     TRY(ensure(ctx, ctx->d_desc, total));
     TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
     TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
-    const size_t aux_bytes = align16(48 + (size_t)nslots * 4);                 // header + survivors per slot, zeroed per call
+    const size_t aux_bytes = align16(64 + (size_t)nslots * 4);                 // header + survivors per slot, zeroed per call
     TRY(ensure(ctx, ctx->d_aux, aux_bytes));
     if (ctx->aux_zeroed != ctx->d_aux.p) {
         CK(cudaMemsetAsync(ctx->d_aux.p, 0, ctx->d_aux.cap, ctx->stream));
@@ -1823,7 +1828,7 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     std::vector<uint8_t>& key = ctx->plan_key_build;
     {
         const int64_t head[6] = {nq, nslots, (int64_t)__float_as_uint_host(ratio), (int64_t)(uintptr_t)ctx->store.f32,
-                                 (int64_t)(uintptr_t)ctx->scratch.n2, (int64_t)(uintptr_t)ctx->d_store_stats};
+                                 (int64_t)(uintptr_t)ctx->scratch.n2, (int64_t)(uintptr_t)ctx->d_store_stats ^ ((int64_t)ctx->store.cap << 20)};
         key.resize(sizeof head + (size_t)nslots * sizeof(LoopSlot));
         memcpy(key.data(), head, sizeof head);
     }
@@ -1879,8 +1884,8 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
         const unsigned grid = (unsigned)std::min<size_t>(nunits, (size_t)ctx->num_sms);
         uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
         CK(launch_pdl(tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, ctx->stream, ctx->scratch.map,
-                      ctx->store.map, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, d_unit_counter,
-                      ctx->d_recs.p, ctx->d_dump));
+                      ctx->store.map, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, (const uint32_t*)nullptr,
+                      d_unit_counter, ctx->d_recs.p, ctx->d_dump));
         ctx->launches++;
         if (ctx->profiling) {
             CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
@@ -1890,40 +1895,58 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     LoopParams P;
     memset(&P, 0, sizeof P);
     P.slots = reinterpret_cast<const LoopSlot*>(dd + off_slot);
+    P.units = reinterpret_cast<const TcUnit*>(dd + off_unit);
     P.nslots = nslots; P.nq = nq; P.words_per_slot = wps;
     P.q_f32 = ctx->scratch.f32;
+    P.q_n2 = ctx->scratch.n2;
     P.store_f32 = ctx->store.f32;
+    P.t_stats = ctx->d_store_stats;
     P.masks = reinterpret_cast<const uint32_t*>(dl + o_mask);
     P.word_base = reinterpret_cast<uint32_t*>(dl + o_base);
     P.pair_keys = reinterpret_cast<unsigned long long*>(dl + o_keys);
+    P.pair_ref = reinterpret_cast<PairRef*>(dl + o_ref);
     P.stage = reinterpret_cast<DMatch*>(dl + o_stage);
     P.pair_cap = pair_cap;
+    P.units2 = reinterpret_cast<TcUnit*>(dl + o_unit2);
+    P.hints2 = reinterpret_cast<uint32_t*>(dl + o_hint2);
+    P.recs2 = ctx->d_recs.p;
+    P.unit2_cap = unit2_cap;
     P.counters = reinterpret_cast<uint32_t*>(ctx->d_aux.p);
     P.work = ctx->d_work.p;
     P.work_cap = ctx->work_cap;
-    P.slot_good = reinterpret_cast<int32_t*>(ctx->d_aux.p + 48);
+    P.slot_good = reinterpret_cast<int32_t*>(ctx->d_aux.p + 64);
     P.slot_off = reinterpret_cast<int64_t*>(dl + o_off);
     P.ratio = ratio;
+    P.skip_ratio2 = skip_r2(ratio);
     P.min_matches = min_matches;
     P.out_head = reinterpret_cast<int32_t*>(ctx->h_result + h_head);
+    P.out_good = reinterpret_cast<int32_t*>(ctx->h_result + h_good);
     P.out_cands = reinterpret_cast<LoopCand*>(ctx->h_result + h_cand);
     P.cand_cap = nslots;
     P.out_matches = reinterpret_cast<DMatch*>(ctx->h_result + h_match);
     P.match_cap = pair_cap;
+    const unsigned ublocks = (unsigned)std::max<size_t>(1, std::min<size_t>((nunits + 7) / 8, (size_t)ctx->num_sms * 8));
     const unsigned wblocks = (unsigned)std::max<size_t>(1, std::min<size_t>((nwords + 7) / 8, (size_t)ctx->num_sms * 8));
     ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
-    CK(launch_pdl(loop_open_plan_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));
+    CK(launch_pdl(loop_open_plan_kernel, dim3(ublocks), dim3(256), 0, ctx->stream, P));
+    {
+        // second tensor-core pass: only the units that hold an open pair (list and length built on the device)
+        const unsigned grid = (unsigned)std::min<size_t>(std::min<size_t>(nunits, unit2_cap), (size_t)ctx->num_sms);
+        CK(launch_pdl(tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, ctx->stream, ctx->scratch.map,
+                      ctx->store.map, (const TcUnit*)P.units2, (int)unit2_cap, (const uint32_t*)(P.counters + 12), P.counters + 13,
+                      ctx->d_recs.p, ctx->d_dump));
+    }
+    CK(launch_pdl(loop_select_kernel, dim3((unsigned)ctx->num_sms * 4), dim3(SELECT_WARPS * 32), 0, ctx->stream, P));
     CK(launch_pdl(rescan_kernel, dim3((unsigned)ctx->num_sms * 2), dim3(256), 0, ctx->stream, (const WorkItem*)ctx->d_work.p,
                   (const unsigned long long*)ctx->d_counters, ctx->work_cap));
     CK(launch_pdl(loop_finish_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));
     CK(launch_pdl(loop_emit_kernel, dim3(1), dim3(1024), 0, ctx->stream, P));
-    ctx->launches += 4;
+    ctx->launches += 6;
     if (ctx->profiling) {
         CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
         ctx->timed_sel = true;
     }
-    if (nslots) CK(cudaMemcpyAsync(ctx->h_result + h_good, P.slot_good, (size_t)nslots * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    TRY(end_call(ctx, true));
+    TRY(end_call(ctx, true));                                          // every output was written into pinned host memory
     const int32_t* head = reinterpret_cast<const int32_t*>(ctx->h_result + h_head);
     ctx->seg_open_rate = (float)(uint32_t)head[3] / (float)std::max<int64_t>((int64_t)nslots * nq, 1);
     if (head[2]) { *overflow = true; return VSM_OK; }

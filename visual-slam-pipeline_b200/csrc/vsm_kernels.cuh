@@ -451,10 +451,13 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
 }
 
 // ---- LoopCloser::detect, compact form (src/LoopCloser.cpp:43-62) ---------------------------------
-// The tensor-core pass (fused units, TcUnit maps bit 3) leaves one bit per (eligible keyframe, query):
-// "the ratio test could not be dismissed" = an OPEN pair.  Everything after it is O(open pairs):
-//   loop_open_plan_kernel  numbers the open pairs, zeroes their result keys, queues exact scans
-//   rescan_kernel          exact top-2 of the query inside the keyframe (canonical fp32 distances)
+// The first tensor-core pass (fused units, TcUnit maps bit 3) leaves one bit per (eligible keyframe,
+// query): "the ratio test could not be dismissed" = an OPEN pair.  Everything after it is O(open):
+//   loop_open_plan_kernel  numbers the open pairs and builds, ON THE DEVICE, the work-unit list of a
+//                          second tensor-core pass over the (keyframe, query tile) units that hold one
+//   tc_top3_kernel (again) those units with the ordinary top-4 epilogue: ~4 candidates per open pair
+//   loop_select_kernel     exact top-2 of every open pair from its candidates (canonical fp32 distance)
+//   rescan_kernel          exact scans for the rare pair whose four recorded entries overflowed
 //   loop_finish_kernel     ratio test per open pair (src/LoopCloser.cpp:55-60), survivors per keyframe
 //   loop_emit_kernel       the >= MIN_MATCHES gate (:62) and the surviving keyframes' lists, in query
 //                          order, packed -- nothing of size keyframes x queries ever exists
@@ -468,69 +471,178 @@ struct LoopCand {                      // mirrors vsm_loop_candidate
     int32_t count;
     int64_t offset;
 };
+struct PairRef {                       // one open (query, keyframe) pair
+    int32_t q, slot, unit2, pad;
+};
 struct LoopParams {
     const LoopSlot* slots;
+    const TcUnit* units;                       // first-pass units, [nslots][words_per_slot / 4]
     int32_t nslots, nq, words_per_slot;        // words_per_slot = 4 * query tiles
     const float* q_f32;                        // query rows (scratch arena)
+    const float* q_n2;
     const float* store_f32;
+    const uint32_t* t_stats;                   // norm statistics of the store
     const uint32_t* masks;                     // [nslots][words_per_slot]
     uint32_t* word_base;                       // [nslots][words_per_slot]: pair index of a word's first open bit
     unsigned long long* pair_keys;             // [pair_cap][2]
+    PairRef* pair_ref;                         // [pair_cap]
     DMatch* stage;                             // [pair_cap]: the pair's match, trainIdx = -1 if it fails the ratio test
     uint32_t pair_cap;
-    uint32_t* counters;                        // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag
+    TcUnit* units2;                            // [unit2_cap] second-pass units, built by loop_open_plan_kernel
+    uint32_t* hints2;                          // [unit2_cap][128]
+    const PartialRec* recs2;                   // [unit2_cap][128][2]
+    uint32_t unit2_cap;
+    // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag, [12] second-pass units
+    uint32_t* counters;
     WorkItem* work;
     uint32_t work_cap;
     int32_t* slot_good;                        // [nslots] survivors per eligible keyframe
     int64_t* slot_off;                         // [nslots] offset of its list in the output, -1 = below the gate
     float ratio;
+    float skip_ratio2;
     int32_t min_matches;
-    // outputs (pinned host memory for small results, else device)
+    // outputs (pinned host memory)
     int32_t* out_head;                         // [0] candidates, [1] survivors emitted, [2] overflow, [3] open pairs
+    int32_t* out_good;                         // [nslots] survivors per eligible keyframe (the caller's status array)
     LoopCand* out_cands;
     int32_t cand_cap;
     DMatch* out_matches;
     int64_t match_cap;
 };
 
+// One warp per first-pass unit (a keyframe x 128 queries = four mask words).
 __global__ void __launch_bounds__(256)
 loop_open_plan_kernel(const LoopParams P) {
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
-    const int64_t nwords = (int64_t)P.nslots * P.words_per_slot;
+    const int upk = P.words_per_slot / 4;
+    const int64_t nunits = (int64_t)P.nslots * upk;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += nwarps) {
-        const uint32_t m = P.masks[w];
-        if (m == 0u) continue;                                   // the usual case: no loop in sight
-        const int slot = (int)(w / P.words_per_slot);
-        const int q = (int)(w % P.words_per_slot) * 32 + lane;
-        uint32_t base = 0;
-        if (lane == 0) {
-            base = atomicAdd(P.counters + 5, (uint32_t)__popc(m));
-            P.word_base[w] = base;
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (!((m >> lane) & 1u)) continue;
-        const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
-        if (p >= P.pair_cap) { P.counters[7] = 1u; continue; }
-        P.pair_keys[2 * (size_t)p] = 0ull;
-        P.pair_keys[2 * (size_t)p + 1] = 0ull;
-        const LoopSlot sl = P.slots[slot];
-        const uint32_t nitem = (uint32_t)((sl.count + RESCAN_ROWS - 1) / RESCAN_ROWS);
-        const uint32_t wb = atomicAdd(P.counters + 4, nitem);
-        if (wb + nitem > P.work_cap) {
-            P.counters[7] = 1u;
-            for (uint32_t k = wb; k < P.work_cap && k < wb + nitem; k++) {       // void what this reservation still owns
-                WorkItem v = {nullptr, nullptr, nullptr, {0, 0, -1, 0}, 0, 0};
-                P.work[k] = v;
+    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < nunits; u += nwarps) {
+        const uint32_t mw = lane < 4 ? P.masks[u * 4 + lane] : 0u;
+        if (__ballot_sync(0xffffffffu, mw != 0u) == 0u) continue;      // the usual case: no loop in sight
+        const int slot = (int)(u / upk);
+        // a second-pass unit: the same rows and queries with the ordinary top-4 epilogue
+        uint32_t u2 = 0;
+        if (lane == 0) u2 = atomicAdd(P.counters + 12, 1u);
+        u2 = __shfl_sync(0xffffffffu, u2, 0);
+        const bool u2_ok = u2 < P.unit2_cap;
+        if (!u2_ok && lane == 0) P.counters[7] = 1u;
+        if (u2_ok) {
+            if (lane == 0) {
+                TcUnit t = P.units[u];
+                t.rec_base = (int64_t)u2 * TILE_M * 2;
+                t.rec_stride = 2;
+                t.seg_tiles = 64;                                       // one slice segment: the whole keyframe
+                t.maps = 2;                                             // train rows in the store; top-4 records
+                t.hint = P.hints2 + (size_t)u2 * TILE_M;
+                P.units2[u2] = t;
             }
-            continue;
+            reinterpret_cast<uint4*>(P.hints2 + (size_t)u2 * TILE_M)[lane] = make_uint4(0u, 0u, 0u, 0u);
         }
-        for (uint32_t k = 0; k < nitem; k++) {
-            WorkItem it = {P.q_f32 + (size_t)q * VSM_DIM, P.store_f32 + (size_t)sl.row0 * VSM_DIM, P.pair_keys + 2 * (size_t)p,
-                           {0, sl.count, -1, 0}, (int32_t)(k * RESCAN_ROWS), 0};
-            P.work[wb + k] = it;
+        for (int w = 0; w < 4; w++) {
+            const uint32_t m = __shfl_sync(0xffffffffu, mw, w);
+            if (m == 0u) continue;
+            const int64_t wi = u * 4 + w;
+            uint32_t base = 0;
+            if (lane == 0) {
+                base = atomicAdd(P.counters + 5, (uint32_t)__popc(m));
+                P.word_base[wi] = base;
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!((m >> lane) & 1u)) continue;
+            const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+            if (p >= P.pair_cap) { P.counters[7] = 1u; continue; }
+            PairRef r = {(int32_t)((u % upk) * TILE_M + w * 32 + lane), slot, u2_ok ? (int32_t)u2 : -1, 0};
+            P.pair_ref[p] = r;
+        }
+    }
+}
+
+// One warp per open pair: candidates of the second pass's two records (one per column half of the
+// keyframe) -> canonical fp32 distances -> the pair's exact top-2; a half whose four entries overflowed
+// is re-scanned exactly by rescan_kernel.
+__global__ void __launch_bounds__(SELECT_WARPS * 32)
+loop_select_kernel(const LoopParams P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
+    const unsigned full = 0xffffffffu;
+    const uint32_t npairs = min(P.counters[5], P.pair_cap);
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npairs; p += nwarps) {
+        const PairRef r = P.pair_ref[p];
+        unsigned long long* keys = P.pair_keys + 2 * (size_t)p;
+        if (r.unit2 < 0) { if (lane == 0) { keys[0] = 0ull; keys[1] = 0ull; } continue; }       // overflow: the call is repeated on the record path
+        const LoopSlot sl = P.slots[r.slot];
+        const PartialRec* rq = P.recs2 + ((size_t)r.unit2 * TILE_M + (r.q % TILE_M)) * 2;
+        // lanes 0..7 hold the eight recorded entries (two halves x top-4)
+        float v = -INFINITY;
+        if (lane < 8) v = rq[lane >> 2].s[lane & 3];
+        // the two largest of the eight
+        float a0 = v, a1 = -INFINITY;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const float b0 = __shfl_xor_sync(full, a0, o), b1 = __shfl_xor_sync(full, a1, o);
+            if (b0 > a0) { a1 = fmaxf(a0, b1); a0 = b0; } else a1 = fmaxf(a1, b0);
+        }
+        a0 = __shfl_sync(full, a0, 0);
+        a1 = __shfl_sync(full, a1, 0);
+        float tmin2, tmax2;
+        stats_read(P.t_stats, tmin2, tmax2);
+        const float qn2 = __ldg(P.q_n2 + r.q);
+        const float margin = dot_margin(qn2, tmin2, tmax2);
+        // with the true second-largest dot the ratio-only test is sharper than the first pass's
+        if (P.skip_ratio2 > 0.f && a1 > VALID_FLOOR) {
+            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
+            const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
+            if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) {
+                if (lane == 0) { keys[0] = 0ull; keys[1] = 0ull; }
+                continue;
+            }
+        }
+        const float thr = a1 - 2.f * margin;
+        // a half is flagged when its 4th entry is still above the threshold: a needed row may have been displaced
+        const float v3a = __shfl_sync(full, v, 3), v3b = __shfl_sync(full, v, 7);
+        const bool flag_a = v3a > VALID_FLOOR && v3a > thr, flag_b = v3b > VALID_FLOOR && v3b > thr;
+        const bool mine_flagged = (lane >> 2) ? flag_b : flag_a;
+        const bool is_cand = lane < 8 && !mine_flagged && v > VALID_FLOOR && v > thr;
+        const uint32_t c = __float_as_uint(v) & ~PACK_MASK;
+        const int32_t row = (int32_t)(c / HALF_N) * TILE_N + (lane >> 2) * HALF_N + (int32_t)(c % HALF_N);
+        unsigned cm = __ballot_sync(full, is_cand);
+        float qreg[16];
+        load_qreg(qreg, P.q_f32 + (size_t)r.q * VSM_DIM, l16);
+        const float* t_f32 = P.store_f32 + (size_t)sl.row0 * VSM_DIM;
+        Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
+        while (cm) {                                             // two candidates per round, one per half-warp
+            const int l0 = __ffs(cm) - 1;
+            cm &= cm - 1;
+            int l1 = -1;
+            if (cm) { l1 = __ffs(cm) - 1; cm &= cm - 1; }
+            const int32_t j0 = __shfl_sync(full, row, l0);
+            const int32_t j1 = __shfl_sync(full, row, l1 < 0 ? 0 : l1);
+            score_pair(qreg, t_f32, h == 0 ? j0 : (l1 < 0 ? -1 : j1), l16, best);
+        }
+        const float od0 = __shfl_sync(full, best.d0, 16), od1 = __shfl_sync(full, best.d1, 16);
+        const int32_t oi0 = __shfl_sync(full, best.i0, 16), oi1 = __shfl_sync(full, best.i1, 16);
+        if (lane == 0) {
+            if (oi0 >= 0) insert2(od0, oi0, best.d0, best.i0, best.d1, best.i1);
+            if (oi1 >= 0) insert2(od1, oi1, best.d0, best.i0, best.d1, best.i1);
+            keys[0] = best.i0 >= 0 ? result_key(best.d0, best.i0) : 0ull;      // plain stores: rescan_kernel runs after this kernel
+            keys[1] = best.i1 >= 0 ? result_key(best.d1, best.i1) : 0ull;
+            for (int hf = 0; hf < 2; hf++) {
+                if (!(hf ? flag_b : flag_a)) continue;
+                const SliceInfo si = {0, sl.count, hf, 0};
+                const uint32_t nitem = (uint32_t)((slice_span(si) + RESCAN_ROWS - 1) / RESCAN_ROWS);
+                const uint32_t wb = atomicAdd(P.counters + 4, nitem);
+                const bool fits = wb + nitem <= P.work_cap;
+                if (!fits) P.counters[7] = 1u;
+                for (uint32_t k = 0; k < nitem && wb + k < P.work_cap; k++) {
+                    WorkItem it = {P.q_f32 + (size_t)r.q * VSM_DIM, t_f32, fits ? keys : nullptr, si, (int32_t)(k * RESCAN_ROWS), 0};
+                    P.work[wb + k] = it;
+                }
+            }
         }
     }
 }
@@ -573,16 +685,20 @@ __global__ void __launch_bounds__(1024)
 loop_emit_kernel(const LoopParams P) {
     pdl_launch_dependents();
     pdl_wait();
+    constexpr int LIST_CAP = 1024;              // candidate keyframes remembered in shared memory (more: found again by scanning)
     __shared__ long long s_off;                 // running survivor offset
     __shared__ int s_cand;                      // running candidate count
     __shared__ int wcnt[32];
     __shared__ long long wsum[32];
+    __shared__ int c_slot[LIST_CAP];
+    __shared__ long long c_off[LIST_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { s_off = 0; s_cand = 0; }
     __syncthreads();
     for (int s0 = 0; s0 < P.nslots; s0 += 1024) {
         const int s = s0 + threadIdx.x;
         const int g = s < P.nslots ? P.slot_good[s] : 0;
+        if (s < P.nslots) P.out_good[s] = g;
         const bool cand = s < P.nslots && g >= P.min_matches && g > 0;
         // block-wide exclusive scan of (cand, g) in slot order
         const unsigned bal = __ballot_sync(0xffffffffu, cand);
@@ -600,10 +716,15 @@ loop_emit_kernel(const LoopParams P) {
         for (int w2 = 0; w2 < warp; w2++) { off += wsum[w2]; ci += wcnt[w2]; }
         off += incl - v;
         ci += __popc(bal & ((1u << lane) - 1u));
-        if (s < P.nslots) P.slot_off[s] = cand ? off : -1;
-        if (cand && ci < P.cand_cap) {
-            LoopCand c = {P.slots[s].kf_pos, g, off};
-            P.out_cands[ci] = c;
+        if (cand) {
+            if (ci < P.cand_cap) {
+                LoopCand c = {P.slots[s].kf_pos, g, off};
+                P.out_cands[ci] = c;
+            }
+            if (ci < LIST_CAP) { c_slot[ci] = s; c_off[ci] = off; P.slot_off[s] = -1; }
+            else P.slot_off[s] = off;
+        } else if (s < P.nslots) {
+            P.slot_off[s] = -1;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -622,9 +743,7 @@ loop_emit_kernel(const LoopParams P) {
         P.out_head[3] = (int32_t)P.counters[5];
     }
     // lists: one warp per surviving keyframe, words in query order
-    for (int s = warp; s < P.nslots; s += 32) {
-        long long off = P.slot_off[s];
-        if (off < 0) continue;
+    auto emit = [&](int s, long long off) {
         for (int w = 0; w < P.words_per_slot; w++) {
             const int64_t wi = (int64_t)s * P.words_per_slot + w;
             const uint32_t m = P.masks[wi];
@@ -640,7 +759,14 @@ loop_emit_kernel(const LoopParams P) {
             if (dm.trainIdx >= 0 && pos < P.match_cap) P.out_matches[pos] = dm;
             off += __popc(gb);
         }
-    }
+    };
+    const int ncand = s_cand;
+    for (int c = warp; c < min(ncand, LIST_CAP); c += 32) emit(c_slot[c], c_off[c]);
+    if (ncand > LIST_CAP)                                   // the rest were marked in slot_off
+        for (int s = warp; s < P.nslots; s += 32) {
+            const long long off = P.slot_off[s];
+            if (off >= 0) emit(s, off);
+        }
 }
 
 // ---- match_features filter loop --------------------------------------------------

@@ -278,8 +278,8 @@ __device__ __forceinline__ void mask32(uint32_t (&r)[32], int32_t ucol0, int32_t
 template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_constant__ CUtensorMap map_store,
-               const TcUnit* __restrict__ units, int nunits, uint32_t* __restrict__ work_counter,
-               PartialRec* __restrict__ recs, float* __restrict__ dump) {
+               const TcUnit* __restrict__ units, int nunits_host, const uint32_t* __restrict__ nunits_dev,
+               uint32_t* __restrict__ work_counter, PartialRec* __restrict__ recs, float* __restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -337,6 +337,9 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         if (lane == 0) {
             int slot = 0;
             uint32_t ph = 0;
+            // the unit list may have been built on the device (second pass of the compact loop search): its
+            // length is then read here, after the producer kernel has completed
+            const int nunits = nunits_dev ? min((int)*nunits_dev, nunits_host) : nunits_host;
             // the queue is read one unit ahead: the atomic and the descriptor load of unit i+1 are
             // in flight while unit i streams, so a unit boundary costs no L2 round trips
             int idx = (int)atomicAdd(work_counter, 1u);
