@@ -396,6 +396,12 @@ int vsm_group_db_top2(vsm_group* g, const float* query, int32_t nq, int64_t* idx
  * live keyframes in insertion order (= handle while nothing has been removed). */
 int vsm_group_loop_detect(vsm_group* g, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
                           int32_t nq, float ratio, int32_t* status, vsm_dmatch* matches);
+/* vsm_loop_detect_compact over the group's list: each member gates and packs on its own device, the
+ * host orders the surviving keyframes by list position (cands[k].keyframe). */
+int vsm_group_loop_detect_compact(vsm_group* g, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
+                                  int32_t nq, float ratio, int32_t min_matches, int32_t* status, vsm_loop_candidate* cands,
+                                  int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches, int64_t match_cap,
+                                  int64_t* n_matches);
 
 /* Raw CUDA stream of the context (cudaStream_t as void*), for event timing. */
 void* vsm_stream(vsm_ctx* ctx);

@@ -50,6 +50,13 @@ def test_group_search_and_loop_detect_equal_oracle(devices):
         for s in range(nkf):
             if ost[s] >= 0:
                 assert lists[s].tobytes() == ol[s].tobytes(), s
+        # the compact form: gate and packing on the members' devices, candidates ordered by list position
+        for mm in (30, 1):
+            cst, clists = g.loop_detect_compact(cur_id, q, 0.75, min_gap=200, every=3, min_matches=mm)
+            assert np.array_equal(cst, ost)
+            assert set(clists) == {s for s in range(nkf) if ost[s] >= mm}
+            for s in clists:
+                assert clists[s].tobytes() == ol[s].tobytes(), s
         # pageable and pinned query buffers give the same answer
         import torch
         pq = torch.from_numpy(q).pin_memory().numpy()

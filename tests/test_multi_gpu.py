@@ -83,6 +83,21 @@ def _worker(rank, world, port, exchange, out):
                     fails.append(f"loop_detect list of keyframe {g} differs")
             elif g in mine:
                 fails.append(f"keyframe {g} should have been skipped")
+        # the compact form (gate on the device) and the host-buffer collective search (one C-ABI call per rank)
+        whole_c, mine_c = sdb.loop_detect_compact(cur_id, q, 0.75, gap, every, min_matches=20)
+        if not np.array_equal(whole_c.numpy(), ost):
+            fails.append(f"loop_detect_compact status differs (cur {cur_id})")
+        want_c = {g for g in range(k0, k1) if ost[g] >= 20}
+        if set(mine_c) != want_c:
+            fails.append(f"loop_detect_compact candidates differ (cur {cur_id})")
+        for g in want_c & set(mine_c):
+            want = ol[g].copy()
+            want["imgIdx"] = g
+            if mine_c[g].tobytes() != want.tobytes():
+                fails.append(f"loop_detect_compact list of keyframe {g} differs")
+    ai, ad = sdb.search_host_abi(q)
+    if not (np.array_equal(ai, wi.astype(np.int64)) and np.array_equal(ad.view(np.uint32), wd.view(np.uint32))):
+        fails.append("search_host_abi (vsm_db_top2_xchg) differs")
     # more ranks than keyframes: one rank holds an empty shard and still takes part in the exchange
     one = np.array([0, int(seg_off[7 + 1] - seg_off[7])], np.int64)
     db1 = db[seg_off[7]:seg_off[8]]

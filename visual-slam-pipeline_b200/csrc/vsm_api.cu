@@ -1981,29 +1981,24 @@ static int loop_eligible(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, in
     return any;
 }
 
-int vsm_loop_detect_compact(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, int32_t checked_before,
-                            const float* query, int32_t nq, float ratio, int32_t min_matches, int32_t* status,
-                            vsm_loop_candidate* cands, int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches,
-                            int64_t match_cap, int64_t* n_matches, int32_t* checked_after) {
-    if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || checked_before < 0 || cand_cap < 0 || match_cap < 0 ||
-        !n_cands || !n_matches || (cand_cap > 0 && !cands) || (match_cap > 0 && !matches))
-        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect_compact: bad argument") : VSM_ERR_INVALID;
-    static_assert(sizeof(vsm_loop_candidate) == sizeof(LoopCand), "vsm_loop_candidate layout");
+// The compact search over the keyframes with eligible[s] != 0 (positions in get_keyframes() order);
+// status[s] of those keyframes is set; cands / matches as in vsm_loop_detect_compact.
+static int loop_compact_eligible(vsm_ctx* ctx, const std::vector<char>& eligible, const float* query, int32_t nq, float ratio,
+                                 int32_t min_matches, int32_t* status, vsm_loop_candidate* cands, int32_t cand_cap,
+                                 int32_t* n_cands, vsm_dmatch* matches, int64_t match_cap, int64_t* n_matches) {
     *n_cands = 0;
     *n_matches = 0;
-    std::vector<char> eligible;
-    const int any = loop_eligible(ctx, cur_frame_id, min_gap, every, checked_before, eligible, status, checked_after);
-    if (nq == 0 || !any) return VSM_OK;                               // :22 (empty current frame)
     std::vector<int32_t> pos;
     bool fits = ctx->engine != VSM_ENGINE_SIMT && ctx->engine != VSM_ENGINE_TENSOR_PAIR;
     for (int s = 0; s < (int)eligible.size(); s++) {
         if (!eligible[s]) continue;
         const int32_t cnt = ctx->segs[ctx->kf_order[s]].count;
+        status[s] = 0;
         if (cnt < 2) continue;                                        // no two-entry list, no survivor (:57): status stays 0
         if (cnt > UNIT_TILES * TILE_N) fits = false;                  // a keyframe must be one work unit
         pos.push_back(s);
     }
-    if (pos.empty()) return VSM_OK;
+    if (pos.empty() || nq == 0) return VSM_OK;
     bool overflow = !fits;
     if (fits)
         TRY(loop_compact_impl(ctx, query, nq, ratio, min_matches, pos, status, cands, cand_cap, n_cands, matches, match_cap,
@@ -2030,6 +2025,23 @@ int vsm_loop_detect_compact(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap,
     *n_cands = nc;
     *n_matches = nm;
     return VSM_OK;
+}
+
+int vsm_loop_detect_compact(vsm_ctx* ctx, int32_t cur_frame_id, int32_t min_gap, int32_t every, int32_t checked_before,
+                            const float* query, int32_t nq, float ratio, int32_t min_matches, int32_t* status,
+                            vsm_loop_candidate* cands, int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches,
+                            int64_t match_cap, int64_t* n_matches, int32_t* checked_after) {
+    if (!ctx || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || checked_before < 0 || cand_cap < 0 || match_cap < 0 ||
+        !n_cands || !n_matches || (cand_cap > 0 && !cands) || (match_cap > 0 && !matches))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_loop_detect_compact: bad argument") : VSM_ERR_INVALID;
+    static_assert(sizeof(vsm_loop_candidate) == sizeof(LoopCand), "vsm_loop_candidate layout");
+    *n_cands = 0;
+    *n_matches = 0;
+    std::vector<char> eligible;
+    const int any = loop_eligible(ctx, cur_frame_id, min_gap, every, checked_before, eligible, status, checked_after);
+    if (nq == 0 || !any) return VSM_OK;                               // :22 (empty current frame)
+    return loop_compact_eligible(ctx, eligible, query, nq, ratio, min_matches, status, cands, cand_cap, n_cands, matches,
+                                 match_cap, n_matches);
 }
 
 int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_xy, const float* desc, int32_t nkp,

@@ -464,3 +464,91 @@ int vsm_group_loop_detect(vsm_group* g, int32_t cur_frame_id, int32_t min_gap, i
         }
     return VSM_OK;
 }
+
+// The same loop in compact form (vsm_loop_detect_compact): every member gates and packs the lists of
+// its own keyframes on its device; the host orders the surviving keyframes by list position.
+int vsm_group_loop_detect_compact(vsm_group* g, int32_t cur_frame_id, int32_t min_gap, int32_t every, const float* query,
+                                  int32_t nq, float ratio, int32_t min_matches, int32_t* status, vsm_loop_candidate* cands,
+                                  int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches, int64_t match_cap,
+                                  int64_t* n_matches) {
+    if (!g || nq < 0 || (nq > 0 && !query) || !status || every <= 0 || cand_cap < 0 || match_cap < 0 || !n_cands || !n_matches ||
+        (cand_cap > 0 && !cands) || (match_cap > 0 && !matches))
+        return g ? group_fail(g, VSM_ERR_INVALID, "vsm_group_loop_detect_compact: bad argument") : VSM_ERR_INVALID;
+    g->err.clear();
+    *n_cands = 0;
+    *n_matches = 0;
+    std::vector<int32_t> live;
+    for (int32_t h = 0; h < (int32_t)g->kfs.size(); h++) if (g->kfs[h].live) live.push_back(h);
+    const int nkf = (int)live.size();
+    std::vector<std::vector<char>> elig(g->n);
+    std::vector<std::vector<int32_t>> st(g->n), pos_of(g->n), local_pos(g->n);
+    for (int r = 0; r < g->n; r++) {
+        vsm_ctx* ctx = g->ctx[r];
+        const int ln = (int)ctx->kf_order.size();
+        elig[r].assign(ln, 0);
+        st[r].assign(std::max(ln, 1), -1);
+        pos_of[r].assign(ln, -1);
+        local_pos[r].assign(ctx->segs.size(), -1);
+        for (int k = 0; k < ln; k++) local_pos[r][ctx->kf_order[k]] = k;
+    }
+    int checked = 0;
+    bool any = false;
+    for (int s = 0; s < nkf; s++) {                                       // src/LoopCloser.cpp:43-48
+        const GKeyframe& k = g->kfs[live[s]];
+        status[s] = -1;
+        const int lp = local_pos[k.member][k.local_handle];
+        pos_of[k.member][lp] = s;
+        if (cur_frame_id - g->ctx[k.member]->segs[k.local_handle].frame_id < min_gap) continue;
+        if (k.count == 0) continue;
+        checked++;
+        if (checked % every != 0) continue;
+        elig[k.member][lp] = 1;
+        status[s] = 0;
+        any = true;
+    }
+    if (nq == 0 || !any) return VSM_OK;
+    const float* staged = nullptr;
+    TRY(group_stage_query(g, query, nq, &staged));
+    struct Part { std::vector<vsm_loop_candidate> c; std::vector<vsm_dmatch> m; int32_t nc = 0; int64_t nm = 0; };
+    std::vector<Part> part(g->n);
+    TRY(group_fan_out(g, [&](int r) -> int {
+        vsm_ctx* ctx = g->ctx[r];
+        bool mine = false;
+        for (char e : elig[r]) mine |= e != 0;
+        if (!mine) return VSM_OK;
+        Part& p = part[r];
+        p.c.resize(64);
+        p.m.resize((size_t)64 * std::max(nq, 1));
+        for (;;) {                                                        // grow the member's buffers if a search returns more
+            TRY(loop_compact_eligible(ctx, elig[r], staged, nq, ratio, min_matches, st[r].data(), p.c.data(), (int32_t)p.c.size(),
+                                      &p.nc, p.m.data(), (int64_t)p.m.size(), &p.nm));
+            if (p.nc <= (int32_t)p.c.size() && p.nm <= (int64_t)p.m.size()) return VSM_OK;
+            p.c.resize(std::max<size_t>(p.c.size(), (size_t)p.nc));
+            p.m.resize(std::max<size_t>(p.m.size(), (size_t)p.nm));
+        }
+    }));
+    // surviving keyframes of all members in list order
+    struct Ref { int32_t pos, member, k; };
+    std::vector<Ref> refs;
+    for (int r = 0; r < g->n; r++) {
+        for (size_t k = 0; k < elig[r].size(); k++) if (elig[r][k]) status[pos_of[r][k]] = st[r][k];
+        for (int k = 0; k < part[r].nc; k++) refs.push_back(Ref{pos_of[r][part[r].c[k].keyframe], r, k});
+    }
+    std::sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) { return a.pos < b.pos; });
+    int64_t nm = 0;
+    int nc = 0;
+    for (const Ref& f : refs) {
+        const vsm_loop_candidate& c = part[f.member].c[f.k];
+        if (nc < cand_cap) cands[nc] = vsm_loop_candidate{f.pos, c.count, nm};
+        for (int i = 0; i < c.count; i++)
+            if (nm + i < match_cap) {
+                matches[nm + i] = part[f.member].m[(size_t)c.offset + i];
+                matches[nm + i].imgIdx = f.pos;
+            }
+        nc++;
+        nm += c.count;
+    }
+    *n_cands = nc;
+    *n_matches = nm;
+    return VSM_OK;
+}

@@ -17,6 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DMATCH = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+CAND = np.dtype([("keyframe", "<i4"), ("count", "<i4"), ("offset", "<i8")])       # vsm_loop_candidate
 ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT, ENGINE_TENSOR_PAIR = 0, 1, 2, 3
 DIM = 256
 
@@ -123,6 +124,9 @@ SYMBOLS = {
     "vsm_group_db_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vsm_group_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                                         C.c_void_p, C.c_void_p]),
+    "vsm_group_loop_detect_compact": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
+                                                C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                                C.c_int64, C.POINTER(C.c_int64)]),
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
     "vsm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsm_sync": (C.c_int, [C.c_void_p]),
@@ -460,10 +464,9 @@ class Matcher:
         q = _rows(frame_desc, "frame_desc")
         nkf = self.store_info()[1]
         status = np.zeros(max(nkf, 1), np.int32)
-        cand_dt = np.dtype([("keyframe", "<i4"), ("count", "<i4"), ("offset", "<i8")])
         cap_c, cap_m = 64, 64 * max(q.shape[0], 1)
         while True:
-            cands = np.zeros(cap_c, cand_dt)
+            cands = np.zeros(cap_c, CAND)
             matches = np.zeros(cap_m, DMATCH)
             nc, nm, after = C.c_int32(0), C.c_int64(0), C.c_int32(0)
             self._ck(self._lib.vsm_loop_detect_compact(self._h, cur_frame_id, min_gap, every, checked_before, q.ctypes.data,
@@ -631,6 +634,25 @@ class Group:
                                              kh.ctypes.data if want_keyframes else None,
                                              kr.ctypes.data if want_keyframes else None))
         return (idx, dist, kh, kr) if want_keyframes else (idx, dist)
+
+    def loop_detect_compact(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, min_matches=30):
+        """LoopCloser::detect's loop with the gate on the devices: (status[nkf], {keyframe position: list})."""
+        q = _rows(frame_desc, "frame_desc")
+        nkf = self.store_info()[1]
+        status = np.zeros(max(nkf, 1), np.int32)
+        cap_c, cap_m = 64, 64 * max(q.shape[0], 1)
+        while True:
+            cands = np.zeros(cap_c, CAND)
+            matches = np.zeros(cap_m, DMATCH)
+            nc, nm = C.c_int32(0), C.c_int64(0)
+            self._ck(self._lib.vsm_group_loop_detect_compact(self._g, cur_frame_id, min_gap, every, q.ctypes.data, q.shape[0],
+                                                             ratio, min_matches, status.ctypes.data, cands.ctypes.data, cap_c,
+                                                             C.byref(nc), matches.ctypes.data, cap_m, C.byref(nm)))
+            if nc.value <= cap_c and nm.value <= cap_m:
+                break
+            cap_c, cap_m = max(cap_c, nc.value), max(cap_m, nm.value)
+        out = {int(c["keyframe"]): matches[c["offset"]:c["offset"] + c["count"]].copy() for c in cands[:nc.value]}
+        return status[:nkf], out
 
     def loop_detect(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, want_matches=True):
         q = _rows(frame_desc, "frame_desc")

@@ -159,6 +159,28 @@ class ShardedDB:
         mine = {k0 + s: lists[s] for s in range(len(st)) if lists is not None and lists[s] is not None}
         return whole, mine
 
+    def loop_detect_compact(self, cur_frame_id, h_q, ratio=0.75, min_gap=200, every=5, min_matches=30):
+        """The same loop in compact form (vsm_loop_detect_compact): gate and packing on each rank's device.
+        Returns (status of the WHOLE list [CPU int32], {global keyframe index: match list} of this rank's
+        keyframes that pass the gate)."""
+        k0 = self._kf_cuts[self.rank]
+        before = loop_checked_before(cur_frame_id, self._kf_ids, self._kf_counts, min_gap, k0)
+        if self.rows == 0:
+            st, lists = [], {}
+        else:
+            st, lists, _ = self.matcher.loop_detect_compact(cur_frame_id, h_q, ratio, min_gap, every, min_matches,
+                                                            checked_before=before)
+        nkf = [self._kf_cuts[r + 1] - self._kf_cuts[r] for r in range(self.world)]
+        import numpy as np
+        st_t = torch.from_numpy(np.asarray(st, np.int32)).to(self.device if self.world > 1 else "cpu")
+        whole = concat_keyframe_status(st_t, nkf, self.world, self.group)
+        out = {}
+        for s, lst in lists.items():
+            lst = lst.copy()
+            lst["imgIdx"] = k0 + s
+            out[k0 + s] = lst
+        return whole, out
+
     def _buffers(self, nq):
         """Per-batch-size device and pinned buffers.  They are only ever used on self.stream through raw
         pointers, so they are allocated under that stream (the caching allocator then orders any reuse
