@@ -17,7 +17,7 @@
  *     throws.  vsm_last_error(ctx) gives the message of the last failure.
  *   - descriptors are row-major fp32, 256 columns, contiguous rows (row stride =
  *     1024 B), exactly what FeatureExtractor produces
- *     (src/FeatureExtractor.cpp:170-205).
+ *     (src/FeatureExtractor.cpp:170-205); the *_strided entry points take a row stride.
  *   - the caller owns all host buffers; the library copies in and never keeps a
  *     host pointer after returning.  Output arrays are caller-allocated.
  *   - results equal cv::BFMatcher(NORM_L2).knnMatch on the same input: identical
@@ -123,6 +123,15 @@ int vsm_match_pair(vsm_ctx* ctx, const float* query, int32_t nq, const float* tr
                    float ratio, int32_t mutual,
                    vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw);
 
+/* The same two calls for rows that are NOT contiguous -- a cv::Mat ROI or any Mat with step > cols * 4
+ * (cv::Mat::step): *_stride = bytes from one row to the next, >= 1024 and a multiple of 4.  The rows are
+ * packed by one strided DMA; no host copy. */
+int vsm_knn2_strided(vsm_ctx* ctx, const float* query, int32_t nq, int64_t q_stride, const float* train, int32_t nt,
+                     int64_t t_stride, int32_t* idx, float* dist);
+int vsm_match_pair_strided(vsm_ctx* ctx, const float* query, int32_t nq, int64_t q_stride, const float* train, int32_t nt,
+                           int64_t t_stride, float ratio, int32_t mutual,
+                           vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw);
+
 /* Ragged batch of independent pairs in one launch (BASELINE configs[4]).
  * query/train: concatenated rows; q_off/t_off: n_pairs+1 row offsets.
  * good: concatenated, pair p's survivors start at good[q_off[p]]; n_good[p] entries. */
@@ -153,6 +162,8 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs,
  * uploads the N x 256 descriptor matrix once; fp32 master + bf16 shadow live on
  * the device.  *handle identifies the frame. */
 int vsm_store_add(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int32_t* handle);
+/* vsm_store_add for a descriptor matrix with a row stride (cv::Mat::step), >= 1024 bytes. */
+int vsm_store_add_strided(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int64_t stride_bytes, int32_t* handle);
 /* Frame::set_keyframe(true) for a frame stored by vsm_track: it joins the keyframes at its own
  * position in insertion order (a bridge keyframe promoted late, src/Slam.cpp:851-863, included). */
 int vsm_store_promote(vsm_ctx* ctx, int32_t handle);
@@ -222,6 +233,31 @@ int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
  * matrix the reference builds (ascending row).  -1 / FLT_MAX when fewer than k rows are selected. */
 int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8_t* mask, int64_t n_mask,
                        int64_t* idx, float* dist);
+
+/* ---- resident map-point table (Map::map_points_, include/MapPoint.h) -------------------------------
+ * The reference re-stacks the descriptors of the selected map points into a fresh cv::Mat on every
+ * search (src/Slam.cpp:552-557, :744-759) -- O(map) host work per call.  Here a point's descriptor, its
+ * valid_ flag and its observations_ live on the device from birth; a search selects, compacts (ascending
+ * point id = the order of the reference's loop) and gathers on the device, nothing is uploaded but the frame.
+ *   vsm_points_add            MapPoint(id, pos, desc) + add_observation(frame_id, .) (src/Slam.cpp:1342-1345,
+ *                             :1566-1568); ids are 0, 1, 2 ... like the reference's next_id
+ *   vsm_points_add_from_frame the same with desc = row kp_idx[i] of a stored frame (row(i).clone(), :1339, :1563):
+ *                             a device-to-device copy; the first observation is that frame's id
+ *   vsm_points_observe        MapPoint::add_observation (src/Slam.cpp:463)
+ *   vsm_points_set_valid      MapPoint::set_valid (src/Slam.cpp:490, :496, :1119, :1123)
+ *   vsm_points_top2           knnMatch(frame, stack of the selected points, 2): selected = valid, and -- when
+ *                             near_frame_id >= 0 -- observed in a frame f with |f - near_frame_id| < range
+ *                             (Config::LC_NEARBY_FRAME_RANGE, :749-754).  idx = POINT IDS (mp_ids_vec[trainIdx],
+ *                             :768), -1 = fewer than k points selected; *n_selected = rows of the stacked matrix
+ *                             (the reference's `all_mp_descs.rows >= 50` / `mp_descs.rows >= 20` gates, :561, :760). */
+int vsm_points_add(vsm_ctx* ctx, const float* desc, int32_t n, int32_t frame_id, int32_t* first_id);
+int vsm_points_add_from_frame(vsm_ctx* ctx, int32_t handle, const int32_t* kp_idx, int32_t n, int32_t* first_id);
+int vsm_points_observe(vsm_ctx* ctx, const int32_t* point_ids, int32_t n, int32_t frame_id);
+int vsm_points_set_valid(vsm_ctx* ctx, const int32_t* point_ids, int32_t n, int32_t valid);
+int vsm_points_info(const vsm_ctx* ctx, int64_t* n_points, int64_t* n_valid, int64_t* n_observations);
+int vsm_points_clear(vsm_ctx* ctx);
+int vsm_points_top2(vsm_ctx* ctx, const float* query, int32_t nq, int32_t near_frame_id, int32_t range, int64_t* idx,
+                    float* dist, int32_t* n_selected);
 
 /* ---- projected-window map-point tracking (Slam::track_local_map, src/Slam.cpp:380-469) ---------
  * For every valid map point: project it with the frame pose (fp64, :417-428), take the keypoints

@@ -67,6 +67,7 @@ static_assert(sizeof(DMatch) == sizeof(vsm_dmatch), "cv::DMatch must be the 16-b
 
 class DescriptorMatcher {
 public:
+    /* One GPU (like the reference's matcher_l2_ member, include/Slam.h:197). */
     explicit DescriptorMatcher(int device = 0, int engine = VSM_ENGINE_AUTO) {
         vsm_opts o;
         vsm_default_opts(&o);
@@ -74,27 +75,44 @@ public:
         o.engine = engine;
         if (vsm_create(&o, &ctx_) != VSM_OK) throw std::runtime_error(std::string("vsm_create: ") + vsm_last_error(nullptr));
     }
-    ~DescriptorMatcher() { vsm_destroy(ctx_); }
+    /* Several GPUs behind this one object: the keyframe database (add_keyframe / search_store /
+     * detect_loop) is dealt to the devices by whole keyframes and searched on all of them per call
+     * (vsm_group_*); pair matching and tracking run on the first device.  The caller stays a single
+     * thread, like the reference's slam_thread (src/main.cpp:1520). */
+    explicit DescriptorMatcher(const std::vector<int>& devices, int engine = VSM_ENGINE_AUTO) {
+        vsm_opts o;
+        vsm_default_opts(&o);
+        o.engine = engine;
+        std::vector<int32_t> d(devices.begin(), devices.end());
+        if (vsm_group_create(d.data(), (int32_t)d.size(), &o, &group_) != VSM_OK)
+            throw std::runtime_error(std::string("vsm_group_create: ") + vsm_group_last_error(nullptr));
+        ctx_ = vsm_group_ctx(group_, 0);
+    }
+    ~DescriptorMatcher() {
+        if (group_) vsm_group_destroy(group_);
+        else vsm_destroy(ctx_);
+    }
     DescriptorMatcher(const DescriptorMatcher&) = delete;
     DescriptorMatcher& operator=(const DescriptorMatcher&) = delete;
 
     /* Slam::match_features for float descriptors (src/Slam.cpp:1140-1172): kNN k=2, raw = every
      * m[0] of a two-entry list, result = those passing m[0].distance < ratio * m[1].distance.
-     * The reference's ratio is Config::L2_RATIO_THRESHOLD = 0.75f (include/Config.h:53). */
+     * The reference's ratio is Config::L2_RATIO_THRESHOLD = 0.75f (include/Config.h:53).
+     * A Mat with a row stride (ROI, non-continuous) is passed as it is: the library packs the rows. */
     std::vector<DMatch> match_features(const Mat& desc1, const Mat& desc2, std::vector<DMatch>* raw_out = nullptr,
                                        float ratio = 0.75f, bool mutual = false) {
         std::vector<DMatch> good;
         if (raw_out) raw_out->clear();
         if (desc1.empty() || desc2.empty()) return good;                  /* src/Slam.cpp:1143 */
-        std::vector<float> b1, b2;
-        const float* q = rows_of(desc1, b1);
-        const float* t = rows_of(desc2, b2);
+        need_f32_256(desc1);
+        need_f32_256(desc2);
         good.resize(desc1.rows);
         if (raw_out) raw_out->resize(desc1.rows);
         int32_t ng = 0, nr = 0;
-        check(vsm_match_pair(ctx_, q, desc1.rows, t, desc2.rows, ratio, mutual ? 1 : 0,
-                             reinterpret_cast<vsm_dmatch*>(good.data()), &ng,
-                             raw_out ? reinterpret_cast<vsm_dmatch*>(raw_out->data()) : nullptr, raw_out ? &nr : nullptr));
+        check(vsm_match_pair_strided(ctx_, desc1.template ptr<float>(0), desc1.rows, stride_of(desc1),
+                                     desc2.template ptr<float>(0), desc2.rows, stride_of(desc2), ratio, mutual ? 1 : 0,
+                                     reinterpret_cast<vsm_dmatch*>(good.data()), &ng,
+                                     raw_out ? reinterpret_cast<vsm_dmatch*>(raw_out->data()) : nullptr, raw_out ? &nr : nullptr));
         good.resize(ng);
         if (raw_out) raw_out->resize(nr);
         return good;
@@ -106,38 +124,60 @@ public:
         if (k != 2) throw std::runtime_error("vsm_cv::knnMatch: only k = 2 (the reference's call sites)");
         knn.assign(query.rows, std::vector<DMatch>());
         if (query.empty()) return;
-        std::vector<float> b1, b2;
-        const float* q = rows_of(query, b1);
-        const float* t = train.empty() ? nullptr : rows_of(train, b2);
+        need_f32_256(query);
+        if (!train.empty()) need_f32_256(train);
         std::vector<int32_t> idx((size_t)query.rows * 2);
         std::vector<float> dist((size_t)query.rows * 2);
-        check(vsm_knn2(ctx_, q, query.rows, t, train.empty() ? 0 : train.rows, idx.data(), dist.data()));
+        check(vsm_knn2_strided(ctx_, query.template ptr<float>(0), query.rows, stride_of(query),
+                               train.empty() ? nullptr : train.template ptr<float>(0), train.empty() ? 0 : train.rows,
+                               train.empty() ? VSM_DIM * (int64_t)sizeof(float) : stride_of(train), idx.data(), dist.data()));
         for (int i = 0; i < query.rows; i++)
             for (int p = 0; p < 2; p++)
                 if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, idx[2 * i + p], 0, dist[2 * i + p]));
     }
 
-    /* Keyframe descriptors kept on the device (Frame::descriptors_, include/Frame.h:61). */
+    /* Keyframe descriptors kept on the device (Frame::descriptors_, include/Frame.h:61).  With several
+     * devices the keyframe goes to the one holding the fewest rows; the handle is then a group handle. */
     int add_keyframe(int frame_id, const Mat& desc) {
         std::vector<float> b;
         int32_t h = -1;
-        check(vsm_store_add(ctx_, frame_id, desc.empty() ? nullptr : rows_of(desc, b), desc.empty() ? 0 : desc.rows, &h));
+        if (group_) {
+            gcheck(vsm_group_store_add(group_, frame_id, desc.empty() ? nullptr : rows_of(desc, b), desc.empty() ? 0 : desc.rows, &h));
+            return h;
+        }
+        if (!desc.empty()) need_f32_256(desc);
+        check(vsm_store_add_strided(ctx_, frame_id, desc.empty() ? nullptr : desc.template ptr<float>(0), desc.empty() ? 0 : desc.rows,
+                                    desc.empty() ? VSM_DIM * (int64_t)sizeof(float) : stride_of(desc), &h));
         return h;
     }
-    void clear_keyframes() { check(vsm_store_clear(ctx_)); }
+    void clear_keyframes() {
+        if (group_) gcheck(vsm_group_store_clear(group_));
+        else check(vsm_store_clear(ctx_));
+    }
     /* Frame::set_keyframe(true) (src/Slam.cpp:1065, :1076, :852) / dropping a frame from the device store. */
-    void promote(int handle) { check(vsm_store_promote(ctx_, handle)); }
-    void remove_frame(int handle) { check(vsm_store_remove(ctx_, handle)); }
+    void promote(int handle) { single("promote"); check(vsm_store_promote(ctx_, handle)); }
+    void remove_frame(int handle) {
+        if (group_) gcheck(vsm_group_store_remove(group_, handle));
+        else check(vsm_store_remove(ctx_, handle));
+    }
     int frame_rows(int handle) {
         int32_t n = 0;
         if (vsm_store_frame_info(ctx_, handle, nullptr, &n, nullptr, nullptr) != VSM_OK)
             throw std::runtime_error("vsm_cv: unknown frame handle");
         return n;
     }
+    int keyframe_count() {
+        int64_t rows = 0;
+        int32_t nkf = 0;
+        if (group_) gcheck(vsm_group_store_info(group_, &rows, &nkf, nullptr));
+        else check(vsm_store_info(ctx_, &rows, &nkf));
+        return nkf;
+    }
 
     /* match_features(ref_kf->descriptors(), cur->descriptors(), raw) with ref_kf resident (src/Slam.cpp:841). */
     std::vector<DMatch> match_features(int keyframe_handle, const Mat& cur,
                                        std::vector<DMatch>* raw_out = nullptr, float ratio = 0.75f, bool mutual = false) {
+        single("match_features(handle, ...)");
         const int keyframe_rows = frame_rows(keyframe_handle);        /* the library's own count sizes the buffers */
         std::vector<DMatch> good(keyframe_rows > 0 ? keyframe_rows : 1);
         if (raw_out) raw_out->assign(good.size(), DMatch());
@@ -155,6 +195,7 @@ public:
      * result[p] = match_features(descriptors of q_handles[p], descriptors of t_handles[p]). */
     std::vector<std::vector<DMatch>> match_features_batch(const std::vector<int>& q_handles, const std::vector<int>& t_handles,
                                                           float ratio = 0.75f, bool mutual = false) {
+        single("match_features_batch");
         if (q_handles.size() != t_handles.size()) throw std::runtime_error("vsm_cv: handle lists differ in length");
         const int n = (int)q_handles.size();
         std::vector<std::vector<DMatch>> out(n);
@@ -174,6 +215,7 @@ public:
      * calls frame->set_keyframe(true)); ref_handle = last_keyframe_ or last_frame_, < 0 = first frame. */
     std::vector<DMatch> track(int ref_handle, int frame_id, const Mat& cur, int* cur_handle,
                               std::vector<DMatch>* raw_out = nullptr, float ratio = 0.75f, bool mutual = false) {
+        single("track");
         const int ref_rows = ref_handle >= 0 ? frame_rows(ref_handle) : 0;
         std::vector<DMatch> good(ref_rows > 0 ? ref_rows : 1);
         if (raw_out) raw_out->assign(good.size(), DMatch());
@@ -192,9 +234,8 @@ public:
      * inside that keyframe.  good_matches[s] is what the reference builds at :54-60; the caller
      * keeps its own eligibility rules (:44-48) and the >= 30 gate (:62). */
     void detect_candidates(const Mat& cur, float ratio, std::vector<std::vector<DMatch>>& good_matches) {
-        int64_t rows = 0;
-        int32_t nkf = 0;
-        check(vsm_store_info(ctx_, &rows, &nkf));
+        single("detect_candidates");
+        const int nkf = keyframe_count();
         good_matches.assign(nkf, std::vector<DMatch>());
         if (cur.empty() || nkf == 0) return;
         std::vector<float> b;
@@ -205,23 +246,69 @@ public:
             good_matches[s].assign(flat.begin() + (size_t)s * cur.rows, flat.begin() + (size_t)s * cur.rows + counts[s]);
     }
 
-    /* The same block INCLUDING the reference's eligibility rules (src/LoopCloser.cpp:44-48): a stored
-     * keyframe is skipped when cur_frame_id - its frame id < min_gap (Config::LC_MIN_FRAME_GAP) or it
-     * is empty, and of the rest only every `every`-th is matched (the reference: 5).  status[s] = -1
-     * for a skipped keyframe, otherwise its number of survivors; only eligible keyframes are matched. */
+    /* LoopCloser::detect's whole candidate loop, lines 43-62 INCLUDING the eligibility rules (:44-48:
+     * gap >= min_gap = Config::LC_MIN_FRAME_GAP, non-empty, every `every`-th = 5) and the gate at :62
+     * (good_matches.size() >= min_matches = Config::MIN_MATCHES).  status[s] = -1 for a skipped keyframe,
+     * otherwise its number of survivors; candidates = (keyframe position, good_matches) of the keyframes
+     * that pass the gate, ascending -- exactly the lists the reference hands to findEssentialMat (:70).
+     * Gate and packing run on the device(s); nothing of size keyframes x queries is allocated. */
+    struct LoopCandidate {
+        int keyframe;
+        std::vector<DMatch> good_matches;
+    };
+    void detect_loop(int cur_frame_id, const Mat& cur, float ratio, int min_gap, int every, int min_matches,
+                     std::vector<int>& status, std::vector<LoopCandidate>& candidates) {
+        const int nkf = keyframe_count();
+        status.assign(nkf, -1);
+        candidates.clear();
+        if (nkf == 0) return;
+        std::vector<float> b;
+        const float* q = cur.empty() ? nullptr : rows_of(cur, b);
+        const int nq = cur.empty() ? 0 : cur.rows;
+        std::vector<int32_t> st(nkf, -1);
+        std::vector<vsm_loop_candidate> cands(16);
+        std::vector<DMatch> flat((size_t)16 * (nq > 0 ? nq : 1));
+        int32_t nc = 0;
+        int64_t nm = 0;
+        for (;;) {
+            if (group_)
+                gcheck(vsm_group_loop_detect_compact(group_, cur_frame_id, min_gap, every, q, nq, ratio, min_matches, st.data(),
+                                                     cands.data(), (int32_t)cands.size(), &nc,
+                                                     reinterpret_cast<vsm_dmatch*>(flat.data()), (int64_t)flat.size(), &nm));
+            else
+                check(vsm_loop_detect_compact(ctx_, cur_frame_id, min_gap, every, 0, q, nq, ratio, min_matches, st.data(),
+                                              cands.data(), (int32_t)cands.size(), &nc,
+                                              reinterpret_cast<vsm_dmatch*>(flat.data()), (int64_t)flat.size(), &nm, nullptr));
+            if (nc <= (int32_t)cands.size() && nm <= (int64_t)flat.size()) break;
+            if (nc > (int32_t)cands.size()) cands.resize(nc);
+            if (nm > (int64_t)flat.size()) flat.resize((size_t)nm);
+        }
+        for (int s = 0; s < nkf; s++) status[s] = st[s];
+        for (int k = 0; k < nc; k++) {
+            LoopCandidate c;
+            c.keyframe = cands[k].keyframe;
+            c.good_matches.assign(flat.begin() + cands[k].offset, flat.begin() + cands[k].offset + cands[k].count);
+            candidates.push_back(std::move(c));
+        }
+    }
+
+    /* The record-based form of the same loop: every eligible keyframe's list comes back (no gate). */
     void detect_loop_candidates(int cur_frame_id, const Mat& cur, float ratio, int min_gap, int every,
                                 std::vector<int>& status, std::vector<std::vector<DMatch>>& good_matches) {
-        int64_t rows = 0;
-        int32_t nkf = 0;
-        check(vsm_store_info(ctx_, &rows, &nkf));
+        const int nkf = keyframe_count();
         status.assign(nkf, -1);
         good_matches.assign(nkf, std::vector<DMatch>());
         if (nkf == 0) return;
         std::vector<float> b;
         std::vector<int32_t> st(nkf, -1);
         std::vector<DMatch> flat(cur.empty() ? 1 : (size_t)nkf * cur.rows);
-        check(vsm_loop_detect(ctx_, cur_frame_id, min_gap, every, cur.empty() ? nullptr : rows_of(cur, b),
-                              cur.empty() ? 0 : cur.rows, ratio, st.data(), reinterpret_cast<vsm_dmatch*>(flat.data())));
+        const float* q = cur.empty() ? nullptr : rows_of(cur, b);
+        if (group_)
+            gcheck(vsm_group_loop_detect(group_, cur_frame_id, min_gap, every, q, cur.empty() ? 0 : cur.rows, ratio, st.data(),
+                                         reinterpret_cast<vsm_dmatch*>(flat.data())));
+        else
+            check(vsm_loop_detect(ctx_, cur_frame_id, min_gap, every, q, cur.empty() ? 0 : cur.rows, ratio, st.data(),
+                                  reinterpret_cast<vsm_dmatch*>(flat.data())));
         for (int s = 0; s < nkf; s++) {
             status[s] = st[s];
             if (st[s] > 0)
@@ -234,6 +321,7 @@ public:
      * keyframe :748-759).  trainIdx is the ORIGINAL store row (the reference's mp_ids_vec[trainIdx], :768). */
     void search_store(const Mat& frame_desc, const std::vector<unsigned char>& valid,
                       std::vector<std::vector<DMatch>>& knn) {
+        single("search_store(valid)");
         knn.assign(frame_desc.rows, std::vector<DMatch>());
         if (frame_desc.empty()) return;
         std::vector<float> b;
@@ -246,30 +334,50 @@ public:
                 if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, (int)idx[2 * i + p], 0, dist[2 * i + p]));
     }
 
-    /* knnMatch(frame_desc, all_descs, knn, 2) over every stored row (src/Slam.cpp:567, :764). */
+    /* knnMatch(frame_desc, all_descs, knn, 2) over every keyframe row (src/Slam.cpp:567, :764).  One
+     * device: trainIdx = store row; several devices: trainIdx = row of the stacked database. */
     void search_store(const Mat& frame_desc, std::vector<std::vector<DMatch>>& knn) {
         knn.assign(frame_desc.rows, std::vector<DMatch>());
         if (frame_desc.empty()) return;
         std::vector<float> b;
         std::vector<int64_t> idx((size_t)frame_desc.rows * 2);
         std::vector<float> dist((size_t)frame_desc.rows * 2);
-        check(vsm_db_top2(ctx_, rows_of(frame_desc, b), frame_desc.rows, 0, idx.data(), dist.data()));
+        if (group_)
+            gcheck(vsm_group_db_top2(group_, rows_of(frame_desc, b), frame_desc.rows, idx.data(), dist.data(), nullptr, nullptr));
+        else
+            check(vsm_db_top2(ctx_, rows_of(frame_desc, b), frame_desc.rows, 0, idx.data(), dist.data()));
         for (int i = 0; i < frame_desc.rows; i++)
             for (int p = 0; p < 2; p++)
                 if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, (int)idx[2 * i + p], 0, dist[2 * i + p]));
     }
 
     vsm_ctx* handle() { return ctx_; }
+    vsm_group* group() { return group_; }
 
 private:
     vsm_ctx* ctx_ = nullptr;
+    vsm_group* group_ = nullptr;
 
     void check(int st) {
         if (st != VSM_OK) throw std::runtime_error(std::string("libvsm: ") + vsm_last_error(ctx_));
     }
+    void gcheck(int st) {
+        if (st != VSM_OK) throw std::runtime_error(std::string("libvsm group: ") + vsm_group_last_error(group_));
+    }
+    void single(const char* what) {
+        if (group_) throw std::runtime_error(std::string("vsm_cv: ") + what + " addresses one device's store; not available on a multi-device matcher");
+    }
+    static void need_f32_256(const Mat& m) {
+        if (!is_f32_256(m)) throw std::runtime_error("vsm_cv: descriptors must be N x 256 CV_32F");
+    }
+    /* bytes from one row to the next (cv::Mat::step) */
+    static int64_t stride_of(const Mat& m) {
+        return m.rows > 1 ? (int64_t)(reinterpret_cast<const char*>(m.template ptr<float>(1)) - reinterpret_cast<const char*>(m.template ptr<float>(0)))
+                          : (int64_t)VSM_DIM * (int64_t)sizeof(float);
+    }
     /* contiguous N x 256 fp32 rows of m (copied only if m is a strided view) */
     static const float* rows_of(const Mat& m, std::vector<float>& tmp) {
-        if (!is_f32_256(m)) throw std::runtime_error("vsm_cv: descriptors must be N x 256 CV_32F");
+        need_f32_256(m);
         if (m.isContinuous()) return m.template ptr<float>(0);
         tmp.resize((size_t)m.rows * VSM_DIM);
         for (int r = 0; r < m.rows; r++) std::memcpy(&tmp[(size_t)r * VSM_DIM], m.template ptr<float>(r), VSM_DIM * sizeof(float));

@@ -3,6 +3,7 @@
 // Build + run: tests/test_cpp_adaptor.py (needs a B200).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,7 +29,10 @@ static bool same(const std::vector<DMatch>& a, const std::vector<vsm_oracle_dmat
     return (int)a.size() == nb && (nb == 0 || std::memcmp(a.data(), b.data(), (size_t)nb * 16) == 0);
 }
 
-int main() {
+static std::vector<int> g_devices;
+
+int main(int argc, char** argv) {
+    for (int i = 1; i < argc; i++) g_devices.push_back(std::atoi(argv[i]));
     vsm_cv::DescriptorMatcher matcher;              // like Slam's matcher_l2_ member (include/Slam.h:197)
     // frame B re-observes part of frame A: B = A + small noise on the first 300 rows
     const int n1 = 500, n2 = 640;
@@ -131,6 +135,24 @@ int main() {
             EXPECT(same(per_kf[s], os, counts[s]));
         }
         EXPECT(matched == 3);                                   // keyframes 0..6 pass the gap rule, every 2nd of them
+        // the compact form: the gate (LoopCloser.cpp:62) on the device, only surviving lists come back
+        for (int min_matches : {30, 1}) {
+            std::vector<int> st2;
+            std::vector<vsm_cv::DescriptorMatcher::LoopCandidate> cands;
+            matcher.detect_loop(cur_id, cur, 0.75f, min_gap, every, min_matches, st2, cands);
+            EXPECT(st2 == status);
+            size_t k = 0;
+            for (int s = 0; s < nkf; s++) {
+                if (status[s] < min_matches || status[s] <= 0) continue;
+                EXPECT(k < cands.size() && cands[k].keyframe == s);
+                if (k < cands.size()) {
+                    std::vector<vsm_oracle_dmatch> os(om.begin() + (size_t)s * nq, om.begin() + (size_t)s * nq + counts[s]);
+                    EXPECT(same(cands[k].good_matches, os, counts[s]));
+                }
+                k++;
+            }
+            EXPECT(k == cands.size());
+        }
         // pairs of stored keyframes in one call = the per-pair calls
         {
             std::vector<int> qh = {0, 5, 11, 3}, th = {1, 0, 11, 7};
@@ -163,6 +185,44 @@ int main() {
                 EXPECT(std::memcmp(&knn2[i][k].distance, &od[2 * i + k], 4) == 0);
             }
         }
+    }
+    // several devices behind one matcher object (vsm_group): device list from the command line,
+    // e.g. "0 0 0" (three contexts on one GPU) or "0 1"
+    if (g_devices.size() > 1) {
+        vsm_cv::DescriptorMatcher multi(g_devices);
+        const int nkf = 14, kf_rows = 120, nq = 100;
+        std::vector<float> db = rows(8, 1, nkf * kf_rows), q = rows(8, 2, nq);
+        std::memcpy(q.data(), &db[(size_t)(9 * kf_rows + 5) * 256], 50 * 1024);          // re-observe 50 rows of keyframe 9
+        for (int s = 0; s < nkf; s++) EXPECT(multi.add_keyframe(25 * s, Mat(kf_rows, 256, &db[(size_t)s * kf_rows * 256])) == s);
+        Mat cur(nq, 256, q.data());
+        std::vector<std::vector<DMatch>> knn3;
+        multi.search_store(cur, knn3);
+        std::vector<int64_t> oi((size_t)nq * 2);
+        std::vector<float> od((size_t)nq * 2);
+        vsm_oracle_knn(q.data(), nq, 256, db.data(), (int64_t)nkf * kf_rows, 256, 2, oi.data(), od.data(), 0);
+        for (int i = 0; i < nq; i++) {
+            EXPECT(knn3[i].size() == 2);
+            for (int k = 0; k < 2 && knn3[i].size() == 2; k++) {
+                EXPECT(knn3[i][k].trainIdx == (int)oi[2 * i + k]);
+                EXPECT(std::memcmp(&knn3[i][k].distance, &od[2 * i + k], 4) == 0);
+            }
+        }
+        std::vector<int64_t> seg(nkf + 1);
+        for (int s = 0; s <= nkf; s++) seg[s] = (int64_t)s * kf_rows;
+        std::vector<int32_t> counts(nkf);
+        std::vector<vsm_oracle_dmatch> om((size_t)nkf * nq);
+        vsm_oracle_segmented(q.data(), nq, db.data(), seg.data(), nkf, 0.75f, counts.data(), om.data(), 0);
+        std::vector<int> st3;
+        std::vector<vsm_cv::DescriptorMatcher::LoopCandidate> cands;
+        multi.detect_loop(1000, cur, 0.75f, 200, 1, 30, st3, cands);
+        EXPECT(cands.size() == 1 && cands[0].keyframe == 9);
+        for (int s = 0; s < nkf; s++) EXPECT(st3[s] == counts[s]);
+        if (cands.size() == 1) {
+            std::vector<vsm_oracle_dmatch> os(om.begin() + (size_t)9 * nq, om.begin() + (size_t)9 * nq + counts[9]);
+            for (auto& m : os) m.imgIdx = 9;
+            EXPECT(same(cands[0].good_matches, os, counts[9]));
+        }
+        std::printf("multi-device matcher on %zu contexts: checked\n", g_devices.size());
     }
     std::printf(fails ? "adaptor test: %d FAILURES\n" : "adaptor test: OK\n", fails);
     return fails ? 1 : 0;

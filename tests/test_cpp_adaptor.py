@@ -28,6 +28,9 @@ def test_adaptor_compiles_and_links(tmp_path):
 @pytest.mark.gpu
 def test_adaptor_matches_oracle(tmp_path):
     exe = build(str(tmp_path))
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import torch
+    n = torch.cuda.device_count()
+    devices = [str(d) for d in range(min(n, 8))] if n >= 2 else ["0", "0", "0"]     # one GPU: three contexts on it
+    out = subprocess.run([exe] + devices, capture_output=True, text=True, timeout=180)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "adaptor test: OK" in out.stdout
+    assert "adaptor test: OK" in out.stdout and "multi-device matcher" in out.stdout

@@ -813,3 +813,91 @@ def test_loop_detect_compact_at_baseline_config2_size(tc):
     # the reference's every-5th rule over the same list
     _check_compact(tc, q, db, seg_off, frame_ids, 10_000, 0.75, 200, 5, 30)
     tc.clear_store()
+
+
+def test_resident_map_point_table(tc):
+    """The map-point searches of Slam::try_pnp_recovery (src/Slam.cpp:546-574: every valid point) and
+    Slam::handle_loop_closure (:744-774: valid points with an observation within 30 frames of the matched
+    keyframe) against a point table that lives on the device: births from host descriptors and from rows
+    of a stored frame (:1339, :1563), add_observation (:463), set_valid (:496, :1119-1123).  The model
+    below IS the reference's loop: stack the selected descriptors in id order, knnMatch, mp_ids_vec."""
+    rng = np.random.default_rng(11)
+    tc.clear_store()
+    tc.clear_map_points()
+    desc, valid, obs = [], [], []                       # the model: per point descriptor, valid_, observation frames
+
+    def check(q, near=-1, rng_=30):
+        sel = [i for i in range(len(desc)) if valid[i] and (near < 0 or any(abs(f - near) < rng_ for f in obs[i]))]
+        gi, gd, ns = tc.search_resident_map_points(q, near, rng_)
+        assert ns == len(sel)
+        if not sel:
+            assert (gi == -1).all()
+            return
+        oi, od = oracle.knn(q, np.stack([desc[i] for i in sel]), 2)
+        ids = np.array(sel, np.int64)
+        want = np.where(oi >= 0, ids[np.maximum(oi, 0)], -1)
+        assert np.array_equal(gi, want) and np.array_equal(bits(gd), bits(od))
+
+    q0 = gen.rows(900, 9, 0, 150)
+    check(q0)                                            # empty table
+    # keyframes arrive; some of their keypoints become map points (depth points: one observation;
+    # triangulated points: a second observation in the previous keyframe)
+    frames = gen.video(901, 12, 300)
+    handles = []
+    for f, d in enumerate(frames):
+        fid = 20 * f
+        h = tc.add_keyframe(fid, d)
+        handles.append(h)
+        kp = np.sort(rng.choice(300, size=60, replace=False)).astype(np.int32)
+        first = tc.add_map_points_from_frame(h, kp)
+        assert first == len(desc)
+        for k in kp:
+            desc.append(d[k]); valid.append(True); obs.append([fid])
+        if f > 0:
+            tri = np.arange(first, first + 60, 3, dtype=np.int32)
+            tc.observe_map_points(tri, 20 * (f - 1))
+            for p in tri:
+                obs[p].append(20 * (f - 1))
+    # a batch born from host descriptors (no stored frame)
+    extra = gen.rows(902, 0, 0, 77)
+    first = tc.add_map_points(extra, 1000)
+    assert first == len(desc)
+    for r in extra:
+        desc.append(r); valid.append(True); obs.append([1000])
+    assert tc.map_point_info() == (len(desc), len(desc), sum(len(o) for o in obs))
+    # queries: noisy re-observations of some points + fresh rows
+    pts = rng.choice(len(desc), size=100, replace=False)
+    vq = gen.int_rows(903, 0, 0, 160).copy()
+    vq[:100] = 1000 * np.rint(np.stack([desc[p] for p in pts]).astype(np.float64) * 3300).astype(np.int64) + 700 * gen.int_rows(904, 0, 0, 100)
+    q = gen._normalize_int(vq)
+    check(q)
+    check(q, near=100)                                   # points seen in frames 71..129: keyframes 80, 100, 120
+    check(q, near=100, rng_=1)                           # exactly frame 100
+    check(q, near=5000)                                  # nobody: empty selection
+    # culling (src/Slam.cpp:1110-1126) and reprojection failures (:496) invalidate points; tracking re-observes others
+    dead = rng.choice(len(desc), size=250, replace=False).astype(np.int32)
+    tc.set_map_points_valid(dead, False)
+    for p in dead:
+        valid[p] = False
+    tc.set_map_points_valid(dead[:10], False)            # idempotent
+    seen = rng.choice(len(desc), size=120, replace=False).astype(np.int32)
+    tc.observe_map_points(seen, 700)
+    for p in seen:
+        obs[p].append(700)
+    assert tc.map_point_info() == (len(desc), sum(valid), sum(len(o) for o in obs))
+    check(q)
+    check(q, near=700, rng_=5)
+    check(q, near=100)
+    tc.set_map_points_valid(dead[:40], True)             # and back
+    for p in dead[:40]:
+        valid[p] = True
+    check(q, near=90)
+    # all but one point invalid: a one-row stacked matrix has no second neighbour (the size()>=2 guard, :570)
+    tc.set_map_points_valid(np.arange(len(desc), dtype=np.int32), False)
+    tc.set_map_points_valid(np.array([5], np.int32), True)
+    valid[:] = [False] * len(desc)
+    valid[5] = True
+    check(q)
+    tc.clear_map_points()
+    assert tc.map_point_info() == (0, 0, 0)
+    tc.clear_store()

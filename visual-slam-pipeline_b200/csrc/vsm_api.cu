@@ -74,6 +74,14 @@ struct Seg {
     uint8_t is_kf;                   // Frame::is_keyframe() (Map::get_keyframes filters on it, src/Map.cpp:40-47)
 };
 
+// A device array that grows in place (virtual memory management; cudaMalloc + copy without it).
+struct GrowArr {
+    VmmRange r;
+    uint8_t* p = nullptr;
+    size_t cap = 0;                  // bytes usable
+    bool vmm = false;
+};
+
 // A run of consecutive store rows that belong to live keyframes (global search skips the rest).
 struct Run {
     int64_t row0, count;
@@ -159,6 +167,11 @@ struct vsm_ctx {
     DevBuf<WorkItem> d_work;
     DevBuf<int32_t> d_sel;                       // selected store rows of a masked search
     DevBuf<uint8_t> d_track;                     // track_local_map: keypoints, map-point positions, results
+    // resident map-point table (MapPoint::descriptor_ / valid_ / observations_, include/MapPoint.h:38-42)
+    GrowArr pt_f32, pt_valid, pt_log;            // descriptors [n][256] fp32, validity [n] u8, observation log [(point, frame)]
+    int64_t n_points = 0, n_log = 0, n_valid = 0;
+    std::vector<uint8_t> pt_valid_h;             // host mirror of the validity flags (set_valid is idempotent, the count is not)
+    DevBuf<uint8_t> d_pt_tmp;                    // per-search: near flags, selection flags, block counts / offsets, total
     DevBuf<uint8_t> d_loop;                      // compact loop search: masks, word bases, pair keys, staged matches, offsets
     std::vector<uint8_t> loop_key;               // plan key of the last compact loop search (descriptor block reuse)
     const void* loop_p_desc = nullptr;
@@ -415,6 +428,41 @@ int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
     if (a.n2) CK(cudaFree(a.n2));
     a.b16 = b16; a.n2 = n2; a.cap = want;
     return encode_map(ctx, a);
+}
+
+// Make [p, p + need) usable; existing content keeps its address (VMM) or is copied (fall-back).
+int grow_arr(vsm_ctx* ctx, GrowArr& a, size_t need, size_t reserve_bytes) {
+    if (need <= a.cap) return VSM_OK;
+    if (ctx->vmm_ok && (a.vmm || !a.p)) {
+        if (!a.vmm) {
+            TRY(vmm_reserve(ctx, a.r, reserve_bytes));
+            a.vmm = true;
+            a.p = reinterpret_cast<uint8_t*>(a.r.base);
+        }
+        const size_t want = std::max(need, a.cap + a.cap / 2);
+        int st = vmm_back(ctx, a.r, std::min(want, a.r.reserved));
+        if (st != VSM_OK) st = vmm_back(ctx, a.r, need);
+        if (st != VSM_OK) return st;
+        a.cap = a.r.mapped;
+        return VSM_OK;
+    }
+    const size_t want = std::max(need, a.cap * 2);
+    uint8_t* np = nullptr;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cudaMalloc(&np, want) != cudaSuccess) { cudaGetLastError(); return fail(ctx, VSM_ERR_CAPACITY, "map-point table: out of device memory"); }
+    if (a.p) {
+        CK(cudaMemcpy(np, a.p, a.cap, cudaMemcpyDeviceToDevice));
+        CK(cudaFree(a.p));
+    }
+    a.p = np;
+    a.cap = want;
+    return VSM_OK;
+}
+
+void grow_arr_free(vsm_ctx* ctx, GrowArr& a) {
+    if (a.vmm) vmm_release(ctx, a.r);
+    else if (a.p) cudaFree(a.p);
+    a = GrowArr();
 }
 
 void arena_free(vsm_ctx* ctx, Arena& a) {
@@ -890,9 +938,17 @@ static const int64_t ZERO_COPY_ROWS = getenv("VSM_ZERO_COPY_ROWS") ? atoll(geten
 // Host rows -> scratch rows [row0, row0+n): fp32 master + queued conversion.  A small pinned buffer
 // is not copied here at all: the call's prologue kernel reads it over PCIe (one launch for upload,
 // conversion and norms).  Otherwise a DMA now, conversion in the prologue.
-int upload_scratch(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n) {
+int upload_scratch(vsm_ctx* ctx, const float* src, int64_t row0, int64_t n, int64_t stride_bytes = VSM_DIM * sizeof(float)) {
     if (n <= 0) return VSM_OK;
     float* dst = ctx->scratch.f32 + row0 * VSM_DIM;
+    if (stride_bytes != (int64_t)(VSM_DIM * sizeof(float))) {
+        // rows of a wider matrix (a cv::Mat ROI / a non-continuous Mat): one strided DMA packs them
+        CK(cudaMemcpy2DAsync(dst, VSM_DIM * sizeof(float), src, (size_t)stride_bytes, VSM_DIM * sizeof(float), (size_t)n,
+                             cudaMemcpyHostToDevice, ctx->stream));
+        ConvJob j = {dst, nullptr, ctx->scratch.b16 + row0 * VSM_DIM, ctx->scratch.n2 + row0, nullptr, n};
+        ctx->pending_conv.push_back(j);
+        return VSM_OK;
+    }
     const float* mapped = n <= ZERO_COPY_ROWS ? host_mapped(src) : nullptr;
     ConvJob j = {mapped ? mapped : dst, mapped ? dst : nullptr, ctx->scratch.b16 + row0 * VSM_DIM, ctx->scratch.n2 + row0,
                  nullptr, n};
@@ -1076,6 +1132,10 @@ void vsm_destroy(vsm_ctx* ctx) {
     if (ctx->d_sel.p) cudaFree(ctx->d_sel.p);
     if (ctx->d_track.p) cudaFree(ctx->d_track.p);
     if (ctx->d_loop.p) cudaFree(ctx->d_loop.p);
+    if (ctx->d_pt_tmp.p) cudaFree(ctx->d_pt_tmp.p);
+    grow_arr_free(ctx, ctx->pt_f32);
+    grow_arr_free(ctx, ctx->pt_valid);
+    grow_arr_free(ctx, ctx->pt_log);
     if (ctx->d_dump) cudaFree(ctx->d_dump);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1151,15 +1211,22 @@ int vsm_sync(vsm_ctx* ctx) {
 }
 
 // ---- pair matching ---------------------------------------------------------------------
-int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt, int32_t* idx,
-             float* dist) {
-    if (!ctx || nq < 0 || nt < 0 || (nq > 0 && (!query || !idx || !dist)) || (nt > 0 && !train))
-        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_knn2: bad argument") : VSM_ERR_INVALID;
+static bool bad_stride(int64_t s) { return s < (int64_t)(VSM_DIM * sizeof(float)) || (s & 3); }
+
+int vsm_knn2(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt, int32_t* idx, float* dist) {
+    return vsm_knn2_strided(ctx, query, nq, VSM_DIM * sizeof(float), train, nt, VSM_DIM * sizeof(float), idx, dist);
+}
+
+int vsm_knn2_strided(vsm_ctx* ctx, const float* query, int32_t nq, int64_t q_stride, const float* train, int32_t nt,
+                     int64_t t_stride, int32_t* idx, float* dist) {
+    if (!ctx || nq < 0 || nt < 0 || (nq > 0 && (!query || !idx || !dist)) || (nt > 0 && !train) || bad_stride(q_stride) ||
+        bad_stride(t_stride))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_knn2: bad argument (row stride must be >= 1024 bytes)") : VSM_ERR_INVALID;
     if (nq == 0) return VSM_OK;
     TRY(begin_call(ctx));
     TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + nt, 0));
-    TRY(upload_scratch(ctx, query, 0, nq));
-    TRY(upload_scratch(ctx, train, nq, nt));
+    TRY(upload_scratch(ctx, query, 0, nq, q_stride));
+    TRY(upload_scratch(ctx, train, nq, nt, t_stride));
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
     TRY(run_problems(ctx, probs, {}, nq, 0));
     TRY(fetch_keys(ctx, nq));
@@ -1197,15 +1264,23 @@ static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int 
 
 int vsm_match_pair(vsm_ctx* ctx, const float* query, int32_t nq, const float* train, int32_t nt, float ratio,
                    int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
-    if (!ctx || nq < 0 || nt < 0 || !n_good || (nq > 0 && (!query || !good)) || (nt > 0 && !train))
-        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_pair: bad argument") : VSM_ERR_INVALID;
+    return vsm_match_pair_strided(ctx, query, nq, VSM_DIM * sizeof(float), train, nt, VSM_DIM * sizeof(float), ratio, mutual,
+                                  good, n_good, raw, n_raw);
+}
+
+int vsm_match_pair_strided(vsm_ctx* ctx, const float* query, int32_t nq, int64_t q_stride, const float* train, int32_t nt,
+                           int64_t t_stride, float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw,
+                           int32_t* n_raw) {
+    if (!ctx || nq < 0 || nt < 0 || !n_good || (nq > 0 && (!query || !good)) || (nt > 0 && !train) || bad_stride(q_stride) ||
+        bad_stride(t_stride))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_match_pair: bad argument (row stride must be >= 1024 bytes)") : VSM_ERR_INVALID;
     *n_good = 0;
     if (n_raw) *n_raw = 0;
     if (nq == 0 || nt == 0) return VSM_OK;                              // src/Slam.cpp:1143
     TRY(begin_call(ctx));
     TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + nt, 0));
-    TRY(upload_scratch(ctx, query, 0, nq));
-    TRY(upload_scratch(ctx, train, nq, nt));
+    TRY(upload_scratch(ctx, query, 0, nq, q_stride));
+    TRY(upload_scratch(ctx, train, nq, nt, t_stride));
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, nt, 0)};
     if (mutual) probs.push_back(scratch_vs_scratch(ctx, nq, nt, 0, nq, nq));
     return match_common(ctx, probs, nq, nt, ratio, mutual, good, n_good, raw, n_raw);
@@ -1339,12 +1414,13 @@ static bool host_pinned(const void* p) {
 }
 
 static int store_append(vsm_ctx* ctx, int32_t frame_id, const float* src, int64_t n, cudaMemcpyKind kind,
-                        bool is_kf, int32_t* handle) {
+                        bool is_kf, int32_t* handle, int64_t stride_bytes = VSM_DIM * sizeof(float)) {
     if (!ctx->store.own_f32) return fail(ctx, VSM_ERR_INVALID, "store was adopted from a device matrix; clear it first");
     int64_t row0 = 0;
     TRY(store_alloc_rows(ctx, n, &row0));
     if (n > 0) {
-        CK(cudaMemcpyAsync(ctx->store.f32 + row0 * VSM_DIM, src, (size_t)n * VSM_DIM * sizeof(float), kind, ctx->stream));
+        CK(cudaMemcpy2DAsync(ctx->store.f32 + row0 * VSM_DIM, VSM_DIM * sizeof(float), src, (size_t)stride_bytes,
+                             VSM_DIM * sizeof(float), (size_t)n, kind, ctx->stream));
         TRY(launch_convert(ctx, ctx->store.f32 + row0 * VSM_DIM, ctx->store.b16 + row0 * VSM_DIM,
                            ctx->store.n2 + row0, n, ctx->d_store_stats));
         // a pageable source has been staged when cudaMemcpyAsync returns; only a pinned one is still
@@ -1357,10 +1433,15 @@ static int store_append(vsm_ctx* ctx, int32_t frame_id, const float* src, int64_
 }
 
 int vsm_store_add(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int32_t* handle) {
-    if (!ctx || n < 0 || (n > 0 && !desc)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_add: bad argument") : VSM_ERR_INVALID;
+    return vsm_store_add_strided(ctx, frame_id, desc, n, VSM_DIM * sizeof(float), handle);
+}
+
+int vsm_store_add_strided(vsm_ctx* ctx, int32_t frame_id, const float* desc, int32_t n, int64_t stride_bytes, int32_t* handle) {
+    if (!ctx || n < 0 || (n > 0 && !desc) || stride_bytes < (int64_t)(VSM_DIM * sizeof(float)) || (stride_bytes & 3))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_store_add: bad argument (row stride must be >= 1024 bytes)") : VSM_ERR_INVALID;
     ctx->err.clear();
     CK(cudaSetDevice(ctx->device));
-    return store_append(ctx, frame_id, desc, n, cudaMemcpyHostToDevice, true, handle);
+    return store_append(ctx, frame_id, desc, n, cudaMemcpyHostToDevice, true, handle, stride_bytes);
 }
 
 int vsm_store_add_device(vsm_ctx* ctx, int32_t frame_id, const float* d_desc, int64_t n, int32_t* handle) {
@@ -1772,6 +1853,178 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
     uint32_t open_pairs = 0;                                      // stream is idle: a 4-byte read
     CK(cudaMemcpy(&open_pairs, reinterpret_cast<const uint8_t*>(ctx->d_counters) + 20, sizeof open_pairs, cudaMemcpyDeviceToHost));
     ctx->seg_open_rate = (float)open_pairs / (float)std::max<int64_t>(total_matches, 1);
+    return VSM_OK;
+}
+
+// ---- resident map-point table ----------------------------------------------------------------------
+static int points_append(vsm_ctx* ctx, int32_t n, int32_t frame_id, int32_t* first_id) {
+    // room for n more points and n more log entries; validity = 1 (MapPoint's constructor, src/MapPoint.cpp:8-13)
+    TRY(grow_arr(ctx, ctx->pt_f32, (size_t)(ctx->n_points + n) * VSM_DIM * sizeof(float), (size_t)1 << 38));
+    TRY(grow_arr(ctx, ctx->pt_valid, (size_t)(ctx->n_points + n), (size_t)1 << 30));
+    TRY(grow_arr(ctx, ctx->pt_log, (size_t)(ctx->n_log + n) * sizeof(PointObs), (size_t)1 << 34));
+    std::vector<PointObs> obs(n);
+    for (int i = 0; i < n; i++) obs[i] = PointObs{(int32_t)(ctx->n_points + i), frame_id};
+    CK(cudaMemsetAsync(ctx->pt_valid.p + ctx->n_points, 1, (size_t)n, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->pt_log.p + (size_t)ctx->n_log * sizeof(PointObs), obs.data(), (size_t)n * sizeof(PointObs),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));                   // `obs` is a local; the caller may reuse its buffers
+    if (first_id) *first_id = (int32_t)ctx->n_points;
+    ctx->pt_valid_h.resize((size_t)(ctx->n_points + n), 1);
+    ctx->n_points += n;
+    ctx->n_log += n;
+    ctx->n_valid += n;
+    return VSM_OK;
+}
+
+int vsm_points_add(vsm_ctx* ctx, const float* desc, int32_t n, int32_t frame_id, int32_t* first_id) {
+    if (!ctx || n < 0 || (n > 0 && !desc)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_add: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (first_id) *first_id = (int32_t)ctx->n_points;
+    if (n == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    TRY(grow_arr(ctx, ctx->pt_f32, (size_t)(ctx->n_points + n) * VSM_DIM * sizeof(float), (size_t)1 << 38));
+    CK(cudaMemcpyAsync(ctx->pt_f32.p + (size_t)ctx->n_points * VSM_DIM * sizeof(float), desc, (size_t)n * VSM_DIM * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    return points_append(ctx, n, frame_id, first_id);
+}
+
+int vsm_points_add_from_frame(vsm_ctx* ctx, int32_t handle, const int32_t* kp_idx, int32_t n, int32_t* first_id) {
+    if (!ctx || n < 0 || (n > 0 && !kp_idx)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_add_from_frame: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (!seg_live(ctx, handle)) return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_points_add_from_frame: unknown frame handle");
+    const Seg sg = ctx->segs[handle];
+    for (int i = 0; i < n; i++)
+        if (kp_idx[i] < 0 || kp_idx[i] >= sg.count) return fail(ctx, VSM_ERR_INVALID, "vsm_points_add_from_frame: keypoint index outside the frame");
+    if (first_id) *first_id = (int32_t)ctx->n_points;
+    if (n == 0) return VSM_OK;
+    CK(cudaSetDevice(ctx->device));
+    TRY(grow_arr(ctx, ctx->pt_f32, (size_t)(ctx->n_points + n) * VSM_DIM * sizeof(float), (size_t)1 << 38));
+    // descriptor = frame->descriptors().row(kp).clone() (src/Slam.cpp:1339, :1563): a device-side row gather
+    std::vector<int32_t> rows(n);
+    for (int i = 0; i < n; i++) rows[i] = (int32_t)(sg.row0 + kp_idx[i]);
+    TRY(ensure(ctx, ctx->d_sel, (size_t)n));
+    CK(cudaMemcpyAsync(ctx->d_sel.p, rows.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)ctx->num_sms * 16);
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->store.f32, ctx->d_sel.p, n,
+                                                                  reinterpret_cast<float*>(ctx->pt_f32.p) + (size_t)ctx->n_points * VSM_DIM);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));                   // `rows` is a local
+    return points_append(ctx, n, sg.frame_id, first_id);
+}
+
+int vsm_points_observe(vsm_ctx* ctx, const int32_t* point_ids, int32_t n, int32_t frame_id) {
+    if (!ctx || n < 0 || (n > 0 && !point_ids)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_observe: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (n == 0) return VSM_OK;
+    for (int i = 0; i < n; i++)
+        if (point_ids[i] < 0 || point_ids[i] >= ctx->n_points) return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_points_observe: unknown map point");
+    CK(cudaSetDevice(ctx->device));
+    TRY(grow_arr(ctx, ctx->pt_log, (size_t)(ctx->n_log + n) * sizeof(PointObs), (size_t)1 << 34));
+    std::vector<PointObs> obs(n);
+    for (int i = 0; i < n; i++) obs[i] = PointObs{point_ids[i], frame_id};
+    CK(cudaMemcpyAsync(ctx->pt_log.p + (size_t)ctx->n_log * sizeof(PointObs), obs.data(), (size_t)n * sizeof(PointObs),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_log += n;
+    return VSM_OK;
+}
+
+int vsm_points_set_valid(vsm_ctx* ctx, const int32_t* point_ids, int32_t n, int32_t valid) {
+    if (!ctx || n < 0 || (n > 0 && !point_ids)) return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_set_valid: bad argument") : VSM_ERR_INVALID;
+    ctx->err.clear();
+    if (n == 0) return VSM_OK;
+    for (int i = 0; i < n; i++)
+        if (point_ids[i] < 0 || point_ids[i] >= ctx->n_points) return fail(ctx, VSM_ERR_NOT_FOUND, "vsm_points_set_valid: unknown map point");
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t f = valid ? 1 : 0;
+    for (int i = 0; i < n; i++) {
+        uint8_t& h = ctx->pt_valid_h[(size_t)point_ids[i]];
+        ctx->n_valid += (int64_t)f - (int64_t)h;
+        h = f;
+    }
+    TRY(ensure(ctx, ctx->d_sel, (size_t)n));
+    CK(cudaMemcpyAsync(ctx->d_sel.p, point_ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    points_set_valid_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_sel.p, n, f, ctx->pt_valid.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));                   // the caller may reuse point_ids
+    return VSM_OK;
+}
+
+int vsm_points_info(const vsm_ctx* ctx, int64_t* n_points, int64_t* n_valid, int64_t* n_observations) {
+    if (!ctx) return VSM_ERR_INVALID;
+    if (n_points) *n_points = ctx->n_points;
+    if (n_valid) *n_valid = ctx->n_valid;
+    if (n_observations) *n_observations = ctx->n_log;
+    return VSM_OK;
+}
+
+int vsm_points_clear(vsm_ctx* ctx) {
+    if (!ctx) return VSM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_points = ctx->n_log = ctx->n_valid = 0;
+    ctx->pt_valid_h.clear();
+    return VSM_OK;
+}
+
+int vsm_points_top2(vsm_ctx* ctx, const float* query, int32_t nq, int32_t near_frame_id, int32_t range, int64_t* idx, float* dist,
+                    int32_t* n_selected) {
+    if (!ctx || nq < 0 || (nq > 0 && (!query || !idx || !dist)) || (near_frame_id >= 0 && range <= 0))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_top2: bad argument") : VSM_ERR_INVALID;
+    if (n_selected) *n_selected = 0;
+    for (int i = 0; i < nq * 2; i++) { idx[i] = -1; dist[i] = FLT_MAX; }
+    const int64_t np = ctx->n_points;
+    if (np == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    // 1. selection on the device: valid (:553 / :747) and, for the loop-verification search, seen near the matched keyframe (:748-756)
+    const int nblocks = (int)((np + POINTS_PER_BLOCK - 1) / POINTS_PER_BLOCK);
+    const size_t o_near = 0, o_flag = align16(o_near + (size_t)np), o_cnt = align16(o_flag + (size_t)np),
+                 o_off = align16(o_cnt + (size_t)nblocks * 4), o_total = align16(o_off + (size_t)nblocks * 4), tmp_bytes = o_total + 16;
+    TRY(ensure(ctx, ctx->d_pt_tmp, tmp_bytes));
+    TRY(ensure(ctx, ctx->d_sel, (size_t)np));
+    uint8_t* t = ctx->d_pt_tmp.p;
+    const uint8_t* near = nullptr;
+    if (near_frame_id >= 0) {
+        CK(cudaMemsetAsync(t + o_near, 0, (size_t)np, ctx->stream));
+        if (ctx->n_log > 0)
+            points_mark_near_kernel<<<(unsigned)((ctx->n_log + 255) / 256), 256, 0, ctx->stream>>>(
+                reinterpret_cast<const PointObs*>(ctx->pt_log.p), ctx->n_log, near_frame_id, range, t + o_near);
+        near = t + o_near;
+        ctx->launches++;
+    }
+    points_count_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->pt_valid.p, near, np, t + o_flag, reinterpret_cast<int32_t*>(t + o_cnt));
+    points_scan_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const int32_t*>(t + o_cnt), nblocks,
+                                                    reinterpret_cast<int32_t*>(t + o_off), reinterpret_cast<int32_t*>(t + o_total));
+    points_scatter_kernel<<<nblocks, 256, 0, ctx->stream>>>(t + o_flag, np, reinterpret_cast<const int32_t*>(t + o_off), ctx->d_sel.p);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    int32_t ns = 0;                                              // the search is planned on the host: one 4-byte read
+    CK(cudaMemcpyAsync(&ns, t + o_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_selected) *n_selected = ns;
+    if (nq == 0 || ns == 0) return end_call(ctx, true);
+    // 2. the stacked matrix the reference builds by push_back (:556, :757), gathered on the device; then the ordinary search
+    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + ns, 0));
+    TRY(upload_scratch(ctx, query, 0, nq));
+    const int64_t blocks = std::min<int64_t>(((int64_t)ns + 7) / 8, (int64_t)ctx->num_sms * 16);
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(ctx->pt_f32.p), ctx->d_sel.p, ns,
+                                                                  ctx->scratch.f32 + (int64_t)nq * VSM_DIM);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, ns, 0)};
+    queue_convert(ctx, ctx->scratch.f32 + (int64_t)nq * VSM_DIM, nq, ns);
+    TRY(run_problems(ctx, probs, {}, nq, 0));
+    // 3. trainIdx -> point id (the reference's mp_ids_vec[m[0].trainIdx], :768), straight into pinned host memory
+    const size_t nb = (size_t)nq * 2 * (sizeof(int64_t) + sizeof(float));
+    TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(nb, 16)));
+    int64_t* h_idx = reinterpret_cast<int64_t*>(ctx->h_result);
+    float* h_dist = reinterpret_cast<float*>(ctx->h_result + (size_t)nq * 2 * sizeof(int64_t));
+    points_result_kernel<<<(nq * 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_out_key, nq * 2, ctx->d_sel.p, h_idx, h_dist);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    TRY(end_call(ctx, true));
+    memcpy(idx, h_idx, (size_t)nq * 2 * sizeof(int64_t));
+    memcpy(dist, h_dist, (size_t)nq * 2 * sizeof(float));
     return VSM_OK;
 }
 

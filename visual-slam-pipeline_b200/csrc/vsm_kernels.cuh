@@ -872,6 +872,125 @@ gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ se
     }
 }
 
+// ---- resident map-point table: selection of the rows a map-point search scans ------------------------
+// The reference re-stacks the descriptors of the selected map points on the host for every search
+// (src/Slam.cpp:552-557: valid points; :744-759: valid points with an observation within
+// LC_NEARBY_FRAME_RANGE frames of the matched keyframe).  Here the points live on the device with their
+// validity flags and their observation log; a search compacts the selection on the device, in
+// ascending point id -- the order of the reference's loop, i.e. of its stacked matrix and its ties.
+struct PointObs {
+    int32_t point, frame;
+};
+// near[p] = 1 if point p has an observation with |frame - near_frame| < range  (:749-754)
+__global__ void points_mark_near_kernel(const PointObs* __restrict__ log, int64_t nlog, int32_t near_frame, int32_t range,
+                                        uint8_t* __restrict__ near) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlog) return;
+    const PointObs o = log[i];
+    int32_t d = o.frame - near_frame;
+    if (d < 0) d = -d;
+    if (d < range) near[o.point] = 1;
+}
+constexpr int POINTS_PER_BLOCK = 2048;
+// selected = valid (and near, if given); per-block counts
+__global__ void __launch_bounds__(256)
+points_count_kernel(const uint8_t* __restrict__ valid, const uint8_t* __restrict__ near, int64_t n, uint8_t* __restrict__ selflag,
+                    int32_t* __restrict__ block_count) {
+    const int64_t base = (int64_t)blockIdx.x * POINTS_PER_BLOCK;
+    int c = 0;
+    for (int k = threadIdx.x; k < POINTS_PER_BLOCK; k += 256) {
+        const int64_t i = base + k;
+        if (i >= n) break;
+        const uint8_t f = (valid[i] != 0 && (near == nullptr || near[i] != 0)) ? 1 : 0;
+        selflag[i] = f;
+        c += f;
+    }
+    __shared__ int ws[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) t += ws[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+// one block: exclusive scan of the per-block counts; total[0] = number of selected points
+__global__ void __launch_bounds__(1024)
+points_scan_kernel(const int32_t* __restrict__ block_count, int nblocks, int32_t* __restrict__ block_off, int32_t* __restrict__ total) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < nblocks ? block_count[b] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int off = carry;
+        for (int w = 0; w < warp; w++) off += wsum[w];
+        if (b < nblocks) block_off[b] = off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; w++) t += wsum[w];
+            carry += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[0] = carry;
+}
+// sel[rank of point i among the selected] = i, ascending
+__global__ void __launch_bounds__(256)
+points_scatter_kernel(const uint8_t* __restrict__ selflag, int64_t n, const int32_t* __restrict__ block_off, int32_t* __restrict__ sel) {
+    const int64_t base = (int64_t)blockIdx.x * POINTS_PER_BLOCK;
+    __shared__ int ws[8];
+    __shared__ int run;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) run = block_off[blockIdx.x];
+    __syncthreads();
+    for (int k0 = 0; k0 < POINTS_PER_BLOCK; k0 += 256) {
+        const int64_t i = base + k0 + threadIdx.x;
+        const bool f = i < n && selflag[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) ws[warp] = __popc(bal);
+        __syncthreads();
+        int off = run;
+        for (int w = 0; w < warp; w++) off += ws[w];
+        if (f) sel[off + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; w++) t += ws[w];
+            run += t;
+        }
+        __syncthreads();
+    }
+}
+// result keys over the compacted rows -> (point id, distance); -1 / FLT_MAX = no such neighbour
+__global__ void points_result_kernel(const unsigned long long* __restrict__ out_key, int n, const int32_t* __restrict__ sel,
+                                     int64_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t j; float d;
+    key_decode(out_key[i], j, d);
+    idx_out[i] = j < 0 ? -1 : (int64_t)sel[j];
+    dist_out[i] = d;
+}
+// valid[ids[k]] = flag
+__global__ void points_set_valid_kernel(const int32_t* __restrict__ ids, int n, uint8_t flag, uint8_t* __restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) valid[ids[i]] = flag;
+}
+
 // local result keys -> keys carrying the GLOBAL index (for a single all-gather across shards)
 __global__ void globalize_keys_kernel(const unsigned long long* __restrict__ out_key, int n, uint32_t row_offset,
                                       unsigned long long* __restrict__ keys) {

@@ -65,6 +65,12 @@ SYMBOLS = {
     "vsm_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "vsm_host_free": (None, [C.c_void_p]),
     "vsm_knn2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vsm_knn2_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
+                                   C.c_void_p]),
+    "vsm_match_pair_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                         C.c_float, C.c_int32, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p,
+                                         C.POINTER(C.c_int32)]),
+    "vsm_store_add_strided": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int32)]),
     "vsm_match_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                                  C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32)]),
     "vsm_match_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -90,6 +96,14 @@ SYMBOLS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     "vsm_db_top2_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vsm_points_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "vsm_points_add_from_frame": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "vsm_points_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "vsm_points_set_valid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "vsm_points_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vsm_points_clear": (C.c_int, [C.c_void_p]),
+    "vsm_points_top2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_int32)]),
     "vsm_db_segmented": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "vsm_loop_detect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                                   C.c_void_p, C.c_void_p]),
@@ -396,6 +410,49 @@ class Matcher:
         self._ck(self._lib.vsm_db_top2_masked(self._h, q.ctypes.data, q.shape[0], mask.ctypes.data, mask.shape[0],
                                               idx.ctypes.data, dist.ctypes.data))
         return idx, dist
+
+    # -- resident map-point table (Map::map_points_) -------------------------------------------------
+    def add_map_points(self, desc, frame_id):
+        """MapPoint births from host descriptors (src/Slam.cpp:1337-1347); returns the first new point id."""
+        d = _rows(desc, "desc")
+        first = C.c_int32(-1)
+        self._ck(self._lib.vsm_points_add(self._h, d.ctypes.data, d.shape[0], frame_id, C.byref(first)))
+        return first.value
+
+    def add_map_points_from_frame(self, handle, kp_idx):
+        """MapPoint births whose descriptor is a row of a stored frame (row(i).clone(), src/Slam.cpp:1339, :1563)."""
+        k = np.ascontiguousarray(kp_idx, np.int32)
+        first = C.c_int32(-1)
+        self._ck(self._lib.vsm_points_add_from_frame(self._h, handle, k.ctypes.data, len(k), C.byref(first)))
+        return first.value
+
+    def observe_map_points(self, point_ids, frame_id):
+        p = np.ascontiguousarray(point_ids, np.int32)
+        self._ck(self._lib.vsm_points_observe(self._h, p.ctypes.data, len(p), frame_id))
+
+    def set_map_points_valid(self, point_ids, valid):
+        p = np.ascontiguousarray(point_ids, np.int32)
+        self._ck(self._lib.vsm_points_set_valid(self._h, p.ctypes.data, len(p), int(valid)))
+
+    def map_point_info(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self._lib.vsm_points_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def clear_map_points(self):
+        self._ck(self._lib.vsm_points_clear(self._h))
+
+    def search_resident_map_points(self, frame_desc, near_frame_id=-1, frame_range=30):
+        """knnMatch(frame, stacked descriptors of the selected map points, 2) with the selection made on the
+        device: valid points (src/Slam.cpp:552-557), optionally only those observed within frame_range frames
+        of near_frame_id (:744-759).  Returns (point ids [nq,2], dist [nq,2], rows of the stacked matrix)."""
+        q = _rows(frame_desc, "frame_desc")
+        idx = np.empty((q.shape[0], 2), np.int64)
+        dist = np.empty((q.shape[0], 2), np.float32)
+        ns = C.c_int32(0)
+        self._ck(self._lib.vsm_points_top2(self._h, q.ctypes.data, q.shape[0], near_frame_id, frame_range, idx.ctypes.data,
+                                           dist.ctypes.data, C.byref(ns)))
+        return idx, dist, ns.value
 
     def track_local_map(self, kp_xy, desc, mp_pos, mp_desc, mp_valid, R_cam, t_cam, indices, cfg=None):
         """Slam::track_local_map (src/Slam.cpp:380-469).  indices is updated in place.
