@@ -278,8 +278,9 @@ typedef struct {
 } vsm_track_cfg;
 
 /* kp_xy: [nkp][2] keypoint pixel coordinates, desc: [nkp][256] the frame's descriptors;
- * mp_pos: [nmp][3] map-point positions, mp_desc: [nmp][256] their descriptors (NULL: the first nmp
- * rows of the keyframe store are the map-point descriptors), mp_valid: [nmp] (NULL = all valid);
+ * mp_pos: [nmp][3] map-point positions, mp_desc: [nmp][256] their descriptors (NULL: points 0 .. nmp-1 of
+ * the resident map-point table, vsm_points_*; if that table is empty, the first nmp rows of the frame
+ * store), mp_valid: [nmp] (NULL = the table's own validity flags, or all valid without the table);
  * R_cam (row-major 3x3), t_cam: world -> camera (the reference's R.t(), -R.t()*t, :404-407).
  * indices: [nkp] in/out = frame->map_point_indices(); obs_mp / obs_ki: [nmp] the (map point,
  * keypoint) pairs for MapPoint::add_observation in the order the reference adds them (:468),

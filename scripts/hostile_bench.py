@@ -1,0 +1,112 @@
+"""Speed and parity of the global top-2 search on HOSTILE data (all other benches use i.i.d. random unit
+rows, the friendliest input for a threshold filter): a clustered database (keyframes of the same place
+hold near-copies of the same descriptors) in database order and shuffled, and a worst case with
+thousands of rows packed inside the margin around the second-best neighbour.
+Prints one JSON object; every case is checked against the CPU oracle on sampled queries.
+  python scripts/hostile_bench.py [rows=4000000] [nq=2000] [seg_tiles=0]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import vsm_b200
+
+
+def unit(x):
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def run_case(name, db, q, seg_tiles, sample, out):
+    from oracle import oracle
+    rows, nq = db.shape[0], q.shape[0]
+    with vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, seg_tiles=seg_tiles) as m:
+        m.adopt_device_matrix(db.data_ptr(), rows)
+        hq = q.cpu().pin_memory().numpy()
+        for _ in range(3):
+            gi, gd = m.search_map_points(hq)
+        ts, dev, tc, sel = [], [], [], []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            gi, gd = m.search_map_points(hq)
+            ts.append((time.perf_counter() - t0) * 1e3)
+            st = m.stats()
+            dev.append(st["device_ms"]); tc.append(st["tc_ms"]); sel.append(st["select_ms"])
+        st = m.stats()
+    host = db.cpu().numpy()
+    qs = np.ascontiguousarray(hq[sample])
+    oi, od = oracle.knn(qs, host, 2)
+    same = (gi[sample] == oi).all(axis=1) & (gd[sample].view(np.uint32) == od.view(np.uint32)).all(axis=1)
+    ties = ~same & (od[:, 0] == od[:, 1])
+    fl = 2.0 * nq * rows * 256
+    med = lambda a: float(np.median(a))
+    out[name] = {"rows": rows, "nq": nq, "p50_ms_e2e": med(ts), "device_ms": med(dev), "tc_ms": med(tc),
+                 "select_plus_rescan_ms": med(sel), "tc_tflops": fl / (med(tc) * 1e-3) / 1e12,
+                 "tflops_e2e": fl / (med(ts) * 1e-3) / 1e12, "candidates_per_query": st["candidates"] / nq,
+                 "flagged_slices": st["flagged_slices"],
+                 "parity_sample": {"queries": int(len(sample)), "identical": int(same.sum()), "exempt_exact_ties": int(ties.sum()),
+                                   "unexplained_mismatches": int((~same & ~ties).sum())}}
+    del host
+
+
+def main():
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+    nq = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+    seg_tiles = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    g = torch.Generator(device="cuda")
+    g.manual_seed(77)
+    out = {"bench": "hostile_data", "seg_tiles": seg_tiles or "auto"}
+    sample = np.arange(0, nq, max(1, nq // 32))[:32]
+
+    def randn(n):
+        return torch.randn((n, 256), generator=g, device="cuda")
+
+    def fill(fn):
+        db = torch.empty((rows, 256), device="cuda")
+        for r0 in range(0, rows, 1 << 19):
+            n = min(1 << 19, rows - r0)
+            db[r0:r0 + n] = fn(r0, n)
+        return db
+
+    # (0) i.i.d. rows, 20 % of the queries re-observe a row (what every other bench uses)
+    db = fill(lambda r0, n: unit(randn(n)))
+    q = unit(randn(nq))
+    src = torch.randint(0, rows, (nq // 5,), generator=g, device="cuda")
+    q[:nq // 5] = unit(db[src] + 0.05 * randn(nq // 5))
+    run_case("iid", db, q, seg_tiles, sample, out)
+    del db
+    # (1) clustered: 4096 centres, rows = centre + sigma * noise; queries drawn from the same centres.
+    #     "contiguous": a cluster's rows are neighbours in the database (keyframes of one place follow each other);
+    #     "shuffled": the same rows in random order
+    ncl = 4096
+    centres = unit(randn(ncl))
+    for sigma in (0.05, 0.10):
+        per = (rows + ncl - 1) // ncl
+        db = fill(lambda r0, n: unit(centres[(torch.arange(r0, r0 + n, device="cuda") // per).clamp(max=ncl - 1)] + sigma * randn(n)))
+        qc = torch.randint(0, ncl, (nq,), generator=g, device="cuda")
+        q = unit(centres[qc] + sigma * randn(nq))
+        run_case(f"clustered_contiguous_sigma{sigma:.2f}", db, q, seg_tiles, sample, out)
+        perm = torch.randperm(rows, generator=g, device="cuda")
+        db = db[perm].contiguous()
+        run_case(f"clustered_shuffled_sigma{sigma:.2f}", db, q, seg_tiles, sample, out)
+        del db, perm
+    # (2) worst case: for every query 3000 database rows at almost the same distance as its second-best
+    #     neighbour (within the bf16 margin), spread over the database in runs of 300
+    db = fill(lambda r0, n: unit(randn(n)))
+    nhard = 64
+    q = unit(randn(nq))
+    base_rows = torch.randint(0, rows - 400, (nhard, 10), generator=g, device="cuda")
+    for k in range(nhard):
+        c = q[k]
+        for r in base_rows[k].tolist():
+            db[r:r + 300] = unit(c[None, :] + 0.02 * randn(300))          # distance ~0.3 +- 1e-3 from the query
+    hard_sample = np.concatenate([np.arange(0, nhard, 4), np.arange(nhard, nq, max(1, (nq - nhard) // 16))[:16]])
+    run_case("packed_margin_64_queries_x_3000_rows", db, q, seg_tiles, hard_sample, out)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,14 @@ def test_track_local_map_matches_reference_loop(seed):
         ind_s[7] = 123456
         tr_s, obs_s, bk_s, _ = m.track_local_map(kp, desc, pos, None, valid, R, t, ind_s)
         assert tr_s == tr_o and obs_s == obs_o and np.array_equal(ind_s, ind_o)
+        # ... and in the resident map-point table, with the table's own validity flags
+        m.clear_store()
+        m.add_map_points(mp_desc, 0)
+        m.set_map_points_valid(np.nonzero(valid == 0)[0].astype(np.int32), False)
+        ind_t = -np.ones(len(kp), np.int32)
+        ind_t[7] = 123456
+        tr_t, obs_t, bk_t, _ = m.track_local_map(kp, desc, pos, None, None, R, t, ind_t)
+        assert tr_t == tr_o and obs_t == obs_o and np.array_equal(ind_t, ind_o) and np.array_equal(bk_t, bk_o)
         # nothing visible / nothing to match
         tr_e, obs_e, _, _ = m.track_local_map(kp, desc, pos + 1000.0, mp_desc, valid, R, t, -np.ones(len(kp), np.int32))
         assert tr_e == 0 and obs_e == []

@@ -2306,8 +2306,11 @@ int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_track_local_map: bad argument") : VSM_ERR_INVALID;
     *tracked = 0;
     if (nkp == 0 || nmp == 0) return VSM_OK;                               // src/Slam.cpp:384
-    if (!mp_desc && ctx->store_rows < nmp)
-        return fail(ctx, VSM_ERR_INVALID, "vsm_track_local_map: the store holds fewer rows than map points");
+    // mp_desc == NULL: the resident map-point table (ids 0 .. nmp-1; its validity flags too if mp_valid is
+    // NULL), or -- when the table is empty -- the first nmp rows of the frame store
+    const bool from_table = !mp_desc && ctx->n_points >= nmp;
+    if (!mp_desc && !from_table && ctx->store_rows < nmp)
+        return fail(ctx, VSM_ERR_INVALID, "vsm_track_local_map: neither the map-point table nor the store holds nmp rows");
     // the reference's visiting order: its cell grid (:391-401), cells row-major, keypoints in push order
     const int GW = (cfg->width + cfg->cell_size - 1) / cfg->cell_size, GH = (cfg->height + cfg->cell_size - 1) / cfg->cell_size;
     std::vector<std::pair<int, int>> order;                                // (cell, ki)
@@ -2344,10 +2347,12 @@ int vsm_track_local_map(vsm_ctx* ctx, const vsm_track_cfg* cfg, const float* kp_
     for (int i = 0; i < 9; i++) tc.R[i] = R_cam[i];
     for (int i = 0; i < 3; i++) tc.t[i] = t_cam[i];
     tc.width = cfg->width; tc.height = cfg->height;
-    const float* d_mp_desc = mp_desc ? ctx->scratch.f32 + (int64_t)nkp * VSM_DIM : ctx->store.f32;
+    const float* d_mp_desc = mp_desc ? ctx->scratch.f32 + (int64_t)nkp * VSM_DIM
+                                     : (from_table ? reinterpret_cast<const float*>(ctx->pt_f32.p) : ctx->store.f32);
+    const uint8_t* d_valid = mp_valid ? d + o_valid : (from_table ? ctx->pt_valid.p : nullptr);
     track_local_map_kernel<<<(unsigned)(((int64_t)nmp * 32 + 255) / 256), 256, 0, ctx->stream>>>(
         tc, reinterpret_cast<const float2*>(d + o_xy), reinterpret_cast<const int32_t*>(d + o_id), nord, ctx->scratch.f32,
-        reinterpret_cast<const double*>(d + o_pos), d_mp_desc, mp_valid ? d + o_valid : nullptr, nmp,
+        reinterpret_cast<const double*>(d + o_pos), d_mp_desc, d_valid, nmp,
         reinterpret_cast<int32_t*>(d + o_bk), reinterpret_cast<double*>(d + o_bd));
     ctx->launches++;
     CK(cudaGetLastError());
