@@ -40,6 +40,19 @@ def run_case(name, db, q, seg_tiles, sample, out):
     qs = np.ascontiguousarray(hq[sample])
     oi, od = oracle.knn(qs, host, 2)
     same = (gi[sample] == oi).all(axis=1) & (gd[sample].view(np.uint32) == od.view(np.uint32)).all(axis=1)
+    if os.environ.get("HOSTILE_DEBUG") and not same.all():
+        with vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, seg_tiles=seg_tiles) as m2:
+            m2.adopt_device_matrix(db.data_ptr(), rows)
+            for rep in range(4):
+                gi2, gd2 = m2.search_map_points(hq)
+                st2 = m2.stats()
+                same2 = (gi2[sample] == oi).all(axis=1)
+                print(name, "fresh matcher rep", rep, "mismatch", int((~same2).sum()), "flagged", st2["flagged_slices"], "cand", st2["candidates"], file=sys.stderr)
+            gi3, gd3 = m2.search_map_points(q.cpu().numpy())
+            print(name, "pageable queries: mismatch", int((~(gi3[sample] == oi).all(axis=1)).sum()), m2.stats()["flagged_slices"], file=sys.stderr)
+        bad = sample[~same]
+        for b in bad[:4]:
+            print("   q", b, "oracle", oi[list(sample).index(b)], od[list(sample).index(b)], "gpu", gi[b], gd[b], file=sys.stderr)
     ties = ~same & (od[:, 0] == od[:, 1])
     fl = 2.0 * nq * rows * 256
     med = lambda a: float(np.median(a))
@@ -93,6 +106,9 @@ def main():
         db = db[perm].contiguous()
         run_case(f"clustered_shuffled_sigma{sigma:.2f}", db, q, seg_tiles, sample, out)
         del db, perm
+    if os.environ.get("HOSTILE_DEBUG"):
+        print(json.dumps(out))
+        return
     # (2) worst case: for every query 3000 database rows at almost the same distance as its second-best
     #     neighbour (within the bf16 margin), spread over the database in runs of 300
     db = fill(lambda r0, n: unit(randn(n)))

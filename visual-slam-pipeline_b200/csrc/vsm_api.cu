@@ -1034,6 +1034,7 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
     ctx->engine = o.engine;
     ctx->num_sms = prop.multiProcessorCount;
     if (o.reserved[0] > 0) ctx->seg_tiles = o.reserved[0];
+    else if (getenv("VSM_SEG_TILES")) ctx->seg_tiles = std::max(0, atoi(getenv("VSM_SEG_TILES")));      // A/B switch
     ctx->work_cap = o.reserved[1] > 0 ? std::min<uint32_t>((uint32_t)o.reserved[1], WORK_CAP) : WORK_CAP;
     auto bail = [&](int code) {
         g_create_error = ctx->err;
@@ -1096,7 +1097,11 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         if (o.reserved[2] > 0) ctx->ring_depth = o.reserved[2];
         if (o.reserved[3] > 0) ctx->pair_cap = (uint32_t)o.reserved[3];
         CK(cudaMalloc(&ctx->d_store_stats, 16));
-        CK(cudaMemset(ctx->d_store_stats, 0, 16));
+        // on the context's own (non-blocking) stream and waited for: a cudaMemset on the legacy default
+        // stream is not ordered with it and could land AFTER the first conversion's atomicMax into the
+        // slot -- an "empty" norm range shrinks dot_margin to ~6e-5 and the exactness guarantee is gone
+        CK(cudaMemsetAsync(ctx->d_store_stats, 0, 16, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaMalloc(&ctx->d_dump, TILE_M * TILE_N * sizeof(float)));
         CK(cudaFuncSetAttribute(tc::tc_top3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
         CK(cudaFuncSetAttribute(tc::tc_top3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
