@@ -88,6 +88,9 @@ typedef struct {
     float   device_ms;           /* device time of the last call (CUDA events, incl. copies) */
     float   tc_ms;               /* device time of the tensor-core kernel of the last call */
     float   select_ms;           /* device time of the select / exact re-score kernel */
+    int32_t slice_tiles;         /* 256-row tiles per record slice of the last planned search (a big database
+                                    search picks 64, or 16 after a search whose slices overflowed often) */
+    int32_t reserved;
 } vsm_stats;
 
 void        vsm_default_opts(vsm_opts* opts);

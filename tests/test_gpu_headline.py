@@ -96,3 +96,43 @@ def test_sharded_merge_of_two_half_databases_equals_oracle(big_db):
     qs = np.ascontiguousarray(q[SAMPLE])
     oi, od = oracle.knn(qs, host, 2)
     assert np.array_equal(gi[SAMPLE], oi) and np.array_equal(bits(gd[SAMPLE]), bits(od))
+
+
+def test_big_search_shortens_its_slices_on_clustered_data():
+    """A clustered database in database order (keyframes of one place next to each other): nearly every
+    query overflows the four recorded entries of its own cluster's slice.  The first big search uses
+    64-tile slices and re-scans them exactly; seeing the overflow count, the next one plans 16-tile slices
+    (4x cheaper re-scans) -- and goes back to 64 on friendly data.  Same exact answers in every regime."""
+    import torch
+    rows, nq, ncl = 1_200_000, 512, 1024
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    centres = _unit(torch, ncl, g)
+    per = (rows + ncl - 1) // ncl
+    cl = (torch.arange(rows, device="cuda") // per).clamp(max=ncl - 1)
+    x = centres[cl] + 0.05 * torch.randn((rows, 256), generator=g, device="cuda")
+    db = x / x.norm(dim=1, keepdim=True)
+    qc = torch.randint(0, ncl, (nq,), generator=g, device="cuda")
+    x = centres[qc] + 0.05 * torch.randn((nq, 256), generator=g, device="cuda")
+    q = (x / x.norm(dim=1, keepdim=True)).cpu().numpy()
+    host = db.cpu().numpy()
+    sample = np.arange(0, nq, 8)
+    oi, od = oracle.knn(np.ascontiguousarray(q[sample]), host, 2)
+    with vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR) as m:
+        m.adopt_device_matrix(db.data_ptr(), rows)
+        seen = []
+        for rep in range(3):
+            gi, gd = m.search_map_points(q)
+            st = m.stats()
+            seen.append((st["slice_tiles"], st["flagged_slices"]))
+            assert np.array_equal(gi[sample], oi) and np.array_equal(bits(gd[sample]), bits(od)), rep
+        assert seen[0][0] == 64 and seen[0][1] * 8 > nq
+        assert seen[1][0] == 16 and seen[2][0] == 16
+        # friendly data again: back to long slices after one search
+        iid = _unit(torch, rows, g)
+        m.adopt_device_matrix(iid.data_ptr(), rows)
+        s2 = []
+        for rep in range(2):
+            m.search_map_points(q)
+            s2.append(m.stats()["slice_tiles"])
+        assert s2 == [16, 64]

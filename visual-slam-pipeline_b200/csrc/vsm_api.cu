@@ -220,6 +220,15 @@ struct vsm_ctx {
     // share of the (query, keyframe) problems of the last per-keyframe search that the ratio-only test
     // could NOT dismiss; starts pessimistic.  Decides the epilogue of the next one (segmented_impl).
     float seg_open_rate = 1.f;
+    // Slice length of a big database search (more than 4096 tiles), chosen from the data: 64-tile slices keep
+    // the record stream and select_kernel's walk over it small, but a slice whose four recorded entries
+    // overflow is re-scanned exactly, 8192 rows per (query, slice).  On clustered databases (keyframes of
+    // one place hold near-copies of the same descriptors, stored next to each other) almost every query
+    // overflows the slice of its own cluster; 16-tile slices make that re-scan four times cheaper for
+    // ~1 % more time on friendly data.  The previous big search's overflow count decides (hysteresis).
+    bool db_short_slices = false;
+    int32_t big_db_nq = 0;               // queries of the big database search of the current call (0 = none)
+    int32_t last_slice_tiles = 0;        // slice length the last planned problem used (vsm_stats)
 };
 
 namespace {
@@ -494,6 +503,7 @@ int begin_call(vsm_ctx* ctx) {
     ctx->err.clear();
     ctx->launches = 0;
     ctx->timed_tc = ctx->timed_sel = false;
+    ctx->big_db_nq = 0;
     ctx->pending_conv.clear();
     CK(cudaSetDevice(ctx->device));
     ctx->timed_call = ctx->profiling;
@@ -512,9 +522,15 @@ int collect_stats(vsm_ctx* ctx) {
     if (ctx->timed_tc) CK(cudaEventElapsedTime(&ctx->stats.tc_ms, ctx->ev_tc0, ctx->ev_tc1));
     if (ctx->timed_sel) CK(cudaEventElapsedTime(&ctx->stats.select_ms, ctx->timed_tc ? ctx->ev_tc1 : ctx->ev_tc0, ctx->ev_sel1));
     unsigned long long c[2] = {0, 0};
-    if (ctx->d_counters && ctx->profiling) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (ctx->d_counters && (ctx->profiling || ctx->big_db_nq)) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.candidates = (int64_t)c[0];
     ctx->stats.flagged_slices = (int64_t)c[1];
+    ctx->stats.slice_tiles = ctx->last_slice_tiles;
+    if (ctx->big_db_nq) {
+        // more than one overflowing slice per 8 queries: shorter slices next time; back when it is 8x rarer
+        if ((int64_t)c[1] * 8 > ctx->big_db_nq) ctx->db_short_slices = true;
+        else if ((int64_t)c[1] * 64 < ctx->big_db_nq) ctx->db_short_slices = false;
+    }
     return VSM_OK;
 }
 
@@ -620,7 +636,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     {
         int64_t uses_slot = 0;
         for (auto& p : probs) if (!p.t_store) uses_slot = 1 + (ctx->call_seq & 1);
-        const int64_t head[8] = {ctx->engine, ctx->seg_tiles, ctx->num_sms, P, (int64_t)jobs.size(), total_out, total_matches, uses_slot};
+        const int64_t head[8] = {ctx->engine, ctx->seg_tiles * 2 + (ctx->db_short_slices ? 1 : 0), ctx->num_sms, P,
+                                 (int64_t)jobs.size(), total_out, total_matches, uses_slot};
         key.resize(sizeof head + sizeof(HProblem) * probs.size() + sizeof(HJob) * jobs.size());
         memcpy(key.data(), head, sizeof head);
         if (P) memcpy(key.data() + sizeof head, probs.data(), sizeof(HProblem) * probs.size());
@@ -690,7 +707,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         // slice length: short slices keep an overflow re-scan cheap, long ones keep the record
         // stream small next to the database stream
         const int seg_pref = ctx->seg_tiles > 0 ? ctx->seg_tiles
-                                                : (ntiles > 4096 ? 64 : (int)std::max<int64_t>(1, std::min<int64_t>(16, ntiles / 16)));
+                                                : (ntiles > 4096 ? (ctx->db_short_slices ? 16 : 64)
+                                                                 : (int)std::max<int64_t>(1, std::min<int64_t>(16, ntiles / 16)));
+        if (ntiles > 4096 && ctx->seg_tiles == 0) ctx->big_db_nq = hp.nq;
+        ctx->last_slice_tiles = seg_pref;
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
         struct Range { int64_t idx0, count; int tiles_after; int slice0; int seg; };
         std::vector<Range> ranges;

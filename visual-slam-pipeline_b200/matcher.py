@@ -47,7 +47,8 @@ class TrackCfg(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [("candidates", C.c_int64), ("flagged_slices", C.c_int64), ("kernel_launches", C.c_int64),
-                ("device_ms", C.c_float), ("tc_ms", C.c_float), ("select_ms", C.c_float)]
+                ("device_ms", C.c_float), ("tc_ms", C.c_float), ("select_ms", C.c_float),
+                ("slice_tiles", C.c_int32), ("reserved", C.c_int32)]
 
 
 def lib_path():
@@ -239,7 +240,7 @@ class Matcher:
         self._ck(self._lib.vsm_get_stats(self._h, C.byref(s)))
         return {"candidates": s.candidates, "flagged_slices": s.flagged_slices,
                 "kernel_launches": s.kernel_launches, "device_ms": s.device_ms,
-                "tc_ms": s.tc_ms, "select_ms": s.select_ms}
+                "tc_ms": s.tc_ms, "select_ms": s.select_ms, "slice_tiles": s.slice_tiles}
 
     # -- cv::DescriptorMatcher::knnMatch(query, train, knn, 2) ---------------------------
     def knn_match(self, query, train):
