@@ -4,6 +4,7 @@ event timings.  Usage: python scripts/profile_case.py <case> [reps]
   pair2000   2000x2000 knn + ratio 0.8 (configs[0])
   ragged64   64 ragged pairs in one call (configs[4])
   seg:<nkf>:<rows>:<nq>  LoopCloser block: per-keyframe top-2 + ratio over nkf stored keyframes
+  loop:<nkf>:<rows>:<nq>  LoopCloser::detect in compact form (fused dismissal, vsm_loop_detect_compact)
   db:<rows>:<nq>   global top-2 of nq queries over a <rows>-row resident DB (configs[2]/[3])
 """
 import os
@@ -64,6 +65,27 @@ def main():
             res = m.match_batch_packed(qa, q_off, ta, t_off, 0.75, True)
             dt = time.perf_counter() - t0
             print(case, "wall_ms", round(dt * 1e3, 3), "matches", int(sum(len(x) for x in res)), m.stats())
+    elif case.startswith("loop"):
+        _, nkf, rows, nq = case.split(":")
+        nkf, rows, nq = int(nkf), int(rows), int(nq)
+        db = torch.empty((nkf * rows, 256), device="cuda")
+        for c0 in range(0, nkf * rows, 1 << 20):
+            n = min(1 << 20, nkf * rows - c0)
+            db[c0:c0 + n] = unit(n, g)
+        q = unit(nq, g)
+        src = (nkf // 2) * rows + torch.randperm(rows, generator=g, device="cuda")[:nq // 5]
+        v = db[src] + 0.06 * torch.randn((nq // 5, 256), generator=g, device="cuda")
+        q[:nq // 5] = v / v.norm(dim=1, keepdim=True)
+        torch.cuda.synchronize()
+        m.adopt_device_matrix(db.data_ptr(), nkf * rows, np.arange(nkf + 1, dtype=np.int64) * rows)
+        hq = q.cpu().pin_memory().numpy()
+        for r in range(reps + 3):
+            t0 = time.perf_counter()
+            st_, lists, _ = m.loop_detect_compact(10**6, hq, 0.75, min_gap=0, every=1, min_matches=30)
+            dt = time.perf_counter() - t0
+            st = m.stats()
+            tf = 2.0 * nq * nkf * rows * 256 / (st["tc_ms"] * 1e-3) / 1e12
+            print(case, "wall_ms", round(dt * 1e3, 3), "tc_TFLOPs", round(tf, 1), "candidates", sorted(lists), st)
     elif case.startswith("seg"):
         _, nkf, rows, nq = case.split(":")
         nkf, rows, nq = int(nkf), int(rows), int(nq)
