@@ -183,8 +183,12 @@ def run_reference(args):
 def committed_traffic(shard_rows):
     """dram bytes per tc_top3_kernel launch from the committed `ncu --set full` capture, or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f)["tc_top3_kernel"].get(str(int(shard_rows)))
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f)["tc_top3_kernel"].get(str(int(shard_rows)))
+            if v is not None:
+                return v
+        return None
     except Exception:
         return None
 
