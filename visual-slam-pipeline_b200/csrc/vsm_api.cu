@@ -2217,9 +2217,8 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     CK(launch_pdl(loop_select_kernel, dim3((unsigned)ctx->num_sms * 4), dim3(SELECT_WARPS * 32), 0, ctx->stream, P));
     CK(launch_pdl(rescan_kernel, dim3((unsigned)ctx->num_sms * 2), dim3(256), 0, ctx->stream, (const WorkItem*)ctx->d_work.p,
                   (const unsigned long long*)ctx->d_counters, ctx->work_cap));
-    CK(launch_pdl(loop_finish_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));
-    CK(launch_pdl(loop_emit_kernel, dim3(1), dim3(1024), 0, ctx->stream, P));
-    ctx->launches += 6;
+    CK(launch_pdl(loop_finish_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));       // its last block gates and emits
+    ctx->launches += 5;
     if (ctx->profiling) {
         CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
         ctx->timed_sel = true;

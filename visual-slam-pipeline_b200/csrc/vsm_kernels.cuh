@@ -458,9 +458,10 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
 //   tc_top3_kernel (again) those units with the ordinary top-4 epilogue: ~4 candidates per open pair
 //   loop_select_kernel     exact top-2 of every open pair from its candidates (canonical fp32 distance)
 //   rescan_kernel          exact scans for the rare pair whose four recorded entries overflowed
-//   loop_finish_kernel     ratio test per open pair (src/LoopCloser.cpp:55-60), survivors per keyframe
-//   loop_emit_kernel       the >= MIN_MATCHES gate (:62) and the surviving keyframes' lists, in query
-//                          order, packed -- nothing of size keyframes x queries ever exists
+//   loop_finish_kernel     ratio test per open pair (src/LoopCloser.cpp:55-60), survivors per keyframe;
+//                          its last block applies the >= MIN_MATCHES gate (:62) and writes the surviving
+//                          keyframes' lists, in query order, packed, straight into pinned host memory --
+//                          nothing of size keyframes x queries ever exists
 struct LoopSlot {                      // one eligible keyframe
     int64_t row0;                      // first store row
     int32_t count;                     // rows (>= 2)
@@ -492,7 +493,8 @@ struct LoopParams {
     uint32_t* hints2;                          // [unit2_cap][128]
     const PartialRec* recs2;                   // [unit2_cap][128][2]
     uint32_t unit2_cap;
-    // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag, [12] second-pass units
+    // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag, [12] second-pass units,
+    // [13] second-pass unit queue head, [14] finished blocks of loop_finish_kernel
     uint32_t* counters;
     WorkItem* work;
     uint32_t work_cap;
@@ -647,57 +649,23 @@ loop_select_kernel(const LoopParams P) {
     }
 }
 
-// One warp per mask word: the reference's test on the pair's exact top-2, survivors counted per keyframe.
-__global__ void __launch_bounds__(256)
-loop_finish_kernel(const LoopParams P) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x & 31;
-    const int64_t nwords = (int64_t)P.nslots * P.words_per_slot;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += nwarps) {
-        const uint32_t m = P.masks[w];
-        if (m == 0u) continue;
-        const int slot = (int)(w / P.words_per_slot);
-        const int q = (int)(w % P.words_per_slot) * 32 + lane;
-        const uint32_t base = P.word_base[w];
-        bool good = false;
-        if ((m >> lane) & 1u) {
-            const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
-            if (p < P.pair_cap) {
-                int32_t i0, i1;
-                float d0, d1;
-                key_decode(P.pair_keys[2 * (size_t)p], i0, d0);
-                key_decode(P.pair_keys[2 * (size_t)p + 1], i1, d1);
-                good = i1 >= 0 && d0 < __fmul_rn(P.ratio, d1);           // m.size() >= 2 && m[0].distance < ratio * m[1].distance
-                DMatch dm = {q, good ? i0 : -1, P.slots[slot].kf_pos, d0};
-                P.stage[p] = dm;
-            }
-        }
-        const int n = __popc(__ballot_sync(0xffffffffu, good));
-        if (lane == 0 && n) atomicAdd(P.slot_good + slot, n);
-    }
-}
-
-// One block: the >= min_matches gate over the eligible keyframes (in list order), then the surviving
-// keyframes' lists packed one after the other, each in query order.
-__global__ void __launch_bounds__(1024)
-loop_emit_kernel(const LoopParams P) {
-    pdl_launch_dependents();
-    pdl_wait();
-    constexpr int LIST_CAP = 1024;              // candidate keyframes remembered in shared memory (more: found again by scanning)
+// The gate over the eligible keyframes (in list order) and the surviving keyframes' lists packed one
+// after the other, each in query order.  Runs in ONE block (the last block of loop_finish_kernel).
+__device__ void loop_emit_block(const LoopParams& P) {
+    constexpr int LIST_CAP = 512;               // candidate keyframes remembered in shared memory (more: found again by scanning)
     __shared__ long long s_off;                 // running survivor offset
     __shared__ int s_cand;                      // running candidate count
     __shared__ int wcnt[32];
     __shared__ long long wsum[32];
     __shared__ int c_slot[LIST_CAP];
     __shared__ long long c_off[LIST_CAP];
+    const int nthreads = blockDim.x, nw = nthreads >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) { s_off = 0; s_cand = 0; }
     __syncthreads();
-    for (int s0 = 0; s0 < P.nslots; s0 += 1024) {
+    for (int s0 = 0; s0 < P.nslots; s0 += nthreads) {
         const int s = s0 + threadIdx.x;
-        const int g = s < P.nslots ? P.slot_good[s] : 0;
+        const int g = s < P.nslots ? __ldcg(P.slot_good + s) : 0;        // written by other blocks' atomics: read at L2
         if (s < P.nslots) P.out_good[s] = g;
         const bool cand = s < P.nslots && g >= P.min_matches && g > 0;
         // block-wide exclusive scan of (cand, g) in slot order
@@ -730,7 +698,7 @@ loop_emit_kernel(const LoopParams P) {
         if (threadIdx.x == 0) {
             long long t = 0;
             int c = 0;
-            for (int w2 = 0; w2 < 32; w2++) { t += wsum[w2]; c += wcnt[w2]; }
+            for (int w2 = 0; w2 < nw; w2++) { t += wsum[w2]; c += wcnt[w2]; }
             s_off += t;
             s_cand += c;
         }
@@ -739,34 +707,88 @@ loop_emit_kernel(const LoopParams P) {
     if (threadIdx.x == 0) {
         P.out_head[0] = s_cand;
         P.out_head[1] = (int32_t)(s_off < 0x7fffffffLL ? s_off : 0x7fffffffLL);
-        P.out_head[2] = (int32_t)P.counters[7];
-        P.out_head[3] = (int32_t)P.counters[5];
+        P.out_head[2] = (int32_t)__ldcg(P.counters + 7);
+        P.out_head[3] = (int32_t)__ldcg(P.counters + 5);
     }
-    // lists: one warp per surviving keyframe, words in query order
+    // lists: one warp per surviving keyframe, words in query order; a warp first loads 32 mask words
+    // (and their pair bases) at once, then walks the non-empty ones
     auto emit = [&](int s, long long off) {
-        for (int w = 0; w < P.words_per_slot; w++) {
+        for (int w0 = 0; w0 < P.words_per_slot; w0 += 32) {
+            const int w = w0 + lane;
             const int64_t wi = (int64_t)s * P.words_per_slot + w;
-            const uint32_t m = P.masks[wi];
-            if (m == 0u) continue;
-            const uint32_t base = P.word_base[wi];
-            DMatch dm = {0, -1, 0, 0.f};
-            if ((m >> lane) & 1u) {
-                const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
-                if (p < P.pair_cap) dm = P.stage[p];
+            const uint32_t my_m = w < P.words_per_slot ? P.masks[wi] : 0u;
+            const uint32_t my_b = my_m ? P.word_base[wi] : 0u;
+            unsigned nz = __ballot_sync(0xffffffffu, my_m != 0u);
+            while (nz) {
+                const int k = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const uint32_t m = __shfl_sync(0xffffffffu, my_m, k);
+                const uint32_t base = __shfl_sync(0xffffffffu, my_b, k);
+                DMatch dm = {0, -1, 0, 0.f};
+                if ((m >> lane) & 1u) {
+                    const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+                    if (p < P.pair_cap) {                           // written by other blocks of this kernel: read at L2
+                        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(P.stage + p));
+                        dm.queryIdx = (int32_t)raw.x; dm.trainIdx = (int32_t)raw.y; dm.imgIdx = (int32_t)raw.z;
+                        dm.distance = __uint_as_float(raw.w);
+                    }
+                }
+                const unsigned gb = __ballot_sync(0xffffffffu, dm.trainIdx >= 0);
+                const long long pos = off + __popc(gb & ((1u << lane) - 1u));
+                if (dm.trainIdx >= 0 && pos < P.match_cap) P.out_matches[pos] = dm;
+                off += __popc(gb);
             }
-            const unsigned gb = __ballot_sync(0xffffffffu, dm.trainIdx >= 0);
-            const long long pos = off + __popc(gb & ((1u << lane) - 1u));
-            if (dm.trainIdx >= 0 && pos < P.match_cap) P.out_matches[pos] = dm;
-            off += __popc(gb);
         }
     };
     const int ncand = s_cand;
-    for (int c = warp; c < min(ncand, LIST_CAP); c += 32) emit(c_slot[c], c_off[c]);
+    for (int c = warp; c < min(ncand, LIST_CAP); c += nw) emit(c_slot[c], c_off[c]);
     if (ncand > LIST_CAP)                                   // the rest were marked in slot_off
-        for (int s = warp; s < P.nslots; s += 32) {
+        for (int s = warp; s < P.nslots; s += nw) {
             const long long off = P.slot_off[s];
             if (off >= 0) emit(s, off);
         }
+}
+
+// One warp per mask word: the reference's test on the pair's exact top-2, survivors counted per keyframe.
+// The block that finishes last (a ticket counter) applies the gate and emits the lists: one launch less.
+__global__ void __launch_bounds__(256)
+loop_finish_kernel(const LoopParams P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t nwords = (int64_t)P.nslots * P.words_per_slot;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += nwarps) {
+        const uint32_t m = P.masks[w];
+        if (m == 0u) continue;
+        const int slot = (int)(w / P.words_per_slot);
+        const int q = (int)(w % P.words_per_slot) * 32 + lane;
+        const uint32_t base = P.word_base[w];
+        bool good = false;
+        if ((m >> lane) & 1u) {
+            const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+            if (p < P.pair_cap) {
+                int32_t i0, i1;
+                float d0, d1;
+                key_decode(__ldcg(P.pair_keys + 2 * (size_t)p), i0, d0);
+                key_decode(__ldcg(P.pair_keys + 2 * (size_t)p + 1), i1, d1);
+                good = i1 >= 0 && d0 < __fmul_rn(P.ratio, d1);           // m.size() >= 2 && m[0].distance < ratio * m[1].distance
+                DMatch dm = {q, good ? i0 : -1, P.slots[slot].kf_pos, d0};
+                P.stage[p] = dm;
+            }
+        }
+        const int n = __popc(__ballot_sync(0xffffffffu, good));
+        if (lane == 0 && n) atomicAdd(P.slot_good + slot, n);
+    }
+    // last block done: every other block's stage[] / slot_good[] writes are visible after its fence + ticket
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(P.counters + 14, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    loop_emit_block(P);
 }
 
 // ---- match_features filter loop --------------------------------------------------
