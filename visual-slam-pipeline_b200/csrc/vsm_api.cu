@@ -228,6 +228,7 @@ struct vsm_ctx {
     // ~1 % more time on friendly data.  The previous big search's overflow count decides (hysteresis).
     bool db_short_slices = false;
     int32_t big_db_nq = 0;               // queries of the big database search of the current call (0 = none)
+    int32_t big_db_feedback_nq = 0;      // ... of the previous call, whose overflow count waits in h_status[6..7]
     int32_t last_slice_tiles = 0;        // slice length the last planned problem used (vsm_stats)
 };
 
@@ -504,6 +505,16 @@ int begin_call(vsm_ctx* ctx) {
     ctx->launches = 0;
     ctx->timed_tc = ctx->timed_sel = false;
     ctx->big_db_nq = 0;
+    if (ctx->big_db_feedback_nq) {
+        // more than one overflowing slice per 8 queries in the previous big search: shorter slices from now
+        // on; back to long ones when overflow is 8x rarer.  (An asynchronous caller that has not waited for
+        // that search yet reads the count of the one before: late by one search, never wrong.)
+        unsigned long long flagged;
+        memcpy(&flagged, ctx->h_status + 6, sizeof flagged);
+        if ((int64_t)flagged * 8 > ctx->big_db_feedback_nq) ctx->db_short_slices = true;
+        else if ((int64_t)flagged * 64 < ctx->big_db_feedback_nq) ctx->db_short_slices = false;
+        ctx->big_db_feedback_nq = 0;
+    }
     ctx->pending_conv.clear();
     CK(cudaSetDevice(ctx->device));
     ctx->timed_call = ctx->profiling;
@@ -522,19 +533,20 @@ int collect_stats(vsm_ctx* ctx) {
     if (ctx->timed_tc) CK(cudaEventElapsedTime(&ctx->stats.tc_ms, ctx->ev_tc0, ctx->ev_tc1));
     if (ctx->timed_sel) CK(cudaEventElapsedTime(&ctx->stats.select_ms, ctx->timed_tc ? ctx->ev_tc1 : ctx->ev_tc0, ctx->ev_sel1));
     unsigned long long c[2] = {0, 0};
-    if (ctx->d_counters && (ctx->profiling || ctx->big_db_nq)) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    if (ctx->d_counters && ctx->profiling) CK(cudaMemcpy(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost));
     ctx->stats.candidates = (int64_t)c[0];
     ctx->stats.flagged_slices = (int64_t)c[1];
     ctx->stats.slice_tiles = ctx->last_slice_tiles;
-    if (ctx->big_db_nq) {
-        // more than one overflowing slice per 8 queries: shorter slices next time; back when it is 8x rarer
-        if ((int64_t)c[1] * 8 > ctx->big_db_nq) ctx->db_short_slices = true;
-        else if ((int64_t)c[1] * 64 < ctx->big_db_nq) ctx->db_short_slices = false;
-    }
     return VSM_OK;
 }
 
 int end_call(vsm_ctx* ctx, bool sync) {
+    if (ctx->big_db_nq && ctx->d_counters) {
+        // the overflow count of a big database search travels to pinned host memory behind the call's own
+        // work (no synchronisation here); the next call reads it and picks its slice length (begin_call)
+        CK(cudaMemcpyAsync(ctx->h_status + 4, ctx->d_counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->big_db_feedback_nq = ctx->big_db_nq;
+    }
     if (ctx->timed_call) CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->stats.kernel_launches = ctx->launches;
     ctx->pending_stats = true;

@@ -375,11 +375,7 @@ int vsm_group_db_top2(vsm_group* g, const float* query, int32_t nq, int64_t* idx
     merge_keys_kernel<<<(nq + 127) / 128, 128, 0, c0->stream>>>(gather, g->n, nq, h_idx, h_dist);
     GCK(cudaGetLastError());
     GCK(cudaStreamSynchronize(c0->stream));
-    for (int r = 0; r < g->n; r++) {                                      // per-member statistics of this call
-        cudaSetDevice(g->dev[r]);
-        if (r) cudaStreamSynchronize(g->ctx[r]->stream);
-        collect_stats(g->ctx[r]);
-    }
+    // (per-member statistics stay pending: vsm_get_stats on a member context collects them on demand)
     memcpy(idx, h_idx, (size_t)nq * 2 * sizeof(int64_t));
     memcpy(dist, h_dist, (size_t)nq * 2 * sizeof(float));
     if (kf_handle || kf_row) {
