@@ -128,6 +128,19 @@ def test_big_search_shortens_its_slices_on_clustered_data():
             assert np.array_equal(gi[sample], oi) and np.array_equal(bits(gd[sample]), bits(od)), rep
         assert seen[0][0] == 64 and seen[0][1] * 8 > nq
         assert seen[1][0] == 16 and seen[2][0] == 16
+        # same store, friendly QUERIES (same shapes: the plan cache hits, the feedback must still flow)
+        qf = _unit(torch, nq, g).cpu().numpy()
+        s1 = []
+        for rep in range(3):
+            m.search_map_points(qf)
+            s1.append(m.stats()["slice_tiles"])
+        assert s1 == [16, 64, 64]
+        s1 = []
+        for rep in range(3):
+            gi, gd = m.search_map_points(q)
+            s1.append(m.stats()["slice_tiles"])
+            assert np.array_equal(gi[sample], oi) and np.array_equal(bits(gd[sample]), bits(od)), rep
+        assert s1 == [64, 16, 16]
         # friendly data again: back to long slices after one search
         iid = _unit(torch, rows, g)
         m.adopt_device_matrix(iid.data_ptr(), rows)

@@ -211,6 +211,7 @@ struct vsm_ctx {
         size_t off_prob = 0, off_unit = 0, off_slice = 0, off_job = 0, total = 0, nunits = 0, nunits2 = 0;
         int64_t nrecs = 0;
         int qb_total = 0;
+        int32_t big_db_nq = 0, slice_tiles = 0;      // what the planning loop noted for the slice-length feedback
         bool valid = false;
     } plan;
     int64_t plan_hits = 0;
@@ -807,8 +808,12 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         pl.nunits2 = units2.size();
         pl.nrecs = nrecs;
         pl.qb_total = qb[P];
+        pl.big_db_nq = ctx->big_db_nq;
+        pl.slice_tiles = ctx->last_slice_tiles;
     } else {
         ctx->plan_hits++;
+        ctx->big_db_nq = pl.big_db_nq;               // the planning loop did not run: same notes as when the plan was made
+        ctx->last_slice_tiles = pl.slice_tiles;
     }
     const size_t off_prob = pl.off_prob;
     const size_t off_qb = align16(off_prob + sizeof(Problem) * P);
