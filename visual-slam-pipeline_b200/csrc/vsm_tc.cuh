@@ -213,20 +213,44 @@ __device__ __forceinline__ float dec_ordered(uint32_t u) {
 struct Top3Core {
     float b0, b1, b2, b3;
 };
+// compare-exchange: hi = max, lo = min (two FMNMX, independent of each other)
+#define VSM_CE(hi, lo)                      \
+    do {                                    \
+        const float mx_ = fmaxf(hi, lo);    \
+        lo = fminf(hi, lo);                 \
+        hi = mx_;                           \
+    } while (0)
+
 __device__ __noinline__ Top3Core top3_push8(Top3Core c, float v0, float v1, float v2, float v3, float v4, float v5,
                                             float v6, float v7, uint32_t scol) {
-    // all eight values are inserted, unconditionally: measured, an `if (v > thr)` around each insert
-    // (skipped by the warp when no lane needs that position) is 50 % SLOWER on small problems --
-    // the divergence bookkeeping costs more than the seven FMNMX it saves
-    const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        const float x = __uint_as_float((__float_as_uint(v[e]) & PACK_MASK) | (scol + e));
-        float t0 = fmaxf(c.b0, x), x1 = fminf(c.b0, x);
-        float t1 = fmaxf(c.b1, x1), x2 = fminf(c.b1, x1);
-        float t2 = fmaxf(c.b2, x2), x3 = fminf(c.b2, x2);
-        c.b0 = t0; c.b1 = t1; c.b2 = t2; c.b3 = fmaxf(c.b3, x3);
-    }
+    // All eight values enter, unconditionally (measured: an `if (v > thr)` around each insert, skipped by
+    // the warp when no lane needs that position, is 50 % SLOWER on small problems).  They used to be
+    // inserted one after the other -- 8 x 7 FMNMX in a dependent chain 32 deep, and with only two epilogue
+    // warps per scheduler that latency, not the issue rate, set the pace of match-heavy small problems
+    // (ncu: 0.66 eligible warps per scheduler).  Now: the eight are sorted as two quads by a network, their
+    // top four are merged with the running top four by two bitonic steps -- 44 FMNMX, depth 9.
+    // Same result: the four largest of the multiset {b0..b3} U {v0..v7}, descending.
+    float a0 = __uint_as_float((__float_as_uint(v0) & PACK_MASK) | (scol + 0));
+    float a1 = __uint_as_float((__float_as_uint(v1) & PACK_MASK) | (scol + 1));
+    float a2 = __uint_as_float((__float_as_uint(v2) & PACK_MASK) | (scol + 2));
+    float a3 = __uint_as_float((__float_as_uint(v3) & PACK_MASK) | (scol + 3));
+    float e0 = __uint_as_float((__float_as_uint(v4) & PACK_MASK) | (scol + 4));
+    float e1 = __uint_as_float((__float_as_uint(v5) & PACK_MASK) | (scol + 5));
+    float e2 = __uint_as_float((__float_as_uint(v6) & PACK_MASK) | (scol + 6));
+    float e3 = __uint_as_float((__float_as_uint(v7) & PACK_MASK) | (scol + 7));
+    // sort each quad descending (5 compare-exchanges, depth 3)
+    VSM_CE(a0, a1); VSM_CE(a2, a3); VSM_CE(e0, e1); VSM_CE(e2, e3);
+    VSM_CE(a0, a2); VSM_CE(a1, a3); VSM_CE(e0, e2); VSM_CE(e1, e3);
+    VSM_CE(a1, a2); VSM_CE(e1, e2);
+    // top four of the eight: max(a_i, e_{3-i}) is a bitonic sequence holding them; sort it (depth 2)
+    float t0 = fmaxf(a0, e3), t1 = fmaxf(a1, e2), t2 = fmaxf(a2, e1), t3 = fmaxf(a3, e0);
+    VSM_CE(t0, t2); VSM_CE(t1, t3);
+    VSM_CE(t0, t1); VSM_CE(t2, t3);
+    // merge with the running top four (both descending): same two steps
+    float r0 = fmaxf(c.b0, t3), r1 = fmaxf(c.b1, t2), r2 = fmaxf(c.b2, t1), r3 = fmaxf(c.b3, t0);
+    VSM_CE(r0, r2); VSM_CE(r1, r3);
+    VSM_CE(r0, r1); VSM_CE(r2, r3);
+    c.b0 = r0; c.b1 = r1; c.b2 = r2; c.b3 = r3;
     return c;
 }
 
