@@ -99,53 +99,43 @@ def test_sharded_merge_of_two_half_databases_equals_oracle(big_db):
 
 
 def test_big_search_shortens_its_slices_on_clustered_data():
-    """A clustered database in database order (keyframes of one place next to each other): nearly every
-    query overflows the four recorded entries of its own cluster's slice.  The first big search uses
-    64-tile slices and re-scans them exactly; seeing the overflow count, the next one plans 16-tile slices
-    (4x cheaper re-scans) -- and goes back to 64 on friendly data.  Same exact answers in every regime."""
+    """A database holding a large cluster of near-copies (keyframes of one place, stored next to each other):
+    every query aimed at it overflows the four recorded entries of the cluster's slices.  A big search
+    starts with 64-tile slices and re-scans the overflowing ones exactly; seeing the overflow count, the
+    next search plans 16-tile slices (4x cheaper re-scans) -- and returns to 64 when queries stop
+    overflowing.  The feedback also flows when the plan cache hits (same shapes, other queries).
+    Exact answers in every regime."""
     import torch
-    rows, nq, ncl = 1_200_000, 512, 1024
+    rows, nq = 1_200_000, 512
     g = torch.Generator(device="cuda")
     g.manual_seed(99)
-    centres = _unit(torch, ncl, g)
-    per = (rows + ncl - 1) // ncl
-    cl = (torch.arange(rows, device="cuda") // per).clamp(max=ncl - 1)
-    x = centres[cl] + 0.05 * torch.randn((rows, 256), generator=g, device="cuda")
-    db = x / x.norm(dim=1, keepdim=True)
-    qc = torch.randint(0, ncl, (nq,), generator=g, device="cuda")
-    x = centres[qc] + 0.05 * torch.randn((nq, 256), generator=g, device="cuda")
-    q = (x / x.norm(dim=1, keepdim=True)).cpu().numpy()
+    db = _unit(torch, rows, g)
+    c0 = _unit(torch, 1, g)
+    x = c0 + 0.05 * torch.randn((40_000, 256), generator=g, device="cuda")
+    db[500_000:540_000] = x / x.norm(dim=1, keepdim=True)
+    x = c0 + 0.05 * torch.randn((nq, 256), generator=g, device="cuda")
+    q_hard = (x / x.norm(dim=1, keepdim=True)).cpu().numpy()            # aimed at the cluster
+    q_easy = _unit(torch, nq, g).cpu().numpy()                          # anywhere
     host = db.cpu().numpy()
     sample = np.arange(0, nq, 8)
-    oi, od = oracle.knn(np.ascontiguousarray(q[sample]), host, 2)
+    want = {}
+    for name, q in (("hard", q_hard), ("easy", q_easy)):
+        want[name] = oracle.knn(np.ascontiguousarray(q[sample]), host, 2)
+
+    def search(m, name, q):
+        gi, gd = m.search_map_points(q)
+        oi, od = want[name]
+        assert np.array_equal(gi[sample], oi) and np.array_equal(bits(gd[sample]), bits(od)), name
+        st = m.stats()
+        return st["slice_tiles"], st["flagged_slices"]
+
     with vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR) as m:
         m.adopt_device_matrix(db.data_ptr(), rows)
-        seen = []
-        for rep in range(3):
-            gi, gd = m.search_map_points(q)
-            st = m.stats()
-            seen.append((st["slice_tiles"], st["flagged_slices"]))
-            assert np.array_equal(gi[sample], oi) and np.array_equal(bits(gd[sample]), bits(od)), rep
-        assert seen[0][0] == 64 and seen[0][1] * 8 > nq
-        assert seen[1][0] == 16 and seen[2][0] == 16
-        # same store, friendly QUERIES (same shapes: the plan cache hits, the feedback must still flow)
-        qf = _unit(torch, nq, g).cpu().numpy()
-        s1 = []
-        for rep in range(3):
-            m.search_map_points(qf)
-            s1.append(m.stats()["slice_tiles"])
-        assert s1 == [16, 64, 64]
-        s1 = []
-        for rep in range(3):
-            gi, gd = m.search_map_points(q)
-            s1.append(m.stats()["slice_tiles"])
-            assert np.array_equal(gi[sample], oi) and np.array_equal(bits(gd[sample]), bits(od)), rep
-        assert s1 == [64, 16, 16]
-        # friendly data again: back to long slices after one search
-        iid = _unit(torch, rows, g)
-        m.adopt_device_matrix(iid.data_ptr(), rows)
-        s2 = []
-        for rep in range(2):
-            m.search_map_points(q)
-            s2.append(m.stats()["slice_tiles"])
-        assert s2 == [16, 64]
+        seen = [search(m, "hard", q_hard) for _ in range(3)]
+        assert seen[0][0] == 64 and seen[0][1] * 8 > nq, seen
+        assert seen[1][0] == 16 and seen[2][0] == 16, seen
+        # other queries, same shapes: the plan cache hits, the overflow feedback must still flow
+        seen = [search(m, "easy", q_easy) for _ in range(3)]
+        assert [s_[0] for s_ in seen] == [16, 64, 64] and seen[0][1] * 64 < nq, seen
+        seen = [search(m, "hard", q_hard) for _ in range(2)]
+        assert [s_[0] for s_ in seen] == [64, 16], seen
