@@ -254,97 +254,6 @@ __device__ __noinline__ Top3Core top3_push8(Top3Core c, float v0, float v1, floa
     return c;
 }
 
-// The whole 32-value chunk at once, for warps in which several groups beat the threshold (match-heavy
-// small problems: with train sets of ~1000 rows some lane of the warp has a candidate in most groups).
-// Four calls of top3_push8 would be a dependent chain (each call's threshold feeds the next test) about
-// 36 FMNMX deep; this network -- eight sorted quads, a three-level tournament of bitonic top-4 merges, a
-// last merge with the running top four -- is 176 FMNMX of depth 15 with eight-fold parallelism at the
-// bottom, so the two epilogue warps of a scheduler keep it busy instead of waiting on each other's latency.
-__device__ __noinline__ Top3Core top3_push32(Top3Core c, uint32_t scol, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, float v8, float v9, float v10, float v11, float v12, float v13, float v14, float v15, float v16, float v17, float v18, float v19, float v20, float v21, float v22, float v23, float v24, float v25, float v26, float v27, float v28, float v29, float v30, float v31) {
-    float x0 = __uint_as_float((__float_as_uint(v0) & PACK_MASK) | (scol + 0));
-    float x1 = __uint_as_float((__float_as_uint(v1) & PACK_MASK) | (scol + 1));
-    float x2 = __uint_as_float((__float_as_uint(v2) & PACK_MASK) | (scol + 2));
-    float x3 = __uint_as_float((__float_as_uint(v3) & PACK_MASK) | (scol + 3));
-    float x4 = __uint_as_float((__float_as_uint(v4) & PACK_MASK) | (scol + 4));
-    float x5 = __uint_as_float((__float_as_uint(v5) & PACK_MASK) | (scol + 5));
-    float x6 = __uint_as_float((__float_as_uint(v6) & PACK_MASK) | (scol + 6));
-    float x7 = __uint_as_float((__float_as_uint(v7) & PACK_MASK) | (scol + 7));
-    float x8 = __uint_as_float((__float_as_uint(v8) & PACK_MASK) | (scol + 8));
-    float x9 = __uint_as_float((__float_as_uint(v9) & PACK_MASK) | (scol + 9));
-    float x10 = __uint_as_float((__float_as_uint(v10) & PACK_MASK) | (scol + 10));
-    float x11 = __uint_as_float((__float_as_uint(v11) & PACK_MASK) | (scol + 11));
-    float x12 = __uint_as_float((__float_as_uint(v12) & PACK_MASK) | (scol + 12));
-    float x13 = __uint_as_float((__float_as_uint(v13) & PACK_MASK) | (scol + 13));
-    float x14 = __uint_as_float((__float_as_uint(v14) & PACK_MASK) | (scol + 14));
-    float x15 = __uint_as_float((__float_as_uint(v15) & PACK_MASK) | (scol + 15));
-    float x16 = __uint_as_float((__float_as_uint(v16) & PACK_MASK) | (scol + 16));
-    float x17 = __uint_as_float((__float_as_uint(v17) & PACK_MASK) | (scol + 17));
-    float x18 = __uint_as_float((__float_as_uint(v18) & PACK_MASK) | (scol + 18));
-    float x19 = __uint_as_float((__float_as_uint(v19) & PACK_MASK) | (scol + 19));
-    float x20 = __uint_as_float((__float_as_uint(v20) & PACK_MASK) | (scol + 20));
-    float x21 = __uint_as_float((__float_as_uint(v21) & PACK_MASK) | (scol + 21));
-    float x22 = __uint_as_float((__float_as_uint(v22) & PACK_MASK) | (scol + 22));
-    float x23 = __uint_as_float((__float_as_uint(v23) & PACK_MASK) | (scol + 23));
-    float x24 = __uint_as_float((__float_as_uint(v24) & PACK_MASK) | (scol + 24));
-    float x25 = __uint_as_float((__float_as_uint(v25) & PACK_MASK) | (scol + 25));
-    float x26 = __uint_as_float((__float_as_uint(v26) & PACK_MASK) | (scol + 26));
-    float x27 = __uint_as_float((__float_as_uint(v27) & PACK_MASK) | (scol + 27));
-    float x28 = __uint_as_float((__float_as_uint(v28) & PACK_MASK) | (scol + 28));
-    float x29 = __uint_as_float((__float_as_uint(v29) & PACK_MASK) | (scol + 29));
-    float x30 = __uint_as_float((__float_as_uint(v30) & PACK_MASK) | (scol + 30));
-    float x31 = __uint_as_float((__float_as_uint(v31) & PACK_MASK) | (scol + 31));
-    VSM_CE(x0, x1); VSM_CE(x2, x3); VSM_CE(x0, x2); VSM_CE(x1, x3); VSM_CE(x1, x2);
-    VSM_CE(x4, x5); VSM_CE(x6, x7); VSM_CE(x4, x6); VSM_CE(x5, x7); VSM_CE(x5, x6);
-    VSM_CE(x8, x9); VSM_CE(x10, x11); VSM_CE(x8, x10); VSM_CE(x9, x11); VSM_CE(x9, x10);
-    VSM_CE(x12, x13); VSM_CE(x14, x15); VSM_CE(x12, x14); VSM_CE(x13, x15); VSM_CE(x13, x14);
-    VSM_CE(x16, x17); VSM_CE(x18, x19); VSM_CE(x16, x18); VSM_CE(x17, x19); VSM_CE(x17, x18);
-    VSM_CE(x20, x21); VSM_CE(x22, x23); VSM_CE(x20, x22); VSM_CE(x21, x23); VSM_CE(x21, x22);
-    VSM_CE(x24, x25); VSM_CE(x26, x27); VSM_CE(x24, x26); VSM_CE(x25, x27); VSM_CE(x25, x26);
-    VSM_CE(x28, x29); VSM_CE(x30, x31); VSM_CE(x28, x30); VSM_CE(x29, x31); VSM_CE(x29, x30);
-    float p0_0 = fmaxf(x0, x7);
-    float p0_1 = fmaxf(x1, x6);
-    float p0_2 = fmaxf(x2, x5);
-    float p0_3 = fmaxf(x3, x4);
-    VSM_CE(p0_0, p0_2); VSM_CE(p0_1, p0_3); VSM_CE(p0_0, p0_1); VSM_CE(p0_2, p0_3);
-    float p1_0 = fmaxf(x8, x15);
-    float p1_1 = fmaxf(x9, x14);
-    float p1_2 = fmaxf(x10, x13);
-    float p1_3 = fmaxf(x11, x12);
-    VSM_CE(p1_0, p1_2); VSM_CE(p1_1, p1_3); VSM_CE(p1_0, p1_1); VSM_CE(p1_2, p1_3);
-    float p2_0 = fmaxf(x16, x23);
-    float p2_1 = fmaxf(x17, x22);
-    float p2_2 = fmaxf(x18, x21);
-    float p2_3 = fmaxf(x19, x20);
-    VSM_CE(p2_0, p2_2); VSM_CE(p2_1, p2_3); VSM_CE(p2_0, p2_1); VSM_CE(p2_2, p2_3);
-    float p3_0 = fmaxf(x24, x31);
-    float p3_1 = fmaxf(x25, x30);
-    float p3_2 = fmaxf(x26, x29);
-    float p3_3 = fmaxf(x27, x28);
-    VSM_CE(p3_0, p3_2); VSM_CE(p3_1, p3_3); VSM_CE(p3_0, p3_1); VSM_CE(p3_2, p3_3);
-    float s0_0 = fmaxf(p0_0, p1_3);
-    float s0_1 = fmaxf(p0_1, p1_2);
-    float s0_2 = fmaxf(p0_2, p1_1);
-    float s0_3 = fmaxf(p0_3, p1_0);
-    VSM_CE(s0_0, s0_2); VSM_CE(s0_1, s0_3); VSM_CE(s0_0, s0_1); VSM_CE(s0_2, s0_3);
-    float s1_0 = fmaxf(p2_0, p3_3);
-    float s1_1 = fmaxf(p2_1, p3_2);
-    float s1_2 = fmaxf(p2_2, p3_1);
-    float s1_3 = fmaxf(p2_3, p3_0);
-    VSM_CE(s1_0, s1_2); VSM_CE(s1_1, s1_3); VSM_CE(s1_0, s1_1); VSM_CE(s1_2, s1_3);
-    float t0 = fmaxf(s0_0, s1_3);
-    float t1 = fmaxf(s0_1, s1_2);
-    float t2 = fmaxf(s0_2, s1_1);
-    float t3 = fmaxf(s0_3, s1_0);
-    VSM_CE(t0, t2); VSM_CE(t1, t3); VSM_CE(t0, t1); VSM_CE(t2, t3);
-    float r0 = fmaxf(c.b0, t3);
-    float r1 = fmaxf(c.b1, t2);
-    float r2 = fmaxf(c.b2, t1);
-    float r3 = fmaxf(c.b3, t0);
-    VSM_CE(r0, r2); VSM_CE(r1, r3); VSM_CE(r0, r1); VSM_CE(r2, r3);
-    c.b0 = r0; c.b1 = r1; c.b2 = r2; c.b3 = r3;
-    return c;
-}
-
 // 32 accumulator values of one thread = slice columns [scol0, scol0+32).
 // Fast path: four max-trees, ONE compare and ONE branch per 32 values.  The rare path re-checks
 // the four groups and pushes only those that beat the threshold (packed top-4 insert).
@@ -357,24 +266,14 @@ __device__ __forceinline__ void scan32(Top3& s, const uint32_t (&r)[32], uint32_
     }
     if (slow && __any_sync(0xffffffffu, fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > s.thr)) (*slow)++;   // debug only
     if (fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > s.thr) {
-        const int ntrip = (m[0] > s.thr) + (m[1] > s.thr) + (m[2] > s.thr) + (m[3] > s.thr);
-        if (__any_sync(__activemask(), ntrip >= 2)) {
-            // several groups qualify (for this lane or a neighbour): one shallow network over the whole chunk
-            const float* v = reinterpret_cast<const float*>(&r[0]);
-            Top3Core c = {s.b0, s.b1, s.b2, s.b3};
-            c = top3_push32(c, scol0, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]);
-            s.b0 = c.b0; s.b1 = c.b1; s.b2 = c.b2; s.b3 = c.b3;
-            top3_update_thr(s);
-        } else {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                if (m[g] > s.thr) {
-                    const float* v = reinterpret_cast<const float*>(&r[8 * g]);
-                    Top3Core c = {s.b0, s.b1, s.b2, s.b3};
-                    c = top3_push8(c, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], scol0 + 8 * g);
-                    s.b0 = c.b0; s.b1 = c.b1; s.b2 = c.b2; s.b3 = c.b3;
-                    top3_update_thr(s);
-                }
+        for (int g = 0; g < 4; g++) {
+            if (m[g] > s.thr) {
+                const float* v = reinterpret_cast<const float*>(&r[8 * g]);
+                Top3Core c = {s.b0, s.b1, s.b2, s.b3};
+                c = top3_push8(c, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], scol0 + 8 * g);
+                s.b0 = c.b0; s.b1 = c.b1; s.b2 = c.b2; s.b3 = c.b3;
+                top3_update_thr(s);
             }
         }
     }
