@@ -725,6 +725,12 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         if (ntiles > 4096 && ctx->seg_tiles == 0) ctx->big_db_nq = hp.nq;
         ctx->last_slice_tiles = seg_pref;
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
+        // small train sets (pairs, tracking, ragged batches): append records -- one slice per (range, column
+        // half), every value above the running threshold stored, no top-4 state in the epilogue (vsm_tc.cuh)
+        static const int64_t append_max_tiles = getenv("VSM_APPEND_TILES") ? atoll(getenv("VSM_APPEND_TILES")) : 16;
+        const bool append = !maxima && !pairs && !hp.runs && !dump_first && ntiles <= append_max_tiles && ctx->seg_tiles == 0;
+        if (append) d.exact |= 4;
+        const int rec_per_slice = append ? APPEND_RECS : 1;
         struct Range { int64_t idx0, count; int tiles_after; int slice0; int seg; };
         std::vector<Range> ranges;
         for (const Run& rn : runs) {
@@ -732,7 +738,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             if (rt == 0) continue;
             const int nr = (rt + tpr_all - 1) / tpr_all;
             const int tpr = (rt + nr - 1) / nr;
-            const int seg = std::min(std::min(tpr, seg_pref), 64);  // 64 tiles x 128 columns = the 13 index bits of a packed entry
+            // 64 tiles x 128 columns = the 13 index bits of a packed entry; an append unit is one segment
+            const int seg = append ? tpr : std::min(std::min(tpr, seg_pref), 64);
             for (int tile0 = 0; tile0 < rt; tile0 += tpr) {
                 const int tile1 = std::min(rt, tile0 + tpr);
                 Range g;
@@ -776,15 +783,15 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 memset(&u, 0, sizeof u);
                 u.q_n2 = hp.q_n2 + (int64_t)qt * TILE_M;
                 u.t_stats = nullptr;                                    // fixed up below
-                u.rec_base = nrecs + (int64_t)qt * TILE_M * d.nslices + g.slice0;
-                u.rec_stride = d.nslices;
+                u.rec_base = nrecs + ((int64_t)qt * TILE_M * d.nslices + g.slice0) * rec_per_slice;
+                u.rec_stride = d.nslices * rec_per_slice;
                 u.q_row = (int32_t)(hp.q_row + (int64_t)qt * TILE_M);
                 u.t_row = (int32_t)(hp.t_row + g.idx0);
                 u.t_index0 = (int32_t)g.idx0;
                 u.t_count = (int32_t)g.count;
                 u.q_valid = std::min(TILE_M, hp.nq - qt * TILE_M);
                 u.seg_tiles = g.seg;
-                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0) | (maxima ? 4 : 0);
+                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0) | (maxima ? 4 : 0) | (append ? 16 : 0);
                 u.dump = (dump_first && units.empty()) ? dump_first : 0;
                 // 1 + the number of tiles past this unit's end that may be prefetched as well
                 u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 + std::min(tc::L2_AHEAD, g.tiles_after) : 0;
@@ -792,7 +799,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 unit_prob.push_back(i);
             }
         }
-        nrecs += (int64_t)hp.nq * d.nslices;
+        nrecs += (int64_t)hp.nq * d.nslices * rec_per_slice;
     }
 
     // descriptor block: [Problem][q_block0][TcUnit][SliceInfo][FilterJob]

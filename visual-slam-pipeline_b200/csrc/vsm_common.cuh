@@ -41,6 +41,11 @@ struct __align__(16) PartialRec {
     float s[VSM_TOPK];
 };
 constexpr uint32_t PACK_MASK = 0xFFFFE000u;
+// Append records (small train sets, TcUnit maps bit 4): per (query, slice) APPEND_CAP floats -- [0] the
+// number of values that passed the running threshold (as an integer), [1..] the first APPEND_CAP - 1 of
+// them, packed like a PartialRec entry.  A count above APPEND_CAP - 1 = overflow: the slice is re-scanned.
+constexpr int APPEND_CAP = 64;
+constexpr int APPEND_RECS = APPEND_CAP * 4 / 16;          // PartialRec slots one append record occupies
 constexpr float MASKED_VALUE = -3.0e38f;       // a column past the end of the train range
 constexpr float VALID_FLOOR = -1.0e38f;        // record entries above this are real columns
 
@@ -58,6 +63,9 @@ struct TcUnit {
     int32_t seg_tiles;             // tiles per slice segment (records flushed every seg_tiles tiles)
     int32_t maps;                  // bit0: query rows in store map, bit1: train rows in store map,
                                    // bit2: maxima-only records (see scan32_max2),
+                                   // bit4: APPEND records (see APPEND_CAP): every value above the running
+                                   //       threshold is appended, no top-4 state -- for small train sets, where
+                                   //       almost every 8-group holds a candidate for some lane of the warp
                                    // bit3 (with bit2): FUSED ratio dismissal -- the unit covers one whole keyframe;
                                    //       no record is written, only a 128-bit mask of the queries the
                                    //       ratio test could not dismiss (rec_base = first mask word of the unit)
@@ -102,6 +110,7 @@ struct Problem {
     int32_t exact;                 // bit0: no tensor-core records, scan every slice exactly;
                                    // bit1: the records hold slice maxima only (TcUnit maps bit2): a query
                                    //       that the ratio-only test cannot dismiss is re-scanned exactly
+                                   // bit2: append records (TcUnit maps bit4), APPEND_RECS slots per (query, slice)
     // > 0: the caller only wants ratio-test survivors of this problem (no raw list; a mutual test, if
     // any, is applied on top by filter_kernel) with this ratio^2 * 1.001: a query whose approximate top-2 already PROVES the ratio test fails is
     // answered "no match" without any exact re-score (select_kernel)

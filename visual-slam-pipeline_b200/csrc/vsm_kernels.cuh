@@ -244,6 +244,109 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     if (P.exact & 1) {
         load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
         for (int s = 0; s < P.nslices; s++) scan_slice<SELECT_U>(qreg, P.t_f32, sl[s], h, l16, best);
+    } else if (P.exact & 4) {
+        // ----- append records (small train sets): per slice a count and up to APPEND_CAP - 1 packed values that
+        // passed the epilogue's running threshold.  Same two passes as below: the second-largest value over
+        // everything recorded gives the final threshold; the survivors are re-scored exactly.
+        const float* rq = reinterpret_cast<const float*>(recs + P.partial_off) + (int64_t)q * P.nslices * APPEND_CAP;
+        load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);          // needed by (almost) every query of a small problem
+        float a0 = -INFINITY, a1 = -INFINITY;
+        bool any_overflow = false;
+        for (int s = 0; s < P.nslices; s++) {
+            const float* rs = rq + (size_t)s * APPEND_CAP;
+            const uint32_t cnt = __float_as_uint(rs[0]);
+            any_overflow |= cnt > (uint32_t)(APPEND_CAP - 1);
+            const uint32_t have = min(cnt, (uint32_t)(APPEND_CAP - 1));
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint32_t e = lane + 32 * k;
+                if (e < have) {
+                    const float v = rs[1 + e];
+                    if (v > a0) { a1 = a0; a0 = v; } else if (v > a1) a1 = v;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float b0 = __shfl_xor_sync(full, a0, o), b1 = __shfl_xor_sync(full, a1, o);
+            if (b0 > a0) { a1 = fmaxf(a0, b1); a0 = b0; } else a1 = fmaxf(a1, b0);
+        }
+        float tmin2, tmax2;
+        stats_read(P.t_stats, tmin2, tmax2);
+        const float qn2 = __ldg(P.q_n2 + q);
+        const float margin = dot_margin(qn2, tmin2, tmax2);
+        const float thr = a1 - 2.f * margin;
+        // ratio-only early-out (see below); a0 / a1 are the true largest values only if no slice overflowed
+        if (P.skip_ratio2 > 0.f && a1 > VALID_FLOOR && !any_overflow) {
+            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
+            const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
+            if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) {
+                if (lane == 0) {
+                    unsigned long long* o = out_key + (P.out_off + q) * 2;
+                    o[0] = 0ull;
+                    o[1] = 0ull;
+                }
+                return;
+            }
+            if (lane == 0) atomicAdd(reinterpret_cast<uint32_t*>(counters + 2) + 1, 1u);
+        }
+        int32_t* list = s_list[warp];
+        int cnt_l = 0;
+        auto drain = [&]() {
+            const int n = min(cnt_l, 2 * SELECT_U), base = cnt_l - n;
+            int32_t j[SELECT_U];
+#pragma unroll
+            for (int u = 0; u < SELECT_U; u++) {
+                const int slot = base + h * SELECT_U + u;
+                j[u] = slot < cnt_l ? list[slot] : -1;
+            }
+            score_n<SELECT_U>(qreg, P.t_f32, j, l16, best);
+            cnt_l = base;
+            __syncwarp();
+        };
+        for (int s = 0; s < P.nslices; s++) {
+            const float* rs = rq + (size_t)s * APPEND_CAP;
+            const SliceInfo my = sl[s];
+            const uint32_t cnt = __float_as_uint(rs[0]);
+            if (cnt > (uint32_t)(APPEND_CAP - 1)) {
+                // more values passed than the record holds: exact scan of the slice (rescan_kernel)
+                n_flag++;
+                int fits = 1;
+                if (lane == 0) {
+                    const int span = slice_span(my);
+                    const uint32_t nitem = (uint32_t)((span + RESCAN_ROWS - 1) / RESCAN_ROWS);
+                    uint32_t* wcount = reinterpret_cast<uint32_t*>(counters + 2);
+                    const uint32_t base = atomicAdd(wcount, nitem);
+                    fits = base + nitem <= work_cap;
+                    for (uint32_t k = 0; k < nitem && base + k < work_cap; k++) {       // list full: the slots are voided
+                        WorkItem w = {P.q_f32 + (size_t)q * VSM_DIM, P.t_f32, fits ? out_key + (P.out_off + q) * 2 : nullptr, my,
+                                      (int32_t)(k * RESCAN_ROWS), 0};
+                        work[base + k] = w;
+                    }
+                }
+                fits = __shfl_sync(full, fits, 0);
+                if (!fits) scan_slice<SELECT_U>(qreg, P.t_f32, my, h, l16, best);           // ... and the slice is scanned here
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint32_t e = lane + 32 * k;
+                float v = -INFINITY;
+                if (e < cnt) v = rs[1 + e];
+                const bool on = v > VALID_FLOOR && v > thr;
+                const uint32_t c = __float_as_uint(v) & ~PACK_MASK;
+                const int32_t cand = my.t_index0 + (int32_t)(c / HALF_N) * TILE_N + my.half * HALF_N + (int32_t)(c % HALF_N);
+                const unsigned bal = __ballot_sync(full, on);
+                if (bal) {
+                    if (on) list[cnt_l + __popc(bal & ((1u << lane) - 1u))] = cand;
+                    cnt_l += __popc(bal);
+                    n_cand += on ? 1 : 0;
+                    __syncwarp();
+                    while (cnt_l >= 2 * SELECT_U) drain();
+                }
+            }
+        }
+        while (cnt_l > 0) drain();
     } else {
         const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
         // pass 1: the second largest approximate dot over every record of the query

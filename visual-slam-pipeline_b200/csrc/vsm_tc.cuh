@@ -292,6 +292,50 @@ __device__ __forceinline__ void scan32_max2(float& g0, float& g1, const uint32_t
     }
 }
 
+// Append form (units with maps bit 4).  Small train sets are match-heavy: with ~1000 rows every warp (32
+// queries) has a value above the threshold in almost every 8-group, so the top-4 insert path ran for ~15
+// of 16 groups per tile with 4 of 32 lanes active (ncu) and the epilogue, not the tensor pipe, set the
+// pace (5500 cycles per tile against 2350 for the MMAs).  Here nothing is inserted and no state is
+// carried from group to group: the running top-2 of the group maxima gives the threshold (a lower
+// bound on the final second best minus the margin, exactly as in the top-4 form), and every value above
+// it is stored straight to the query's record -- a predicated store per value, no dependency chain.
+struct AppendState {
+    float g0, g1;              // running top-2 of the group maxima (g1: a value of another row than g0's)
+    float G;                   // lower bound on the query's global second-best dot (other warps / CTAs)
+    float margin2;
+    float published;
+    uint32_t cnt;              // values that passed so far (stored only while below APPEND_CAP - 1)
+};
+__device__ __forceinline__ void append32(AppendState& s, const uint32_t (&r)[32], uint32_t scol0, float* __restrict__ rec,
+                                         bool row_valid) {
+    float m[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const float* v = reinterpret_cast<const float*>(&r[8 * g]);
+        m[g] = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        s.g1 = fmaxf(s.g1, fminf(s.g0, m[g]));
+        s.g0 = fmaxf(s.g0, m[g]);
+    }
+    // the chunk's own maxima already count: g1 is still a lower bound on the final second best
+    const float thr = fmaxf(fmaxf(s.G, s.g1) - s.margin2, VALID_FLOOR);
+    if (fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > thr) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (m[g] > thr) {
+                const float* v = reinterpret_cast<const float*>(&r[8 * g]);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (v[e] > thr) {
+                        if (row_valid && s.cnt < (uint32_t)(APPEND_CAP - 1))
+                            rec[1 + s.cnt] = __uint_as_float((__float_as_uint(v[e]) & PACK_MASK) | (scol0 + 8 * g + e));
+                        s.cnt++;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // A partial last tile: columns at or past the end of the train range become MASKED_VALUE.
 __device__ __forceinline__ void mask32(uint32_t (&r)[32], int32_t ucol0, int32_t t_count) {
 #pragma unroll
@@ -538,6 +582,60 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         if (lane == 0) u.hint[u.rec_base + quarter] = m;
                     }
                 }
+                continue;
+            }
+            if (u.maps & 16) {
+                // ----- append unit: one slice per column half over the whole range of the unit
+                AppendState a;
+                a.g0 = a.g1 = a.G = a.published = -INFINITY;
+                a.cnt = 0;
+                {
+                    const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 0.f;
+                    float tmin2, tmax2;
+                    stats_read(u.t_stats, tmin2, tmax2);
+                    a.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
+                }
+                float* rec = reinterpret_cast<float*>(recs + u.rec_base + (int64_t)(row_valid ? row : 0) * u.rec_stride + half * APPEND_RECS);
+                volatile uint32_t* hint = u.hint + (row_valid ? row : 0);
+                uint32_t h_next = *hint;
+                for (int n = 0; n < ntiles; n++, tile_it++) {
+                    const int st = tile_it & 1;
+                    const uint32_t h = h_next;
+                    mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
+                    tcgen05_fence_after();
+                    if (h != 0u) a.G = fmaxf(a.G, dec_ordered(h));
+                    const uint32_t taddr = lane_addr + st * TILE_N;
+                    const int32_t ucol = n * TILE_N + half * HALF_N;
+                    const uint32_t scol = (uint32_t)n * HALF_N;
+                    const bool full_tile = (n + 1) * TILE_N <= u.t_count;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr, ra);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 32, rb);
+                    if (!full_tile) mask32(ra, ucol, u.t_count);
+                    append32(a, ra, scol, rec, row_valid);
+                    tmem_ld_wait(rb);
+                    tmem_ld32(taddr + 64, ra);
+                    if (!full_tile) mask32(rb, ucol + 32, u.t_count);
+                    append32(a, rb, scol + 32, rec, row_valid);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 96, rb);
+                    if (!full_tile) mask32(ra, ucol + 64, u.t_count);
+                    append32(a, ra, scol + 64, rec, row_valid);
+                    tmem_ld_wait(rb);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+                    h_next = *hint;
+                    if (!full_tile) mask32(rb, ucol + 96, u.t_count);
+                    append32(a, rb, scol + 96, rec, row_valid);
+                    const float L = fmaxf(a.G, a.g1);
+                    if (row_valid && L > a.published) {
+                        atomicMax(const_cast<uint32_t*>(hint), enc_ordered(L));
+                        a.published = L;
+                    }
+                }
+                if (row_valid) rec[0] = __uint_as_float(a.cnt);
                 continue;
             }
             Top3 s;
