@@ -39,7 +39,10 @@ constexpr uint32_t SMEM_Q = 0;
 constexpr uint32_t SMEM_T = NCHUNK * Q_SUB_BYTES;                 // 65536
 constexpr uint32_t SMEM_BAR = SMEM_T + STAGES * T_STAGE_BYTES;    // 196608
 constexpr uint32_t SMEM_XCHG = SMEM_BAR + 512;                    // [2][128] float2: column-half exchange of fused units
-constexpr uint32_t SMEM_BYTES = SMEM_BAR + 512 + 2048 + 1024;     // barriers + unit ring, exchange, alignment slack
+constexpr int APPEND_SLOTS = 16;                                  // chunks (32 values) a warp stages per round in append mode
+constexpr uint32_t APPEND_WARP_BYTES = APPEND_SLOTS * (32 * 4 + 8);   // values + (threshold, source lane) per slot
+constexpr uint32_t SMEM_APPEND = SMEM_XCHG + 2048;                // [8 epilogue warps][APPEND_WARP_BYTES]
+constexpr uint32_t SMEM_BYTES = SMEM_APPEND + 8 * APPEND_WARP_BYTES + 1024;   // ... + alignment slack
 constexpr int THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr uint32_t TMEM_COLS = 512;
@@ -306,8 +309,14 @@ struct AppendState {
     float published;
     uint32_t cnt;              // values that passed so far (stored only while below APPEND_CAP - 1)
 };
-__device__ __forceinline__ void append32(AppendState& s, const uint32_t (&r)[32], uint32_t scol0, float* __restrict__ rec,
-                                         bool row_valid) {
+// One 32-value chunk of every lane's row.  The lanes whose chunk holds a value above their threshold (a
+// few per warp) stage the chunk in shared memory; then the WHOLE warp works on one staged chunk at a
+// time, one value per lane: compare, ballot, and the passing lanes store to the owner row's record.  The
+// per-value work of the sparse hits runs with all 32 lanes instead of one lane in eight.
+//   stage: this warp's [APPEND_SLOTS][32] floats followed by [APPEND_SLOTS] (threshold, source lane) pairs
+//   rec0:  record of the warp's row 0 (this column half); row r's record is rec0 + r * row_floats
+__device__ __forceinline__ void append32(AppendState& s, const uint32_t (&r)[32], uint32_t scol0, float* __restrict__ stage,
+                                         float* __restrict__ rec0, int64_t row_floats, int rows_valid, int lane) {
     float m[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -318,21 +327,36 @@ __device__ __forceinline__ void append32(AppendState& s, const uint32_t (&r)[32]
     }
     // the chunk's own maxima already count: g1 is still a lower bound on the final second best
     const float thr = fmaxf(fmaxf(s.G, s.g1) - s.margin2, VALID_FLOOR);
-    if (fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > thr) {
+    bool hit = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) > thr;
+    unsigned bal = __ballot_sync(0xffffffffu, hit);
+    float2* meta = reinterpret_cast<float2*>(stage + APPEND_SLOTS * 32);
+    const unsigned lt = (1u << lane) - 1u;
+    while (bal) {                                            // warp-uniform: usually one round of ~4 chunks
+        const int slot = __popc(bal & lt);
+        if (hit && slot < APPEND_SLOTS) {
+            uint4* dst = reinterpret_cast<uint4*>(stage + slot * 32);
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            if (m[g] > thr) {
-                const float* v = reinterpret_cast<const float*>(&r[8 * g]);
-#pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    if (v[e] > thr) {
-                        if (row_valid && s.cnt < (uint32_t)(APPEND_CAP - 1))
-                            rec[1 + s.cnt] = __uint_as_float((__float_as_uint(v[e]) & PACK_MASK) | (scol0 + 8 * g + e));
-                        s.cnt++;
-                    }
-                }
-            }
+            for (int j = 0; j < 8; j++) dst[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            meta[slot] = make_float2(thr, __int_as_float(lane));
+            hit = false;
         }
+        const int n = min(__popc(bal), APPEND_SLOTS);
+        __syncwarp();
+        for (int k = 0; k < n; k++) {
+            const float v = stage[k * 32 + lane];
+            const float2 mt = meta[k];
+            const int src = __float_as_int(mt.y);
+            const bool p = v > mt.x;
+            const unsigned pb = __ballot_sync(0xffffffffu, p);
+            const uint32_t base = __shfl_sync(0xffffffffu, s.cnt, src);
+            const uint32_t idx = base + __popc(pb & lt);
+            const uint32_t cap = src < rows_valid ? (uint32_t)(APPEND_CAP - 1) : 0u;
+            if (p && idx < cap)
+                rec0[(int64_t)src * row_floats + 1 + idx] = __uint_as_float((__float_as_uint(v) & PACK_MASK) | (scol0 + lane));
+            if (lane == src) s.cnt += __popc(pb);
+        }
+        __syncwarp();
+        bal = __ballot_sync(0xffffffffu, hit);
     }
 }
 
@@ -595,7 +619,11 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     stats_read(u.t_stats, tmin2, tmax2);
                     a.margin2 = 2.f * dot_margin(qn2, tmin2, tmax2);
                 }
-                float* rec = reinterpret_cast<float*>(recs + u.rec_base + (int64_t)(row_valid ? row : 0) * u.rec_stride + half * APPEND_RECS);
+                // records of this warp's 32 rows (this column half); rows past q_valid store nothing
+                const int64_t row_floats = (int64_t)u.rec_stride * 4;
+                float* rec0 = reinterpret_cast<float*>(recs + u.rec_base + (int64_t)(quarter * 32) * u.rec_stride + half * APPEND_RECS);
+                const int rows_valid = u.q_valid - quarter * 32;                 // lanes below this own a real query row
+                float* stage = reinterpret_cast<float*>(smem_gen + SMEM_APPEND + (warp - EPI_WARP0) * APPEND_WARP_BYTES);
                 volatile uint32_t* hint = u.hint + (row_valid ? row : 0);
                 uint32_t h_next = *hint;
                 for (int n = 0; n < ntiles; n++, tile_it++) {
@@ -613,29 +641,29 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     tmem_ld_wait(ra);
                     tmem_ld32(taddr + 32, rb);
                     if (!full_tile) mask32(ra, ucol, u.t_count);
-                    append32(a, ra, scol, rec, row_valid);
+                    append32(a, ra, scol, stage, rec0, row_floats, rows_valid, lane);
                     tmem_ld_wait(rb);
                     tmem_ld32(taddr + 64, ra);
                     if (!full_tile) mask32(rb, ucol + 32, u.t_count);
-                    append32(a, rb, scol + 32, rec, row_valid);
+                    append32(a, rb, scol + 32, stage, rec0, row_floats, rows_valid, lane);
                     tmem_ld_wait(ra);
                     tmem_ld32(taddr + 96, rb);
                     if (!full_tile) mask32(ra, ucol + 64, u.t_count);
-                    append32(a, ra, scol + 64, rec, row_valid);
+                    append32(a, ra, scol + 64, stage, rec0, row_floats, rows_valid, lane);
                     tmem_ld_wait(rb);
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
                     h_next = *hint;
                     if (!full_tile) mask32(rb, ucol + 96, u.t_count);
-                    append32(a, rb, scol + 96, rec, row_valid);
+                    append32(a, rb, scol + 96, stage, rec0, row_floats, rows_valid, lane);
                     const float L = fmaxf(a.G, a.g1);
                     if (row_valid && L > a.published) {
                         atomicMax(const_cast<uint32_t*>(hint), enc_ordered(L));
                         a.published = L;
                     }
                 }
-                if (row_valid) rec[0] = __uint_as_float(a.cnt);
+                if (row_valid) rec0[(int64_t)lane * row_floats] = __uint_as_float(a.cnt);
                 continue;
             }
             Top3 s;
