@@ -75,7 +75,9 @@ typedef struct {
     int32_t reserved[8];         /* [0]: tiles per slice segment (0 = automatic);
                                     [1]: rescan work-list capacity (0 = default; tests shrink it);
                                     [2]: plain frames vsm_track keeps before recycling (0 = 2);
-                                    [3]: open (query, keyframe) pairs vsm_loop_detect_compact can hold (0 = 262144; tests shrink it) */
+                                    [3]: open (query, keyframe) pairs vsm_loop_detect_compact can hold (0 = 262144; tests shrink it);
+                                    [4]: train sets of up to this many 256-row tiles use append records instead of
+                                         top-4 records (0 = never: measured slower; kept as a tested option) */
 } vsm_opts;
 
 typedef struct vsm_ctx vsm_ctx;

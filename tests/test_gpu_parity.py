@@ -33,6 +33,14 @@ def pair():
 
 
 @pytest.fixture(scope="module")
+def appendm():
+    """tensor-core pass with APPEND records for train sets of up to 16 tiles (vsm_opts.reserved[4]; off by default)"""
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, append_tiles=16)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
 def simt():
     m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_SIMT)
     yield m
@@ -59,7 +67,7 @@ def test_tensor_core_tile_is_the_bf16_dot(tc):
 
 
 @pytest.mark.parametrize("name", list(cases.PAIR_CASES))
-@pytest.mark.parametrize("engine", ["tc", "pair", "simt"])
+@pytest.mark.parametrize("engine", ["tc", "pair", "simt", "appendm"])
 def test_knn_equals_oracle_and_golden(name, engine, request):
     m = request.getfixturevalue(engine)
     q, t = cases.PAIR_CASES[name]()
@@ -901,3 +909,35 @@ def test_resident_map_point_table(tc):
     tc.clear_map_points()
     assert tc.map_point_info() == (0, 0, 0)
     tc.clear_store()
+
+
+def test_append_records_option_equals_oracle(appendm):
+    """The append-record epilogue (an option, off by default) on match-heavy small problems: pair matching with
+    ratio and mutual tests, a ragged batch, a tracking sequence, rows with unequal norms, and a train set whose
+    near-duplicates overflow the record (exact re-scan of the slice)."""
+    for name in ("pair_1000_video", "pair_777x1301", "pair_2048x200", "mutual_conflict", "neardup_db", "scaled", "nt2"):
+        q, t = cases.PAIR_CASES[name]()
+        for mutual in (False, True):
+            good, raw = appendm.match_features(q, t, 0.75, mutual=mutual)
+            og, orw = oracle.match_features(q, t, 0.75, mutual=mutual)
+            assert good.tobytes() == og.tobytes() and raw.tobytes() == orw.tobytes(), (name, mutual)
+    qs, ts = [], []
+    for p in range(7):
+        a, b, _ = gen.planted(700 + p, 150 + 137 * p, 260 + 211 * p, 0.6, 0.08)
+        qs.append(a)
+        ts.append(b)
+    res = appendm.match_batch(qs, ts, 0.75, mutual=True)
+    for p in range(7):
+        og, _ = oracle.match_features(qs[p], ts[p], 0.75, mutual=True)
+        assert res[p].tobytes() == og.tobytes(), p
+    # 200 near-copies of one row: more values pass the threshold than a record holds
+    base = gen.int_rows(55, 1, 0, 900).copy()
+    base[300:500] = 1000 * base[10] + gen.int_rows(55, 2, 0, 200)
+    t = gen._normalize_int(base)
+    vq = gen.int_rows(55, 0, 0, 64).copy()
+    vq[:32] = 1000 * gen.int_rows(55, 1, 10, 1) + 20 * gen.int_rows(55, 3, 0, 32)
+    q = gen._normalize_int(vq)
+    gi, gd = appendm.knn_match(q, t)
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    assert appendm.stats()["flagged_slices"] > 0

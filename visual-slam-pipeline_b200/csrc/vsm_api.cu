@@ -177,6 +177,7 @@ struct vsm_ctx {
     const void* loop_p_desc = nullptr;
     const void* loop_p_loop = nullptr;
     uint32_t pair_cap = 0;                       // open (query, keyframe) pairs the compact loop search can hold (0 = PAIR_CAP)
+    int64_t append_max_tiles = 0;                // train sets of up to this many tiles use append records (0 = never)
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // event pairs around the tensor-core kernel of the last TC_RING calls (ev_tc0/ev_tc1 = the current
@@ -649,7 +650,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     {
         int64_t uses_slot = 0;
         for (auto& p : probs) if (!p.t_store) uses_slot = 1 + (ctx->call_seq & 1);
-        const int64_t head[8] = {ctx->engine, ctx->seg_tiles * 2 + (ctx->db_short_slices ? 1 : 0), ctx->num_sms, P,
+        const int64_t head[8] = {ctx->engine + 16 * ctx->append_max_tiles, ctx->seg_tiles * 2 + (ctx->db_short_slices ? 1 : 0), ctx->num_sms, P,
                                  (int64_t)jobs.size(), total_out, total_matches, uses_slot};
         key.resize(sizeof head + sizeof(HProblem) * probs.size() + sizeof(HJob) * jobs.size());
         memcpy(key.data(), head, sizeof head);
@@ -727,8 +728,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         const int nqt = (hp.nq + TILE_M - 1) / TILE_M;
         // small train sets (pairs, tracking, ragged batches): append records -- one slice per (range, column
         // half), every value above the running threshold stored, no top-4 state in the epilogue (vsm_tc.cuh)
-        static const int64_t append_max_tiles = getenv("VSM_APPEND_TILES") ? atoll(getenv("VSM_APPEND_TILES")) : 16;
-        const bool append = !maxima && !pairs && !hp.runs && !dump_first && ntiles <= append_max_tiles && ctx->seg_tiles == 0;
+        // -- OFF by default (vsm_opts.reserved[4] = largest train set, in tiles, that uses it): measured SLOWER than
+        // the top-4 records (64 ragged pairs: 0.30 ms against 0.18 ms) because with ~1000 rows
+        // the running threshold matures so slowly that most (lane, chunk) pairs hold a passing value
+        const bool append = !maxima && !pairs && !hp.runs && !dump_first && ntiles <= ctx->append_max_tiles && ctx->seg_tiles == 0;
         if (append) d.exact |= 4;
         const int rec_per_slice = append ? APPEND_RECS : 1;
         struct Range { int64_t idx0, count; int tiles_after; int slice0; int seg; };
@@ -800,6 +803,20 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             }
         }
         nrecs += (int64_t)hp.nq * d.nslices * rec_per_slice;
+    }
+
+    // Several problems of different sizes in one call (ragged batches, per-keyframe searches): the persistent
+    // CTAs take units in list order, so the longest units go first -- otherwise a 8-tile unit handed out last
+    // leaves 147 SMs idle for its whole duration (ncu on 64 ragged pairs: 19 % of the warp samples sat in EXIT).
+    if (!hit && P > 1 && units.size() > 1) {
+        std::vector<size_t> ord(units.size());
+        for (size_t k = 0; k < ord.size(); k++) ord[k] = k;
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return units[a].t_count > units[b].t_count; });
+        std::vector<TcUnit> u2(units.size());
+        std::vector<int> p2(units.size());
+        for (size_t k = 0; k < ord.size(); k++) { u2[k] = units[ord[k]]; p2[k] = unit_prob[ord[k]]; }
+        units.swap(u2);
+        unit_prob.swap(p2);
     }
 
     // descriptor block: [Problem][q_block0][TcUnit][SliceInfo][FilterJob]
@@ -1140,6 +1157,8 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         memset(ctx->h_status, 0, 64);
         if (o.reserved[2] > 0) ctx->ring_depth = o.reserved[2];
         if (o.reserved[3] > 0) ctx->pair_cap = (uint32_t)o.reserved[3];
+        if (o.reserved[4] > 0) ctx->append_max_tiles = o.reserved[4];
+        else if (getenv("VSM_APPEND_TILES")) ctx->append_max_tiles = atoll(getenv("VSM_APPEND_TILES"));
         CK(cudaMalloc(&ctx->d_store_stats, 16));
         // on the context's own (non-blocking) stream and waited for: a cudaMemset on the legacy default
         // stream is not ordered with it and could land AFTER the first conversion's atomicMax into the

@@ -194,7 +194,7 @@ class Matcher:
         return m
 
     def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0, ring=0,
-                 pair_cap=0):
+                 pair_cap=0, append_tiles=0):
         self._lib = load_library()
         o = _Opts()
         self._lib.vsm_default_opts(C.byref(o))
@@ -203,6 +203,7 @@ class Matcher:
         o.reserved[1] = work_cap
         o.reserved[2] = ring
         o.reserved[3] = pair_cap
+        o.reserved[4] = append_tiles
         h = C.c_void_p()
         st = self._lib.vsm_create(C.byref(o), C.byref(h))
         if st != 0:
