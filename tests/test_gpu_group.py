@@ -112,3 +112,22 @@ def test_group_with_adopted_shards_and_duplicates_across_members(devices):
         oi, od = oracle.knn(q, db, 2)
         assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
         assert list(gi[0]) == [50, per - 5] and gd[0, 0] == 0.0 and gd[0, 1] == 0.0
+
+
+def test_group_with_more_members_than_keyframes_and_empty_keyframes():
+    """Four contexts, two keyframes (one of them empty): members without rows answer "no neighbour" and still take
+    part in the merge; the empty keyframe is skipped by the loop search (src/LoopCloser.cpp:45)."""
+    q = gen.rows(61, 0, 0, 50)
+    kf = gen.rows(61, 1, 0, 90)
+    with vsm_b200.Group([0, 0, 0, 0]) as g:
+        gi, gd = g.search_map_points(q)                          # nothing stored at all
+        assert (gi == -1).all()
+        g.add_keyframe(5, np.zeros((0, 256), np.float32))
+        g.add_keyframe(9, kf)
+        gi, gd, kh, kr = g.search_map_points(q, want_keyframes=True)
+        oi, od = oracle.knn(q, kf, 2)
+        assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+        assert (kh == 1).all() and np.array_equal(kr, oi)
+        st, lists = g.loop_detect_compact(500, q, 0.75, min_gap=0, every=1, min_matches=0)
+        og, _ = oracle.match_features(q, kf, 0.75)
+        assert list(st) == [-1, len(og)]

@@ -941,3 +941,71 @@ def test_append_records_option_equals_oracle(appendm):
     oi, od = oracle.knn(q, t, 2)
     assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
     assert appendm.stats()["flagged_slices"] > 0
+
+
+def test_strided_entry_points(tc):
+    """cv::Mat ROIs: rows 1280 / 2048 bytes apart go through the *_strided calls (one strided DMA) and give
+    the answers of the packed matrices; a stride below 1024 bytes is refused."""
+    import ctypes as C
+    q, t, _ = gen.planted(91, 333, 410, 0.6, 0.08)
+    wq = np.zeros((q.shape[0], 320), np.float32)
+    wq[:, :256] = q
+    wt = np.zeros((t.shape[0], 512), np.float32)
+    wt[:, 256:] = t                                              # the ROI starts in the middle of a wider row
+    lib, h = tc.lib, tc.handle
+    idx = np.empty((q.shape[0], 2), np.int32)
+    dist = np.empty((q.shape[0], 2), np.float32)
+    t_ptr = wt.ctypes.data + 256 * 4
+    assert lib.vsm_knn2_strided(h, wq.ctypes.data, q.shape[0], 320 * 4, C.c_void_p(t_ptr), t.shape[0], 512 * 4,
+                                idx.ctypes.data, dist.ctypes.data) == 0
+    oi, od = oracle.knn(q, t, 2)
+    assert np.array_equal(idx, oi) and np.array_equal(bits(dist), bits(od))
+    good = np.zeros(q.shape[0], vsm_b200.DMATCH)
+    ng = C.c_int32(0)
+    assert lib.vsm_match_pair_strided(h, wq.ctypes.data, q.shape[0], 320 * 4, C.c_void_p(t_ptr), t.shape[0], 512 * 4,
+                                      C.c_float(0.75), 1, good.ctypes.data, C.byref(ng), None, None) == 0
+    og, _ = oracle.match_features(q, t, 0.75, mutual=True)
+    assert good[:ng.value].tobytes() == og.tobytes()
+    assert lib.vsm_knn2_strided(h, wq.ctypes.data, q.shape[0], 1000, C.c_void_p(t_ptr), t.shape[0], 512 * 4,
+                                idx.ctypes.data, dist.ctypes.data) != 0
+    # a keyframe added from a strided matrix
+    tc.clear_store()
+    hk = C.c_int32(-1)
+    assert lib.vsm_store_add_strided(h, 7, C.c_void_p(t_ptr), t.shape[0], 512 * 4, C.byref(hk)) == 0
+    g2, _ = tc.match_to_keyframe(hk.value, q, 0.75)
+    o2, _ = oracle.match_features(t, q, 0.75)
+    assert g2.tobytes() == o2.tobytes()
+    tc.clear_store()
+
+
+def test_store_edge_cases(tc):
+    """Empty and one-row keyframes, removal of everything, handles of removed frames, searches on an empty store."""
+    tc.clear_store()
+    q = gen.rows(95, 0, 0, 40)
+    gi, gd = tc.search_map_points(q)
+    assert (gi == -1).all()
+    st, lists, _ = tc.loop_detect_compact(1000, q, 0.75, min_gap=0, every=1, min_matches=1)
+    assert len(st) == 0 and lists == {}
+    z = np.zeros((0, 256), np.float32)
+    h0 = tc.add_keyframe(0, z)
+    h1 = tc.add_keyframe(1, gen.rows(95, 1, 0, 1))
+    h2 = tc.add_keyframe(2, gen.rows(95, 2, 0, 300))
+    st, lists, _ = tc.loop_detect_compact(1000, q, 0.75, min_gap=0, every=1, min_matches=0)
+    assert list(st) == [-1, 0, 0] and lists == {}               # empty: skipped (LoopCloser.cpp:45); one row: no 2-entry list
+    gi, gd = tc.search_map_points(q)
+    db = np.concatenate([gen.rows(95, 1, 0, 1), gen.rows(95, 2, 0, 300)])
+    oi, od = oracle.knn(q, db, 2)
+    assert np.array_equal(gi, oi) and np.array_equal(bits(gd), bits(od))
+    tc.remove_frame(h1)
+    gi, gd = tc.search_map_points(q)                             # the run now starts at row 1
+    oi, od = oracle.knn(q, db[1:], 2)
+    assert np.array_equal(gi, oi + 1) and np.array_equal(bits(gd), bits(od))
+    with pytest.raises(vsm_b200.VsmError):
+        tc.remove_frame(h1)
+    with pytest.raises(vsm_b200.VsmError):
+        tc.promote(12345)
+    tc.remove_frame(h2)
+    tc.remove_frame(h0)
+    assert tc.store_info() == (0, 0)
+    assert (tc.search_map_points(q)[0] == -1).all()
+    tc.clear_store()
