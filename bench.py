@@ -597,6 +597,45 @@ def extra_pair_numbers(torch, vsm_b200, device):
     except Exception as e:                       # informational line: never lose the bench to it
         out["loop_closure_10k_kf_every5_compact"] = {"error": repr(e)[:300]}
     m.clear_store()
+    # Slam::track_local_map (src/Slam.cpp:380-469): 3000 map points projected into a frame of 1000 keypoints,
+    # 12 px window search, sequential assignment -- descriptors from the host per call, and from the
+    # resident map-point table (only keypoints, positions and the pose travel)
+    try:
+        rngt = np.random.default_rng(3)
+        nmp, nkp = 3000, 1000
+        a = 0.05
+        R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        tvec = np.array([0.1, -0.05, 0.2])
+        pos = np.stack([rngt.uniform(-6, 6, nmp), rngt.uniform(-4, 4, nmp), rngt.uniform(1, 12, nmp)], axis=1)
+        mp_desc = unit(nmp).cpu().numpy()
+        cam = (R @ pos.T).T + tvec
+        u_ = 525.0 * cam[:, 0] / cam[:, 2] + 319.5
+        v_ = 525.0 * cam[:, 1] / cam[:, 2] + 239.5
+        vis = np.nonzero((u_ >= 0) & (u_ < 640) & (v_ >= 0) & (v_ < 480))[0]
+        pick = rngt.permutation(vis)[:700]
+        kp = np.stack([rngt.uniform(0, 640, nkp), rngt.uniform(0, 480, nkp)], axis=1).astype(np.float32)
+        kp[:len(pick), 0] = u_[pick] + rngt.normal(0, 3.0, len(pick))
+        kp[:len(pick), 1] = v_[pick] + rngt.normal(0, 3.0, len(pick))
+        kp = np.clip(kp, 0, [639.5, 479.5]).astype(np.float32)
+        desc = unit(nkp).cpu().numpy()
+        noisy = mp_desc[pick] + 0.02 * rngt.standard_normal((len(pick), 256)).astype(np.float32)
+        desc[:len(pick)] = noisy / np.linalg.norm(noisy, axis=1, keepdims=True)
+        valid = np.ones(nmp, np.uint8)
+        res_t = {}
+        m.add_map_points(mp_desc, 0)
+        for name, md, vd in (("descriptors_from_host", mp_desc, valid), ("resident_point_table", None, None)):
+            tl = []
+            for it in range(23):
+                ind = -np.ones(nkp, np.int32)
+                t0 = time.perf_counter()
+                tracked, _, _, _ = m.track_local_map(kp, desc, pos, md, vd, R, tvec, ind)
+                tl.append(time.perf_counter() - t0)
+            tl = sorted(tl[3:])
+            res_t[name] = {"p50_us": tl[len(tl) // 2] * 1e6, "device_ms": m.stats()["device_ms"], "tracked": int(tracked)}
+        m.clear_map_points()
+        out["track_local_map_3000_points_x_1000_keypoints"] = res_t
+    except Exception as e:
+        out["track_local_map_3000_points_x_1000_keypoints"] = {"error": repr(e)[:300]}
     m.close()
     return out
 
