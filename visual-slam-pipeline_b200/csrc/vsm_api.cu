@@ -369,16 +369,22 @@ void vmm_release(vsm_ctx* ctx, VmmRange& r) {
 // VMM support or for an adopted matrix (whose fp32 master is the caller's).
 int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
     if (rows <= a.cap && a.b16) return VSM_OK;
-    if (ctx->vmm_ok && a.own_f32 && (a.vmm || !a.b16)) {
+    if (a.vmm || (ctx->vmm_ok && a.own_f32 && !a.b16)) {
         if (!a.vmm) {
             // address space for as many rows as the device could ever hold (fp32 + bf16 + norm = 1540 B per row)
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             const size_t max_rows = total_b / 1536 + (1u << 20);
-            TRY(vmm_reserve(ctx, a.r_f32, max_rows * VSM_DIM * sizeof(float)));
-            int st = vmm_reserve(ctx, a.r_b16, max_rows * VSM_DIM * sizeof(__nv_bfloat16));
+            int st = vmm_reserve(ctx, a.r_f32, max_rows * VSM_DIM * sizeof(float));
+            if (st == VSM_OK) st = vmm_reserve(ctx, a.r_b16, max_rows * VSM_DIM * sizeof(__nv_bfloat16));
             if (st == VSM_OK) st = vmm_reserve(ctx, a.r_n2, max_rows * sizeof(float));
-            if (st != VSM_OK) { vmm_release(ctx, a.r_f32); vmm_release(ctx, a.r_b16); vmm_release(ctx, a.r_n2); return st; }
+            if (st != VSM_OK) {
+                // no address space to reserve (a restricted environment): this context allocates and copies instead
+                vmm_release(ctx, a.r_f32); vmm_release(ctx, a.r_b16); vmm_release(ctx, a.r_n2);
+                ctx->vmm_ok = false;
+                ctx->err.clear();
+                return arena_reserve(ctx, a, rows, keep);
+            }
             a.vmm = true;
             a.f32 = reinterpret_cast<float*>(a.r_f32.base);
             a.b16 = reinterpret_cast<__nv_bfloat16*>(a.r_b16.base);
@@ -445,9 +451,13 @@ int arena_reserve(vsm_ctx* ctx, Arena& a, int64_t rows, int64_t keep) {
 // Make [p, p + need) usable; existing content keeps its address (VMM) or is copied (fall-back).
 int grow_arr(vsm_ctx* ctx, GrowArr& a, size_t need, size_t reserve_bytes) {
     if (need <= a.cap) return VSM_OK;
-    if (ctx->vmm_ok && (a.vmm || !a.p)) {
+    if (a.vmm || (ctx->vmm_ok && !a.p)) {
         if (!a.vmm) {
-            TRY(vmm_reserve(ctx, a.r, reserve_bytes));
+            if (vmm_reserve(ctx, a.r, reserve_bytes) != VSM_OK) {          // see arena_reserve
+                ctx->vmm_ok = false;
+                ctx->err.clear();
+                return grow_arr(ctx, a, need, reserve_bytes);
+            }
             a.vmm = true;
             a.p = reinterpret_cast<uint8_t*>(a.r.base);
         }
