@@ -954,7 +954,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
         CK(launch_pdl(dump_first ? tc::tc_top3_kernel<true> : tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS),
                       tc::SMEM_BYTES, ctx->stream, ms, mt, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits,
-                      (const uint32_t*)nullptr, d_unit_counter, ctx->d_recs.p, ctx->d_dump));
+                      (const FusedArgs*)nullptr, d_unit_counter, ctx->d_recs.p, ctx->d_dump));
         ctx->launches++;
         if (ctx->profiling) {
             CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
@@ -2138,11 +2138,13 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     TRY(ensure(ctx, ctx->d_loop, loop_bytes));
     TRY(ensure(ctx, ctx->d_recs, (size_t)unit2_cap * TILE_M * 2));
     const size_t off_slot = 0, off_unit = align16(off_slot + sizeof(LoopSlot) * nslots),
-                 total = align16(off_unit + sizeof(TcUnit) * (size_t)nslots * nqt);
+                 off_fused = align16(off_unit + sizeof(TcUnit) * (size_t)nslots * nqt), total = align16(off_fused + sizeof(FusedArgs));
     TRY(ensure(ctx, ctx->d_desc, total));
     TRY(ensure_host(ctx, ctx->h_desc, ctx->h_desc_cap, total));
     TRY(ensure(ctx, ctx->d_work, (size_t)WORK_CAP));
-    const size_t aux_bytes = align16(64 + (size_t)nslots * 4);                 // header + survivors per slot, zeroed per call
+    // header (incl. RedoCtl at bytes 48..63) + survivors per slot + ready flags of the redo units, zeroed per call
+    const size_t o_ready = align16(64 + (size_t)nslots * 4);
+    const size_t aux_bytes = align16(o_ready + (size_t)unit2_cap * 4);
     TRY(ensure(ctx, ctx->d_aux, aux_bytes));
     if (ctx->aux_zeroed != ctx->d_aux.p) {
         CK(cudaMemsetAsync(ctx->d_aux.p, 0, ctx->d_aux.cap, ctx->stream));
@@ -2158,8 +2160,9 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     // descriptor block: rebuilt only when the eligible list (or a buffer) changed since the last search
     std::vector<uint8_t>& key = ctx->plan_key_build;
     {
-        const int64_t head[6] = {nq, nslots, (int64_t)__float_as_uint_host(ratio), (int64_t)(uintptr_t)ctx->store.f32,
-                                 (int64_t)(uintptr_t)ctx->scratch.n2, (int64_t)(uintptr_t)ctx->d_store_stats ^ ((int64_t)ctx->store.cap << 20)};
+        const int64_t head[6] = {nq, nslots, (int64_t)__float_as_uint_host(ratio) | ((int64_t)pair_cap << 32), (int64_t)(uintptr_t)ctx->store.f32,
+                                 (int64_t)(uintptr_t)ctx->scratch.n2 ^ (int64_t)(uintptr_t)ctx->d_aux.p,
+                                 (int64_t)(uintptr_t)ctx->d_store_stats ^ ((int64_t)ctx->store.cap << 20)};
         key.resize(sizeof head + (size_t)nslots * sizeof(LoopSlot));
         memcpy(key.data(), head, sizeof head);
     }
@@ -2187,7 +2190,7 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
                 u.q_row = qt * TILE_M;
                 u.t_row = (int32_t)slots[s].row0;
                 u.t_count = slots[s].count;
-                u.t_index0 = 0;
+                u.t_index0 = s;                                             // fused units: the keyframe's slot (PairRef::slot)
                 u.q_valid = std::min(TILE_M, nq - qt * TILE_M);
                 u.seg_tiles = UNIT_TILES;
                 u.maps = 2 | 4 | 8;                                         // train rows in the store; maxima only; fused dismissal
@@ -2195,6 +2198,17 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
                 u.skip_ratio2 = r2;
                 u.hint = reinterpret_cast<uint32_t*>(dl + o_mask);
             }
+        FusedArgs* fa = reinterpret_cast<FusedArgs*>(blk.data() + off_fused);
+        fa->ctl = reinterpret_cast<RedoCtl*>(ctx->d_aux.p + 48);
+        fa->units2 = reinterpret_cast<TcUnit*>(dl + o_unit2);
+        fa->ready2 = reinterpret_cast<uint32_t*>(ctx->d_aux.p + o_ready);
+        fa->hints2 = reinterpret_cast<uint32_t*>(dl + o_hint2);
+        fa->word_base = reinterpret_cast<uint32_t*>(dl + o_base);
+        fa->pair_ref = reinterpret_cast<PairRef*>(dl + o_ref);
+        fa->counters = reinterpret_cast<uint32_t*>(ctx->d_aux.p);
+        fa->unit2_cap = unit2_cap;
+        fa->pair_cap = pair_cap;
+        fa->n_main = (uint32_t)((size_t)nslots * nqt);
         if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));
         memcpy(ctx->h_desc, blk.data(), total);
         ctx->loop_key = key;
@@ -2215,8 +2229,8 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
         const unsigned grid = (unsigned)std::min<size_t>(nunits, (size_t)ctx->num_sms);
         uint32_t* d_unit_counter = reinterpret_cast<uint32_t*>(ctx->d_aux.p + 24);
         CK(launch_pdl(tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, ctx->stream, ctx->scratch.map,
-                      ctx->store.map, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits, (const uint32_t*)nullptr,
-                      d_unit_counter, ctx->d_recs.p, ctx->d_dump));
+                      ctx->store.map, reinterpret_cast<const TcUnit*>(dd + off_unit), (int)nunits,
+                      reinterpret_cast<const FusedArgs*>(dd + off_fused), d_unit_counter, ctx->d_recs.p, ctx->d_dump));
         ctx->launches++;
         if (ctx->profiling) {
             CK(cudaEventRecord(ctx->ev_tc1, ctx->stream));
@@ -2226,7 +2240,6 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     LoopParams P;
     memset(&P, 0, sizeof P);
     P.slots = reinterpret_cast<const LoopSlot*>(dd + off_slot);
-    P.units = reinterpret_cast<const TcUnit*>(dd + off_unit);
     P.nslots = nslots; P.nq = nq; P.words_per_slot = wps;
     P.q_f32 = ctx->scratch.f32;
     P.q_n2 = ctx->scratch.n2;
@@ -2245,7 +2258,7 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     P.counters = reinterpret_cast<uint32_t*>(ctx->d_aux.p);
     P.work = ctx->d_work.p;
     P.work_cap = ctx->work_cap;
-    P.slot_good = reinterpret_cast<int32_t*>(ctx->d_aux.p + 64);
+    P.slot_good = reinterpret_cast<int32_t*>(ctx->d_aux.p + 64);          // (the ready flags of the redo units follow)
     P.slot_off = reinterpret_cast<int64_t*>(dl + o_off);
     P.ratio = ratio;
     P.skip_ratio2 = skip_r2(ratio);
@@ -2256,22 +2269,13 @@ static int loop_compact_impl(vsm_ctx* ctx, const float* query, int32_t nq, float
     P.cand_cap = nslots;
     P.out_matches = reinterpret_cast<DMatch*>(ctx->h_result + h_match);
     P.match_cap = pair_cap;
-    const unsigned ublocks = (unsigned)std::max<size_t>(1, std::min<size_t>((nunits + 7) / 8, (size_t)ctx->num_sms * 8));
     const unsigned wblocks = (unsigned)std::max<size_t>(1, std::min<size_t>((nwords + 7) / 8, (size_t)ctx->num_sms * 8));
     ctx->d_counters = reinterpret_cast<unsigned long long*>(ctx->d_aux.p);
-    CK(launch_pdl(loop_open_plan_kernel, dim3(ublocks), dim3(256), 0, ctx->stream, P));
-    {
-        // second tensor-core pass: only the units that hold an open pair (list and length built on the device)
-        const unsigned grid = (unsigned)std::min<size_t>(std::min<size_t>(nunits, unit2_cap), (size_t)ctx->num_sms);
-        CK(launch_pdl(tc::tc_top3_kernel<false>, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, ctx->stream, ctx->scratch.map,
-                      ctx->store.map, (const TcUnit*)P.units2, (int)unit2_cap, (const uint32_t*)(P.counters + 12), P.counters + 13,
-                      ctx->d_recs.p, ctx->d_dump));
-    }
     CK(launch_pdl(loop_select_kernel, dim3((unsigned)ctx->num_sms * 4), dim3(SELECT_WARPS * 32), 0, ctx->stream, P));
     CK(launch_pdl(rescan_kernel, dim3((unsigned)ctx->num_sms * 2), dim3(256), 0, ctx->stream, (const WorkItem*)ctx->d_work.p,
                   (const unsigned long long*)ctx->d_counters, ctx->work_cap));
     CK(launch_pdl(loop_finish_kernel, dim3(wblocks), dim3(256), 0, ctx->stream, P));       // its last block gates and emits
-    ctx->launches += 5;
+    ctx->launches += 3;
     if (ctx->profiling) {
         CK(cudaEventRecord(ctx->ev_sel1, ctx->stream));
         ctx->timed_sel = true;

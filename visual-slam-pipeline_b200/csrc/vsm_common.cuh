@@ -50,7 +50,7 @@ constexpr float MASKED_VALUE = -3.0e38f;       // a column past the end of the t
 constexpr float VALID_FLOOR = -1.0e38f;        // record entries above this are real columns
 
 // One CTA of the tensor-core kernel: one 128-query tile x a contiguous train range.
-struct TcUnit {
+struct __align__(16) TcUnit {
     const float*    q_n2;          // squared norms of the tile's query rows
     const uint32_t* t_stats;       // norm statistics of the train set (see stats_read)
     int64_t rec_base;              // record index of (tile row 0, the unit's first slice)
@@ -74,6 +74,31 @@ struct TcUnit {
     float skip_ratio2;             // bit3 units: ratio^2 * 1.001 of the caller's ratio test (Problem::skip_ratio2)
     uint32_t* hint;                // per query row: shared lower bound on the global second-best dot
                                    // (bit3 units: the open-pair mask words, uint32 [units][4])
+};
+
+// ---- compact loop search (vsm_loop_detect_compact): the second pass runs INSIDE the first pass's kernel ----
+// A fused unit (maps bit 3) whose ratio test could not be dismissed for some query re-enters the same
+// persistent kernel as a top-4 unit: the epilogue that found the open pairs numbers them and pushes a redo
+// unit per 32-row quarter; the schedulers of all CTAs drain that queue after the first-pass list.
+struct PairRef {                   // one open (query, keyframe) pair
+    int32_t q, slot, unit2, pad;
+};
+struct RedoCtl {                   // device memory, zeroed per call
+    uint32_t produced;             // redo units reserved so far (above unit2_cap: overflow, the call falls back)
+    uint32_t head;                 // redo units taken by the schedulers
+    uint32_t main_done;            // finished (first-pass unit, quarter) epilogues: 4 per unit, then nothing is produced any more
+    uint32_t finish_ticket;        // loop_finish_kernel's last-block ticket
+};
+struct FusedArgs {                 // lives in the call's descriptor block
+    RedoCtl* ctl;
+    TcUnit* units2;                // [unit2_cap]
+    uint32_t* ready2;              // [unit2_cap] 1 = units2[i] is complete (zeroed per call)
+    uint32_t* hints2;              // [unit2_cap][128]
+    uint32_t* word_base;           // [mask words] pair index of a word's first open bit
+    PairRef* pair_ref;             // [pair_cap]
+    uint32_t* counters;            // aux block as uint32: [5] open pairs, [7] overflow flag
+    uint32_t unit2_cap, pair_cap;
+    uint32_t n_main, pad;          // first-pass units
 };
 
 // A slice = the train rows one epilogue thread scanned for one record:

@@ -556,9 +556,10 @@ rescan_kernel(const WorkItem* __restrict__ work, const unsigned long long* __res
 // ---- LoopCloser::detect, compact form (src/LoopCloser.cpp:43-62) ---------------------------------
 // The first tensor-core pass (fused units, TcUnit maps bit 3) leaves one bit per (eligible keyframe,
 // query): "the ratio test could not be dismissed" = an OPEN pair.  Everything after it is O(open):
-//   loop_open_plan_kernel  numbers the open pairs and builds, ON THE DEVICE, the work-unit list of a
-//                          second tensor-core pass over the (keyframe, query tile) units that hold one
-//   tc_top3_kernel (again) those units with the ordinary top-4 epilogue: ~4 candidates per open pair
+//   (tc_top3_kernel)       the epilogue that finds open pairs numbers them and pushes the unit back into the
+//                          kernel's own queue as a top-4 unit (FusedArgs / RedoCtl in vsm_common.cuh): the
+//                          second pass over the few (keyframe, query quarter) units that hold an open pair
+//                          runs inside the same launch, ~4 candidates per open pair
 //   loop_select_kernel     exact top-2 of every open pair from its candidates (canonical fp32 distance)
 //   rescan_kernel          exact scans for the rare pair whose four recorded entries overflowed
 //   loop_finish_kernel     ratio test per open pair (src/LoopCloser.cpp:55-60), survivors per keyframe;
@@ -575,12 +576,8 @@ struct LoopCand {                      // mirrors vsm_loop_candidate
     int32_t count;
     int64_t offset;
 };
-struct PairRef {                       // one open (query, keyframe) pair
-    int32_t q, slot, unit2, pad;
-};
 struct LoopParams {
     const LoopSlot* slots;
-    const TcUnit* units;                       // first-pass units, [nslots][words_per_slot / 4]
     int32_t nslots, nq, words_per_slot;        // words_per_slot = 4 * query tiles
     const float* q_f32;                        // query rows (scratch arena)
     const float* q_n2;
@@ -592,12 +589,11 @@ struct LoopParams {
     PairRef* pair_ref;                         // [pair_cap]
     DMatch* stage;                             // [pair_cap]: the pair's match, trainIdx = -1 if it fails the ratio test
     uint32_t pair_cap;
-    TcUnit* units2;                            // [unit2_cap] second-pass units, built by loop_open_plan_kernel
+    TcUnit* units2;                            // [unit2_cap] redo units, pushed by the first pass's epilogue
     uint32_t* hints2;                          // [unit2_cap][128]
     const PartialRec* recs2;                   // [unit2_cap][128][2]
     uint32_t unit2_cap;
-    // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag, [12] second-pass units,
-    // [13] second-pass unit queue head, [14] finished blocks of loop_finish_kernel
+    // aux block as uint32: [4] rescan work count, [5] open pairs, [7] overflow flag, [12..15] RedoCtl
     uint32_t* counters;
     WorkItem* work;
     uint32_t work_cap;
@@ -614,56 +610,6 @@ struct LoopParams {
     DMatch* out_matches;
     int64_t match_cap;
 };
-
-// One warp per first-pass unit (a keyframe x 128 queries = four mask words).
-__global__ void __launch_bounds__(256)
-loop_open_plan_kernel(const LoopParams P) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int lane = threadIdx.x & 31;
-    const int upk = P.words_per_slot / 4;
-    const int64_t nunits = (int64_t)P.nslots * upk;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < nunits; u += nwarps) {
-        const uint32_t mw = lane < 4 ? P.masks[u * 4 + lane] : 0u;
-        if (__ballot_sync(0xffffffffu, mw != 0u) == 0u) continue;      // the usual case: no loop in sight
-        const int slot = (int)(u / upk);
-        // a second-pass unit: the same rows and queries with the ordinary top-4 epilogue
-        uint32_t u2 = 0;
-        if (lane == 0) u2 = atomicAdd(P.counters + 12, 1u);
-        u2 = __shfl_sync(0xffffffffu, u2, 0);
-        const bool u2_ok = u2 < P.unit2_cap;
-        if (!u2_ok && lane == 0) P.counters[7] = 1u;
-        if (u2_ok) {
-            if (lane == 0) {
-                TcUnit t = P.units[u];
-                t.rec_base = (int64_t)u2 * TILE_M * 2;
-                t.rec_stride = 2;
-                t.seg_tiles = 64;                                       // one slice segment: the whole keyframe
-                t.maps = 2;                                             // train rows in the store; top-4 records
-                t.hint = P.hints2 + (size_t)u2 * TILE_M;
-                P.units2[u2] = t;
-            }
-            reinterpret_cast<uint4*>(P.hints2 + (size_t)u2 * TILE_M)[lane] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        for (int w = 0; w < 4; w++) {
-            const uint32_t m = __shfl_sync(0xffffffffu, mw, w);
-            if (m == 0u) continue;
-            const int64_t wi = u * 4 + w;
-            uint32_t base = 0;
-            if (lane == 0) {
-                base = atomicAdd(P.counters + 5, (uint32_t)__popc(m));
-                P.word_base[wi] = base;
-            }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!((m >> lane) & 1u)) continue;
-            const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
-            if (p >= P.pair_cap) { P.counters[7] = 1u; continue; }
-            PairRef r = {(int32_t)((u % upk) * TILE_M + w * 32 + lane), slot, u2_ok ? (int32_t)u2 : -1, 0};
-            P.pair_ref[p] = r;
-        }
-    }
-}
 
 // One warp per open pair: candidates of the second pass's two records (one per column half of the
 // keyframe) -> canonical fp32 distances -> the pair's exact top-2; a half whose four entries overflowed
@@ -887,7 +833,7 @@ loop_finish_kernel(const LoopParams P) {
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(P.counters + 14, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(P.counters + 15, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();

@@ -367,10 +367,56 @@ __device__ __forceinline__ void mask32(uint32_t (&r)[32], int32_t ucol0, int32_t
         if (ucol0 + e >= t_count) r[e] = __float_as_uint(MASKED_VALUE);
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+    return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+// A redo unit written by another SM (after its ready flag was seen and a fence): read at L2.
+__device__ __forceinline__ TcUnit load_unit_cg(const TcUnit* p) {
+    TcUnit u;
+    static_assert(sizeof(TcUnit) % 16 == 0, "TcUnit is copied in 16-byte pieces");
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4* dst = reinterpret_cast<uint4*>(&u);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(TcUnit) / 16); i++) dst[i] = __ldcg(src + i);
+    return u;
+}
+// Blocking: the next redo unit of the compact loop search, or false once every first-pass epilogue has
+// finished (nothing can be produced any more) and the queue is drained.  Bounded like the mbarrier waits.
+__device__ __noinline__ bool take_redo(const FusedArgs* fa, TcUnit& out) {
+    RedoCtl* ctl = fa->ctl;
+    long long t0 = 0;
+    for (uint32_t it = 0;; it++) {
+        const uint32_t cnt = min(ld_relaxed(&ctl->produced), fa->unit2_cap);
+        const uint32_t h = ld_relaxed(&ctl->head);
+        if (h < cnt) {
+            if (atomicCAS(&ctl->head, h, h + 1u) != h) continue;
+            for (uint32_t w = 0; ld_relaxed(fa->ready2 + h) == 0u; w++)
+                if ((w & 4095u) == 4095u) {
+                    const long long now = clock64();
+                    if (t0 == 0) t0 = now; else if (now - t0 > 4000000000LL) __trap();
+                }
+            __threadfence();
+            out = load_unit_cg(fa->units2 + h);
+            return true;
+        }
+        if (ld_relaxed(&ctl->main_done) >= 4u * fa->n_main) {
+            __threadfence();
+            const uint32_t cnt2 = min(ld_relaxed(&ctl->produced), fa->unit2_cap);
+            if (ld_relaxed(&ctl->head) >= cnt2) return false;
+            continue;
+        }
+        __nanosleep(200);
+        if ((it & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now; else if (now - t0 > 4000000000LL) __trap();     // ~2 s
+        }
+    }
+}
+
 template <bool DEBUG>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_constant__ CUtensorMap map_store,
-               const TcUnit* __restrict__ units, int nunits_host, const uint32_t* __restrict__ nunits_dev,
+               const TcUnit* __restrict__ units, int nunits_host, const FusedArgs* __restrict__ fargs,
                uint32_t* __restrict__ work_counter, PartialRec* __restrict__ recs, float* __restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B operands need 1024-byte alignment
@@ -429,23 +475,34 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
         if (lane == 0) {
             int slot = 0;
             uint32_t ph = 0;
-            // the unit list may have been built on the device (second pass of the compact loop search): its
-            // length is then read here, after the producer kernel has completed
-            const int nunits = nunits_dev ? min((int)*nunits_dev, nunits_host) : nunits_host;
-            // the queue is read one unit ahead: the atomic and the descriptor load of unit i+1 are
-            // in flight while unit i streams, so a unit boundary costs no L2 round trips
-            int idx = (int)atomicAdd(work_counter, 1u);
+            const int nunits = nunits_host;
+            // The queue is read one unit ahead: the atomic and the descriptor load of unit i+1 are in flight
+            // while unit i streams, so a unit boundary costs no L2 round trips.  When the first-pass list of
+            // a compact loop search is exhausted the scheduler turns to the redo queue (take_redo), which it
+            // may only wait on AFTER the loads of its current unit are out: that unit's epilogue must be able
+            // to finish, or main_done never completes.
+            bool phase_a = true;
             TcUnit u;
-            if (idx < nunits) u = units[idx]; else u.t_count = 0;            // t_count 0 = no more work
+            bool have = false;
+            {
+                const int i = (int)atomicAdd(work_counter, 1u);
+                if (i < nunits) { u = units[i]; have = true; }
+                else { phase_a = false; if (fargs) have = take_redo(fargs, u); }
+            }
             for (uint32_t ui = 0;; ui++) {
                 const int us = ui & 1;
                 mbar_wait(BAR_UEMPTY + 8 * us, ((ui >> 1) & 1) ^ 1);
+                if (!have) u.t_count = 0;                                    // t_count 0 = no more work
                 unit_ring[us] = u;
                 mbar_arrive(BAR_UFULL + 8 * us);                             // release: publishes the slot
-                if (idx >= nunits) break;
-                const int idx_next = (int)atomicAdd(work_counter, 1u);       // result first used after tile 0 is issued
+                if (!have) break;
+                int idx_next = -1;                                           // result first used after tile 0 is issued
+                if (phase_a) {
+                    idx_next = (int)atomicAdd(work_counter, 1u);
+                    if (idx_next >= nunits) { idx_next = -1; phase_a = false; }
+                }
                 TcUnit u_next;
-                u_next.t_count = 0;
+                bool have_next = false;
                 const CUtensorMap* mq = (u.maps & 1) ? &map_store : &map_scratch;
                 const CUtensorMap* mt = (u.maps & 2) ? &map_store : &map_scratch;
                 const int ntiles = (u.t_count + TILE_N - 1) / TILE_N;
@@ -475,10 +532,11 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         tma_load_2d(dst + T_STAGE_BYTES / 2, mt, c * KCHUNK, row + TILE_N / 2, BAR_FULL + 8 * slot);
                         if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
-                    if (n == 0 && idx_next < nunits) u_next = units[idx_next];   // lands while the other tiles stream
+                    if (n == 0 && idx_next >= 0) { u_next = units[idx_next]; have_next = true; }   // lands while the other tiles stream
                 }
-                idx = idx_next;
+                if (!have_next && !phase_a && fargs) have_next = take_redo(fargs, u_next);
                 u = u_next;
+                have = have_next;
             }
         }
     } else if (warp == 1) {
@@ -604,6 +662,52 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, open);
                         if (lane == 0) u.hint[u.rec_base + quarter] = m;
+                        if (fargs) {
+                            // Open pairs in this quarter: number them, and push the unit back into this
+                            // kernel's queue as a top-4 unit (the second pass runs inside the same launch, on
+                            // whichever CTA gets to it; only this quarter's 32 rows matter to it).
+                            if (m != 0u) {
+                                uint32_t u2 = 0, base = 0;
+                                if (lane == 0) {
+                                    u2 = atomicAdd(&fargs->ctl->produced, 1u);
+                                    base = atomicAdd(fargs->counters + 5, (uint32_t)__popc(m));
+                                    fargs->word_base[u.rec_base + quarter] = base;
+                                }
+                                u2 = __shfl_sync(0xffffffffu, u2, 0);
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                const bool ok = u2 < fargs->unit2_cap;
+                                if (ok) {
+                                    reinterpret_cast<uint4*>(fargs->hints2 + (size_t)u2 * TILE_M)[lane] = make_uint4(0u, 0u, 0u, 0u);
+                                    if (lane == 0) {
+                                        TcUnit t = u;
+                                        t.rec_base = (int64_t)u2 * TILE_M * 2;
+                                        t.rec_stride = 2;
+                                        t.seg_tiles = 64;                       // one slice segment: the whole keyframe
+                                        t.maps = 2;                             // train rows in the store; top-4 records
+                                        t.prefetch = 1;
+                                        t.hint = fargs->hints2 + (size_t)u2 * TILE_M;
+                                        fargs->units2[u2] = t;
+                                    }
+                                    __threadfence();
+                                    __syncwarp();
+                                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(fargs->ready2 + u2) = 1u;
+                                } else if (lane == 0) {
+                                    fargs->counters[7] = 1u;                     // queue full: the call repeats on the record path
+                                }
+                                if ((m >> lane) & 1u) {
+                                    const uint32_t p = base + __popc(m & ((1u << lane) - 1u));
+                                    if (p < fargs->pair_cap) {
+                                        PairRef r = {u.q_row + row, u.t_index0, ok ? (int32_t)u2 : -1, 0};
+                                        fargs->pair_ref[p] = r;
+                                    } else {
+                                        fargs->counters[7] = 1u;
+                                    }
+                                }
+                            }
+                            __threadfence();
+                            __syncwarp();
+                            if (lane == 0) atomicAdd(&fargs->ctl->main_done, 1u);
+                        }
                     }
                 }
                 continue;
