@@ -482,6 +482,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
             // may only wait on AFTER the loads of its current unit are out: that unit's epilogue must be able
             // to finish, or main_done never completes.
             bool phase_a = true;
+            int pending_idx = -1;
             TcUnit u;
             bool have = false;
             {
@@ -496,10 +497,10 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                 unit_ring[us] = u;
                 mbar_arrive(BAR_UFULL + 8 * us);                             // release: publishes the slot
                 if (!have) break;
-                int idx_next = -1;                                           // result first used after tile 0 is issued
-                if (phase_a) {
-                    idx_next = (int)atomicAdd(work_counter, 1u);
-                    if (idx_next >= nunits) { idx_next = -1; phase_a = false; }
+                // a claimed first-pass unit that has not been scheduled yet (result first used after tile 0 is issued)
+                if (pending_idx < 0 && phase_a) {
+                    pending_idx = (int)atomicAdd(work_counter, 1u);
+                    if (pending_idx >= nunits) { pending_idx = -1; phase_a = false; }
                 }
                 TcUnit u_next;
                 bool have_next = false;
@@ -532,9 +533,28 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         tma_load_2d(dst + T_STAGE_BYTES / 2, mt, c * KCHUNK, row + TILE_N / 2, BAR_FULL + 8 * slot);
                         if (++slot == STAGES) { slot = 0; ph ^= 1; }
                     }
-                    if (n == 0 && idx_next >= 0) { u_next = units[idx_next]; have_next = true; }   // lands while the other tiles stream
+                    if (n == 0) {
+                        // Redo units go FIRST (a compact loop search): taken as soon as they exist, they overlap
+                        // the first pass instead of forming a tail of a few busy SMs after it.
+                        int redo = -1;
+                        if (fargs) {
+                            const uint32_t cnt = min(ld_relaxed(&fargs->ctl->produced), fargs->unit2_cap);
+                            const uint32_t h = ld_relaxed(&fargs->ctl->head);
+                            if (h < cnt && atomicCAS(&fargs->ctl->head, h, h + 1u) == h) redo = (int)h;
+                        }
+                        if (redo >= 0) {
+                            while (ld_relaxed(fargs->ready2 + redo) == 0u) {}                    // written right after the reservation
+                            __threadfence();
+                            u_next = load_unit_cg(fargs->units2 + redo);
+                            have_next = true;                                                    // pending_idx keeps its unit for the next round
+                        } else if (pending_idx >= 0) {
+                            u_next = units[pending_idx];                                         // lands while the other tiles stream
+                            pending_idx = -1;
+                            have_next = true;
+                        }
+                    }
                 }
-                if (!have_next && !phase_a && fargs) have_next = take_redo(fargs, u_next);
+                if (!have_next && !phase_a && pending_idx < 0 && fargs) have_next = take_redo(fargs, u_next);
                 u = u_next;
                 have = have_next;
             }
