@@ -502,6 +502,12 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     pending_idx = (int)atomicAdd(work_counter, 1u);
                     if (pending_idx >= nunits) { pending_idx = -1; phase_a = false; }
                 }
+                // the redo queue's counters: loaded here, looked at after tile 0 is issued (latency hidden)
+                uint32_t redo_cnt = 0, redo_head = 0;
+                if (fargs) {
+                    redo_cnt = ld_relaxed(&fargs->ctl->produced);
+                    redo_head = ld_relaxed(&fargs->ctl->head);
+                }
                 TcUnit u_next;
                 bool have_next = false;
                 const CUtensorMap* mq = (u.maps & 1) ? &map_store : &map_scratch;
@@ -538,9 +544,8 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         // the first pass instead of forming a tail of a few busy SMs after it.
                         int redo = -1;
                         if (fargs) {
-                            const uint32_t cnt = min(ld_relaxed(&fargs->ctl->produced), fargs->unit2_cap);
-                            const uint32_t h = ld_relaxed(&fargs->ctl->head);
-                            if (h < cnt && atomicCAS(&fargs->ctl->head, h, h + 1u) == h) redo = (int)h;
+                            const uint32_t cnt = min(redo_cnt, fargs->unit2_cap);
+                            if (redo_head < cnt && atomicCAS(&fargs->ctl->head, redo_head, redo_head + 1u) == redo_head) redo = (int)redo_head;
                         }
                         if (redo >= 0) {
                             while (ld_relaxed(fargs->ready2 + redo) == 0u) {}                    // written right after the reservation
