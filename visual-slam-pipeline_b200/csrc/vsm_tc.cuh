@@ -728,8 +728,8 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                                         fargs->counters[7] = 1u;
                                     }
                                 }
+                                __threadfence();                 // the pushes above, before this quarter counts as finished
                             }
-                            __threadfence();
                             __syncwarp();
                             if (lane == 0) atomicAdd(&fargs->ctl->main_done, 1u);
                         }
