@@ -351,6 +351,41 @@ public:
                 if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, (int)idx[2 * i + p], 0, dist[2 * i + p]));
     }
 
+    /* ---- Map::map_points_ on the device (first device of a multi-device matcher) --------------------
+     * add_map_points: MapPoint births whose descriptor is frame->descriptors().row(kp).clone() of a stored
+     * frame (src/Slam.cpp:1337-1347, :1561-1570); returns the first new id (ids follow the reference's next_id).
+     * observe_map_points / set_map_points_valid: MapPoint::add_observation (:463) / set_valid (:496, :1119-1123).
+     * search_map_points: the searches of src/Slam.cpp:546-574 (near_frame_id < 0: every valid point) and
+     * :744-774 (valid points observed within `range` frames of near_frame_id); trainIdx = POINT ID
+     * (mp_ids_vec[m[0].trainIdx], :768); returns the rows of the stacked matrix (the >= 50 / >= 20 gates). */
+    int add_map_points(int frame_handle, const std::vector<int>& keypoint_idx) {
+        std::vector<int32_t> k(keypoint_idx.begin(), keypoint_idx.end());
+        int32_t first = -1;
+        check(vsm_points_add_from_frame(ctx_, frame_handle, k.data(), (int32_t)k.size(), &first));
+        return first;
+    }
+    void observe_map_points(const std::vector<int>& point_ids, int frame_id) {
+        std::vector<int32_t> p(point_ids.begin(), point_ids.end());
+        check(vsm_points_observe(ctx_, p.data(), (int32_t)p.size(), frame_id));
+    }
+    void set_map_points_valid(const std::vector<int>& point_ids, bool valid) {
+        std::vector<int32_t> p(point_ids.begin(), point_ids.end());
+        check(vsm_points_set_valid(ctx_, p.data(), (int32_t)p.size(), valid ? 1 : 0));
+    }
+    int search_map_points(const Mat& frame_desc, int near_frame_id, int range, std::vector<std::vector<DMatch>>& knn) {
+        knn.assign(frame_desc.rows, std::vector<DMatch>());
+        std::vector<float> b;
+        std::vector<int64_t> idx((size_t)(frame_desc.rows > 0 ? frame_desc.rows : 1) * 2);
+        std::vector<float> dist(idx.size());
+        int32_t rows_stacked = 0;
+        check(vsm_points_top2(ctx_, frame_desc.empty() ? nullptr : rows_of(frame_desc, b), frame_desc.empty() ? 0 : frame_desc.rows,
+                              near_frame_id, range, idx.data(), dist.data(), &rows_stacked));
+        for (int i = 0; i < frame_desc.rows; i++)
+            for (int p = 0; p < 2; p++)
+                if (idx[2 * i + p] >= 0) knn[i].push_back(DMatch(i, (int)idx[2 * i + p], 0, dist[2 * i + p]));
+        return rows_stacked;
+    }
+
     vsm_ctx* handle() { return ctx_; }
     vsm_group* group() { return group_; }
 

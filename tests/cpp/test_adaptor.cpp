@@ -186,6 +186,62 @@ int main(int argc, char** argv) {
             }
         }
     }
+    // the resident map-point table through the adaptor: points born from rows of two stored keyframes, one
+    // observed again later, some invalidated; both searches of Slam.cpp (:546-574 all valid, :744-774 near a frame)
+    {
+        matcher.clear_keyframes();
+        std::vector<float> k0 = rows(9, 1, 200), k1 = rows(9, 2, 200);
+        const int h0 = matcher.add_keyframe(100, Mat(200, 256, k0.data()));
+        const int h1 = matcher.add_keyframe(300, Mat(200, 256, k1.data()));
+        std::vector<int> kp0, kp1;
+        for (int i = 0; i < 200; i += 2) kp0.push_back(i);
+        for (int i = 1; i < 200; i += 4) kp1.push_back(i);
+        EXPECT(matcher.add_map_points(h0, kp0) == 0);
+        EXPECT(matcher.add_map_points(h1, kp1) == (int)kp0.size());
+        matcher.observe_map_points({3, 4, 5}, 310);                         // points of keyframe 100 seen again near frame 300
+        matcher.set_map_points_valid({0, 1, 2, 4}, false);
+        // the model: descriptors / valid / observation frames per point id
+        std::vector<const float*> pd;
+        std::vector<std::vector<int>> obs;
+        for (int k : kp0) { pd.push_back(&k0[(size_t)k * 256]); obs.push_back({100}); }
+        for (int k : kp1) { pd.push_back(&k1[(size_t)k * 256]); obs.push_back({300}); }
+        for (int p : {3, 4, 5}) obs[p].push_back(310);
+        std::vector<char> valid(pd.size(), 1);
+        for (int p : {0, 1, 2, 4}) valid[p] = 0;
+        const int nq = 60;
+        std::vector<float> q = rows(9, 3, nq);
+        std::memcpy(q.data(), k0.data() + (size_t)6 * 256, 1024);            // query 0 = point 3's descriptor (keypoint 6 of keyframe 100)
+        std::memcpy(q.data() + 256, k1.data() + (size_t)5 * 256, 1024);      // query 1 = a point of keyframe 300
+        Mat fq(nq, 256, q.data());
+        for (int near : {-1, 300}) {
+            std::vector<int> ids;
+            std::vector<float> sub;
+            for (size_t p = 0; p < pd.size(); p++) {
+                bool sel = valid[p];
+                if (sel && near >= 0) {
+                    sel = false;
+                    for (int f : obs[p]) sel |= std::abs(f - near) < 30;
+                }
+                if (sel) { ids.push_back((int)p); sub.insert(sub.end(), pd[p], pd[p] + 256); }
+            }
+            std::vector<std::vector<DMatch>> knn4;
+            const int stacked = matcher.search_map_points(fq, near, 30, knn4);
+            EXPECT(stacked == (int)ids.size());
+            std::vector<int64_t> oi((size_t)nq * 2);
+            std::vector<float> od((size_t)nq * 2);
+            vsm_oracle_knn(q.data(), nq, 256, sub.data(), (int64_t)ids.size(), 256, 2, oi.data(), od.data(), 0);
+            for (int i = 0; i < nq; i++) {
+                EXPECT(knn4[i].size() == 2);
+                for (int k = 0; k < 2 && knn4[i].size() == 2; k++) {
+                    EXPECT(knn4[i][k].trainIdx == ids[(size_t)oi[2 * i + k]]);
+                    EXPECT(std::memcmp(&knn4[i][k].distance, &od[2 * i + k], 4) == 0);
+                }
+            }
+            EXPECT(knn4[0][0].trainIdx == 3 && knn4[0][0].distance == 0.f);   // seen at frames 100 and 310: selected in both searches
+        }
+        vsm_points_clear(matcher.handle());
+        matcher.clear_keyframes();
+    }
     // several devices behind one matcher object (vsm_group): device list from the command line,
     // e.g. "0 0 0" (three contexts on one GPU) or "0 1"
     if (g_devices.size() > 1) {

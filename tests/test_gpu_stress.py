@@ -31,7 +31,10 @@ def _scaled(t, rng):
 
 
 def test_random_call_sequence():
-    rng = np.random.default_rng(2026)
+    import os
+    # VSM_SOAK_SEED / VSM_SOAK_ITERS: a longer soak with another seed (run by hand on the GPU box)
+    rng = np.random.default_rng(int(os.environ.get("VSM_SOAK_SEED", "2026")))
+    iters = int(os.environ.get("VSM_SOAK_ITERS", "160"))
     m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, scratch_rows=256)
     # model of the store: keyframes in Map::get_keyframes() order as (handle, matrix); the reference frame
     kf, prev_handle, prev_frame, prev_is_kf = [], -1, None, False
@@ -50,11 +53,11 @@ def test_random_call_sequence():
         s_ = np.clip(np.searchsorted(seg, np.maximum(oi, 0), side="right") - 1, 0, len(row0) - 1)
         return np.where(oi >= 0, row0[s_] + (oi - seg[s_]), -1)
 
-    for it in range(160):
+    for it in range(iters):
         if rng.random() < 0.15:
             m.set_profiling(bool(rng.integers(0, 2)))
         op = rng.choice(["knn", "match", "match", "track", "track", "add", "global", "segmented", "masked", "batch",
-                         "repeat", "remove"])
+                         "repeat", "remove", "compact", "compact"])
         counts[op] = counts.get(op, 0) + 1
         nq, nt = int(rng.integers(1, 700)), int(rng.integers(1, 1100))
         q, t, _ = gen.planted(1000 + it, nq, nt, 0.5, 0.09)
@@ -106,6 +109,17 @@ def test_random_call_sequence():
             assert np.array_equal(c, oc), (it, op)
             for s in range(len(kf)):
                 assert lists[s].tobytes() == ol[s].tobytes(), (it, op, s)
+        elif kf and op == "compact":
+            db, seg, _ = layout()
+            ids = np.array([m.frame_info(h)[1] for h, _ in kf], np.int32)
+            every, mm, gap = int(rng.integers(1, 4)), int(rng.choice([0, 1, 5, 30])), int(rng.choice([0, 40]))
+            cur = it + 20
+            st_c, lists_c, _ = m.loop_detect_compact(cur, _maybe_pinned(q, rng), 0.75, min_gap=gap, every=every, min_matches=mm)
+            ost, ol = oracle.loop_detect(q, db, seg, ids, cur, 0.75, min_gap=gap, every=every)
+            assert np.array_equal(st_c, ost), (it, op)
+            assert set(lists_c) == {s for s in range(len(ost)) if ost[s] >= max(mm, 1)}, (it, op)
+            for s in lists_c:
+                assert lists_c[s].tobytes() == ol[s].tobytes(), (it, op, s)
         elif kf and op == "masked":
             # the mask runs over store rows; only rows of live keyframes are offered here
             db, seg, row0 = layout()
