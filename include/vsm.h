@@ -233,7 +233,8 @@ int vsm_db_segmented(vsm_ctx* ctx, const float* query, int32_t nq, float ratio,
 /* The same search restricted to the store rows with mask[row] != 0 -- the map-point searches of
  * src/Slam.cpp:546-574 (only valid map points, :553) and :744-774 (only points observed near the
  * loop keyframe, :748-756), which the reference implements by re-stacking the selected
- * descriptors on every call.  n_mask must equal the store's row count.  idx holds ORIGINAL store
+ * descriptors on every call.  The mask is copied to the device as it is and the selection (numbering in
+ * ascending row order, gather) happens there.  n_mask must equal the store's row count.  idx holds ORIGINAL store
  * rows (the reference's mp_ids_vec[trainIdx], :768); order and ties are those of the compacted
  * matrix the reference builds (ascending row).  -1 / FLT_MAX when fewer than k rows are selected. */
 int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8_t* mask, int64_t n_mask,

@@ -2045,54 +2045,43 @@ int vsm_points_clear(vsm_ctx* ctx) {
     return VSM_OK;
 }
 
-int vsm_points_top2(vsm_ctx* ctx, const float* query, int32_t nq, int32_t near_frame_id, int32_t range, int64_t* idx, float* dist,
-                    int32_t* n_selected) {
-    if (!ctx || nq < 0 || (nq > 0 && (!query || !idx || !dist)) || (near_frame_id >= 0 && range <= 0))
-        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_top2: bad argument") : VSM_ERR_INVALID;
-    if (n_selected) *n_selected = 0;
-    for (int i = 0; i < nq * 2; i++) { idx[i] = -1; dist[i] = FLT_MAX; }
-    const int64_t np = ctx->n_points;
-    if (np == 0) return VSM_OK;
-    TRY(begin_call(ctx));
-    // 1. selection on the device: valid (:553 / :747) and, for the loop-verification search, seen near the matched keyframe (:748-756)
-    const int nblocks = (int)((np + POINTS_PER_BLOCK - 1) / POINTS_PER_BLOCK);
-    const size_t o_near = 0, o_flag = align16(o_near + (size_t)np), o_cnt = align16(o_flag + (size_t)np),
-                 o_off = align16(o_cnt + (size_t)nblocks * 4), o_total = align16(o_off + (size_t)nblocks * 4), tmp_bytes = o_total + 16;
-    TRY(ensure(ctx, ctx->d_pt_tmp, tmp_bytes));
-    TRY(ensure(ctx, ctx->d_sel, (size_t)np));
-    uint8_t* t = ctx->d_pt_tmp.p;
-    const uint8_t* near = nullptr;
-    if (near_frame_id >= 0) {
-        CK(cudaMemsetAsync(t + o_near, 0, (size_t)np, ctx->stream));
-        if (ctx->n_log > 0)
-            points_mark_near_kernel<<<(unsigned)((ctx->n_log + 255) / 256), 256, 0, ctx->stream>>>(
-                reinterpret_cast<const PointObs*>(ctx->pt_log.p), ctx->n_log, near_frame_id, range, t + o_near);
-        near = t + o_near;
-        ctx->launches++;
-    }
-    points_count_kernel<<<nblocks, 256, 0, ctx->stream>>>(ctx->pt_valid.p, near, np, t + o_flag, reinterpret_cast<int32_t*>(t + o_cnt));
-    points_scan_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const int32_t*>(t + o_cnt), nblocks,
-                                                    reinterpret_cast<int32_t*>(t + o_off), reinterpret_cast<int32_t*>(t + o_total));
-    points_scatter_kernel<<<nblocks, 256, 0, ctx->stream>>>(t + o_flag, np, reinterpret_cast<const int32_t*>(t + o_off), ctx->d_sel.p);
+// knnMatch(query, stack of the rows i of src_f32 with d_valid[i] != 0 (and d_near[i] != 0 if given), 2) with the
+// selection made on the device: count / scan / scatter the selected row numbers in ascending order (the order
+// of the reference's re-stacking loops, src/Slam.cpp:552-557, :744-759), gather the rows, run the ordinary
+// search, map trainIdx back to row numbers.  d_tmp: scratch of at least select_tmp_bytes(n) bytes whose first n
+// bytes may hold d_near.  One 4-byte read (the selection size) is the only host round trip.
+static size_t select_tmp_bytes(int64_t n) {
+    const size_t nblocks = (size_t)((n + POINTS_PER_BLOCK - 1) / POINTS_PER_BLOCK);
+    return align16((size_t)n) * 2 + align16(nblocks * 4) * 2 + 32;
+}
+static int select_and_search(vsm_ctx* ctx, const float* query, int32_t nq, const uint8_t* d_valid, const uint8_t* d_near,
+                             int64_t n, const float* src_f32, uint8_t* d_tmp, int64_t* idx, float* dist, int32_t* n_selected) {
+    const int nblocks = (int)((n + POINTS_PER_BLOCK - 1) / POINTS_PER_BLOCK);
+    const size_t o_flag = align16((size_t)n), o_cnt = o_flag + align16((size_t)n), o_off = o_cnt + align16((size_t)nblocks * 4),
+                 o_total = o_off + align16((size_t)nblocks * 4);
+    TRY(ensure(ctx, ctx->d_sel, (size_t)n));
+    points_count_kernel<<<nblocks, 256, 0, ctx->stream>>>(d_valid, d_near, n, d_tmp + o_flag, reinterpret_cast<int32_t*>(d_tmp + o_cnt));
+    points_scan_kernel<<<1, 1024, 0, ctx->stream>>>(reinterpret_cast<const int32_t*>(d_tmp + o_cnt), nblocks,
+                                                    reinterpret_cast<int32_t*>(d_tmp + o_off), reinterpret_cast<int32_t*>(d_tmp + o_total));
+    points_scatter_kernel<<<nblocks, 256, 0, ctx->stream>>>(d_tmp + o_flag, n, reinterpret_cast<const int32_t*>(d_tmp + o_off), ctx->d_sel.p);
     ctx->launches += 3;
     CK(cudaGetLastError());
     int32_t ns = 0;                                              // the search is planned on the host: one 4-byte read
-    CK(cudaMemcpyAsync(&ns, t + o_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ns, d_tmp + o_total, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (n_selected) *n_selected = ns;
     if (nq == 0 || ns == 0) return end_call(ctx, true);
-    // 2. the stacked matrix the reference builds by push_back (:556, :757), gathered on the device; then the ordinary search
+    // the stacked matrix the reference builds by push_back (:556, :757), gathered on the device; then the ordinary search
     TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + ns, 0));
     TRY(upload_scratch(ctx, query, 0, nq));
     const int64_t blocks = std::min<int64_t>(((int64_t)ns + 7) / 8, (int64_t)ctx->num_sms * 16);
-    gather_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const float*>(ctx->pt_f32.p), ctx->d_sel.p, ns,
-                                                                  ctx->scratch.f32 + (int64_t)nq * VSM_DIM);
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src_f32, ctx->d_sel.p, ns, ctx->scratch.f32 + (int64_t)nq * VSM_DIM);
     ctx->launches++;
     CK(cudaGetLastError());
     std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, ns, 0)};
     queue_convert(ctx, ctx->scratch.f32 + (int64_t)nq * VSM_DIM, nq, ns);
     TRY(run_problems(ctx, probs, {}, nq, 0));
-    // 3. trainIdx -> point id (the reference's mp_ids_vec[m[0].trainIdx], :768), straight into pinned host memory
+    // trainIdx -> row number (the reference's mp_ids_vec[m[0].trainIdx], :768), straight into pinned host memory
     const size_t nb = (size_t)nq * 2 * (sizeof(int64_t) + sizeof(float));
     TRY(ensure_host(ctx, ctx->h_result, ctx->h_result_cap, std::max<size_t>(nb, 16)));
     int64_t* h_idx = reinterpret_cast<int64_t*>(ctx->h_result);
@@ -2104,6 +2093,31 @@ int vsm_points_top2(vsm_ctx* ctx, const float* query, int32_t nq, int32_t near_f
     memcpy(idx, h_idx, (size_t)nq * 2 * sizeof(int64_t));
     memcpy(dist, h_dist, (size_t)nq * 2 * sizeof(float));
     return VSM_OK;
+}
+
+int vsm_points_top2(vsm_ctx* ctx, const float* query, int32_t nq, int32_t near_frame_id, int32_t range, int64_t* idx, float* dist,
+                    int32_t* n_selected) {
+    if (!ctx || nq < 0 || (nq > 0 && (!query || !idx || !dist)) || (near_frame_id >= 0 && range <= 0))
+        return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_points_top2: bad argument") : VSM_ERR_INVALID;
+    if (n_selected) *n_selected = 0;
+    for (int i = 0; i < nq * 2; i++) { idx[i] = -1; dist[i] = FLT_MAX; }
+    const int64_t np = ctx->n_points;
+    if (np == 0) return VSM_OK;
+    TRY(begin_call(ctx));
+    // valid (:553 / :747) and, for the loop-verification search, seen near the matched keyframe (:748-756)
+    TRY(ensure(ctx, ctx->d_pt_tmp, select_tmp_bytes(np)));
+    uint8_t* t = ctx->d_pt_tmp.p;
+    const uint8_t* near = nullptr;
+    if (near_frame_id >= 0) {
+        CK(cudaMemsetAsync(t, 0, (size_t)np, ctx->stream));
+        if (ctx->n_log > 0)
+            points_mark_near_kernel<<<(unsigned)((ctx->n_log + 255) / 256), 256, 0, ctx->stream>>>(
+                reinterpret_cast<const PointObs*>(ctx->pt_log.p), ctx->n_log, near_frame_id, range, t);
+        near = t;
+        ctx->launches++;
+    }
+    return select_and_search(ctx, query, nq, ctx->pt_valid.p, near, np, reinterpret_cast<const float*>(ctx->pt_f32.p), t, idx, dist,
+                             n_selected);
 }
 
 // ---- LoopCloser::detect, compact form ------------------------------------------------------------
@@ -2466,32 +2480,15 @@ int vsm_db_top2_masked(vsm_ctx* ctx, const float* query, int32_t nq, const uint8
         return ctx ? fail(ctx, VSM_ERR_INVALID, "vsm_db_top2_masked: bad argument (mask length must equal the store rows)")
                    : VSM_ERR_INVALID;
     if (nq == 0) return VSM_OK;
-    std::vector<int32_t> sel;                                            // the reference's mp_ids_vec (src/Slam.cpp:757)
-    for (int64_t r = 0; r < n_mask; r++) if (mask[r]) sel.push_back((int32_t)r);
-    const int64_t ns = (int64_t)sel.size();
+    for (int i = 0; i < nq * 2; i++) { idx[i] = -1; dist[i] = FLT_MAX; }
+    if (n_mask == 0) return VSM_OK;
     TRY(begin_call(ctx));
-    TRY(arena_reserve(ctx, ctx->scratch, (int64_t)nq + ns, 0));
-    TRY(upload_scratch(ctx, query, 0, nq));
-    if (ns > 0) {
-        TRY(ensure(ctx, ctx->d_sel, (size_t)ns));
-        CK(cudaMemcpyAsync(ctx->d_sel.p, sel.data(), (size_t)ns * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-        const int64_t blocks = std::min<int64_t>((ns + 7) / 8, (int64_t)ctx->num_sms * 16);
-        gather_rows_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->store.f32, ctx->d_sel.p, ns,
-                                                                      ctx->scratch.f32 + (int64_t)nq * VSM_DIM);
-        ctx->launches++;
-        CK(cudaGetLastError());
-    }
-    std::vector<HProblem> probs{scratch_vs_scratch(ctx, 0, nq, nq, (int)ns, 0)};
-    queue_convert(ctx, ctx->scratch.f32 + (int64_t)nq * VSM_DIM, nq, ns);        // the gathered rows
-    TRY(run_problems(ctx, probs, {}, nq, 0));
-    TRY(fetch_keys(ctx, nq));
-    TRY(end_call(ctx, true));                                            // also keeps `sel` alive past the H2D
-    const unsigned long long* k = reinterpret_cast<const unsigned long long*>(ctx->h_result);
-    for (int i = 0; i < nq * 2; i++) {
-        decode_key(k[i], idx[i], dist[i]);
-        if (idx[i] >= 0) idx[i] = sel[(size_t)idx[i]];
-    }
-    return VSM_OK;
+    // the mask goes to the device as it is (one byte per store row); the selected rows (the reference's
+    // mp_ids_vec, src/Slam.cpp:757) are found, numbered and gathered there -- no O(rows) loop on the host
+    TRY(ensure(ctx, ctx->d_pt_tmp, select_tmp_bytes(n_mask) + align16((size_t)n_mask)));
+    uint8_t* d_mask = ctx->d_pt_tmp.p + select_tmp_bytes(n_mask);
+    CK(cudaMemcpyAsync(d_mask, mask, (size_t)n_mask, cudaMemcpyHostToDevice, ctx->stream));
+    return select_and_search(ctx, query, nq, d_mask, nullptr, n_mask, ctx->store.f32, ctx->d_pt_tmp.p, idx, dist, nullptr);
 }
 
 int vsm_db_top2_keys_device(vsm_ctx* ctx, const float* d_query, int32_t nq, int64_t row_offset, uint64_t* d_keys,
