@@ -446,6 +446,11 @@ int vsm_group_loop_detect_compact(vsm_group* g, int32_t cur_frame_id, int32_t mi
                                   int32_t cand_cap, int32_t* n_cands, vsm_dmatch* matches, int64_t match_cap,
                                   int64_t* n_matches);
 
+/* vsm_match_batch with the pairs dealt to the members in contiguous blocks of near-equal input size
+ * (replicas: a pair is never split); every member uploads its block over its own PCIe link. */
+int vsm_group_match_batch(vsm_group* g, int32_t n_pairs, const float* query, const int32_t* q_off, const float* train,
+                          const int32_t* t_off, float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good);
+
 /* Raw CUDA stream of the context (cudaStream_t as void*), for event timing. */
 void* vsm_stream(vsm_ctx* ctx);
 /* Run on a caller-owned stream (e.g. the stream an NCCL collective is enqueued on). */

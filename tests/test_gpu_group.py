@@ -131,3 +131,26 @@ def test_group_with_more_members_than_keyframes_and_empty_keyframes():
         st, lists = g.loop_detect_compact(500, q, 0.75, min_gap=0, every=1, min_matches=0)
         og, _ = oracle.match_features(q, kf, 0.75)
         assert list(st) == [-1, len(og)]
+
+
+@pytest.mark.parametrize("devices", device_lists()[1:], ids=lambda d: "dev" + "".join(map(str, d)))
+def test_group_ragged_batch_equals_single_context(devices):
+    """vsm_group_match_batch: the ragged batch cut into contiguous blocks of pairs, one per member (replicas)."""
+    rng = np.random.default_rng(4)
+    qs, ts = [], []
+    for p in range(13):
+        a, b, _ = gen.planted(800 + p, int(rng.integers(1, 500)), int(rng.integers(1, 600)), 0.6, 0.08)
+        qs.append(a)
+        ts.append(b)
+    qs[5] = qs[5][:0]                                             # a pair without queries
+    q_off = np.zeros(14, np.int32)
+    t_off = np.zeros(14, np.int32)
+    q_off[1:] = np.cumsum([len(a) for a in qs])
+    t_off[1:] = np.cumsum([len(a) for a in ts])
+    qa, ta = np.ascontiguousarray(np.concatenate(qs)), np.ascontiguousarray(np.concatenate(ts))
+    with vsm_b200.Group(devices) as g:
+        for mutual in (False, True):
+            res = g.match_batch_packed(qa, q_off, ta, t_off, 0.75, mutual)
+            for p in range(13):
+                og, _ = oracle.match_features(qs[p], ts[p], 0.75, mutual=mutual)
+                assert res[p].tobytes() == og.tobytes(), (p, mutual)

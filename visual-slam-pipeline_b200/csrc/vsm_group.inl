@@ -548,3 +548,39 @@ int vsm_group_loop_detect_compact(vsm_group* g, int32_t cur_frame_id, int32_t mi
     *n_matches = nm;
     return VSM_OK;
 }
+
+// Ragged batch of independent pairs (vsm_match_batch, BASELINE configs[4]) over the group: pair matching does not
+// shard (one pair is ~1 us of tensor time) but independent pairs are replicas -- the batch is cut into
+// contiguous blocks of pairs with near-equal input bytes, one block per member, so the upload (what bounds
+// the call: 150 MB for 64 pairs of up to 2048 keypoints) runs over every member's own PCIe link at once.
+int vsm_group_match_batch(vsm_group* g, int32_t n_pairs, const float* query, const int32_t* q_off, const float* train,
+                          const int32_t* t_off, float ratio, int32_t mutual, vsm_dmatch* good, int32_t* n_good) {
+    if (!g || n_pairs < 0 || (n_pairs > 0 && (!q_off || !t_off || !n_good)))
+        return g ? group_fail(g, VSM_ERR_INVALID, "vsm_group_match_batch: bad argument") : VSM_ERR_INVALID;
+    g->err.clear();
+    if (n_pairs == 0) return VSM_OK;
+    for (int p = 0; p < n_pairs; p++) {
+        if (q_off[p + 1] < q_off[p] || t_off[p + 1] < t_off[p]) return group_fail(g, VSM_ERR_INVALID, "vsm_group_match_batch: offsets must be non-decreasing");
+        n_good[p] = 0;
+    }
+    const int64_t total = (int64_t)q_off[n_pairs] + t_off[n_pairs];
+    if (q_off[n_pairs] == 0) return VSM_OK;
+    if (!query || !good || (t_off[n_pairs] > 0 && !train)) return group_fail(g, VSM_ERR_INVALID, "vsm_group_match_batch: null buffer");
+    // cut points: member r takes pairs [cut[r], cut[r+1]) -- the first pair whose cumulative rows reach r/n of the total
+    std::vector<int> cut(g->n + 1, n_pairs);
+    cut[0] = 0;
+    for (int r = 1, p = 0; r < g->n; r++) {
+        const int64_t target = total * r / g->n;
+        while (p < n_pairs && (int64_t)q_off[p] + t_off[p] < target) p++;
+        cut[r] = p;
+    }
+    return group_fan_out(g, [&](int r) -> int {
+        const int p0 = cut[r], p1 = cut[r + 1];
+        if (p1 <= p0) return VSM_OK;
+        std::vector<int32_t> qo(p1 - p0 + 1), to(p1 - p0 + 1);
+        for (int p = p0; p <= p1; p++) { qo[p - p0] = q_off[p] - q_off[p0]; to[p - p0] = t_off[p] - t_off[p0]; }
+        return vsm_match_batch(g->ctx[r], p1 - p0, query + (size_t)q_off[p0] * VSM_DIM, qo.data(),
+                               train ? train + (size_t)t_off[p0] * VSM_DIM : nullptr, to.data(), ratio, mutual,
+                               good + q_off[p0], n_good + p0);
+    });
+}

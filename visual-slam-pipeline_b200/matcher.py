@@ -142,6 +142,8 @@ SYMBOLS = {
     "vsm_group_loop_detect_compact": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
                                                 C.c_int64, C.POINTER(C.c_int64)]),
+    "vsm_group_match_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "vsm_stream": (C.c_void_p, [C.c_void_p]),
     "vsm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vsm_sync": (C.c_int, [C.c_void_p]),
@@ -693,6 +695,15 @@ class Group:
                                              kh.ctypes.data if want_keyframes else None,
                                              kr.ctypes.data if want_keyframes else None))
         return (idx, dist, kh, kr) if want_keyframes else (idx, dist)
+
+    def match_batch_packed(self, qa, q_off, ta, t_off, ratio=0.75, mutual=False, out=None):
+        """Ragged batch of pairs dealt to the members (vsm_group_match_batch); same result as Matcher.match_batch_packed."""
+        n = len(q_off) - 1
+        good = out if out is not None else np.zeros(max(int(q_off[-1]), 1), DMATCH)
+        n_good = np.zeros(max(n, 1), np.int32)
+        self._ck(self._lib.vsm_group_match_batch(self._g, n, qa.ctypes.data, q_off.ctypes.data, ta.ctypes.data,
+                                                 t_off.ctypes.data, ratio, int(mutual), good.ctypes.data, n_good.ctypes.data))
+        return [good[q_off[p]:q_off[p] + n_good[p]] for p in range(n)]
 
     def loop_detect_compact(self, cur_frame_id, frame_desc, ratio=0.75, min_gap=200, every=5, min_matches=30):
         """LoopCloser::detect's loop with the gate on the devices: (status[nkf], {keyframe position: list})."""
