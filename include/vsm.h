@@ -77,7 +77,10 @@ typedef struct {
                                     [2]: plain frames vsm_track keeps before recycling (0 = 2);
                                     [3]: open (query, keyframe) pairs vsm_loop_detect_compact can hold (0 = 262144; tests shrink it);
                                     [4]: train sets of up to this many 256-row tiles use append records instead of
-                                         top-4 records (0 = never: measured slower; kept as a tested option) */
+                                         top-4 records (0 = never: measured slower; kept as a tested option);
+                                    [5]: 1 = pair matching (match_features without a raw list, its mutual reverse
+                                         problem) keeps the threshold-driven top-4 records instead of the tile top-2
+                                         records it uses by default on train sets of up to 8192 rows (A/B, tests) */
 } vsm_opts;
 
 typedef struct vsm_ctx vsm_ctx;

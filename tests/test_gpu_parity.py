@@ -41,6 +41,15 @@ def appendm():
 
 
 @pytest.fixture(scope="module")
+def top4m():
+    """pair matching with the threshold-driven top-4 records (vsm_opts.reserved[5] = 1): the default for pair
+    matching is the tile top-2 epilogue, this keeps the other one covered on the same cases"""
+    m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_TENSOR, tile_top2=False)
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
 def simt():
     m = vsm_b200.Matcher(engine=vsm_b200.ENGINE_SIMT)
     yield m
@@ -1009,3 +1018,59 @@ def test_store_edge_cases(tc):
     assert tc.store_info() == (0, 0)
     assert (tc.search_map_points(q)[0] == -1).all()
     tc.clear_store()
+
+
+def _band_case(seed, nq, nt, ratio):
+    """Planted pairs whose noise is spread so that d0 / d1 covers [0.5 * ratio, 1.1]: plenty of queries land inside
+    the narrow band around `ratio` where the tile top-2 path cannot decide from bounds and re-scores exactly."""
+    vt = gen.int_rows(seed, 1, 0, nt)
+    vq = gen.int_rows(seed, 0, 0, nq).copy()
+    rows = gen._perm(seed, 7, nt)[np.arange(nq) % nt]
+    noise = gen.int_rows(seed, 2, 0, nq)
+    amp = (300 + (np.arange(nq) * 2500) // nq).astype(np.int64)[:, None]           # noise amplitude sweeps 0.3 .. 2.8
+    vq[:] = 1000 * vt[rows] + (amp * noise) // 1
+    return gen._normalize_int(vq), gen._normalize_int(vt)
+
+
+def test_tile_top2_path_equals_oracle_and_top4_path(tc, top4m):
+    """Pair matching without a raw list runs on tile top-2 records (small problems): same survivors as the
+    oracle and as the top-4 path -- planted pairs, a noise sweep that fills the undecidable band around the ratio,
+    near-duplicate clusters (slices whose second entry is a candidate: re-scan), exact duplicates (ties), train sets
+    of 1 / 2 / 3 rows, scaled rows, partial tiles, a train set at the 32-tile limit and one above it."""
+    named = ("pair_1000_video", "pair_777x1301", "pair_2048x200", "pair_129x257", "mutual_conflict", "dups", "neardup_db",
+             "nt1", "nt2", "nt3", "nq1", "scaled")
+    todo = [(n,) + tuple(cases.PAIR_CASES[n]()) for n in named]
+    todo.append(("band_075",) + _band_case(91, 1500, 1700, 0.75))
+    todo.append(("band_wide",) + _band_case(92, 700, 8192, 0.8))                    # 32 tiles: the largest tile top-2 train set
+    todo.append(("above_limit",) + gen.planted(93, 300, 8192 + 256, 0.6, 0.08)[:2])  # 33 tiles: top-4 records
+    for name, q, t in todo:
+        for ratio in (0.7, 0.75, 0.8, 1.0):
+            for mutual in (False, True):
+                good, _ = tc.match_features(q, t, ratio, mutual=mutual, want_raw=False)
+                og, _ = oracle.match_features(q, t, ratio, mutual=mutual)
+                assert good.tobytes() == og.tobytes(), (name, ratio, mutual)
+                if ratio == 0.75:
+                    g4, _ = top4m.match_features(q, t, ratio, mutual=mutual, want_raw=False)
+                    assert g4.tobytes() == og.tobytes(), (name, ratio, mutual, "top-4 records")
+    # the point of it: a matching query costs one or two exact distances instead of ~4 per direction
+    q, t = cases.PAIR_CASES["pair_1000_video"]()
+    tc.match_features(q, t, 0.75, mutual=True, want_raw=False)
+    c2 = tc.stats()["candidates"]
+    top4m.match_features(q, t, 0.75, mutual=True, want_raw=False)
+    c4 = top4m.stats()["candidates"]
+    assert 0 < c2 < c4, (c2, c4)
+    # near-duplicates: the band cases and the reverse problem's ties go through re-scans of single tile halves
+    q, t = cases.PAIR_CASES["neardup_db"]()
+    tc.match_features(q, t, 0.75, mutual=True, want_raw=False)
+    assert tc.stats()["flagged_slices"] > 0
+    # ragged batch and stored pairs take the same path
+    qs, ts = [], []
+    for p in range(9):
+        a, b = _band_case(300 + p, 100 + 211 * p, 90 + 283 * p, 0.75)
+        qs.append(a)
+        ts.append(b)
+    for mutual in (False, True):
+        res = tc.match_batch(qs, ts, 0.75, mutual=mutual)
+        for p in range(9):
+            og, _ = oracle.match_features(qs[p], ts[p], 0.75, mutual=mutual)
+            assert res[p].tobytes() == og.tobytes(), (p, mutual)

@@ -94,6 +94,11 @@ struct HProblem {
     int64_t out_off;
     float skip_ratio2 = 0.f;     // see Problem::skip_ratio2
     int32_t maxima_only = 0;     // with skip_ratio2: records = slice maxima only (matches are rare: LoopCloser's loop)
+    // pair matching on small train sets: tile top-2 records (Problem::exact bit 3).  1 = forward problem of a
+    // ratio-only caller (needs skip_ratio2 > 0 and 0 < ratio <= 1), 2 = reverse problem of a mutual test
+    // (only the nearest neighbour's index is read)
+    int32_t t2 = 0;
+    float ratio = 0.f;
     // train rows = these runs of STORE rows (logical train index = store row; t_row = 0, nt = the store's
     // high-water mark); nullptr = the one contiguous range [t_row, t_row + nt)
     const std::vector<Run>* runs = nullptr;
@@ -106,7 +111,10 @@ struct HJob {
     int64_t fwd_off, back_off, good_off, raw_off;
     int nq, nt, img_idx;
     float ratio;
+    int64_t back_prob = -1;      // index of the reverse problem in the call's list (mutual test), -1 = none
 };
+
+static_assert(sizeof(HProblem) == 88 && sizeof(HJob) == 56, "plan keys compare these byte for byte: no padding allowed");
 
 template <class T>
 struct DevBuf {
@@ -178,6 +186,7 @@ struct vsm_ctx {
     const void* loop_p_loop = nullptr;
     uint32_t pair_cap = 0;                       // open (query, keyframe) pairs the compact loop search can hold (0 = PAIR_CAP)
     int64_t append_max_tiles = 0;                // train sets of up to this many tiles use append records (0 = never)
+    bool t2_off = false;                         // vsm_opts.reserved[5] = 1 / VSM_NO_T2: pair matching keeps the top-4 records
     float* d_dump = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // event pairs around the tensor-core kernel of the last TC_RING calls (ev_tc0/ev_tc1 = the current
@@ -660,7 +669,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     {
         int64_t uses_slot = 0;
         for (auto& p : probs) if (!p.t_store) uses_slot = 1 + (ctx->call_seq & 1);
-        const int64_t head[8] = {ctx->engine + 16 * ctx->append_max_tiles, ctx->seg_tiles * 2 + (ctx->db_short_slices ? 1 : 0), ctx->num_sms, P,
+        const int64_t head[8] = {ctx->engine + 16 * ctx->append_max_tiles + (ctx->t2_off ? 8 : 0), ctx->seg_tiles * 2 + (ctx->db_short_slices ? 1 : 0), ctx->num_sms, P,
                                  (int64_t)jobs.size(), total_out, total_matches, uses_slot};
         key.resize(sizeof head + sizeof(HProblem) * probs.size() + sizeof(HJob) * jobs.size());
         memcpy(key.data(), head, sizeof head);
@@ -700,6 +709,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         d.partial_off = nrecs;
         d.exact = (exact || hp.nt == 0) ? 1 : 0;
         d.skip_ratio2 = hp.skip_ratio2;
+        d.ratio = hp.ratio;
         const bool maxima = hp.maxima_only && hp.skip_ratio2 > 0.f && !d.exact && !pairs;
         if (maxima) d.exact |= 2;
         qb[i + 1] = qb[i] + (hp.nq + SELECT_WARPS - 1) / SELECT_WARPS;
@@ -743,6 +753,11 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         // the running threshold matures so slowly that most (lane, chunk) pairs hold a passing value
         const bool append = !maxima && !pairs && !hp.runs && !dump_first && ntiles <= ctx->append_max_tiles && ctx->seg_tiles == 0;
         if (append) d.exact |= 4;
+        // small train sets of pair matching: tile top-2 records -- a slice per (tile, column half), no running state
+        // in the epilogue, one exact distance per matching query in select_kernel (vsm_common.cuh, t2_scale)
+        const bool t2 = hp.t2 && !ctx->t2_off && !maxima && !append && !pairs && !hp.runs && !dump_first && ctx->seg_tiles == 0 &&
+                        ntiles <= T2_MAX_TILES && (hp.t2 == 2 || (hp.skip_ratio2 > 0.f && hp.ratio > 0.f && hp.ratio <= 1.f));
+        if (t2) d.exact |= 8 | (hp.t2 == 2 ? 16 : 0);
         const int rec_per_slice = append ? APPEND_RECS : 1;
         struct Range { int64_t idx0, count; int tiles_after; int slice0; int seg; };
         std::vector<Range> ranges;
@@ -752,7 +767,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             const int nr = (rt + tpr_all - 1) / tpr_all;
             const int tpr = (rt + nr - 1) / nr;
             // 64 tiles x 128 columns = the 13 index bits of a packed entry; an append unit is one segment
-            const int seg = append ? tpr : std::min(std::min(tpr, seg_pref), 64);
+            const int seg = append ? tpr : t2 ? 1 : std::min(std::min(tpr, seg_pref), 64);
             for (int tile0 = 0; tile0 < rt; tile0 += tpr) {
                 const int tile1 = std::min(rt, tile0 + tpr);
                 Range g;
@@ -804,7 +819,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 u.t_count = (int32_t)g.count;
                 u.q_valid = std::min(TILE_M, hp.nq - qt * TILE_M);
                 u.seg_tiles = g.seg;
-                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0) | (maxima ? 4 : 0) | (append ? 16 : 0);
+                u.maps = (hp.q_store ? 1 : 0) | (hp.t_store ? 2 : 0) | (maxima ? 4 : 0) | (append ? 16 : 0) | (t2 ? 32 : 0);
                 u.dump = (dump_first && units.empty()) ? dump_first : 0;
                 // 1 + the number of tiles past this unit's end that may be prefetched as well
                 u.prefetch = (qt == 0 || qt == nqt / 2) ? 1 + std::min(tc::L2_AHEAD, g.tiles_after) : 0;
@@ -909,6 +924,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         fj.fwd_off = jobs[j].fwd_off; fj.back_off = jobs[j].back_off;
         fj.good_off = jobs[j].good_off; fj.raw_off = jobs[j].raw_off;
         fj.nq = jobs[j].nq; fj.nt = jobs[j].nt; fj.img_idx = jobs[j].img_idx; fj.ratio = jobs[j].ratio;
+        const int64_t bp = jobs[j].back_prob;
+        fj.back_prob = (bp >= 0 && bp < P && (dp[bp].exact & 16)) ? (int32_t)bp : -1;
         memcpy(h + off_job + j * sizeof(FilterJob), &fj, sizeof fj);
     }
     if (ctx->desc_copy_pending) CK(cudaEventSynchronize(ctx->ev_desc));       // h_desc may still be read by the last prologue
@@ -988,7 +1005,9 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         DMatch* dm = reinterpret_cast<DMatch*>(rbase);
         int32_t* dc = reinterpret_cast<int32_t*>(rbase + (size_t)total_matches * sizeof(DMatch));
         CK(launch_pdl(filter_kernel, dim3((unsigned)jobs.size()), dim3(FILTER_THREADS), 0, ctx->stream,
-                      reinterpret_cast<const FilterJob*>(dd + off_job), (const unsigned long long*)ctx->d_out_key, dm, dc));
+                      reinterpret_cast<const FilterJob*>(dd + off_job), ctx->d_out_key, dm, dc,
+                      reinterpret_cast<const Problem*>(dd + off_prob), (const PartialRec*)ctx->d_recs.p,
+                      reinterpret_cast<const SliceInfo*>(dd + off_slice)));
         ctx->launches++;
     }
     return VSM_OK;
@@ -1169,6 +1188,7 @@ int vsm_create(const vsm_opts* opts, vsm_ctx** out) {
         if (o.reserved[3] > 0) ctx->pair_cap = (uint32_t)o.reserved[3];
         if (o.reserved[4] > 0) ctx->append_max_tiles = o.reserved[4];
         else if (getenv("VSM_APPEND_TILES")) ctx->append_max_tiles = atoll(getenv("VSM_APPEND_TILES"));
+        ctx->t2_off = o.reserved[5] == 1 || (getenv("VSM_NO_T2") && atoi(getenv("VSM_NO_T2")));
         CK(cudaMalloc(&ctx->d_store_stats, 16));
         // on the context's own (non-blocking) stream and waited for: a cudaMemset on the legacy default
         // stream is not ordered with it and could land AFTER the first conversion's atomicMax into the
@@ -1321,10 +1341,16 @@ int vsm_knn2_strided(vsm_ctx* ctx, const float* query, int32_t nq, int64_t q_str
 static int match_common(vsm_ctx* ctx, std::vector<HProblem>& probs, int nq, int nt, float ratio, int mutual,
                         vsm_dmatch* good, int32_t* n_good, vsm_dmatch* raw, int32_t* n_raw) {
     const bool want_raw = raw && n_raw;
-    if (!want_raw) probs[0].skip_ratio2 = skip_r2(ratio);        // forward problem: a survivor must pass the ratio test
+    if (!want_raw) {                                             // forward problem: a survivor must pass the ratio test
+        probs[0].skip_ratio2 = skip_r2(ratio);
+        probs[0].t2 = 1;
+        probs[0].ratio = ratio;
+    }
+    if (mutual && probs.size() > 1) probs[1].t2 = 2;             // reverse problem: only its nearest index is read
     HJob j;
     j.fwd_off = 0; j.back_off = mutual ? nq : -1; j.good_off = 0; j.raw_off = want_raw ? nq : -1;
     j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
+    j.back_prob = mutual && probs.size() > 1 ? 1 : -1;
     const int64_t total_matches = (int64_t)nq * (want_raw ? 2 : 1);
     TRY(run_problems(ctx, probs, {j}, (int64_t)nq + (mutual ? nt : 0), total_matches));
     const size_t bytes = (size_t)total_matches * sizeof(DMatch) + 2 * sizeof(int32_t);
@@ -1387,10 +1413,16 @@ int vsm_match_batch(vsm_ctx* ctx, int32_t n_pairs, const float* query, const int
         const int nq = q_off[p + 1] - q_off[p], nt = t_off[p + 1] - t_off[p];
         probs.push_back(scratch_vs_scratch(ctx, q_off[p], nq, NQ + t_off[p], nt, q_off[p]));
         probs.back().skip_ratio2 = skip_r2(ratio);               // forward problem only; the reverse one feeds the mutual test
-        if (mutual) probs.push_back(scratch_vs_scratch(ctx, NQ + t_off[p], nt, q_off[p], nq, NQ + t_off[p]));
+        probs.back().t2 = 1;
+        probs.back().ratio = ratio;
+        if (mutual) {
+            probs.push_back(scratch_vs_scratch(ctx, NQ + t_off[p], nt, q_off[p], nq, NQ + t_off[p]));
+            probs.back().t2 = 2;
+        }
         HJob j;
         j.fwd_off = q_off[p]; j.back_off = mutual ? NQ + t_off[p] : -1; j.good_off = q_off[p]; j.raw_off = -1;
         j.nq = nq; j.nt = nt; j.img_idx = 0; j.ratio = ratio;
+        j.back_prob = mutual ? (int64_t)probs.size() - 1 : -1;
         jobs.push_back(j);
     }
     TRY(run_problems(ctx, probs, jobs, NQ + (mutual ? NT : 0), NQ));
@@ -1749,9 +1781,12 @@ int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handl
         f.q_f32 = ctx->store.f32 + a.row0 * VSM_DIM; f.q_n2 = ctx->store.n2 + a.row0; f.q_row = a.row0; f.q_store = 1; f.nq = a.count;
         f.t_f32 = ctx->store.f32 + b.row0 * VSM_DIM; f.t_row = b.row0; f.t_store = 1; f.nt = b.count; f.out_off = good_off[p];
         f.skip_ratio2 = skip_r2(ratio);
+        f.t2 = 1;
+        f.ratio = ratio;
         probs.push_back(f);
         if (mutual) {
             HProblem r;
+            r.t2 = 2;
             r.q_f32 = f.t_f32; r.q_n2 = ctx->store.n2 + b.row0; r.q_row = b.row0; r.q_store = 1; r.nq = b.count;
             r.t_f32 = f.q_f32; r.t_row = a.row0; r.t_store = 1; r.nt = a.count; r.out_off = NQ + t_off[p];
             probs.push_back(r);
@@ -1759,6 +1794,7 @@ int vsm_match_batch_stored(vsm_ctx* ctx, int32_t n_pairs, const int32_t* q_handl
         HJob j;
         j.fwd_off = good_off[p]; j.back_off = mutual ? NQ + t_off[p] : -1; j.good_off = good_off[p]; j.raw_off = -1;
         j.nq = a.count; j.nt = b.count; j.img_idx = 0; j.ratio = ratio;
+        j.back_prob = mutual ? (int64_t)probs.size() - 1 : -1;
         jobs.push_back(j);
     }
     TRY(run_problems(ctx, probs, jobs, NQ + (mutual ? NT : 0), NQ));

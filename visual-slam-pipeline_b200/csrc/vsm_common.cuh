@@ -66,6 +66,9 @@ struct __align__(16) TcUnit {
                                    // bit4: APPEND records (see APPEND_CAP): every value above the running
                                    //       threshold is appended, no top-4 state -- for small train sets, where
                                    //       almost every 8-group holds a candidate for some lane of the warp
+                                   // bit5: TILE TOP-2 records (small train sets of pair matching): no running state
+                                   //       at all -- per (query, tile, column half) the exact two largest values with
+                                   //       their column, found by a fixed comparison tree (t2_chunk); data-independent
                                    // bit3 (with bit2): FUSED ratio dismissal -- the unit covers one whole keyframe;
                                    //       no record is written, only a 128-bit mask of the queries the
                                    //       ratio test could not dismiss (rec_base = first mask word of the unit)
@@ -136,10 +139,15 @@ struct Problem {
                                    // bit1: the records hold slice maxima only (TcUnit maps bit2): a query
                                    //       that the ratio-only test cannot dismiss is re-scanned exactly
                                    // bit2: append records (TcUnit maps bit4), APPEND_RECS slots per (query, slice)
+                                   // bit3: tile top-2 records (TcUnit maps bit5, see t2_scale): one slice per (tile,
+                                   //       column half), each holding the EXACT two largest approximate dots
+                                   // bit4 (with bit3): only the nearest neighbour's INDEX is wanted (the reverse
+                                   //       problem of a mutual test, read by filter_kernel)
     // > 0: the caller only wants ratio-test survivors of this problem (no raw list; a mutual test, if
     // any, is applied on top by filter_kernel) with this ratio^2 * 1.001: a query whose approximate top-2 already PROVES the ratio test fails is
     // answered "no match" without any exact re-score (select_kernel)
     float skip_ratio2;
+    float ratio;                   // tile top-2 problems with skip_ratio2 > 0: the caller's ratio itself (fp32 test d0 < ratio * d1)
 };
 
 // One pair for the filter kernel (match_features semantics).
@@ -150,7 +158,8 @@ struct FilterJob {
     int64_t raw_off;               // -1: no raw output
     int32_t nq, nt;
     int32_t img_idx;
-    int32_t pad;
+    int32_t back_prob;             // >= 0: the reverse problem (index into the call's Problem list) keeps tile top-2
+                                   // records and left its ambiguous rows DEFERRED: filter_kernel resolves those it needs
     float   ratio;
     int32_t pad2;
 };
@@ -217,6 +226,29 @@ __device__ __forceinline__ void load_qreg(float (&qreg)[16], const float* __rest
 __device__ __forceinline__ float dot_margin(float qn2, float tmin2, float tmax2) {
     float qn = sqrtf(qn2), tn = sqrtf(tmax2);
     return 0.0059f * qn * tn + 0.25f * (tmax2 - tmin2) + 6.2e-5f * (qn2 + tmax2);
+}
+
+
+// ---- tile top-2 records (TcUnit maps bit 5, Problem exact bit 3) -------------------------------------------
+// Small train sets (a frame pair, a ragged batch: <= T2_MAX_TILES tiles) are match-heavy: with ~1000 train rows
+// some lane of every warp holds a candidate in almost every group of eight values, so a threshold-driven epilogue
+// runs its insert path all the time.  Here the epilogue carries no state and takes no data-dependent branch: each
+// accumulator value v becomes a KEY, a float in [1, 2) whose upper 16 mantissa bits hold v quantised on a grid
+// of 2^-16 / s (s = t2_scale, so that |v * s| < 0.49) and whose low 7 bits hold the column inside the tile half:
+//     q   = fma(v, s, 192)            -> 192 + n * 2^-16       (the addition rounds v * s to the grid)
+//     key = (q - 190.5) + col * 2^-23 -> 1.5 + n * 2^-16 + col * 2^-23, both additions exact
+// Keys order like (quantised value, column); the exact top-2 of a tile half is a fixed tree of FMNMX / FMNMX3.
+// The quantisation moves a value by <= 2^-17 / s < 1.7e-5 |q||t| -- far inside what dot_margin() reserves for the
+// 13-bit packing of the other record kinds.
+constexpr int T2_MAX_TILES = 32;
+__device__ __forceinline__ float t2_scale(float qn2, float tmax2) {
+    return 0.48f / fmaxf(1.01f * sqrtf(qn2) * sqrtf(tmax2), 1e-20f);
+}
+__device__ __forceinline__ bool t2_valid(float key) { return key >= 1.0f; }            // masked columns / empty: below 1 (or NaN)
+__device__ __forceinline__ int t2_col(float key) { return (int)(__float_as_uint(key) & 127u); }
+__device__ __forceinline__ float t2_value(float key, float inv_s) {                    // approximate dot product behind a key
+    const int n = (int)((__float_as_uint(key) & 0x7FFFFFu) >> 7) - 32768;
+    return (float)n * 1.52587890625e-5f * inv_s;
 }
 
 }  // namespace vsm

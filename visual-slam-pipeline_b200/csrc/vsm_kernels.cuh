@@ -219,6 +219,73 @@ struct WorkItem {                      // self-contained: no descriptor look-ups
     int32_t r0, pad;
 };
 
+// Reverse rows of a mutual test on tile top-2 records whose nearest neighbour is not decided by the records alone.
+constexpr unsigned long long T2_DEFERRED = 1ull;          // decodes to index -2: never equal to a query
+
+// One warp: exact nearest neighbour (canonical distance, lowest index on ties) of query row q of a tile top-2
+// problem -- every recorded entry within 2*margin of the largest is re-scored, a slice whose two entries are both
+// that close may hide a third and is scanned whole (128 rows).  Returns the result key (valid in every lane).
+__device__ __noinline__ unsigned long long t2_resolve_top1(const Problem& P, const PartialRec* __restrict__ recs,
+                                                           const SliceInfo* __restrict__ slices, int q, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int h = lane >> 4, l16 = lane & 15;
+    const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
+    const SliceInfo* sl = slices + P.slice_off;
+    float k[4];
+    float K0 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int s = lane + 32 * j;
+        float2 kv = make_float2(0.f, 0.f);
+        if (s < P.nslices) kv = *reinterpret_cast<const float2*>(rq + s);
+        k[2 * j] = kv.x;
+        k[2 * j + 1] = kv.y;
+        K0 = fmaxf(K0, kv.x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) K0 = fmaxf(K0, __shfl_xor_sync(full, K0, o));
+    if (!t2_valid(K0)) return 0ull;
+    float tmin2, tmax2;
+    stats_read(P.t_stats, tmin2, tmax2);
+    const float qn2 = __ldg(P.q_n2 + q);
+    const float inv_s = 1.f / t2_scale(qn2, tmax2);
+    const float thr = t2_value(K0, inv_s) - 2.f * dot_margin(qn2, tmin2, tmax2);
+    float qreg[16];
+    load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
+    Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int s = lane + 32 * j;
+        const bool have = s < P.nslices;
+        const float v0 = have && t2_valid(k[2 * j]) ? t2_value(k[2 * j], inv_s) : -INFINITY;
+        const float v1 = have && t2_valid(k[2 * j + 1]) ? t2_value(k[2 * j + 1], inv_s) : -INFINITY;
+        unsigned scan = __ballot_sync(full, v1 > thr);
+        unsigned one = __ballot_sync(full, v0 > thr && !(v1 > thr));
+        while (scan) {
+            const int l0 = __ffs(scan) - 1; scan &= scan - 1;
+            scan_slice<SELECT_U>(qreg, P.t_f32, sl[l0 + 32 * j], h, l16, best);
+        }
+        while (one) {                                                // two candidates per step, one per half-warp
+            const int la = __ffs(one) - 1; one &= one - 1;
+            int lb = -1;
+            if (one) { lb = __ffs(one) - 1; one &= one - 1; }
+            const int src = h ? lb : la;
+            const float ks = __shfl_sync(full, k[2 * j], src < 0 ? 0 : src);
+            int32_t jrow[1];
+            jrow[0] = -1;
+            if (src >= 0) { const SliceInfo si = sl[src + 32 * j]; jrow[0] = si.t_index0 + slice_row(si, t2_col(ks)); }
+            score_n<1>(qreg, P.t_f32, jrow, l16, best);
+        }
+    }
+    const float od0 = __shfl_sync(full, best.d0, 16), od1 = __shfl_sync(full, best.d1, 16);
+    const int32_t oi0 = __shfl_sync(full, best.i0, 16), oi1 = __shfl_sync(full, best.i1, 16);
+    if (oi0 >= 0) insert2(od0, oi0, best.d0, best.i0, best.d1, best.i1);
+    if (oi1 >= 0) insert2(od1, oi1, best.d0, best.i0, best.d1, best.i1);
+    const float d = __shfl_sync(full, best.d0, 0);
+    const int32_t i = __shfl_sync(full, best.i0, 0);
+    return i >= 0 ? result_key(d, i) : 0ull;
+}
+
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
 select_kernel(const Problem* __restrict__ problems, int problem0,
               const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
@@ -244,6 +311,152 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     if (P.exact & 1) {
         load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
         for (int s = 0; s < P.nslices; s++) scan_slice<SELECT_U>(qreg, P.t_f32, sl[s], h, l16, best);
+    } else if (P.exact & 8) {
+        // ----- tile top-2 records (pair matching on small train sets, see t2_scale): per (tile, column half) the
+        // exact two largest approximate dots with their column.  Their union holds the exact two largest values
+        // a0 >= a1 of the whole train set, and every row not recorded lies below its slice's second entry.
+        //   forward problem of a ratio-only caller (skip_ratio2 > 0):
+        //     (1) dismissal from a0 / a1 alone, as for the other record kinds: no re-score;
+        //     (2) a1 < a0 - 2*margin: the nearest neighbour is the row behind a0 and nobody else -- ONE exact
+        //         distance e0 (the other half-warp scores the row behind a1: e1c >= the true second distance d1);
+        //         e0 >= ratio * e1c  ->  the test fails (exactly: d1 <= e1c and fp32 rounding is monotone);
+        //         e0 clearly below ratio * (a lower bound on every other row's distance)  ->  it passes, and the
+        //         second slot gets a sentinel distance (FLT_MAX) that makes filter_kernel's fp32 test pass;
+        //     (3) otherwise (the ratio lands inside the bf16 band, ~1 % of the matching queries): the general path;
+        //   reverse problem of a mutual test (exact bit 4; filter_kernel reads only the nearest INDEX):
+        //     a1 < a0 - 2*margin: the index is the row behind a0, nothing is loaded or scored; else general path;
+        //   general path: every recorded entry above thr (a1 - 2*margin, or a0 - 2*margin when only the nearest
+        //     is wanted) is re-scored exactly; a slice whose SECOND entry is above thr may hide a third one and is
+        //     re-scanned by rescan_kernel (128 rows, one work item).
+        const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
+        const bool top1 = (P.exact & 16) != 0;
+        float k[4];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int s = lane + 32 * j;
+            float2 kv = make_float2(0.f, 0.f);
+            if (s < P.nslices) kv = *reinterpret_cast<const float2*>(rq + s);
+            k[2 * j] = kv.x;
+            k[2 * j + 1] = kv.y;
+        }
+        // the two largest keys over all slices, each with its slice
+        float K0 = k[0], K1 = k[1];
+        int S0 = lane, S1 = lane;
+        if (k[2] > K0) { K1 = fmaxf(K0, k[3]); S1 = K0 >= k[3] ? S0 : lane + 32; K0 = k[2]; S0 = lane + 32; }
+        else if (k[2] > K1) { K1 = k[2]; S1 = lane + 32; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float b0 = __shfl_xor_sync(full, K0, o), b1 = __shfl_xor_sync(full, K1, o);
+            const int t0 = __shfl_xor_sync(full, S0, o), t1 = __shfl_xor_sync(full, S1, o);
+            if (b0 > K0) {
+                if (K0 >= b1) { K1 = K0; S1 = S0; } else { K1 = b1; S1 = t1; }
+                K0 = b0; S0 = t0;
+            } else if (b0 > K1) { K1 = b0; S1 = t0; }
+        }
+        // equal keys of different slices may leave the lanes with different (equally good) answers: lane 0's counts
+        K0 = __shfl_sync(full, K0, 0); K1 = __shfl_sync(full, K1, 0);
+        S0 = __shfl_sync(full, S0, 0); S1 = __shfl_sync(full, S1, 0);
+        float tmin2, tmax2;
+        stats_read(P.t_stats, tmin2, tmax2);
+        const float qn2 = __ldg(P.q_n2 + q);
+        const float margin = dot_margin(qn2, tmin2, tmax2);
+        const float inv_s = 1.f / t2_scale(qn2, tmax2);
+        unsigned long long* o = out_key + (P.out_off + q) * 2;
+        if (!t2_valid(K0)) {                                         // no train row at all
+            if (lane == 0) { o[0] = 0ull; o[1] = 0ull; }
+            return;
+        }
+        const float a0 = t2_value(K0, inv_s);
+        const bool has1 = t2_valid(K1);
+        const float a1 = has1 ? t2_value(K1, inv_s) : -INFINITY;
+        const int32_t i0c = sl[S0].t_index0 + slice_row(sl[S0], t2_col(K0));
+        const bool unique = a1 < a0 - 2.f * margin;
+        if (top1) {
+            // unique: the nearest neighbour is the row behind a0, nothing is scored.  Otherwise the row is left
+            // DEFERRED: filter_kernel resolves it (t2_resolve_top1) only if some surviving forward match points at
+            // it -- unmatched rows, whose two best are both noise and usually within the margin of each other, are
+            // hardly ever asked for.
+            if (lane == 0) { o[0] = unique ? result_key(0.f, i0c) : T2_DEFERRED; o[1] = 0ull; }
+            return;
+        } else if (P.skip_ratio2 > 0.f && has1) {
+            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
+            const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
+            if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) {
+                if (lane == 0) { o[0] = 0ull; o[1] = 0ull; }
+                return;
+            }
+            if (unique) {
+                load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
+                const int32_t i1c = sl[S1].t_index0 + slice_row(sl[S1], t2_col(K1));
+                const float d2 = canon_l2sqr_halfwarp(qreg, P.t_f32 + (size_t)(h ? i1c : i0c) * VSM_DIM, l16);
+                const float e = __fsqrt_rn(d2);
+                const float e0 = __shfl_sync(full, e, 0), e1c = __shfl_sync(full, e, 16);
+                int verdict = 0;                                      // 1 = fails, 2 = passes, 0 = undecided
+                if (!(e0 < __fmul_rn(P.ratio, e1c))) verdict = 1;
+                else {
+                    const float lo1 = qn2 + tmin2 - 2.f * (a1 + margin);         // every row but i0c is at least this far (squared)
+                    if (lo1 > 0.f && e0 * e0 * 1.002f < P.ratio * P.ratio * lo1) verdict = 2;
+                }
+                if (verdict) {
+                    if (lane == 0) {
+                        o[0] = verdict == 2 ? result_key(e0, i0c) : 0ull;
+                        o[1] = verdict == 2 ? result_key(FLT_MAX, 0) : 0ull;
+                        atomicAdd(counters, 2ull);
+                    }
+                    return;
+                }
+            }
+        }
+        // general path
+        load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
+        const float thr = a1 - 2.f * margin;
+        int32_t* list = s_list[warp];
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int s = lane + 32 * j;
+            const bool have = s < P.nslices;
+            const SliceInfo my = have ? sl[s] : SliceInfo{0, 0, 0, 0};
+            const float v0 = have && t2_valid(k[2 * j]) ? t2_value(k[2 * j], inv_s) : -INFINITY;
+            const float v1 = have && t2_valid(k[2 * j + 1]) ? t2_value(k[2 * j + 1], inv_s) : -INFINITY;
+            const bool flagged = v1 > thr;                            // both entries above: a third may be hidden
+            const bool on0 = !flagged && v0 > thr;                    // (v1 <= thr here, so at most one candidate)
+            const unsigned bal = __ballot_sync(full, on0);
+            if (on0) list[cnt + __popc(bal & ((1u << lane) - 1u))] = my.t_index0 + slice_row(my, t2_col(k[2 * j]));
+            cnt += __popc(bal);
+            n_cand += on0 ? 1 : 0;
+            n_flag += __popc(__ballot_sync(full, flagged));
+            bool inline_scan = false;
+            if (flagged) {
+                const int span = slice_span(my);
+                const uint32_t nitem = (uint32_t)((span + RESCAN_ROWS - 1) / RESCAN_ROWS);
+                uint32_t* wcount = reinterpret_cast<uint32_t*>(counters + 2);
+                const uint32_t base = atomicAdd(wcount, nitem);
+                if (base + nitem <= work_cap) {
+                    for (uint32_t kk = 0; kk < nitem; kk++) {
+                        WorkItem w = {P.q_f32 + (size_t)q * VSM_DIM, P.t_f32, o, my, (int32_t)(kk * RESCAN_ROWS), 0};
+                        work[base + kk] = w;
+                    }
+                } else {
+                    inline_scan = true;
+                    for (uint32_t kk = base; kk < work_cap && kk < base + nitem; kk++) {
+                        WorkItem w = {nullptr, nullptr, nullptr, my, 0, 0};
+                        work[kk] = w;
+                    }
+                }
+            }
+            unsigned fm = __ballot_sync(full, inline_scan);
+            while (fm) {
+                const int l0 = __ffs(fm) - 1; fm &= fm - 1;
+                scan_slice<SELECT_U>(qreg, P.t_f32, sl[l0 + 32 * j], h, l16, best);
+            }
+        }
+        __syncwarp();
+        for (int base = 0; base < cnt; base += 2) {
+            int32_t jrow[1];
+            jrow[0] = base + h < cnt ? list[base + h] : -1;
+            score_n<1>(qreg, P.t_f32, jrow, l16, best);
+        }
     } else if (P.exact & 4) {
         // ----- append records (small train sets): per slice a count and up to APPEND_CAP - 1 packed values that
         // passed the epilogue's running threshold.  Same two passes as below: the second-largest value over
@@ -846,8 +1059,9 @@ loop_finish_kernel(const LoopParams P) {
 // Query order is preserved (block-wide scan per 1024 queries).
 constexpr int FILTER_THREADS = 1024;
 __global__ void __launch_bounds__(FILTER_THREADS)
-filter_kernel(const FilterJob* __restrict__ jobs, const unsigned long long* __restrict__ out_key,
-              DMatch* __restrict__ matches, int32_t* __restrict__ counts) {
+filter_kernel(const FilterJob* __restrict__ jobs, unsigned long long* __restrict__ out_key,
+              DMatch* __restrict__ matches, int32_t* __restrict__ counts, const Problem* __restrict__ problems,
+              const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices) {
     pdl_launch_dependents();
     pdl_wait();
     const FilterJob J = jobs[blockIdx.x];
@@ -860,6 +1074,7 @@ filter_kernel(const FilterJob* __restrict__ jobs, const unsigned long long* __re
         const int q = q0 + threadIdx.x;
         bool is_raw = false, is_good = false;
         DMatch m = {q, -1, J.img_idx, 0.f};
+        unsigned long long bk = 0ull;
         if (q < J.nq) {
             const int64_t o = (J.fwd_off + q) * 2;
             int32_t i0, i1;
@@ -869,11 +1084,23 @@ filter_kernel(const FilterJob* __restrict__ jobs, const unsigned long long* __re
             m.trainIdx = i0; m.distance = d0;
             is_raw = i1 >= 0;                                    // m.size() >= 2   (Slam.cpp:1152)
             is_good = is_raw && d0 < __fmul_rn(J.ratio, d1);     // fp32 product   (Slam.cpp:1154)
-            if (is_good && J.back_off >= 0) {
-                int32_t bi; float bd;
-                key_decode(out_key[(J.back_off + i0) * 2], bi, bd);
-                is_good = bi == q;
+            if (is_good && J.back_off >= 0) bk = __ldcg(out_key + (J.back_off + i0) * 2);
+        }
+        if (J.back_prob >= 0) {
+            // reverse rows the select pass left undecided, asked for by a surviving forward match: resolved here,
+            // one warp per row (several matches may point at the same row: same answer, written twice)
+            unsigned need = __ballot_sync(0xffffffffu, is_good && bk == T2_DEFERRED);
+            while (need) {
+                const int l0 = __ffs(need) - 1; need &= need - 1;
+                const int t = __shfl_sync(0xffffffffu, m.trainIdx, l0);
+                const unsigned long long r = t2_resolve_top1(problems[J.back_prob], recs, slices, t, lane);
+                if (lane == l0) { bk = r; out_key[(J.back_off + t) * 2] = r; }
             }
+        }
+        if (is_good && J.back_off >= 0) {
+            int32_t bi; float bd;
+            key_decode(bk, bi, bd);
+            is_good = bi == q;
         }
         const unsigned br = __ballot_sync(0xffffffffu, is_raw), bg = __ballot_sync(0xffffffffu, is_good);
         if (lane == 0) { wsum[0][warp] = __popc(bg); wsum[1][warp] = __popc(br); }

@@ -360,6 +360,35 @@ __device__ __forceinline__ void append32(AppendState& s, const uint32_t (&r)[32]
     }
 }
 
+// Tile top-2 form (units with maps bit 5, see t2_scale in vsm_common.cuh): 32 accumulator values become keys
+// (3 instructions each on the FMA pipe), 16 sorted pairs (2 per pair), a 4-level tree of top-2 merges (3 per
+// merge: max, min, FMNMX3) and one merge into the tile's running (H, L) -- ~5.5 instructions per value split
+// over two pipes, whatever the data.
+template <int COL0>
+__device__ __forceinline__ void t2_chunk(float& H, float& L, const uint32_t (&r)[32], float s) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float qa = __fmaf_rn(__uint_as_float(r[2 * i]), s, 192.0f);
+        const float qb = __fmaf_rn(__uint_as_float(r[2 * i + 1]), s, 192.0f);
+        const float ka = __fadd_rn(__fadd_rn(qa, -190.5f), (float)(COL0 + 2 * i) * 1.1920928955078125e-7f);
+        const float kb = __fadd_rn(__fadd_rn(qb, -190.5f), (float)(COL0 + 2 * i + 1) * 1.1920928955078125e-7f);
+        hi[i] = fmaxf(ka, kb);
+        lo[i] = fminf(ka, kb);
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; i++) {
+            const float h = fmaxf(hi[i], hi[i + w]);
+            lo[i] = fmaxf(fmaxf(fminf(hi[i], hi[i + w]), lo[i]), lo[i + w]);
+            hi[i] = h;
+        }
+    const float h = fmaxf(H, hi[0]);
+    L = fmaxf(fmaxf(fminf(H, hi[0]), L), lo[0]);
+    H = h;
+}
+
 // A partial last tile: columns at or past the end of the train range become MASKED_VALUE.
 __device__ __forceinline__ void mask32(uint32_t (&r)[32], int32_t ucol0, int32_t t_count) {
 #pragma unroll
@@ -793,6 +822,48 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     }
                 }
                 if (row_valid) rec0[(int64_t)lane * row_floats] = __uint_as_float(a.cnt);
+                continue;
+            }
+            if (u.maps & 32) {
+                // ----- tile top-2 unit: one record per (query, tile, column half) = the exact two largest keys
+                float sc;
+                {
+                    const float qn2 = row_valid ? __ldg(u.q_n2 + row) : 1.f;
+                    float tmin2, tmax2;
+                    stats_read(u.t_stats, tmin2, tmax2);
+                    sc = t2_scale(qn2, tmax2);
+                }
+                PartialRec* rec = recs + u.rec_base + (int64_t)row * u.rec_stride + half;
+                for (int n = 0; n < ntiles; n++, tile_it++) {
+                    const int st = tile_it & 1;
+                    mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t taddr = lane_addr + st * TILE_N;
+                    const int32_t ucol = n * TILE_N + half * HALF_N;
+                    const bool full_tile = (n + 1) * TILE_N <= u.t_count;
+                    float H = -INFINITY, L = -INFINITY;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr, ra);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 32, rb);
+                    if (!full_tile) mask32(ra, ucol, u.t_count);
+                    t2_chunk<0>(H, L, ra, sc);
+                    tmem_ld_wait(rb);
+                    tmem_ld32(taddr + 64, ra);
+                    if (!full_tile) mask32(rb, ucol + 32, u.t_count);
+                    t2_chunk<32>(H, L, rb, sc);
+                    tmem_ld_wait(ra);
+                    tmem_ld32(taddr + 96, rb);
+                    if (!full_tile) mask32(ra, ucol + 64, u.t_count);
+                    t2_chunk<64>(H, L, ra, sc);
+                    tmem_ld_wait(rb);
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+                    if (!full_tile) mask32(rb, ucol + 96, u.t_count);
+                    t2_chunk<96>(H, L, rb, sc);
+                    if (row_valid) *reinterpret_cast<float4*>(rec + n * 2) = make_float4(H, L, -INFINITY, -INFINITY);
+                }
                 continue;
             }
             Top3 s;

@@ -196,7 +196,7 @@ class Matcher:
         return m
 
     def __init__(self, device=0, engine=ENGINE_AUTO, scratch_rows=0, store_rows=0, seg_tiles=0, work_cap=0, ring=0,
-                 pair_cap=0, append_tiles=0):
+                 pair_cap=0, append_tiles=0, tile_top2=True):
         self._lib = load_library()
         o = _Opts()
         self._lib.vsm_default_opts(C.byref(o))
@@ -206,6 +206,7 @@ class Matcher:
         o.reserved[2] = ring
         o.reserved[3] = pair_cap
         o.reserved[4] = append_tiles
+        o.reserved[5] = 0 if tile_top2 else 1      # pair matching: tile top-2 records (default) or the top-4 records
         h = C.c_void_p()
         st = self._lib.vsm_create(C.byref(o), C.byref(h))
         if st != 0:
