@@ -144,6 +144,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// The same load under a warp-uniform predicate (off: the registers keep their values).  (ptxas turns it into a
+// branch around the load.)
+__device__ __forceinline__ void tmem_ld32_if(bool on, uint32_t taddr, uint32_t (&r)[32]) {
+    __syncwarp();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %33, 0;\n\t"
+        "@p tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t}"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        : "r"(taddr), "r"((uint32_t)on)
+        : "memory");
+}
 // Wait for this thread's outstanding tcgen05.ld; the registers pass through the
 // statement so no use of them can be scheduled above it.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
@@ -360,32 +376,39 @@ __device__ __forceinline__ void append32(AppendState& s, const uint32_t (&r)[32]
     }
 }
 
-// Tile top-2 form (units with maps bit 5, see t2_scale in vsm_common.cuh): 32 accumulator values become keys
-// (3 instructions each on the FMA pipe), 16 sorted pairs (2 per pair), a 4-level tree of top-2 merges (3 per
-// merge: max, min, FMNMX3) and one merge into the tile's running (H, L) -- ~5.5 instructions per value split
-// over two pipes, whatever the data.
-template <int COL0>
-__device__ __forceinline__ void t2_chunk(float& H, float& L, const uint32_t (&r)[32], float s) {
-    float hi[16], lo[16];
+// Tile top-2 form (units with maps bit 5, see t2_scale in vsm_common.cuh).  Per value: three FMA-pipe
+// instructions make the key, ~2.5 ALU-pipe instructions find the exact top-2 (sorted pairs, top-2 merges of
+// max, min and FMNMX3); no branch depends on the data.  The column inside the chunk (5 bits) goes into the
+// keys, the chunk's first column (colbase = col0 * 2^-23) is added to the chunk's two winners only.
+// Both pipes accept one warp instruction every other cycle and there are only two epilogue warps per scheduler.
+// Written as "all keys, then the tree" the two kinds of work alternated, and the two warps -- released by the
+// same barrier -- alternated in step (ncu: 0.43 IPC per scheduler, neither pipe above 42 %).  So the chunk is cut
+// into eight sub-blocks of four values and the KEYS of sub-block i+1 are written between the TREE steps of
+// sub-block i: consecutive instructions go to different pipes.
+__device__ __forceinline__ void t2_step(float& H, float& L, const uint32_t (&r)[32], float s, float colbase) {
+    float k[32];
+    float CH = -INFINITY, CL = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const float qa = __fmaf_rn(__uint_as_float(r[2 * i]), s, 192.0f);
-        const float qb = __fmaf_rn(__uint_as_float(r[2 * i + 1]), s, 192.0f);
-        const float ka = __fadd_rn(__fadd_rn(qa, -190.5f), (float)(COL0 + 2 * i) * 1.1920928955078125e-7f);
-        const float kb = __fadd_rn(__fadd_rn(qb, -190.5f), (float)(COL0 + 2 * i + 1) * 1.1920928955078125e-7f);
-        hi[i] = fmaxf(ka, kb);
-        lo[i] = fminf(ka, kb);
-    }
+    for (int sb = 0; sb <= 8; sb++) {
+        if (sb < 8) {
 #pragma unroll
-    for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-        for (int i = 0; i < w; i++) {
-            const float h = fmaxf(hi[i], hi[i + w]);
-            lo[i] = fmaxf(fmaxf(fminf(hi[i], hi[i + w]), lo[i]), lo[i + w]);
-            hi[i] = h;
+            for (int e = 4 * sb; e < 4 * sb + 4; e++)
+                k[e] = __fadd_rn(__fadd_rn(__fmaf_rn(__uint_as_float(r[e]), s, 192.0f), -190.5f), (float)e * 1.1920928955078125e-7f);
         }
-    const float h = fmaxf(H, hi[0]);
-    L = fmaxf(fmaxf(fminf(H, hi[0]), L), lo[0]);
+        if (sb > 0) {
+            const int b = 4 * (sb - 1);
+            const float h0 = fmaxf(k[b], k[b + 1]), l0 = fminf(k[b], k[b + 1]);
+            const float h1 = fmaxf(k[b + 2], k[b + 3]), l1 = fminf(k[b + 2], k[b + 3]);
+            const float h = fmaxf(h0, h1);
+            const float l = fmaxf(fmaxf(fminf(h0, h1), l0), l1);
+            const float nh = fmaxf(CH, h);
+            CL = fmaxf(fmaxf(fminf(CH, h), CL), l);
+            CH = nh;
+        }
+    }
+    const float ch = __fadd_rn(CH, colbase), cl = __fadd_rn(CL, colbase);
+    const float h = fmaxf(H, ch);
+    L = fmaxf(fmaxf(fminf(H, ch), L), cl);
     H = h;
 }
 
@@ -844,24 +867,26 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     float H = -INFINITY, L = -INFINITY;
                     uint32_t ra[32], rb[32];
                     tmem_ld32(taddr, ra);
-                    tmem_ld_wait(ra);
-                    tmem_ld32(taddr + 32, rb);
-                    if (!full_tile) mask32(ra, ucol, u.t_count);
-                    t2_chunk<0>(H, L, ra, sc);
-                    tmem_ld_wait(rb);
-                    tmem_ld32(taddr + 64, ra);
-                    if (!full_tile) mask32(rb, ucol + 32, u.t_count);
-                    t2_chunk<32>(H, L, rb, sc);
-                    tmem_ld_wait(ra);
-                    tmem_ld32(taddr + 96, rb);
-                    if (!full_tile) mask32(ra, ucol + 64, u.t_count);
-                    t2_chunk<64>(H, L, ra, sc);
-                    tmem_ld_wait(rb);
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
-                    if (!full_tile) mask32(rb, ucol + 96, u.t_count);
-                    t2_chunk<96>(H, L, rb, sc);
+                    // the four chunks as a loop of two double steps (not unrolled: 12 KB of straight-line code made
+                    // instruction fetch a stall reason of its own)
+#pragma unroll 1
+                    for (int c = 0; c < 4; c += 2) {
+                        tmem_ld_wait(ra);
+                        tmem_ld32(taddr + 32 * c + 32, rb);
+                        if (!full_tile && ucol + 32 * c + 32 > u.t_count) mask32(ra, ucol + 32 * c, u.t_count);
+                        t2_step(H, L, ra, sc, (float)(32 * c) * 1.1920928955078125e-7f);
+                        tmem_ld_wait(rb);
+                        if (c == 0) {
+                            tmem_ld32(taddr + 64, ra);
+                        } else {
+                            // all TMEM reads of this stage are complete: hand it back to the MMA warp
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * st);
+                        }
+                        if (!full_tile && ucol + 32 * c + 64 > u.t_count) mask32(rb, ucol + 32 * c + 32, u.t_count);
+                        t2_step(H, L, rb, sc, (float)(32 * c + 32) * 1.1920928955078125e-7f);
+                    }
                     if (row_valid) *reinterpret_cast<float4*>(rec + n * 2) = make_float4(H, L, -INFINITY, -INFINITY);
                 }
                 continue;
