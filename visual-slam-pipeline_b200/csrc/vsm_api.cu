@@ -220,7 +220,9 @@ struct vsm_ctx {
         const void* p_stats = nullptr;
         size_t off_prob = 0, off_unit = 0, off_slice = 0, off_job = 0, total = 0, nunits = 0, nunits2 = 0;
         int64_t nrecs = 0;
-        int qb_total = 0;
+        int qb_total = 0;                            // 32-query groups of tile top-2 problems
+        bool any_classic = false;                    // problems answered by select_kernel
+        int t2_gshift = 5;                           // log2 of the queries per warp in t2_select_kernel
         int32_t big_db_nq = 0, slice_tiles = 0;      // what the planning loop noted for the slice-length feedback
         bool valid = false;
     } plan;
@@ -691,6 +693,14 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
     std::vector<int> unit_prob;
     std::vector<SliceInfo> slices;
     int64_t nrecs = 0;
+    bool any_classic = false;                                // some problem is answered by select_kernel
+    // queries per warp of t2_select_kernel: enough warps to fill the device first, then up to 32 per warp
+    int t2_gshift = 1;
+    {
+        int64_t nq_all = 0;
+        for (auto& p : probs) if (p.t2) nq_all += p.nq;
+        while (t2_gshift < 5 && (nq_all >> (t2_gshift + 1)) >= (int64_t)ctx->num_sms * 16) t2_gshift++;
+    }
 
     // scheduling granularity: query tiles on SMs, or pairs of query tiles on SM pairs
     int64_t total_qtiles = 0;
@@ -712,9 +722,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         d.ratio = hp.ratio;
         const bool maxima = hp.maxima_only && hp.skip_ratio2 > 0.f && !d.exact && !pairs;
         if (maxima) d.exact |= 2;
-        qb[i + 1] = qb[i] + (hp.nq + SELECT_WARPS - 1) / SELECT_WARPS;
+        qb[i + 1] = qb[i];                                   // 32-query groups of the tile top-2 problems (t2_select_kernel)
         if (hp.nq <= 0 || hp.nt <= 0) { d.nslices = 0; continue; }
         if (d.exact & 1) {
+            any_classic = true;
             if (hp.runs) {
                 for (const Run& rn : *hp.runs) { SliceInfo si = {(int32_t)rn.row0, (int32_t)rn.count, -1, 0}; slices.push_back(si); }
             } else {
@@ -757,7 +768,12 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         // in the epilogue, one exact distance per matching query in select_kernel (vsm_common.cuh, t2_scale)
         const bool t2 = hp.t2 && !ctx->t2_off && !maxima && !append && !pairs && !hp.runs && !dump_first && ctx->seg_tiles == 0 &&
                         ntiles <= T2_MAX_TILES && (hp.t2 == 2 || (hp.skip_ratio2 > 0.f && hp.ratio > 0.f && hp.ratio <= 1.f));
-        if (t2) d.exact |= 8 | (hp.t2 == 2 ? 16 : 0);
+        if (t2) {
+            d.exact |= 8 | (hp.t2 == 2 ? 16 : 0);
+            qb[i + 1] = qb[i] + ((hp.nq + (1 << t2_gshift) - 1) >> t2_gshift);
+        } else {
+            any_classic = true;
+        }
         const int rec_per_slice = append ? APPEND_RECS : 1;
         struct Range { int64_t idx0, count; int tiles_after; int slice0; int seg; };
         std::vector<Range> ranges;
@@ -813,6 +829,10 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 u.t_stats = nullptr;                                    // fixed up below
                 u.rec_base = nrecs + ((int64_t)qt * TILE_M * d.nslices + g.slice0) * rec_per_slice;
                 u.rec_stride = d.nslices * rec_per_slice;
+                if (t2) {                                               // one record per (query, tile): both column halves
+                    u.rec_base = nrecs + ((int64_t)qt * TILE_M * d.nslices + g.slice0) / 2;
+                    u.rec_stride = d.nslices / 2;
+                }
                 u.q_row = (int32_t)(hp.q_row + (int64_t)qt * TILE_M);
                 u.t_row = (int32_t)(hp.t_row + g.idx0);
                 u.t_index0 = (int32_t)g.idx0;
@@ -827,7 +847,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                 unit_prob.push_back(i);
             }
         }
-        nrecs += (int64_t)hp.nq * d.nslices * rec_per_slice;
+        nrecs += t2 ? (int64_t)hp.nq * (d.nslices / 2) : (int64_t)hp.nq * d.nslices * rec_per_slice;
     }
 
     // Several problems of different sizes in one call (ragged batches, per-keyframe searches): the persistent
@@ -857,6 +877,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
         pl.nunits2 = units2.size();
         pl.nrecs = nrecs;
         pl.qb_total = qb[P];
+        pl.any_classic = any_classic;
+        pl.t2_gshift = t2_gshift;
         pl.big_db_nq = ctx->big_db_nq;
         pl.slice_tiles = ctx->last_slice_tiles;
     } else {
@@ -978,10 +1000,18 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
             ctx->timed_tc = true;
         }
     }
-    if (pl.qb_total > 0) {
+    if (pl.qb_total > 0 || pl.any_classic) {
+        if (pl.qb_total > 0) {
+            CK(launch_pdl(t2_select_kernel, dim3((unsigned)((pl.qb_total + T2_SELECT_WARPS - 1) / T2_SELECT_WARPS)),
+                          dim3(T2_SELECT_WARPS * 32), 0, ctx->stream, reinterpret_cast<const Problem*>(dd + off_prob), P,
+                          reinterpret_cast<const int32_t*>(dd + off_qb), (const PartialRec*)ctx->d_recs.p,
+                          reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters,
+                          ctx->d_work.p, ctx->work_cap, pl.t2_gshift));
+            ctx->launches++;
+        }
         int max_blocks = 0;
         for (int i = 0; i < P; i++) max_blocks = std::max(max_blocks, (probs[i].nq + SELECT_WARPS - 1) / SELECT_WARPS);
-        for (int p0 = 0; p0 < P; p0 += 65535) {                           // gridDim.y limit
+        for (int p0 = 0; p0 < P && pl.any_classic; p0 += 65535) {         // gridDim.y limit
             const int np = std::min(65535, P - p0);
             CK(launch_pdl(select_kernel, dim3((unsigned)max_blocks, (unsigned)np), dim3(SELECT_WARPS * 32), 0, ctx->stream,
                           reinterpret_cast<const Problem*>(dd + off_prob), p0, (const PartialRec*)ctx->d_recs.p,

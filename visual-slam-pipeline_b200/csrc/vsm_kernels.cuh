@@ -219,48 +219,110 @@ struct WorkItem {                      // self-contained: no descriptor look-ups
     int32_t r0, pad;
 };
 
-// Reverse rows of a mutual test on tile top-2 records whose nearest neighbour is not decided by the records alone.
+// ---- pair matching on tile top-2 records (Problem::exact bit 3, see t2_scale in vsm_common.cuh) -----------------
+// Record layout: one PartialRec per (query, tile) = {H, L of column half 0, H, L of column half 1}: the exact two
+// largest keys of each tile half.  Their union holds the exact two largest approximate dots a0 >= a1 of the whole
+// train set, and every row not recorded lies below its slice's second entry (slice = tile * 2 + half).
+//   forward problem of a ratio-only caller (skip_ratio2 > 0):
+//     (1) dismissal from a0 / a1 alone, as for the other record kinds: no exact distance at all;
+//     (2) a1 < a0 - 2*margin: the nearest neighbour is the row behind a0 and nobody else -- ONE exact distance e0;
+//         e0 clearly above ratio * (upper bound on the second distance, from a1)  -> the test fails;
+//         e0 clearly below ratio * (lower bound on every other row's distance)    -> it passes, and the second slot
+//         gets a sentinel distance (FLT_MAX) that makes filter_kernel's fp32 test pass;
+//     (3) otherwise (the ratio lands inside the bf16 band, ~2 % of the matching queries): t2_general_top2;
+//   reverse problem of a mutual test (exact bit 4; filter_kernel reads only the nearest INDEX):
+//     a1 < a0 - 2*margin: the index is the row behind a0, nothing is loaded or scored.  Otherwise the row is left
+//     DEFERRED: filter_kernel resolves it (t2_resolve_top1) only if a surviving forward match points at it --
+//     unmatched rows, whose two best are both noise and usually within the margin of each other, are hardly
+//     ever asked for.
 constexpr unsigned long long T2_DEFERRED = 1ull;          // decodes to index -2: never equal to a query
 
-// One warp: exact nearest neighbour (canonical distance, lowest index on ties) of query row q of a tile top-2
-// problem -- every recorded entry within 2*margin of the largest is re-scored, a slice whose two entries are both
-// that close may hide a third and is scanned whole (128 rows).  Returns the result key (valid in every lane).
-__device__ __noinline__ unsigned long long t2_resolve_top1(const Problem& P, const PartialRec* __restrict__ recs,
-                                                           const SliceInfo* __restrict__ slices, int q, int lane) {
+struct T2Top {                       // the two largest keys of a query over all its slices
+    float K0, K1;
+    int S0, S1;
+};
+__device__ __forceinline__ void t2_merge(T2Top& t, float hk, float lk, int s) {      // (hk >= lk) of slice s
+    if (hk > t.K0) {
+        if (t.K0 >= lk) { t.K1 = t.K0; t.S1 = t.S0; } else { t.K1 = lk; t.S1 = s; }
+        t.K0 = hk; t.S0 = s;
+    } else if (hk > t.K1) { t.K1 = hk; t.S1 = s; }
+}
+__device__ __forceinline__ int32_t t2_row(const SliceInfo* sl, int s, float key) {
+    const SliceInfo si = sl[s];
+    return si.t_index0 + slice_row(si, t2_col(key));
+}
+
+// One warp, general case of one query: every recorded entry above thr is re-scored exactly (canonical distance),
+// a slice whose SECOND entry is above thr may hide a third one and is re-scanned whole (128 rows): by rescan_kernel
+// through `work` (key != nullptr: the result is pushed into key[0..1] by the caller, the re-scans by the atomic
+// cascade), or right here (work == nullptr).  top1: thr = a0 - 2*margin, else a1 - 2*margin.
+__device__ __noinline__ Best2 t2_general(const Problem& P, const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
+                                         int q, int lane, bool top1, unsigned long long* key, WorkItem* work, uint32_t work_cap,
+                                         unsigned long long* counters) {
     const unsigned full = 0xffffffffu;
     const int h = lane >> 4, l16 = lane & 15;
-    const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
+    const int ntiles = P.nslices >> 1;
+    const PartialRec* rq = recs + P.partial_off + (int64_t)q * ntiles;
     const SliceInfo* sl = slices + P.slice_off;
+    // lane = slice (two rounds cover the 64 slices of the largest tile top-2 problem)
     float k[4];
-    float K0 = 0.f;
+    T2Top t = {0.f, 0.f, 0, 0};
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const int s = lane + 32 * j;
         float2 kv = make_float2(0.f, 0.f);
-        if (s < P.nslices) kv = *reinterpret_cast<const float2*>(rq + s);
+        if (s < P.nslices) kv = reinterpret_cast<const float2*>(rq)[s];
         k[2 * j] = kv.x;
         k[2 * j + 1] = kv.y;
-        K0 = fmaxf(K0, kv.x);
+        t2_merge(t, kv.x, kv.y, s);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) K0 = fmaxf(K0, __shfl_xor_sync(full, K0, o));
-    if (!t2_valid(K0)) return 0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float b0 = __shfl_xor_sync(full, t.K0, o), b1 = __shfl_xor_sync(full, t.K1, o);
+        t2_merge(t, b0, b1, 0);
+    }
+    Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
+    const float Ktop = __shfl_sync(full, top1 ? t.K0 : t.K1, 0);
     float tmin2, tmax2;
     stats_read(P.t_stats, tmin2, tmax2);
     const float qn2 = __ldg(P.q_n2 + q);
     const float inv_s = 1.f / t2_scale(qn2, tmax2);
-    const float thr = t2_value(K0, inv_s) - 2.f * dot_margin(qn2, tmin2, tmax2);
+    const float thr = t2_valid(Ktop) ? t2_value(Ktop, inv_s) - 2.f * dot_margin(qn2, tmin2, tmax2) : -INFINITY;
     float qreg[16];
     load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
-    Best2 best = {FLT_MAX, FLT_MAX, -1, -1};
+    unsigned long long n_cand = 0, n_flag = 0;
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         const int s = lane + 32 * j;
         const bool have = s < P.nslices;
         const float v0 = have && t2_valid(k[2 * j]) ? t2_value(k[2 * j], inv_s) : -INFINITY;
         const float v1 = have && t2_valid(k[2 * j + 1]) ? t2_value(k[2 * j + 1], inv_s) : -INFINITY;
-        unsigned scan = __ballot_sync(full, v1 > thr);
-        unsigned one = __ballot_sync(full, v0 > thr && !(v1 > thr));
+        const bool flagged = v1 > thr;                               // both entries above: a third may be hidden
+        unsigned one = __ballot_sync(full, v0 > thr && !flagged);
+        n_flag += __popc(__ballot_sync(full, flagged));
+        n_cand += __popc(one);
+        bool inline_scan = flagged && work == nullptr;
+        if (flagged && work != nullptr) {
+            const SliceInfo my = sl[s];
+            const int span = slice_span(my);
+            const uint32_t nitem = (uint32_t)((span + RESCAN_ROWS - 1) / RESCAN_ROWS);
+            uint32_t* wcount = reinterpret_cast<uint32_t*>(counters + 2);
+            const uint32_t base = atomicAdd(wcount, nitem);
+            if (base + nitem <= work_cap) {
+                for (uint32_t kk = 0; kk < nitem; kk++) {
+                    WorkItem w = {P.q_f32 + (size_t)q * VSM_DIM, P.t_f32, key, my, (int32_t)(kk * RESCAN_ROWS), 0};
+                    work[base + kk] = w;
+                }
+            } else {
+                // list full: scan inline, and void the slots this reservation still owns
+                inline_scan = true;
+                for (uint32_t kk = base; kk < work_cap && kk < base + nitem; kk++) {
+                    WorkItem w = {nullptr, nullptr, nullptr, my, 0, 0};
+                    work[kk] = w;
+                }
+            }
+        }
+        unsigned scan = __ballot_sync(full, inline_scan);
         while (scan) {
             const int l0 = __ffs(scan) - 1; scan &= scan - 1;
             scan_slice<SELECT_U>(qreg, P.t_f32, sl[l0 + 32 * j], h, l16, best);
@@ -272,8 +334,7 @@ __device__ __noinline__ unsigned long long t2_resolve_top1(const Problem& P, con
             const int src = h ? lb : la;
             const float ks = __shfl_sync(full, k[2 * j], src < 0 ? 0 : src);
             int32_t jrow[1];
-            jrow[0] = -1;
-            if (src >= 0) { const SliceInfo si = sl[src + 32 * j]; jrow[0] = si.t_index0 + slice_row(si, t2_col(ks)); }
+            jrow[0] = src >= 0 ? t2_row(sl, src + 32 * j, ks) : -1;
             score_n<1>(qreg, P.t_f32, jrow, l16, best);
         }
     }
@@ -281,9 +342,135 @@ __device__ __noinline__ unsigned long long t2_resolve_top1(const Problem& P, con
     const int32_t oi0 = __shfl_sync(full, best.i0, 16), oi1 = __shfl_sync(full, best.i1, 16);
     if (oi0 >= 0) insert2(od0, oi0, best.d0, best.i0, best.d1, best.i1);
     if (oi1 >= 0) insert2(od1, oi1, best.d0, best.i0, best.d1, best.i1);
-    const float d = __shfl_sync(full, best.d0, 0);
-    const int32_t i = __shfl_sync(full, best.i0, 0);
-    return i >= 0 ? result_key(d, i) : 0ull;
+    best.d0 = __shfl_sync(full, best.d0, 0); best.d1 = __shfl_sync(full, best.d1, 0);
+    best.i0 = __shfl_sync(full, best.i0, 0); best.i1 = __shfl_sync(full, best.i1, 0);
+    if (lane == 0 && counters) {
+        if (n_cand) atomicAdd(counters, n_cand);
+        if (n_flag) atomicAdd(counters + 1, n_flag);
+    }
+    return best;
+}
+
+// filter_kernel's lazy resolution of a DEFERRED reverse row: exact nearest neighbour, slices scanned in place.
+__device__ __forceinline__ unsigned long long t2_resolve_top1(const Problem& P, const PartialRec* __restrict__ recs,
+                                                              const SliceInfo* __restrict__ slices, int q, int lane) {
+    const Best2 b = t2_general(P, recs, slices, q, lane, true, nullptr, nullptr, 0u, nullptr);
+    return b.i0 >= 0 ? result_key(b.d0, b.i0) : 0ull;
+}
+
+// Lane = query (a warp takes 2^gshift <= 32 consecutive queries of one tile top-2 problem; groups[] = cumulative
+// number of such warps per problem).  Reading the records, the dismissal and the uniqueness test are per-lane
+// arithmetic; only the queries that need an exact distance take the warp's time: two at a time, one per half-warp.
+// The host picks the group size from the size of the call: 32 queries per warp when there are plenty (a ragged
+// batch: 141K queries), 2 when the call is one frame pair and latency is what counts.
+constexpr int T2_SELECT_WARPS = 8;
+__global__ void __launch_bounds__(T2_SELECT_WARPS * 32)
+t2_select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t* __restrict__ groups,
+                 const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
+                 unsigned long long* __restrict__ out_key, unsigned long long* __restrict__ counters,
+                 WorkItem* __restrict__ work, uint32_t work_cap, int gshift) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
+    const unsigned full = 0xffffffffu;
+    const int g = (int)blockIdx.x * T2_SELECT_WARPS + (threadIdx.x >> 5);
+    if (g >= groups[nproblems]) return;
+    int lo = 0, hi = nproblems;                              // the problem with groups[p] <= g < groups[p + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (groups[mid] <= g) lo = mid; else hi = mid;
+    }
+    const Problem P = problems[lo];
+    const SliceInfo* sl = slices + P.slice_off;
+    const int q = ((g - groups[lo]) << gshift) + lane;
+    const bool live = lane < (1 << gshift) && q < P.nq;
+    const int ntiles = P.nslices >> 1;
+    const bool top1 = (P.exact & 16) != 0;
+
+    // per lane: the two largest keys of the query, with their slices
+    T2Top t = {0.f, 0.f, 0, 0};
+    if (live) {
+        const float4* rq = reinterpret_cast<const float4*>(recs + P.partial_off + (int64_t)q * ntiles);
+        for (int n0 = 0; n0 < ntiles; n0 += 4) {             // four independent loads in flight: one latency per round
+            float4 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) r[j] = n0 + j < ntiles ? rq[n0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                t2_merge(t, r[j].x, r[j].y, 2 * (n0 + j));
+                t2_merge(t, r[j].z, r[j].w, 2 * (n0 + j) + 1);
+            }
+        }
+    }
+    float tmin2, tmax2;
+    stats_read(P.t_stats, tmin2, tmax2);
+    const float qn2 = live ? __ldg(P.q_n2 + q) : 1.f;
+    const float margin = dot_margin(qn2, tmin2, tmax2);
+    const float inv_s = 1.f / t2_scale(qn2, tmax2);
+    unsigned long long* o = out_key + (P.out_off + (live ? q : 0)) * 2;
+    const bool has0 = live && t2_valid(t.K0), has1 = has0 && t2_valid(t.K1);
+    const float a0 = has0 ? t2_value(t.K0, inv_s) : 0.f;
+    const float a1 = has1 ? t2_value(t.K1, inv_s) : -INFINITY;
+    const int32_t i0c = has0 ? t2_row(sl, t.S0, t.K0) : -1;
+    const bool unique = a1 < a0 - 2.f * margin;
+    // 0 = answered here, 1 = one exact distance decides, 2 = general case
+    int cls = 0;
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    float lo1 = 0.f, hi1 = 0.f;
+    if (has0) {
+        if (top1) {
+            k0 = unique ? result_key(0.f, i0c) : T2_DEFERRED;
+        } else if (P.skip_ratio2 > 0.f && has1) {
+            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
+            hi1 = qn2 + tmax2 - 2.f * (a1 - margin);                 // the row behind a1 is at most this far (squared)
+            lo1 = qn2 + tmin2 - 2.f * (a1 + margin);                 // every row but i0c is at least this far
+            if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) cls = 0;    // the ratio test cannot pass
+            else cls = unique ? 1 : 2;
+        } else {
+            cls = 2;
+        }
+    }
+    // one exact distance: two queries per step, one per half-warp
+    float e0 = 0.f;
+    unsigned pend = __ballot_sync(full, cls == 1);
+    unsigned n_cand = __popc(pend);
+    while (pend) {
+        const int la = __ffs(pend) - 1; pend &= pend - 1;
+        int lb = -1;
+        if (pend) { lb = __ffs(pend) - 1; pend &= pend - 1; }
+        const int src = h ? lb : la;
+        const int ssrc = src < 0 ? la : src;
+        const int qq = __shfl_sync(full, q, ssrc);
+        const int32_t row = __shfl_sync(full, i0c, ssrc);
+        float qreg[16];
+        load_qreg(qreg, P.q_f32 + (size_t)qq * VSM_DIM, l16);
+        const float d2 = canon_l2sqr_halfwarp(qreg, P.t_f32 + (size_t)row * VSM_DIM, l16);
+        const float e = __fsqrt_rn(d2);
+        const float ea = __shfl_sync(full, e, 0), eb = __shfl_sync(full, e, 16);
+        if (lane == la) e0 = ea;
+        if (lane == lb) e0 = eb;
+    }
+    if (cls == 1) {
+        const float r2 = P.ratio * P.ratio, e2 = e0 * e0;
+        if (hi1 > 0.f && e2 >= r2 * hi1 * 1.002f) cls = 0;                                   // fails whatever the second is
+        else if (lo1 > 0.f && e2 * 1.002f < r2 * lo1) { cls = 0; k0 = result_key(e0, i0c); k1 = result_key(FLT_MAX, 0); }
+        else cls = 2;
+    }
+    if (live && cls == 0) { o[0] = k0; o[1] = k1; }
+    // general case, one query at a time
+    unsigned gen = __ballot_sync(full, cls == 2);
+    while (gen) {
+        const int l0 = __ffs(gen) - 1; gen &= gen - 1;
+        const int qq = __shfl_sync(full, q, l0);
+        unsigned long long* oq = out_key + (P.out_off + qq) * 2;
+        const Best2 b = t2_general(P, recs, slices, qq, lane, false, oq, work, work_cap, counters);
+        // plain stores: this warp is the only writer of the slots until rescan_kernel runs
+        if (lane == 0) {
+            oq[0] = b.i0 >= 0 ? result_key(b.d0, b.i0) : 0ull;
+            oq[1] = b.i1 >= 0 ? result_key(b.d1, b.i1) : 0ull;
+        }
+    }
+    if (lane == 0 && n_cand) atomicAdd(counters, (unsigned long long)n_cand);
 }
 
 __global__ void __launch_bounds__(SELECT_WARPS * 32)
@@ -297,7 +484,7 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     const Problem P = problems[problem0 + blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = (int)blockIdx.x * SELECT_WARPS + warp;
-    if (q >= P.nq) return;
+    if (q >= P.nq || (P.exact & 8)) return;                 // tile top-2 problems: t2_select_kernel
     const int h = lane >> 4, l16 = lane & 15;
     const unsigned full = 0xffffffffu;
 
@@ -311,152 +498,6 @@ select_kernel(const Problem* __restrict__ problems, int problem0,
     if (P.exact & 1) {
         load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
         for (int s = 0; s < P.nslices; s++) scan_slice<SELECT_U>(qreg, P.t_f32, sl[s], h, l16, best);
-    } else if (P.exact & 8) {
-        // ----- tile top-2 records (pair matching on small train sets, see t2_scale): per (tile, column half) the
-        // exact two largest approximate dots with their column.  Their union holds the exact two largest values
-        // a0 >= a1 of the whole train set, and every row not recorded lies below its slice's second entry.
-        //   forward problem of a ratio-only caller (skip_ratio2 > 0):
-        //     (1) dismissal from a0 / a1 alone, as for the other record kinds: no re-score;
-        //     (2) a1 < a0 - 2*margin: the nearest neighbour is the row behind a0 and nobody else -- ONE exact
-        //         distance e0 (the other half-warp scores the row behind a1: e1c >= the true second distance d1);
-        //         e0 >= ratio * e1c  ->  the test fails (exactly: d1 <= e1c and fp32 rounding is monotone);
-        //         e0 clearly below ratio * (a lower bound on every other row's distance)  ->  it passes, and the
-        //         second slot gets a sentinel distance (FLT_MAX) that makes filter_kernel's fp32 test pass;
-        //     (3) otherwise (the ratio lands inside the bf16 band, ~1 % of the matching queries): the general path;
-        //   reverse problem of a mutual test (exact bit 4; filter_kernel reads only the nearest INDEX):
-        //     a1 < a0 - 2*margin: the index is the row behind a0, nothing is loaded or scored; else general path;
-        //   general path: every recorded entry above thr (a1 - 2*margin, or a0 - 2*margin when only the nearest
-        //     is wanted) is re-scored exactly; a slice whose SECOND entry is above thr may hide a third one and is
-        //     re-scanned by rescan_kernel (128 rows, one work item).
-        const PartialRec* rq = recs + P.partial_off + (int64_t)q * P.nslices;
-        const bool top1 = (P.exact & 16) != 0;
-        float k[4];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int s = lane + 32 * j;
-            float2 kv = make_float2(0.f, 0.f);
-            if (s < P.nslices) kv = *reinterpret_cast<const float2*>(rq + s);
-            k[2 * j] = kv.x;
-            k[2 * j + 1] = kv.y;
-        }
-        // the two largest keys over all slices, each with its slice
-        float K0 = k[0], K1 = k[1];
-        int S0 = lane, S1 = lane;
-        if (k[2] > K0) { K1 = fmaxf(K0, k[3]); S1 = K0 >= k[3] ? S0 : lane + 32; K0 = k[2]; S0 = lane + 32; }
-        else if (k[2] > K1) { K1 = k[2]; S1 = lane + 32; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float b0 = __shfl_xor_sync(full, K0, o), b1 = __shfl_xor_sync(full, K1, o);
-            const int t0 = __shfl_xor_sync(full, S0, o), t1 = __shfl_xor_sync(full, S1, o);
-            if (b0 > K0) {
-                if (K0 >= b1) { K1 = K0; S1 = S0; } else { K1 = b1; S1 = t1; }
-                K0 = b0; S0 = t0;
-            } else if (b0 > K1) { K1 = b0; S1 = t0; }
-        }
-        // equal keys of different slices may leave the lanes with different (equally good) answers: lane 0's counts
-        K0 = __shfl_sync(full, K0, 0); K1 = __shfl_sync(full, K1, 0);
-        S0 = __shfl_sync(full, S0, 0); S1 = __shfl_sync(full, S1, 0);
-        float tmin2, tmax2;
-        stats_read(P.t_stats, tmin2, tmax2);
-        const float qn2 = __ldg(P.q_n2 + q);
-        const float margin = dot_margin(qn2, tmin2, tmax2);
-        const float inv_s = 1.f / t2_scale(qn2, tmax2);
-        unsigned long long* o = out_key + (P.out_off + q) * 2;
-        if (!t2_valid(K0)) {                                         // no train row at all
-            if (lane == 0) { o[0] = 0ull; o[1] = 0ull; }
-            return;
-        }
-        const float a0 = t2_value(K0, inv_s);
-        const bool has1 = t2_valid(K1);
-        const float a1 = has1 ? t2_value(K1, inv_s) : -INFINITY;
-        const int32_t i0c = sl[S0].t_index0 + slice_row(sl[S0], t2_col(K0));
-        const bool unique = a1 < a0 - 2.f * margin;
-        if (top1) {
-            // unique: the nearest neighbour is the row behind a0, nothing is scored.  Otherwise the row is left
-            // DEFERRED: filter_kernel resolves it (t2_resolve_top1) only if some surviving forward match points at
-            // it -- unmatched rows, whose two best are both noise and usually within the margin of each other, are
-            // hardly ever asked for.
-            if (lane == 0) { o[0] = unique ? result_key(0.f, i0c) : T2_DEFERRED; o[1] = 0ull; }
-            return;
-        } else if (P.skip_ratio2 > 0.f && has1) {
-            const float lo0 = qn2 + tmin2 - 2.f * (a0 + margin);
-            const float hi1 = qn2 + tmax2 - 2.f * (a1 - margin);
-            if (hi1 > 0.f && lo0 >= P.skip_ratio2 * hi1) {
-                if (lane == 0) { o[0] = 0ull; o[1] = 0ull; }
-                return;
-            }
-            if (unique) {
-                load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
-                const int32_t i1c = sl[S1].t_index0 + slice_row(sl[S1], t2_col(K1));
-                const float d2 = canon_l2sqr_halfwarp(qreg, P.t_f32 + (size_t)(h ? i1c : i0c) * VSM_DIM, l16);
-                const float e = __fsqrt_rn(d2);
-                const float e0 = __shfl_sync(full, e, 0), e1c = __shfl_sync(full, e, 16);
-                int verdict = 0;                                      // 1 = fails, 2 = passes, 0 = undecided
-                if (!(e0 < __fmul_rn(P.ratio, e1c))) verdict = 1;
-                else {
-                    const float lo1 = qn2 + tmin2 - 2.f * (a1 + margin);         // every row but i0c is at least this far (squared)
-                    if (lo1 > 0.f && e0 * e0 * 1.002f < P.ratio * P.ratio * lo1) verdict = 2;
-                }
-                if (verdict) {
-                    if (lane == 0) {
-                        o[0] = verdict == 2 ? result_key(e0, i0c) : 0ull;
-                        o[1] = verdict == 2 ? result_key(FLT_MAX, 0) : 0ull;
-                        atomicAdd(counters, 2ull);
-                    }
-                    return;
-                }
-            }
-        }
-        // general path
-        load_qreg(qreg, P.q_f32 + (size_t)q * VSM_DIM, l16);
-        const float thr = a1 - 2.f * margin;
-        int32_t* list = s_list[warp];
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int s = lane + 32 * j;
-            const bool have = s < P.nslices;
-            const SliceInfo my = have ? sl[s] : SliceInfo{0, 0, 0, 0};
-            const float v0 = have && t2_valid(k[2 * j]) ? t2_value(k[2 * j], inv_s) : -INFINITY;
-            const float v1 = have && t2_valid(k[2 * j + 1]) ? t2_value(k[2 * j + 1], inv_s) : -INFINITY;
-            const bool flagged = v1 > thr;                            // both entries above: a third may be hidden
-            const bool on0 = !flagged && v0 > thr;                    // (v1 <= thr here, so at most one candidate)
-            const unsigned bal = __ballot_sync(full, on0);
-            if (on0) list[cnt + __popc(bal & ((1u << lane) - 1u))] = my.t_index0 + slice_row(my, t2_col(k[2 * j]));
-            cnt += __popc(bal);
-            n_cand += on0 ? 1 : 0;
-            n_flag += __popc(__ballot_sync(full, flagged));
-            bool inline_scan = false;
-            if (flagged) {
-                const int span = slice_span(my);
-                const uint32_t nitem = (uint32_t)((span + RESCAN_ROWS - 1) / RESCAN_ROWS);
-                uint32_t* wcount = reinterpret_cast<uint32_t*>(counters + 2);
-                const uint32_t base = atomicAdd(wcount, nitem);
-                if (base + nitem <= work_cap) {
-                    for (uint32_t kk = 0; kk < nitem; kk++) {
-                        WorkItem w = {P.q_f32 + (size_t)q * VSM_DIM, P.t_f32, o, my, (int32_t)(kk * RESCAN_ROWS), 0};
-                        work[base + kk] = w;
-                    }
-                } else {
-                    inline_scan = true;
-                    for (uint32_t kk = base; kk < work_cap && kk < base + nitem; kk++) {
-                        WorkItem w = {nullptr, nullptr, nullptr, my, 0, 0};
-                        work[kk] = w;
-                    }
-                }
-            }
-            unsigned fm = __ballot_sync(full, inline_scan);
-            while (fm) {
-                const int l0 = __ffs(fm) - 1; fm &= fm - 1;
-                scan_slice<SELECT_U>(qreg, P.t_f32, sl[l0 + 32 * j], h, l16, best);
-            }
-        }
-        __syncwarp();
-        for (int base = 0; base < cnt; base += 2) {
-            int32_t jrow[1];
-            jrow[0] = base + h < cnt ? list[base + h] : -1;
-            score_n<1>(qreg, P.t_f32, jrow, l16, best);
-        }
     } else if (P.exact & 4) {
         // ----- append records (small train sets): per slice a count and up to APPEND_CAP - 1 packed values that
         // passed the epilogue's running threshold.  Same two passes as below: the second-largest value over

@@ -856,7 +856,8 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                     stats_read(u.t_stats, tmin2, tmax2);
                     sc = t2_scale(qn2, tmax2);
                 }
-                PartialRec* rec = recs + u.rec_base + (int64_t)row * u.rec_stride + half;
+                // one PartialRec per (query, tile): {H, L of column half 0, H, L of column half 1}
+                PartialRec* rec = recs + u.rec_base + (int64_t)row * u.rec_stride;
                 for (int n = 0; n < ntiles; n++, tile_it++) {
                     const int st = tile_it & 1;
                     mbar_wait(BAR_TFULL + 8 * st, (tile_it >> 1) & 1);
@@ -887,7 +888,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                         if (!full_tile && ucol + 32 * c + 64 > u.t_count) mask32(rb, ucol + 32 * c + 32, u.t_count);
                         t2_step(H, L, rb, sc, (float)(32 * c + 32) * 1.1920928955078125e-7f);
                     }
-                    if (row_valid) *reinterpret_cast<float4*>(rec + n * 2) = make_float4(H, L, -INFINITY, -INFINITY);
+                    if (row_valid) reinterpret_cast<float2*>(rec + n)[half] = make_float2(H, L);
                 }
                 continue;
             }
