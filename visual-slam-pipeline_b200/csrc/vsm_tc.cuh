@@ -538,7 +538,9 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
             TcUnit u;
             bool have = false;
             {
-                const int i = (int)atomicAdd(work_counter, 1u);
+                // the first unit of a CTA is its own index (grid <= units): no atomic round trip before the first
+                // load of a short call; the queue hands out gridDim.x, gridDim.x + 1, ...
+                const int i = (int)blockIdx.x;
                 if (i < nunits) { u = units[i]; have = true; }
                 else { phase_a = false; if (fargs) have = take_redo(fargs, u); }
             }
@@ -551,7 +553,7 @@ tc_top3_kernel(const __grid_constant__ CUtensorMap map_scratch, const __grid_con
                 if (!have) break;
                 // a claimed first-pass unit that has not been scheduled yet (result first used after tile 0 is issued)
                 if (pending_idx < 0 && phase_a) {
-                    pending_idx = (int)atomicAdd(work_counter, 1u);
+                    pending_idx = (int)(gridDim.x + atomicAdd(work_counter, 1u));
                     if (pending_idx >= nunits) { pending_idx = -1; phase_a = false; }
                 }
                 // the redo queue's counters: loaded here, looked at after tile 0 is issued (latency hidden)
