@@ -508,6 +508,22 @@ def extra_pair_numbers(torch, vsm_b200, device):
                                        "device_ms": st["device_ms"], "tc_ms": st["tc_ms"], "select_ms": st["select_ms"],
                                        "useful_tflops_e2e": flops / tb[len(tb) // 2] / 1e12}
     m.clear_store()
+    # A/B of the pair-matching record kinds on the same 64 resident pairs: the threshold-driven top-4 records
+    # (vsm_opts.reserved[5] = 1) against the tile top-2 records every number above was taken with
+    m4 = vsm_b200.Matcher(device=device, engine=vsm_b200.ENGINE_TENSOR, tile_top2=False)
+    try:
+        qh4 = [m4.add_keyframe(2 * p, qs[p]) for p in range(64)]
+        th4 = [m4.add_keyframe(2 * p + 1, tsets[p]) for p in range(64)]
+        for _ in range(3):
+            res4 = m4.match_batch_stored(qh4, th4, 0.75, True, capacity=cap)
+        st4 = m4.stats()
+        out["ragged_batch_64_resident_top4_records"] = {
+            "device_ms": st4["device_ms"], "tc_ms": st4["tc_ms"], "select_ms": st4["select_ms"],
+            "exact_distances": st4["candidates"], "same_matches": bool(all(a.tobytes() == b.tobytes() for a, b in zip(res2, res4))),
+            "note": "tile top-2 records (default): device_ms / tc_ms / select_ms in ragged_batch_64_resident"}
+        out["ragged_batch_64_resident"]["exact_distances"] = st["candidates"]
+    finally:
+        m4.close()
     # configs[2]: 1000 queries vs a 500-keyframe database (500K rows), both forms the reference uses:
     # the stacked global top-2 (src/Slam.cpp:546-574) and LoopCloser::detect's per-keyframe kNN +
     # ratio test (src/LoopCloser.cpp:43-62); queries come from pinned host memory, results go back
