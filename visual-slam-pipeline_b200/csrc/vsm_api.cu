@@ -770,7 +770,8 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                         ntiles <= T2_MAX_TILES && (hp.t2 == 2 || (hp.skip_ratio2 > 0.f && hp.ratio > 0.f && hp.ratio <= 1.f));
         if (t2) {
             d.exact |= 8 | (hp.t2 == 2 ? 16 : 0);
-            qb[i + 1] = qb[i] + ((hp.nq + (1 << t2_gshift) - 1) >> t2_gshift);
+            d.gshift = hp.t2 == 2 ? t2_gshift : std::max(1, t2_gshift - 2);
+            qb[i + 1] = qb[i] + ((hp.nq + (1 << d.gshift) - 1) >> d.gshift);
         } else {
             any_classic = true;
         }
@@ -1006,7 +1007,7 @@ int run_problems(vsm_ctx* ctx, const std::vector<HProblem>& probs, const std::ve
                           dim3(T2_SELECT_WARPS * 32), 0, ctx->stream, reinterpret_cast<const Problem*>(dd + off_prob), P,
                           reinterpret_cast<const int32_t*>(dd + off_qb), (const PartialRec*)ctx->d_recs.p,
                           reinterpret_cast<const SliceInfo*>(dd + off_slice), ctx->d_out_key, ctx->d_counters,
-                          ctx->d_work.p, ctx->work_cap, pl.t2_gshift));
+                          ctx->d_work.p, ctx->work_cap));
             ctx->launches++;
         }
         int max_blocks = 0;

@@ -148,6 +148,7 @@ struct Problem {
     // answered "no match" without any exact re-score (select_kernel)
     float skip_ratio2;
     float ratio;                   // tile top-2 problems with skip_ratio2 > 0: the caller's ratio itself (fp32 test d0 < ratio * d1)
+    int32_t gshift;                // tile top-2 problems: log2 of the queries one warp of t2_select_kernel takes
 };
 
 // One pair for the filter kernel (match_features semantics).

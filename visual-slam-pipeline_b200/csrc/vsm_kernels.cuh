@@ -256,6 +256,7 @@ __device__ __forceinline__ int32_t t2_row(const SliceInfo* sl, int s, float key)
 // a slice whose SECOND entry is above thr may hide a third one and is re-scanned whole (128 rows): by rescan_kernel
 // through `work` (key != nullptr: the result is pushed into key[0..1] by the caller, the re-scans by the atomic
 // cascade), or right here (work == nullptr).  top1: thr = a0 - 2*margin, else a1 - 2*margin.
+template <int CALLER>              // one copy per calling kernel: each is compiled under its caller's register budget
 __device__ __noinline__ Best2 t2_general(const Problem& P, const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
                                          int q, int lane, bool top1, unsigned long long* key, WorkItem* work, uint32_t work_cap,
                                          unsigned long long* counters) {
@@ -354,21 +355,24 @@ __device__ __noinline__ Best2 t2_general(const Problem& P, const PartialRec* __r
 // filter_kernel's lazy resolution of a DEFERRED reverse row: exact nearest neighbour, slices scanned in place.
 __device__ __forceinline__ unsigned long long t2_resolve_top1(const Problem& P, const PartialRec* __restrict__ recs,
                                                               const SliceInfo* __restrict__ slices, int q, int lane) {
-    const Best2 b = t2_general(P, recs, slices, q, lane, true, nullptr, nullptr, 0u, nullptr);
+    const Best2 b = t2_general<1>(P, recs, slices, q, lane, true, nullptr, nullptr, 0u, nullptr);
     return b.i0 >= 0 ? result_key(b.d0, b.i0) : 0ull;
 }
 
-// Lane = query (a warp takes 2^gshift <= 32 consecutive queries of one tile top-2 problem; groups[] = cumulative
-// number of such warps per problem).  Reading the records, the dismissal and the uniqueness test are per-lane
-// arithmetic; only the queries that need an exact distance take the warp's time: two at a time, one per half-warp.
-// The host picks the group size from the size of the call: 32 queries per warp when there are plenty (a ragged
-// batch: 141K queries), 2 when the call is one frame pair and latency is what counts.
+// Lane = query (a warp takes 2^gshift <= 32 consecutive queries of one tile top-2 problem, Problem::gshift;
+// groups[] = cumulative number of such warps per problem).  Reading the records, the dismissal and the uniqueness
+// test are per-lane arithmetic; only the queries that need an exact distance take the warp's time: two at a time,
+// one per half-warp.  The host picks the group size from the size of the call: 32 queries per warp when there are
+// plenty (a ragged batch: 141K queries), 2 when the call is one frame pair and latency is what counts -- and a
+// quarter of that for forward problems, whose warps walk through their exact distances one step after the other
+// while the warps of reverse problems finish at once (ncu on the ragged batch: the kernel is bound by the latency
+// of that walk, achieved occupancy 22 % of a possible 50 %).
 constexpr int T2_SELECT_WARPS = 8;
 __global__ void __launch_bounds__(T2_SELECT_WARPS * 32)
 t2_select_kernel(const Problem* __restrict__ problems, int nproblems, const int32_t* __restrict__ groups,
                  const PartialRec* __restrict__ recs, const SliceInfo* __restrict__ slices,
                  unsigned long long* __restrict__ out_key, unsigned long long* __restrict__ counters,
-                 WorkItem* __restrict__ work, uint32_t work_cap, int gshift) {
+                 WorkItem* __restrict__ work, uint32_t work_cap) {
     pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
@@ -382,8 +386,8 @@ t2_select_kernel(const Problem* __restrict__ problems, int nproblems, const int3
     }
     const Problem P = problems[lo];
     const SliceInfo* sl = slices + P.slice_off;
-    const int q = ((g - groups[lo]) << gshift) + lane;
-    const bool live = lane < (1 << gshift) && q < P.nq;
+    const int q = ((g - groups[lo]) << P.gshift) + lane;
+    const bool live = lane < (1 << P.gshift) && q < P.nq;
     const int ntiles = P.nslices >> 1;
     const bool top1 = (P.exact & 16) != 0;
 
@@ -463,7 +467,7 @@ t2_select_kernel(const Problem* __restrict__ problems, int nproblems, const int3
         const int l0 = __ffs(gen) - 1; gen &= gen - 1;
         const int qq = __shfl_sync(full, q, l0);
         unsigned long long* oq = out_key + (P.out_off + qq) * 2;
-        const Best2 b = t2_general(P, recs, slices, qq, lane, false, oq, work, work_cap, counters);
+        const Best2 b = t2_general<0>(P, recs, slices, qq, lane, false, oq, work, work_cap, counters);
         // plain stores: this warp is the only writer of the slots until rescan_kernel runs
         if (lane == 0) {
             oq[0] = b.i0 >= 0 ? result_key(b.d0, b.i0) : 0ull;
