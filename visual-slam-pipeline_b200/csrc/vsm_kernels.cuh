@@ -247,9 +247,11 @@ __device__ __forceinline__ void t2_merge(T2Top& t, float hk, float lk, int s) { 
         t.K0 = hk; t.S0 = s;
     } else if (hk > t.K1) { t.K1 = hk; t.S1 = s; }
 }
-__device__ __forceinline__ int32_t t2_row(const SliceInfo* sl, int s, float key) {
-    const SliceInfo si = sl[s];
-    return si.t_index0 + slice_row(si, t2_col(key));
+// Train index behind a key of slice s: a tile top-2 problem is one contiguous train range starting at index 0
+// (the planner admits no run lists), slice s = (tile s / 2, column half s % 2) -- no SliceInfo load on the way to
+// the exact distance.
+__device__ __forceinline__ int32_t t2_row(const SliceInfo*, int s, float key) {
+    return (s >> 1) * TILE_N + (s & 1) * HALF_N + t2_col(key);
 }
 
 // One warp, general case of one query: every recorded entry above thr is re-scored exactly (canonical distance),
