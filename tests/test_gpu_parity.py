@@ -436,7 +436,9 @@ def test_per_keyframe_search_adapts_its_epilogue():
     q, db, seg_off = cases.db_case()                       # 30 % of the queries re-observe two keyframes
     nkf = len(seg_off) - 1
     q_none = gen.rows(77, 0, 0, 300)                       # a frame that matches nothing
-    m = vsm_b200.Matcher()
+    # (keyframes of up to 8192 rows keep tile top-2 records by default; the two adaptive record kinds are what
+    # larger keyframes get, and what vsm_opts.reserved[5] = 1 selects here)
+    m = vsm_b200.Matcher(tile_top2=False)
     for s in range(nkf):
         m.add_keyframe(s, db[seg_off[s]:seg_off[s + 1]])
 
@@ -459,6 +461,17 @@ def test_per_keyframe_search_adapts_its_epilogue():
     status, _ = m.loop_detect(900, q, 0.75, min_gap=200, every=1)
     ost, _ = oracle.loop_detect(q, db, seg_off, list(range(nkf)), 900, 0.75, 200, 1)
     assert np.array_equal(status, ost)
+    top4_candidates = st["candidates"]
+    m.close()
+    # the default for keyframes of this size: tile top-2 records, whatever the previous search saw -- same answers,
+    # one exact distance per match instead of ~4 per open pair
+    m = vsm_b200.Matcher()
+    for s in range(nkf):
+        m.add_keyframe(s, db[seg_off[s]:seg_off[s + 1]])
+    for qq in (q, q_none, q):
+        st, best = run(qq)
+        assert st["flagged_slices"] < 20
+    assert 0 < st["candidates"] < top4_candidates
     m.close()
 
 

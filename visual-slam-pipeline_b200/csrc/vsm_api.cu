@@ -1971,6 +1971,17 @@ static int segmented_impl(vsm_ctx* ctx, const float* query, int32_t nq, float ra
         // pairs is measured by every per-keyframe search (either epilogue); the next search uses the
         // maxima-only epilogue only if it was below 0.1 % (no loop in sight: the usual case).
         p.maxima_only = ctx->seg_open_rate < 1e-3f ? 1 : 0;
+        // Keyframes of up to 8192 rows (every keyframe of the reference: SP_MAX_KEYPOINTS = 400, include/Config.h:42)
+        // keep tile top-2 records instead: their cost does not depend on the number of matches either, their
+        // select pass is per-lane arithmetic plus one exact distance per match, and that beats both record kinds
+        // above (500 keyframes x 1000 rows x 1000 queries: tensor-core pass 0.25 ms + select 0.09 ms, against
+        // 0.20 + 0.22 ms maxima-only and 0.44 + 0.18 ms top-4)
+        if (!ctx->t2_off && ratio > 0.f && ratio <= 1.f && (sg.count + TILE_N - 1) / TILE_N <= T2_MAX_TILES &&
+            (sg.count + TILE_N - 1) / TILE_N > ctx->append_max_tiles) {
+            p.maxima_only = 0;
+            p.t2 = 1;
+            p.ratio = ratio;
+        }
         probs.push_back(p);
         HJob j;
         j.fwd_off = p.out_off; j.back_off = -1; j.good_off = slot * nq; j.raw_off = -1;

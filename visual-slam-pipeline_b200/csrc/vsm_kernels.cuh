@@ -436,6 +436,12 @@ t2_select_kernel(const Problem* __restrict__ problems, int nproblems, const int3
             cls = 2;
         }
     }
+    // ratio-only queries the records could not dismiss: counted, so that the host can tell how rare matches are
+    // (segmented_impl picks the next per-keyframe search's record kind from it)
+    if (!top1 && P.skip_ratio2 > 0.f) {
+        const unsigned open = __ballot_sync(full, has1 && cls != 0);     // (a train set of one row never matches)
+        if (lane == 0 && open) atomicAdd(reinterpret_cast<uint32_t*>(counters + 2) + 1, (uint32_t)__popc(open));
+    }
     // one exact distance: two queries per step, one per half-warp
     float e0 = 0.f;
     unsigned pend = __ballot_sync(full, cls == 1);
