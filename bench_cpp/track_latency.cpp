@@ -53,12 +53,16 @@ int main(int argc, char** argv) {
     vsm_ctx* ctx = nullptr;
     if (vsm_create(&o, &ctx) != VSM_OK) { std::fprintf(stderr, "%s\n", vsm_last_error(nullptr)); return 1; }
     vsm_set_profiling(ctx, 0);
-    std::vector<vsm_dmatch> good(n);
-    int32_t ng = 0, h = -1, h2 = -1;
+    std::vector<vsm_dmatch> good(n), raw(n);
+    int32_t ng = 0, nr = 0, h = -1, h2 = -1;
+    // VSM_TRACK_RAW=1: also ask for the raw list, as the reference's own tracking call does (src/Slam.cpp:839-844)
+    const bool want_raw = std::getenv("VSM_TRACK_RAW") && std::atoi(std::getenv("VSM_TRACK_RAW"));
+    vsm_dmatch* rawp = want_raw ? raw.data() : nullptr;
+    int32_t* nrp = want_raw ? &nr : nullptr;
     auto fail = [&](const char* what) { std::fprintf(stderr, "%s: %s\n", what, vsm_last_error(ctx)); std::exit(1); };
     if (vsm_track(ctx, -1, 0, frames, n, 0.75f, 1, good.data(), &ng, nullptr, nullptr, &h) != VSM_OK) fail("first frame");
     for (int f = 1; f <= 20; f++) {                          // warm-up
-        if (vsm_track(ctx, h, f, frames + (size_t)(f % nframes) * n * 256, n, 0.75f, 1, good.data(), &ng, nullptr, nullptr, &h2) != VSM_OK) fail("warm-up");
+        if (vsm_track(ctx, h, f, frames + (size_t)(f % nframes) * n * 256, n, 0.75f, 1, good.data(), &ng, rawp, nrp, &h2) != VSM_OK) fail("warm-up");
         h = h2;
     }
     std::vector<double> us(npairs);
@@ -67,7 +71,7 @@ int main(int argc, char** argv) {
     for (int f = 0; f < npairs; f++) {
         const float* cur = frames + (size_t)((f + 21) % nframes) * n * 256;
         const auto t0 = std::chrono::steady_clock::now();
-        if (vsm_track(ctx, h, f + 21, cur, n, 0.75f, 1, good.data(), &ng, nullptr, nullptr, &h2) != VSM_OK) fail("track");
+        if (vsm_track(ctx, h, f + 21, cur, n, 0.75f, 1, good.data(), &ng, rawp, nrp, &h2) != VSM_OK) fail("track");
         if (f % 5 == 4 && vsm_store_promote(ctx, h2) != VSM_OK) fail("promote");      // inside the timed step
         us[f] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         h = h2;

@@ -9,4 +9,6 @@ g++ -O2 -std=c++17 -I include bench_cpp/track_latency.cpp -L $LIB -lvsm -Wl,-rpa
 N=${1:-2544}
 echo -n '{"tile_top2": '; /tmp/vsm_bench/track_latency $N | tr -d '\n'
 echo -n ', "top4": '; VSM_NO_T2=1 /tmp/vsm_bench/track_latency $N | tr -d '\n'
+echo -n ', "tile_top2_with_raw_list": '; VSM_TRACK_RAW=1 /tmp/vsm_bench/track_latency $N | tr -d '\n'
+echo -n ', "top4_with_raw_list": '; VSM_TRACK_RAW=1 VSM_NO_T2=1 /tmp/vsm_bench/track_latency $N | tr -d '\n'
 echo '}'

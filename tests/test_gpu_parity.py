@@ -1076,6 +1076,24 @@ def test_tile_top2_path_equals_oracle_and_top4_path(tc, top4m):
     q, t = cases.PAIR_CASES["neardup_db"]()
     tc.match_features(q, t, 0.75, mutual=True, want_raw=False)
     assert tc.stats()["flagged_slices"] > 0
+    # one call that mixes the record kinds: a per-keyframe search over keyframes of 300 rows (tile top-2 records)
+    # and one of 9000 rows (above the 32-tile limit: maxima-only / top-4 records) -- both select kernels run
+    sizes = [300, 9000, 300, 2, 700]
+    seg_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    vdb = gen.int_rows(95, 1, 0, int(seg_off[-1]))
+    vq = gen.int_rows(95, 0, 0, 260).copy()
+    vq[:60] = 1000 * vdb[seg_off[1] + 17 * np.arange(60)] + 900 * gen.int_rows(95, 2, 0, 60)      # matches in the big keyframe
+    vq[60:120] = 1000 * vdb[seg_off[4] + 5 * np.arange(60)] + 900 * gen.int_rows(95, 3, 0, 60)    # ... and in a small one
+    qd, db = gen._normalize_int(vq), gen._normalize_int(vdb)
+    with vsm_b200.Matcher() as mm:
+        for k in range(len(sizes)):
+            mm.add_keyframe(k, db[seg_off[k]:seg_off[k + 1]])
+        for _ in range(2):                                         # second call: the adaptive kind may have changed
+            c, lists = mm.detect_candidates(qd, 0.75)
+            oc, ol = oracle.segmented(qd, db, seg_off, 0.75)
+            assert np.array_equal(c, oc) and c[1] > 30 and c[4] > 30
+            for k in range(len(sizes)):
+                assert lists[k].tobytes() == ol[k].tobytes(), k
     # ragged batch and stored pairs take the same path
     qs, ts = [], []
     for p in range(9):
