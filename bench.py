@@ -506,7 +506,10 @@ def extra_pair_numbers(torch, vsm_b200, device):
                                        "matches": int(sum(len(r) for r in res2)), "same_matches_as_from_host": bool(
                                            all(a.tobytes() == b.tobytes() for a, b in zip(res, res2))),
                                        "device_ms": st["device_ms"], "tc_ms": st["tc_ms"], "select_ms": st["select_ms"],
-                                       "useful_tflops_e2e": flops / tb[len(tb) // 2] / 1e12}
+                                       "useful_tflops_e2e": flops / tb[len(tb) // 2] / 1e12,
+                                       # `useful_gflop` counts the forward direction only (BASELINE's 2*nq*nt*256 per pair); the
+                                       # mutual test needs the reverse contraction as well, and the kernel computes both
+                                       "tc_tflops_both_directions": 2 * flops / (st["tc_ms"] * 1e-3) / 1e12 if st["tc_ms"] else None}
     m.clear_store()
     # A/B of the pair-matching record kinds on the same 64 resident pairs: the threshold-driven top-4 records
     # (vsm_opts.reserved[5] = 1) against the tile top-2 records every number above was taken with
